@@ -1,0 +1,262 @@
+// C-ABI entry points of libgplite_b200.so (include/gplite_b200.h): context management,
+// covariance evaluation and the dense linear-algebra hooks.  Fits, energy/gradient and
+// prediction live in fit.cu.
+#include "cf.cuh"
+#include "fit.cuh"
+
+#include <stdarg.h>
+#include <string.h>
+
+namespace gpl {
+
+static thread_local char g_err[1024] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int cf_eval_dev(Ctx* ctx, const gpl_cf_model* cf, const double* d_x1, int64_t n1, int64_t ldx1,
+                const double* d_x2, int64_t n2, int64_t ldx2, int d, bool same,
+                uint64_t term_mask, bool diag_only, double jitter, double* d_out, int64_t ldk) {
+  HostPlan hp;
+  GPL_TRY(make_plan(cf, d, term_mask, &hp));
+  const int F = hp.plan.nfeat;
+  double *z1 = nullptr, *z2 = nullptr;
+  const int64_t ldz1 = n1 > 0 ? n1 : 1, ldz2 = n2 > 0 ? n2 : 1;
+  if (F > 0) {
+    GPL_CUDA(cudaMallocAsync(&z1, sizeof(double) * ldz1 * F, ctx->stream));
+    GPL_TRY(prep_features(ctx, hp, d_x1, n1, ldx1, z1, ldz1));
+    if (!same) {
+      GPL_CUDA(cudaMallocAsync(&z2, sizeof(double) * ldz2 * F, ctx->stream));
+      GPL_TRY(prep_features(ctx, hp, d_x2, n2, ldx2, z2, ldz2));
+    }
+  }
+  int rc;
+  if (diag_only) {
+    const int64_t n = same ? n1 : (n1 < n2 ? n1 : n2);
+    rc = cf_diag(ctx, hp.plan, z1, ldz1, same ? z1 : z2, same ? ldz1 : ldz2, n, jitter, d_out);
+  } else {
+    rc = cf_pairwise(ctx, hp.plan, z1, n1, ldz1, z2, n2, ldz2, same, jitter, d_out, ldk);
+  }
+  if (z1) GPL_CUDA(cudaFreeAsync(z1, ctx->stream));
+  if (z2) GPL_CUDA(cudaFreeAsync(z2, ctx->stream));
+  return rc;
+}
+
+}  // namespace gpl
+
+using namespace gpl;
+
+extern "C" {
+
+int gpl_abi_version(void) { return GPL_ABI_VERSION; }
+
+const char* gpl_last_error(void) { return g_err; }
+
+int gpl_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+int gpl_ctx_create(int device, uint64_t stream, gpl_ctx** out) {
+  if (!out) return GPL_ERR_BAD_ARG;
+  *out = nullptr;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    set_error("no CUDA device available (%s); libgplite_b200 has no CPU fallback",
+              e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
+    return GPL_ERR_CUDA;
+  }
+  GPL_CUDA(cudaSetDevice(device));
+  Ctx* c = new Ctx();
+  c->device = device;
+  if (stream) {
+    c->stream = (cudaStream_t)(uintptr_t)stream;
+    c->own_stream = false;
+  } else {
+    GPL_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    c->own_stream = true;
+  }
+  cudaDeviceProp prop;
+  GPL_CUDA(cudaGetDeviceProperties(&prop, device));
+  c->sm_count = prop.multiProcessorCount;
+  GPL_CUDA(cudaMalloc(&c->d_info, sizeof(int32_t) * 4));
+  GPL_CUDA(cudaMalloc(&c->d_scal, sizeof(double) * 256));
+  GPL_CUDA(cudaMallocHost(&c->h_scal, sizeof(double) * 256));
+  // keep freed async allocations cached in the pool: fits reuse multi-GB buffers
+  cudaMemPool_t pool;
+  if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+    uint64_t thr = UINT64_MAX;
+    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+  }
+  *out = reinterpret_cast<gpl_ctx*>(c);
+  return GPL_OK;
+}
+
+int gpl_ctx_destroy(gpl_ctx* h) {
+  Ctx* c = reinterpret_cast<Ctx*>(h);
+  if (!c) return GPL_OK;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  if (c->dinv) cudaFree(c->dinv);
+  if (c->d_info) cudaFree(c->d_info);
+  if (c->d_scal) cudaFree(c->d_scal);
+  if (c->h_scal) cudaFreeHost(c->h_scal);
+  if (c->own_stream) cudaStreamDestroy(c->stream);
+  delete c;
+  return GPL_OK;
+}
+
+int gpl_ctx_sync(gpl_ctx* h) {
+  Ctx* c = reinterpret_cast<Ctx*>(h);
+  GPL_CUDA(cudaStreamSynchronize(c->stream));
+  return GPL_OK;
+}
+
+int64_t gpl_ctx_launch_count(gpl_ctx* h) { return reinterpret_cast<Ctx*>(h)->launches; }
+
+int gpl_dev_alloc(gpl_ctx* h, uint64_t bytes, void** dptr) {
+  Ctx* c = reinterpret_cast<Ctx*>(h);
+  GPL_CUDA(cudaSetDevice(c->device));
+  cudaError_t e = cudaMalloc(dptr, bytes ? bytes : 16);
+  if (e == cudaErrorMemoryAllocation) {
+    cudaGetLastError();
+    set_error("device allocation of %llu bytes failed", (unsigned long long)bytes);
+    return GPL_ERR_NOMEM;
+  }
+  GPL_CUDA(e);
+  return GPL_OK;
+}
+
+int gpl_dev_free(gpl_ctx* h, void* dptr) {
+  Ctx* c = reinterpret_cast<Ctx*>(h);
+  GPL_CUDA(cudaStreamSynchronize(c->stream));
+  GPL_CUDA(cudaFree(dptr));
+  return GPL_OK;
+}
+
+int gpl_memcpy_h2d(gpl_ctx* h, void* dst, const void* src, uint64_t bytes) {
+  Ctx* c = reinterpret_cast<Ctx*>(h);
+  GPL_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, c->stream));
+  GPL_CUDA(cudaStreamSynchronize(c->stream));
+  return GPL_OK;
+}
+
+int gpl_memcpy_d2h(gpl_ctx* h, void* dst, const void* src, uint64_t bytes) {
+  Ctx* c = reinterpret_cast<Ctx*>(h);
+  GPL_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, c->stream));
+  GPL_CUDA(cudaStreamSynchronize(c->stream));
+  return GPL_OK;
+}
+
+int gpl_cf_eval_dev(gpl_ctx* h, const gpl_cf_model* cf, const double* d_x1, int64_t n1,
+                    const double* d_x2, int64_t n2, int32_t d, int32_t same, uint64_t term_mask,
+                    int32_t diag_only, double jitter, double* d_out, int64_t ldk) {
+  Ctx* c = reinterpret_cast<Ctx*>(h);
+  if (n1 < 0 || n2 < 0 || d <= 0 || !d_out || (!diag_only && ldk < n1)) {
+    set_error("gpl_cf_eval_dev: bad dimensions");
+    return GPL_ERR_BAD_ARG;
+  }
+  return cf_eval_dev(c, cf, d_x1, n1, n1 > 0 ? n1 : 1, same ? d_x1 : d_x2, same ? n1 : n2,
+                     same ? (n1 > 0 ? n1 : 1) : (n2 > 0 ? n2 : 1), d, same != 0, term_mask,
+                     diag_only != 0, jitter, d_out, ldk);
+}
+
+int gpl_cf_eval(gpl_ctx* h, const gpl_cf_model* cf, const double* x1, int64_t n1, const double* x2,
+                int64_t n2, int32_t d, int32_t same, uint64_t term_mask, int32_t diag_only,
+                double jitter, double* out) {
+  Ctx* c = reinterpret_cast<Ctx*>(h);
+  if (same) { x2 = x1; n2 = n1; }
+  if (n1 < 0 || n2 < 0 || d <= 0) {
+    set_error("gpl_cf_eval: bad dimensions");
+    return GPL_ERR_BAD_ARG;
+  }
+  const int64_t nout = diag_only ? (n1 < n2 ? n1 : n2) : n1 * n2;
+  if (nout == 0) return GPL_OK;
+  double *dx1 = nullptr, *dx2 = nullptr, *dk = nullptr;
+  cudaStream_t s = c->stream;
+  GPL_CUDA(cudaMallocAsync(&dx1, sizeof(double) * n1 * d, s));
+  GPL_CUDA(cudaMemcpyAsync(dx1, x1, sizeof(double) * n1 * d, cudaMemcpyHostToDevice, s));
+  if (!same) {
+    GPL_CUDA(cudaMallocAsync(&dx2, sizeof(double) * n2 * d, s));
+    GPL_CUDA(cudaMemcpyAsync(dx2, x2, sizeof(double) * n2 * d, cudaMemcpyHostToDevice, s));
+  }
+  {
+    cudaError_t e = cudaMallocAsync(&dk, sizeof(double) * nout, s);
+    if (e == cudaErrorMemoryAllocation) {
+      cudaGetLastError();
+      set_error("gpl_cf_eval: cannot allocate %lld bytes for K", (long long)(nout * 8));
+      return GPL_ERR_NOMEM;
+    }
+    GPL_CUDA(e);
+  }
+  int rc = cf_eval_dev(c, cf, dx1, n1, n1, same ? dx1 : dx2, n2, n2, d, same != 0, term_mask,
+                       diag_only != 0, jitter, dk, n1);
+  if (rc == GPL_OK) {
+    GPL_CUDA(cudaMemcpyAsync(out, dk, sizeof(double) * nout, cudaMemcpyDeviceToHost, s));
+  }
+  GPL_CUDA(cudaFreeAsync(dx1, s));
+  if (dx2) GPL_CUDA(cudaFreeAsync(dx2, s));
+  GPL_CUDA(cudaFreeAsync(dk, s));
+  GPL_CUDA(cudaStreamSynchronize(s));
+  return rc;
+}
+
+static int native_cf(gpl_ctx* h, int kind, const double* x1, int64_t n1, const double* x2,
+                     int64_t n2, int32_t d, double p0, double p1, double p2, int32_t diag_only,
+                     double* out) {
+  gpl_cf_factor f;
+  memset(&f, 0, sizeof(f));
+  f.kind = kind;
+  f.p[0] = p0; f.p[1] = p1; f.p[2] = p2;
+  gpl_cf_model m{1, 1, &f};
+  return gpl_cf_eval(h, &m, x1, n1, x2, n2, d, 0, 0, diag_only, 0.0, out);
+}
+
+int gpl_cf_sexp_c(gpl_ctx* h, const double* x1, int64_t n1, const double* x2, int64_t n2,
+                  int32_t d, double lscale, double magn, int32_t diag_only, double* out) {
+  return native_cf(h, GPL_CF_SEXP, x1, n1, x2, n2, d, lscale, magn, 0, diag_only, out);
+}
+int gpl_cf_matern32_c(gpl_ctx* h, const double* x1, int64_t n1, const double* x2, int64_t n2,
+                      int32_t d, double lscale, double magn, int32_t diag_only, double* out) {
+  return native_cf(h, GPL_CF_MATERN32, x1, n1, x2, n2, d, lscale, magn, 0, diag_only, out);
+}
+int gpl_cf_matern52_c(gpl_ctx* h, const double* x1, int64_t n1, const double* x2, int64_t n2,
+                      int32_t d, double lscale, double magn, int32_t diag_only, double* out) {
+  return native_cf(h, GPL_CF_MATERN52, x1, n1, x2, n2, d, lscale, magn, 0, diag_only, out);
+}
+int gpl_cf_nn_c(gpl_ctx* h, const double* x1, int64_t n1, const double* x2, int64_t n2, int32_t d,
+                double sigma0, double sigma, double magn, int32_t diag_only, double* out) {
+  return native_cf(h, GPL_CF_NN, x1, n1, x2, n2, d, sigma0, sigma, magn, diag_only, out);
+}
+
+int gpl_dgemm_dev(gpl_ctx* h, int32_t transa, int32_t transb, int64_t m, int64_t n, int64_t k,
+                  double alpha, const double* A, int64_t lda, const double* B, int64_t ldb,
+                  double beta, double* C, int64_t ldc, int32_t lower) {
+  return dgemm(reinterpret_cast<Ctx*>(h), transa != 0, transb != 0, m, n, k, alpha, A, lda, B, ldb,
+               beta, C, ldc, lower != 0);
+}
+
+int gpl_dpotrf_dev(gpl_ctx* h, int64_t n, double* A, int64_t lda, int32_t* info, double* logdet) {
+  return dpotrf(reinterpret_cast<Ctx*>(h), n, A, lda, info, logdet);
+}
+
+int gpl_dtrsm_right_dev(gpl_ctx* h, int32_t trans, int64_t m, int64_t n, const double* L,
+                        int64_t ldl, double* B, int64_t ldb) {
+  return dtrsm_right(reinterpret_cast<Ctx*>(h), trans != 0, m, n, L, ldl, B, ldb, 0);
+}
+
+int gpl_dpotri_dev(gpl_ctx* h, int64_t n, double* A, int64_t lda) {
+  return dpotri(reinterpret_cast<Ctx*>(h), n, A, lda);
+}
+
+}  // extern "C"

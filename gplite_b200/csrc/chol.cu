@@ -1,0 +1,344 @@
+// Blocked FP64 Cholesky, triangular solves and SPD inverse, all built on dgemm() (DMMA).
+//
+// The factorisation is the recursive right-looking form: factor the leading half, solve the
+// panel below it, SYRK-update the trailing half, recurse.  Every flop above the 128x128 base
+// block is a large DMMA GEMM/SYRK (K = n/2, n/4, ...), so trailing updates run at tensor-pipe
+// speed and the trailing matrix is re-read only O(log n) times.  The base block is factored
+// in one CTA's shared memory, which also emits the block's explicit inverse; triangular solves
+// against a base block then become a K=128 GEMM (in place: a tile only overwrites rows/cols it
+// alone read).  The same block inverses seed trtri, and lauum finishes (L L^T)^-1.
+//
+// Replaces base-R chol() / forwardsolve() / backsolve() (LAPACK dpotrf, BLAS dtrsm) at
+// R/laplace.R:28-29, R/ep.R:39-42, R/gp_fit.R:108-110, R/linear_algebra.R:28-32,
+// R/gp_pred.R:218.
+#include "common.cuh"
+
+#include <math.h>
+
+namespace gpl {
+
+namespace {
+
+constexpr int PLD = NB + 1;
+constexpr int POTF2_THREADS = 1024;
+constexpr int POTF2_SMEM = NB * PLD * (int)sizeof(double);
+
+// Factor one nb x nb (nb <= 128) diagonal block in shared memory and emit its inverse.
+//   A    : in/out, lower triangle replaced by L
+//   Linv : out, 128 x 128 (ld 128), lower = L^-1, strict upper = 0, identity padding beyond nb
+//   info : device int; set to the smallest 1-based global pivot index that was not > 0
+__global__ void __launch_bounds__(POTF2_THREADS, 1)
+potf2_inv_kernel(double* __restrict__ A, int64_t lda, int nb, double* __restrict__ Linv,
+                 int* __restrict__ info, int pivot_base) {
+  extern __shared__ double S[];
+  const int tid = threadIdx.x;
+  const int ti = tid & (NB - 1);      // row owned in the sweeps
+  const int tc = tid >> 7;            // column phase 0..7
+  constexpr int TC = POTF2_THREADS / NB;
+
+  for (int idx = tid; idx < NB * NB; idx += POTF2_THREADS) {
+    const int i = idx & (NB - 1), c = idx >> 7;
+    double v = (i == c) ? 1.0 : 0.0;
+    if (i < nb && c < nb && i >= c) v = A[(int64_t)c * lda + i];
+    S[c * PLD + i] = v;
+  }
+  __syncthreads();
+
+  // Right-looking elimination on unscaled columns: after step j column j holds a_ij (not yet
+  // divided by sqrt(d_j)); the update uses a_ij * a_kj / d_j == l_ij * l_kj.
+  for (int j = 0; j < NB - 1; ++j) {
+    const double d = S[j * PLD + j];
+    if (tid == 0 && !(d > 0.0) && j < nb) atomicMin(info, pivot_base + j + 1);
+    if (ti > j) {
+      const double w = S[j * PLD + ti] / d;
+      for (int k = j + 1 + tc; k <= ti; k += TC) S[k * PLD + ti] -= w * S[j * PLD + k];
+    }
+    __syncthreads();
+  }
+  if (tid == 0 && !(S[(NB - 1) * PLD + NB - 1] > 0.0) && NB - 1 < nb)
+    atomicMin(info, pivot_base + NB);
+
+  // scale columns: L_ij = a_ij / sqrt(d_j)
+  {
+    double v[NB * NB / POTF2_THREADS];
+#pragma unroll
+    for (int q = 0; q < NB * NB / POTF2_THREADS; ++q) {
+      const int c = tc + q * TC;
+      const double l = sqrt(S[c * PLD + c]);
+      const double a = S[c * PLD + ti];
+      v[q] = (ti == c) ? l : ((ti > c) ? a / l : 0.0);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < NB * NB / POTF2_THREADS; ++q) {
+      const int c = tc + q * TC;
+      S[c * PLD + ti] = v[q];
+      if (ti < nb && c < nb && ti >= c) A[(int64_t)c * lda + ti] = v[q];
+    }
+  }
+  __syncthreads();
+
+  // In-place inverse by forward substitution on unscaled rows U: at step k every row i > k does
+  // U[i][c] -= (L[i][k] / L[k][k]) * U[k][c] (c < k) and U[i][k] = -(L[i][k] / L[k][k]).
+  // Column k+1 of L is prefetched before the barrier, so the overwrite of column k is safe.
+  double l_next = (ti > 0) ? S[0 * PLD + ti] : 0.0;
+  double d_next = S[0];
+  for (int k = 0; k < NB - 1; ++k) {
+    const double lx = l_next / d_next;
+    if (ti > k) {
+      for (int c = tc; c < k; c += TC) S[c * PLD + ti] -= lx * S[c * PLD + k];
+    }
+    l_next = (ti > k + 1) ? S[(k + 1) * PLD + ti] : 0.0;
+    d_next = S[(k + 1) * PLD + k + 1];
+    if (ti > k && tc == (k & (TC - 1))) S[k * PLD + ti] = -lx;
+    __syncthreads();
+  }
+  {
+    double v[NB * NB / POTF2_THREADS];
+    const double dii = S[ti * PLD + ti];
+#pragma unroll
+    for (int q = 0; q < NB * NB / POTF2_THREADS; ++q) {
+      const int c = tc + q * TC;
+      v[q] = (ti == c) ? 1.0 / dii : ((ti > c) ? S[c * PLD + ti] / dii : 0.0);
+    }
+#pragma unroll
+    for (int q = 0; q < NB * NB / POTF2_THREADS; ++q) {
+      const int c = tc + q * TC;
+      Linv[c * NB + ti] = v[q];
+    }
+  }
+}
+
+__global__ void diag_logsum_kernel(const double* __restrict__ A, int64_t lda, int64_t n,
+                                   double* __restrict__ out) {
+  __shared__ double red[32];
+  double s = 0.0;
+  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) s += log(A[i * lda + i]);
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    s = (threadIdx.x < (blockDim.x >> 5)) ? red[threadIdx.x] : 0.0;
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (threadIdx.x == 0) out[0] = 2.0 * s;
+  }
+}
+
+__global__ void copy_block_kernel(const double* __restrict__ src, int64_t lds, double* dst,
+                                  int64_t ldd, int rows, int cols) {
+  for (int idx = threadIdx.x + blockIdx.x * blockDim.x; idx < rows * cols;
+       idx += blockDim.x * gridDim.x) {
+    const int i = idx % rows, c = idx / rows;
+    dst[(int64_t)c * ldd + i] = src[(int64_t)c * lds + i];
+  }
+}
+
+inline int64_t split(int64_t n) {
+  const int64_t nblk = (n + NB - 1) / NB;
+  return (nblk / 2) * NB;
+}
+
+struct Fac {
+  Ctx* ctx;
+  double* dinv;   // block inverses of the factor being built / used
+};
+
+int potf2(const Fac& f, double* A, int64_t lda, int64_t n, int64_t blk0) {
+  static bool configured = false;
+  if (!configured) {
+    GPL_CUDA(cudaFuncSetAttribute(potf2_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  POTF2_SMEM));
+    configured = true;
+  }
+  potf2_inv_kernel<<<1, POTF2_THREADS, POTF2_SMEM, f.ctx->stream>>>(
+      A, lda, (int)n, f.dinv + blk0 * NB * NB, f.ctx->d_info, (int)(blk0 * NB));
+  GPL_LAUNCH_CHECK(f.ctx);
+  return GPL_OK;
+}
+
+// B (m x n) <- B L^-T   (trans) or   B L^-1   (!trans); L is n x n lower with block inverses
+int trsm_right_rec(const Fac& f, bool trans, int64_t m, int64_t n, const double* L, int64_t ldl,
+                   double* B, int64_t ldb, int64_t blk0) {
+  if (m <= 0 || n <= 0) return GPL_OK;
+  if (n <= NB) {
+    return dgemm(f.ctx, false, trans, m, n, n, 1.0, B, ldb, f.dinv + blk0 * NB * NB, NB, 0.0, B,
+                 ldb, false);
+  }
+  const int64_t n1 = split(n), n2 = n - n1;
+  const double* L21 = L + n1;
+  const double* L22 = L + n1 * ldl + n1;
+  double* B2 = B + n1 * ldb;
+  if (trans) {
+    GPL_TRY(trsm_right_rec(f, true, m, n1, L, ldl, B, ldb, blk0));
+    GPL_TRY(dgemm(f.ctx, false, true, m, n2, n1, -1.0, B, ldb, L21, ldl, 1.0, B2, ldb, false));
+    GPL_TRY(trsm_right_rec(f, true, m, n2, L22, ldl, B2, ldb, blk0 + n1 / NB));
+  } else {
+    GPL_TRY(trsm_right_rec(f, false, m, n2, L22, ldl, B2, ldb, blk0 + n1 / NB));
+    GPL_TRY(dgemm(f.ctx, false, false, m, n1, n2, -1.0, B2, ldb, L21, ldl, 1.0, B, ldb, false));
+    GPL_TRY(trsm_right_rec(f, false, m, n1, L, ldl, B, ldb, blk0));
+  }
+  return GPL_OK;
+}
+
+int potrf_rec(const Fac& f, double* A, int64_t lda, int64_t n, int64_t blk0) {
+  if (n <= NB) return potf2(f, A, lda, n, blk0);
+  const int64_t n1 = split(n), n2 = n - n1;
+  double* A21 = A + n1;
+  double* A22 = A + n1 * lda + n1;
+  GPL_TRY(potrf_rec(f, A, lda, n1, blk0));
+  GPL_TRY(trsm_right_rec(f, true, n2, n1, A, lda, A21, lda, blk0));
+  GPL_TRY(dgemm(f.ctx, false, true, n2, n2, n1, -1.0, A21, lda, A21, lda, 1.0, A22, lda, true));
+  GPL_TRY(potrf_rec(f, A22, lda, n2, blk0 + n1 / NB));
+  return GPL_OK;
+}
+
+// B (m x n) <- B X,  X n x n lower triangular with clean (zero) upper parts in its diagonal blocks
+int trmm_right_lower(const Fac& f, int64_t m, int64_t n, const double* X, int64_t ldx, double* B,
+                     int64_t ldb) {
+  if (m <= 0 || n <= 0) return GPL_OK;
+  if (n <= NB) return dgemm(f.ctx, false, false, m, n, n, 1.0, B, ldb, X, ldx, 0.0, B, ldb, false);
+  const int64_t n1 = split(n), n2 = n - n1;
+  double* B2 = B + n1 * ldb;
+  GPL_TRY(trmm_right_lower(f, m, n1, X, ldx, B, ldb));
+  GPL_TRY(dgemm(f.ctx, false, false, m, n1, n2, 1.0, B2, ldb, X + n1, ldx, 1.0, B, ldb, false));
+  GPL_TRY(trmm_right_lower(f, m, n2, X + n1 * ldx + n1, ldx, B2, ldb));
+  return GPL_OK;
+}
+
+// B (n x m) <- alpha X B
+int trmm_left_lower(const Fac& f, double alpha, int64_t n, int64_t m, const double* X, int64_t ldx,
+                    double* B, int64_t ldb) {
+  if (m <= 0 || n <= 0) return GPL_OK;
+  if (n <= NB) return dgemm(f.ctx, false, false, n, m, n, alpha, X, ldx, B, ldb, 0.0, B, ldb, false);
+  const int64_t n1 = split(n), n2 = n - n1;
+  double* B2 = B + n1;
+  GPL_TRY(trmm_left_lower(f, alpha, n2, m, X + n1 * ldx + n1, ldx, B2, ldb));
+  GPL_TRY(dgemm(f.ctx, false, false, n2, m, n1, alpha, X + n1, ldx, B, ldb, 1.0, B2, ldb, false));
+  GPL_TRY(trmm_left_lower(f, alpha, n1, m, X, ldx, B, ldb));
+  return GPL_OK;
+}
+
+// B (n x m) <- X^T B
+int trmm_left_lowerT(const Fac& f, int64_t n, int64_t m, const double* X, int64_t ldx, double* B,
+                     int64_t ldb) {
+  if (m <= 0 || n <= 0) return GPL_OK;
+  if (n <= NB) return dgemm(f.ctx, true, false, n, m, n, 1.0, X, ldx, B, ldb, 0.0, B, ldb, false);
+  const int64_t n1 = split(n), n2 = n - n1;
+  double* B2 = B + n1;
+  GPL_TRY(trmm_left_lowerT(f, n1, m, X, ldx, B, ldb));
+  GPL_TRY(dgemm(f.ctx, true, false, n1, m, n2, 1.0, X + n1, ldx, B2, ldb, 1.0, B, ldb, false));
+  GPL_TRY(trmm_left_lowerT(f, n2, m, X + n1 * ldx + n1, ldx, B2, ldb));
+  return GPL_OK;
+}
+
+// L (n x n lower, factor with block inverses) <- L^-1 in place
+int trtri_rec(const Fac& f, double* L, int64_t ldl, int64_t n, int64_t blk0) {
+  if (n <= NB) {
+    copy_block_kernel<<<16, 256, 0, f.ctx->stream>>>(f.dinv + blk0 * NB * NB, NB, L, ldl, (int)n,
+                                                     (int)n);
+    GPL_LAUNCH_CHECK(f.ctx);
+    return GPL_OK;
+  }
+  const int64_t n1 = split(n), n2 = n - n1;
+  double* L21 = L + n1;
+  double* L22 = L + n1 * ldl + n1;
+  GPL_TRY(trtri_rec(f, L, ldl, n1, blk0));
+  GPL_TRY(trtri_rec(f, L22, ldl, n2, blk0 + n1 / NB));
+  GPL_TRY(trmm_right_lower(f, n2, n1, L, ldl, L21, ldl));          // L21 X11
+  GPL_TRY(trmm_left_lower(f, -1.0, n2, n1, L22, ldl, L21, ldl));   // -X22 (L21 X11)
+  return GPL_OK;
+}
+
+// X (n x n lower) <- X^T X (lower triangle; diagonal blocks come out full)
+int lauum_rec(const Fac& f, double* X, int64_t ldx, int64_t n) {
+  if (n <= NB) return dgemm(f.ctx, true, false, n, n, n, 1.0, X, ldx, X, ldx, 0.0, X, ldx, false);
+  const int64_t n1 = split(n), n2 = n - n1;
+  double* X21 = X + n1;
+  double* X22 = X + n1 * ldx + n1;
+  GPL_TRY(lauum_rec(f, X, ldx, n1));
+  GPL_TRY(dgemm(f.ctx, true, false, n1, n1, n2, 1.0, X21, ldx, X21, ldx, 1.0, X, ldx, true));
+  GPL_TRY(trmm_left_lowerT(f, n2, n1, X22, ldx, X21, ldx));
+  GPL_TRY(lauum_rec(f, X22, ldx, n2));
+  return GPL_OK;
+}
+
+}  // namespace
+
+int ensure_dinv(Ctx* ctx, int64_t n) {
+  const int64_t nblk = (n + NB - 1) / NB;
+  if (nblk > ctx->dinv_blocks) {
+    if (ctx->dinv) GPL_CUDA(cudaFree(ctx->dinv));
+    ctx->dinv = nullptr;
+    ctx->dinv_blocks = 0;
+    GPL_CUDA(cudaMalloc(&ctx->dinv, (size_t)nblk * NB * NB * sizeof(double)));
+    ctx->dinv_blocks = nblk;
+  }
+  return GPL_OK;
+}
+
+int dpotrf_with(Ctx* ctx, double* dinv, int64_t n, double* A, int64_t lda, int32_t* info_host,
+                double* logdet_host) {
+  if (n <= 0) {
+    if (info_host) *info_host = 0;
+    if (logdet_host) *logdet_host = 0.0;
+    return GPL_OK;
+  }
+  if ((lda & 1) || ((uintptr_t)A & 15)) {
+    set_error("dpotrf: A must be 16-byte aligned with an even leading dimension");
+    return GPL_ERR_BAD_ARG;
+  }
+  const int32_t big = 0x7fffffff;
+  GPL_CUDA(cudaMemcpyAsync(ctx->d_info, &big, sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+  Fac f{ctx, dinv};
+  GPL_TRY(potrf_rec(f, A, lda, n, 0));
+  diag_logsum_kernel<<<1, 1024, 0, ctx->stream>>>(A, lda, n, ctx->d_scal);
+  GPL_LAUNCH_CHECK(ctx);
+  int32_t info = 0;
+  double ld = 0.0;
+  GPL_CUDA(cudaMemcpyAsync(&info, ctx->d_info, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+  GPL_CUDA(cudaMemcpyAsync(&ld, ctx->d_scal, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  GPL_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (info == big) info = 0;
+  if (info_host) *info_host = info;
+  if (logdet_host) *logdet_host = ld;
+  if (info != 0) {
+    set_error("the leading minor of order %d is not positive definite", info);
+    return GPL_ERR_NOT_PD;
+  }
+  return GPL_OK;
+}
+
+int dpotrf(Ctx* ctx, int64_t n, double* A, int64_t lda, int32_t* info_host, double* logdet_host) {
+  GPL_TRY(ensure_dinv(ctx, n));
+  return dpotrf_with(ctx, ctx->dinv, n, A, lda, info_host, logdet_host);
+}
+
+int dtrsm_right_with(Ctx* ctx, double* dinv, bool trans, int64_t m, int64_t n, const double* L,
+                     int64_t ldl, double* B, int64_t ldb) {
+  Fac f{ctx, dinv};
+  return trsm_right_rec(f, trans, m, n, L, ldl, B, ldb, 0);
+}
+
+int dtrsm_right(Ctx* ctx, bool trans, int64_t m, int64_t n, const double* L, int64_t ldl,
+                double* B, int64_t ldb, int64_t blk0) {
+  Fac f{ctx, ctx->dinv};
+  return trsm_right_rec(f, trans, m, n, L, ldl, B, ldb, blk0);
+}
+
+int dpotri_with(Ctx* ctx, double* dinv, int64_t n, double* A, int64_t lda) {
+  Fac f{ctx, dinv};
+  GPL_TRY(trtri_rec(f, A, lda, n, 0));
+  GPL_TRY(lauum_rec(f, A, lda, n));
+  return GPL_OK;
+}
+
+int dtrtri_with(Ctx* ctx, double* dinv, int64_t n, double* A, int64_t lda) {
+  Fac f{ctx, dinv};
+  return trtri_rec(f, A, lda, n, 0);
+}
+
+int dpotri(Ctx* ctx, int64_t n, double* A, int64_t lda) {
+  return dpotri_with(ctx, ctx->dinv, n, A, lda);
+}
+
+}  // namespace gpl

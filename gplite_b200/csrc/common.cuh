@@ -1,0 +1,73 @@
+// Internal declarations shared by the translation units of libgplite_b200.so.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <vector>
+
+#include "gplite_b200.h"
+
+namespace gpl {
+
+constexpr int NB = 128;   // base block of the recursive factorisation / solves
+
+void set_error(const char* fmt, ...);
+
+struct Ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  int sm_count = 148;
+  int64_t launches = 0;
+  // scratch: diagonal-block inverses of the most recent factorisation living in this ctx
+  double* dinv = nullptr;       // nblk * NB * NB doubles
+  int64_t dinv_blocks = 0;
+  int32_t* d_info = nullptr;    // device int[4]
+  double* d_scal = nullptr;     // device double[64] for small reductions
+  double* h_scal = nullptr;     // pinned host mirror
+};
+
+#define GPL_CUDA(call)                                                              \
+  do {                                                                              \
+    cudaError_t e__ = (call);                                                       \
+    if (e__ != cudaSuccess) {                                                       \
+      gpl::set_error("%s:%d CUDA error %s: %s", __FILE__, __LINE__,                 \
+                     cudaGetErrorName(e__), cudaGetErrorString(e__));               \
+      return GPL_ERR_CUDA;                                                          \
+    }                                                                               \
+  } while (0)
+
+#define GPL_TRY(call)                      \
+  do {                                     \
+    int s__ = (call);                      \
+    if (s__ != GPL_OK) return s__;         \
+  } while (0)
+
+#define GPL_LAUNCH_CHECK(ctx)                                                       \
+  do {                                                                              \
+    (ctx)->launches++;                                                              \
+    cudaError_t e__ = cudaGetLastError();                                           \
+    if (e__ != cudaSuccess) {                                                       \
+      gpl::set_error("%s:%d kernel launch failed %s: %s", __FILE__, __LINE__,       \
+                     cudaGetErrorName(e__), cudaGetErrorString(e__));               \
+      return GPL_ERR_CUDA;                                                          \
+    }                                                                               \
+  } while (0)
+
+inline int64_t round_up(int64_t a, int64_t b) { return (a + b - 1) / b * b; }
+
+// ---- gemm_f64.cu ----
+int dgemm(Ctx* ctx, bool ta, bool tb, int64_t m, int64_t n, int64_t k, double alpha,
+          const double* A, int64_t lda, const double* B, int64_t ldb, double beta, double* C,
+          int64_t ldc, bool lower);
+
+// ---- chol.cu ----
+int ensure_dinv(Ctx* ctx, int64_t n);
+int dpotrf(Ctx* ctx, int64_t n, double* A, int64_t lda, int32_t* info_host, double* logdet_host);
+int dtrsm_right(Ctx* ctx, bool trans, int64_t m, int64_t n, const double* L, int64_t ldl,
+                double* B, int64_t ldb, int64_t blk0);
+int dpotri(Ctx* ctx, int64_t n, double* A, int64_t lda);
+
+}  // namespace gpl

@@ -1,0 +1,140 @@
+// Vector / elementwise / likelihood kernels and the device-resident fit object.
+#pragma once
+
+#include "cf.cuh"
+
+namespace gpl {
+
+// chol.cu (explicit block-inverse buffer variants)
+int dpotrf_with(Ctx* ctx, double* dinv, int64_t n, double* A, int64_t lda, int32_t* info_host,
+                double* logdet_host);
+int dtrsm_right_with(Ctx* ctx, double* dinv, bool trans, int64_t m, int64_t n, const double* L,
+                     int64_t ldl, double* B, int64_t ldb);
+int dpotri_with(Ctx* ctx, double* dinv, int64_t n, double* A, int64_t lda);
+int dtrtri_with(Ctx* ctx, double* dinv, int64_t n, double* A, int64_t lda);
+
+// RAII device buffer on the context's stream-ordered pool
+struct DevBuf {
+  Ctx* ctx = nullptr;
+  void* p = nullptr;
+  DevBuf() {}
+  DevBuf(const DevBuf&) = delete;
+  DevBuf& operator=(const DevBuf&) = delete;
+  ~DevBuf() { release(); }
+  int alloc(Ctx* c, size_t bytes);
+  void release();
+  double* d() const { return static_cast<double*>(p); }
+};
+
+// ---- vec_kernels.cu -------------------------------------------------------------------------
+// B_ij = delta_ij + s_i (K_ij s_j), lower triangle (R/laplace.R:27)
+int build_B(Ctx* ctx, int64_t n, const double* K, int64_t ldk, const double* s, double* B,
+            int64_t ldb);
+// y = A^T x (A is m x n, y has n entries); for symmetric A this is A x
+int gemv_t(Ctx* ctx, int64_t m, int64_t n, const double* A, int64_t lda, const double* x, double* y);
+// y = A x  (A is m x n)
+int gemv_n(Ctx* ctx, int64_t m, int64_t n, const double* A, int64_t lda, const double* x, double* y);
+// x <- L^-1 b  /  x <- L^-T b using the factor's block inverses; b is destroyed, x != b
+int trsv_lower(Ctx* ctx, const double* dinv, bool trans, int64_t n, const double* L, int64_t ldl,
+               double* b, double* x);
+// out_j = sum_{i >= j} X_ij^2  (column sums of squares of a lower-triangular matrix)
+int lower_colsumsq(Ctx* ctx, int64_t n, const double* X, int64_t ldx, double* out);
+// out_i = sum_j A_ij^2 (row sums of squares, A m x n)
+int rowsumsq(Ctx* ctx, int64_t m, int64_t n, const double* A, int64_t lda, double* out);
+// A[:, j] *= s_j
+int scale_cols(Ctx* ctx, int64_t m, int64_t n, double* A, int64_t lda, const double* s);
+// A[i, :] *= s_i
+int scale_rows(Ctx* ctx, int64_t m, int64_t n, double* A, int64_t lda, const double* s);
+
+enum VecOp {
+  VOP_DIV = 0,        // out = a / b
+  VOP_MUL = 1,        // out = a * b
+  VOP_RSQRT_INV = 2,  // out = sqrt(1 / a)
+  VOP_SQRT = 3,       // out = sqrt(a)
+  VOP_FILL = 4,       // out = alpha
+  VOP_INV = 5,        // out = 1 / a
+  VOP_SUB = 6,        // out = a - b
+  VOP_ADD = 7,        // out = a + b
+  VOP_AXPBY = 8,      // out = alpha a + beta b
+  VOP_COPY = 9
+};
+int vec_op(Ctx* ctx, VecOp op, int64_t n, const double* a, const double* b, double* out,
+           double alpha = 0.0, double beta = 0.0);
+
+enum RedOp {
+  RED_SUM = 0,        // sum a
+  RED_DOT = 1,        // sum a*b
+  RED_SUMLOG = 2,     // sum log a
+  RED_MAXABSDIFF = 3, // max |a - b|
+  RED_MIN = 4,        // min a
+  RED_COUNT_NAN = 5,  // number of NaNs in a (and b if given)
+  RED_SUMSQ = 6,      // sum a^2
+  RED_SUMLOG_PROD = 7 // sum log(a*b)
+};
+// result lands in ctx->d_scal[slot]; fetch_scalars() copies the first `count` slots to the host
+int reduce(Ctx* ctx, RedOp op, int64_t n, const double* a, const double* b, int slot);
+int fetch_scalars(Ctx* ctx, int count, double* host_out);
+
+// ---- likelihood kernels (R/lik.R) -------------------------------------------------------------
+struct LikDev {
+  int kind, link;
+  double param;
+  const double* trials;   // device, may be null
+  const double* offset;   // device, may be null
+};
+// z, V from f, y  (get_pseudodata_la, R/lik.R:188-201)
+int lik_pseudodata_la(Ctx* ctx, const LikDev& lik, int64_t n, const double* f, const double* y,
+                      double* z, double* V);
+// sum_i loglik(f_i, y_i) into d_scal[slot] (get_loglik, R/lik.R:297-366)
+int lik_loglik_sum(Ctx* ctx, const LikDev& lik, int64_t n, const double* f, const double* y,
+                   int slot);
+// EP site update (get_pseudodata_ep + get_tilted_moments, R/lik.R:207-270)
+struct EpSiteArgs {
+  const double* fmean; const double* fvar; const double* z_old; const double* P_old;
+  const double* y;
+  double* z_new; double* V_new; double* P_new;
+  double* cav_mean; double* cav_var; double* logZ;
+  double damping;
+  int quad_order;
+  const double* quad_x;   // device
+  const double* quad_w;   // device
+};
+int lik_ep_sites(Ctx* ctx, const LikDev& lik, int64_t n, const EpSiteArgs& a, int* d_flags);
+// EP evidence terms: sum logZ + 0.5 sum log(vc + V) + 0.5 sum (mc - z)^2 / (vc + V) -> slot
+int ep_evidence_terms(Ctx* ctx, int64_t n, const double* logZ, const double* vc, const double* mc,
+                      const double* z, const double* V, int slot);
+
+// ---- gradient trace (new capability; see gpl_energy_grad) -----------------------------------
+struct GradParam {
+  int factor;   // index into plan.f, or -1 for the likelihood sigma (handled outside)
+  int slot;     // which parameter of the factor: 0.. as in gpl_cf_factor.p ; 3 = period
+};
+constexpr int MAX_GRAD_PARAMS = 24;
+// out[j] = sum_{i,k} (alpha_i alpha_k - s_i Binv_ik s_k) dK_ik/dlog(theta_j), Binv lower triangle
+int grad_trace(Ctx* ctx, const CfPlan& plan, const double* z, int64_t ldz, const double* zaux,
+               int64_t n, const double* Binv, int64_t ldb, const double* s, const double* alpha,
+               int nparam, const GradParam* params, double* d_out /* device, nparam doubles */);
+
+// ---- fit object --------------------------------------------------------------------------------
+struct Fit {
+  int method = 0;        // 0 full, 1 fitc
+  int64_t n = 0, m = 0;
+  int d = 0;
+  int64_t ld = 0;        // leading dimension of Lb
+  DevBuf x;              // n x d training inputs (gp$x)
+  DevBuf Lb;             // factor of B = I + V^-1/2 K V^-1/2  (C_chol = diag(sqrtV) Lb)
+  DevBuf dinv;           // its diagonal-block inverses
+  DevBuf sqrtV;          // n
+  DevBuf alpha;          // n
+  // FITC
+  DevBuf zind;           // m x d
+  DevBuf Kxz;            // n x m (ld = ldx_)
+  int64_t ldkxz = 0;
+  DevBuf Kz_chol, Kz_dinv;   // m x m factor of Kz (+ jitter)
+  DevBuf Lm, Lm_dinv;        // m x m factor of Kz + Kzx S^-1 Kxz  (inv_lemma chol)
+  int64_t ldm = 0;
+  DevBuf S;              // D + V
+  DevBuf Dg;             // FITC diagonal correction D
+};
+
+}  // namespace gpl

@@ -1,0 +1,644 @@
+// HBM-bound vector / matrix-vector / elementwise kernels of the fit loops, the likelihood maths
+// (R/lik.R) and the EP site sweep.  All of these are single-pass, coalesced along the
+// column-major leading dimension, and leave their scalar results in ctx->d_scal so that one
+// small D2H copy per Newton iteration / EP sweep carries every convergence quantity.
+#include "fit.cuh"
+
+#include <math.h>
+
+namespace gpl {
+
+int DevBuf::alloc(Ctx* c, size_t bytes) {
+  release();
+  ctx = c;
+  cudaError_t e = cudaMallocAsync(&p, bytes ? bytes : 16, c->stream);
+  if (e == cudaErrorMemoryAllocation) {
+    cudaGetLastError();
+    p = nullptr;
+    set_error("device allocation of %zu bytes failed", bytes);
+    return GPL_ERR_NOMEM;
+  }
+  GPL_CUDA(e);
+  return GPL_OK;
+}
+
+void DevBuf::release() {
+  if (p && ctx) cudaFreeAsync(p, ctx->stream);
+  p = nullptr;
+}
+
+namespace {
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// block-wide sum, result valid in thread 0
+__device__ __forceinline__ double block_sum(double v, double* red) {
+  v = warp_sum(v);
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  __syncthreads();
+  if (lane == 0) red[w] = v;
+  __syncthreads();
+  if (w == 0) {
+    v = (lane < (int)(blockDim.x >> 5)) ? red[lane] : 0.0;
+    v = warp_sum(v);
+  }
+  return v;
+}
+
+__global__ void build_B_kernel(int64_t n, const double* __restrict__ K, int64_t ldk,
+                               const double* __restrict__ s, double* __restrict__ B, int64_t ldb) {
+  const int64_t j0 = (int64_t)blockIdx.y * 8;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if ((int64_t)(blockIdx.x + 1) * blockDim.x <= j0) return;   // block entirely above the diagonal
+  if (i >= n) return;
+  const double si = s[i];
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    const int64_t j = j0 + c;
+    if (j < n && i >= j) {
+      const double v = si * (K[j * ldk + i] * s[j]);
+      B[j * ldb + i] = (i == j) ? 1.0 + v : v;
+    }
+  }
+}
+
+__global__ void gemv_t_kernel(int64_t m, int64_t n, const double* __restrict__ A, int64_t lda,
+                              const double* __restrict__ x, double* __restrict__ y) {
+  const int lane = threadIdx.x & 31;
+  const int64_t j = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (j >= n) return;
+  const double* col = A + j * lda;
+  double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+  int64_t i = lane;
+  for (; i + 96 < m; i += 128) {
+    s0 = fma(col[i], x[i], s0);
+    s1 = fma(col[i + 32], x[i + 32], s1);
+    s2 = fma(col[i + 64], x[i + 64], s2);
+    s3 = fma(col[i + 96], x[i + 96], s3);
+  }
+  for (; i < m; i += 32) s0 = fma(col[i], x[i], s0);
+  const double s = warp_sum((s0 + s1) + (s2 + s3));
+  if (lane == 0) y[j] = s;
+}
+
+// partial[split][m]: row-wise reduction over a column range. MODE 0: sum A_ij x_j, 1: sum A_ij^2
+template <int MODE>
+__global__ void row_reduce_kernel(int64_t m, int64_t n, const double* __restrict__ A, int64_t lda,
+                                  const double* __restrict__ x, double* __restrict__ partial,
+                                  int64_t cols_per_split) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= m) return;
+  const int64_t j0 = (int64_t)blockIdx.y * cols_per_split;
+  int64_t j1 = j0 + cols_per_split;
+  if (j1 > n) j1 = n;
+  double s0 = 0.0, s1 = 0.0;
+  int64_t j = j0;
+  for (; j + 1 < j1; j += 2) {
+    const double a0 = A[j * lda + i], a1 = A[(j + 1) * lda + i];
+    if (MODE == 0) {
+      s0 = fma(a0, x[j], s0);
+      s1 = fma(a1, x[j + 1], s1);
+    } else {
+      s0 = fma(a0, a0, s0);
+      s1 = fma(a1, a1, s1);
+    }
+  }
+  if (j < j1) {
+    const double a0 = A[j * lda + i];
+    s0 = (MODE == 0) ? fma(a0, x[j], s0) : fma(a0, a0, s0);
+  }
+  partial[(int64_t)blockIdx.y * m + i] = s0 + s1;
+}
+
+__global__ void sum_partials_kernel(int64_t m, int nsplit, const double* __restrict__ partial,
+                                    double* __restrict__ y) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= m) return;
+  double s = 0.0;
+  for (int k = 0; k < nsplit; ++k) s += partial[(int64_t)k * m + i];
+  y[i] = s;
+}
+
+// one block-step of the forward solve L w = b.  Every CTA recomputes w_k = Linv_kk b_k in
+// shared memory; CTA 0 publishes it into x, all CTAs update their rows of b below the block.
+__global__ void trsv_fwd_step_kernel(int64_t n, int64_t k0, int nbk, const double* __restrict__ L,
+                                     int64_t ldl, const double* __restrict__ Linv,
+                                     double* __restrict__ b, double* __restrict__ x) {
+  // b: work vector (rows below the block are updated), x: solution (distinct buffer -- other
+  // CTAs still read b_k while CTA 0 publishes w_k)
+  __shared__ double bk[NB], w[NB];
+  const int tid = threadIdx.x;
+  if (tid < NB) bk[tid] = (tid < nbk) ? b[k0 + tid] : 0.0;
+  __syncthreads();
+  if (tid < NB) {
+    double s = 0.0;
+    for (int c = 0; c <= tid; ++c) s = fma(Linv[c * NB + tid], bk[c], s);
+    w[tid] = s;
+    if (blockIdx.x == 0 && tid < nbk) x[k0 + tid] = s;
+  }
+  __syncthreads();
+  const int64_t i = k0 + nbk + (int64_t)blockIdx.x * blockDim.x + tid;
+  if (i >= n) return;
+  double s0 = 0.0, s1 = 0.0;
+  const double* Lp = L + k0 * ldl + i;
+  for (int c = 0; c + 1 < nbk; c += 2) {
+    s0 = fma(Lp[(int64_t)c * ldl], w[c], s0);
+    s1 = fma(Lp[(int64_t)(c + 1) * ldl], w[c + 1], s1);
+  }
+  if (nbk & 1) s0 = fma(Lp[(int64_t)(nbk - 1) * ldl], w[nbk - 1], s0);
+  b[i] -= s0 + s1;
+}
+
+// one block-step of the backward solve L^T v = w: v_k = Linv_kk^T w_k, then every column
+// j < k0 gets w_j -= L[k0:k0+nbk, j] . v_k (one warp per column, 1 KB contiguous reads)
+__global__ void trsv_bwd_step_kernel(int64_t k0, int nbk, const double* __restrict__ L,
+                                     int64_t ldl, const double* __restrict__ Linv,
+                                     double* __restrict__ b, double* __restrict__ x) {
+  __shared__ double bk[NB], v[NB];
+  const int tid = threadIdx.x;
+  if (tid < NB) bk[tid] = (tid < nbk) ? b[k0 + tid] : 0.0;
+  __syncthreads();
+  if (tid < NB) {
+    double s = 0.0;
+    for (int r = tid; r < NB; ++r) s = fma(Linv[tid * NB + r], bk[r], s);
+    v[tid] = s;
+    if (blockIdx.x == 0 && tid < nbk) x[k0 + tid] = s;
+  }
+  __syncthreads();
+  const int lane = tid & 31;
+  const int64_t j = (int64_t)blockIdx.x * (blockDim.x >> 5) + (tid >> 5);
+  if (j >= k0) return;
+  const double* col = L + j * ldl + k0;
+  double s = 0.0;
+  for (int r = lane; r < nbk; r += 32) s = fma(col[r], v[r], s);
+  s = warp_sum(s);
+  if (lane == 0) b[j] -= s;
+}
+
+__global__ void lower_colsumsq_kernel(int64_t n, const double* __restrict__ X, int64_t ldx,
+                                      double* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t j = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (j >= n) return;
+  const double* col = X + j * ldx;
+  double s0 = 0.0, s1 = 0.0;
+  int64_t i = j + lane;
+  for (; i + 32 < n; i += 64) {
+    const double a = col[i], b = col[i + 32];
+    s0 = fma(a, a, s0);
+    s1 = fma(b, b, s1);
+  }
+  if (i < n) s0 = fma(col[i], col[i], s0);
+  const double s = warp_sum(s0 + s1);
+  if (lane == 0) out[j] = s;
+}
+
+__global__ void scale_kernel(int64_t m, int64_t n, double* __restrict__ A, int64_t lda,
+                             const double* __restrict__ s, int by_col) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t j = blockIdx.y;
+  if (i >= m || j >= n) return;
+  A[j * lda + i] *= by_col ? s[j] : s[i];
+}
+
+__global__ void vec_op_kernel(int op, int64_t n, const double* __restrict__ a,
+                              const double* __restrict__ b, double* __restrict__ out, double alpha,
+                              double beta) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double v = 0.0;
+  switch (op) {
+    case VOP_DIV: v = a[i] / b[i]; break;
+    case VOP_MUL: v = a[i] * b[i]; break;
+    case VOP_RSQRT_INV: v = sqrt(1.0 / a[i]); break;
+    case VOP_SQRT: v = sqrt(a[i]); break;
+    case VOP_FILL: v = alpha; break;
+    case VOP_INV: v = 1.0 / a[i]; break;
+    case VOP_SUB: v = a[i] - b[i]; break;
+    case VOP_ADD: v = a[i] + b[i]; break;
+    case VOP_AXPBY: v = alpha * a[i] + beta * b[i]; break;
+    case VOP_COPY: v = a[i]; break;
+  }
+  out[i] = v;
+}
+
+__global__ void reduce_kernel(int op, int64_t n, const double* __restrict__ a,
+                              const double* __restrict__ b, double* __restrict__ out) {
+  __shared__ double red[32];
+  double acc = (op == RED_MIN) ? INFINITY : 0.0;
+  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
+    switch (op) {
+      case RED_SUM: acc += a[i]; break;
+      case RED_DOT: acc = fma(a[i], b[i], acc); break;
+      case RED_SUMLOG: acc += log(a[i]); break;
+      case RED_MAXABSDIFF: {
+        const double dlt = fabs(a[i] - b[i]);
+        acc = (dlt > acc || dlt != dlt) ? dlt : acc;    // NaN propagates
+        break;
+      }
+      case RED_MIN: acc = (a[i] < acc || a[i] != a[i]) ? a[i] : acc; break;
+      case RED_COUNT_NAN: acc += (a[i] != a[i]) ? 1.0 : 0.0; if (b) acc += (b[i] != b[i]) ? 1.0 : 0.0; break;
+      case RED_SUMSQ: acc = fma(a[i], a[i], acc); break;
+      case RED_SUMLOG_PROD: acc += log(a[i] * b[i]); break;
+    }
+  }
+  if (op == RED_MAXABSDIFF || op == RED_MIN) {
+    const bool is_max = (op == RED_MAXABSDIFF);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const double other = __shfl_xor_sync(0xffffffffu, acc, o);
+      if (other != other) acc = other;
+      else if (acc == acc) acc = is_max ? fmax(acc, other) : fmin(acc, other);
+    }
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (lane == 0) red[w] = acc;
+    __syncthreads();
+    if (w == 0) {
+      acc = (lane < (int)(blockDim.x >> 5)) ? red[lane] : (is_max ? 0.0 : INFINITY);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const double other = __shfl_xor_sync(0xffffffffu, acc, o);
+        if (other != other) acc = other;
+        else if (acc == acc) acc = is_max ? fmax(acc, other) : fmin(acc, other);
+      }
+      if (lane == 0) out[0] = acc;
+    }
+  } else {
+    const double s = block_sum(acc, red);
+    if (threadIdx.x == 0) out[0] = s;
+  }
+}
+
+// ---- likelihood maths (R/lik.R) ----------------------------------------------------------------
+
+__device__ __forceinline__ double digamma_dev(double x) {
+  // recurrence up to x >= 10, then the asymptotic series
+  double r = 0.0;
+  while (x < 10.0) {
+    r -= 1.0 / x;
+    x += 1.0;
+  }
+  const double xi = 1.0 / x, x2 = xi * xi;
+  const double ser = x2 * (1.0 / 12 - x2 * (1.0 / 120 - x2 * (1.0 / 252 - x2 * (1.0 / 240 -
+                     x2 * (1.0 / 132 - x2 * (691.0 / 32760 - x2 * (1.0 / 12)))))));
+  return r + log(x) - 0.5 * xi - ser;
+}
+
+__device__ __forceinline__ double xlogy_dev(double x, double y) { return x == 0.0 ? 0.0 : x * log(y); }
+__device__ __forceinline__ double xlog1py_dev(double x, double y) { return x == 0.0 ? 0.0 : x * log1p(y); }
+
+struct LikP {
+  int kind, link;
+  double param;
+};
+
+__device__ __forceinline__ double response_dev(const LikP& l, double f) {   // R/lik.R:458-498
+  if (l.link == GPL_LINK_LOGIT) return 1.0 / (1.0 + exp(-f));
+  if (l.link == GPL_LINK_PROBIT) return normcdf(f);
+  if (l.link == GPL_LINK_LOG) return exp(f);
+  return f;
+}
+
+// f already includes the offset
+__device__ __forceinline__ double loglik_dev(const LikP& l, double f, double y, double t) {
+  switch (l.kind) {
+    case GPL_LIK_GAUSSIAN: {                                                // R/lik.R:301-308
+      const double r = (y - f) / l.param;
+      return -(0.918938533204672741780329736406 + log(l.param) + 0.5 * r * r);
+    }
+    case GPL_LIK_BERNOULLI:
+    case GPL_LIK_BINOMIAL: {                                                // R/lik.R:314-330
+      const double mu = response_dev(l, f);
+      const double lch = lgamma(t + 1.0) - lgamma(y + 1.0) - lgamma(t - y + 1.0);
+      return lch + xlogy_dev(y, mu) + xlog1py_dev(t - y, -mu);
+    }
+    case GPL_LIK_BETABINOM: {                                               // R/lik.R:332-353
+      const double mu = response_dev(l, f);
+      const double a = mu / l.param, b = (1.0 - mu) / l.param;
+      const double t1 = lgamma(t + 1.0) - lgamma(y + 1.0) - lgamma(t - y + 1.0);
+      const double t2 = lgamma(y + a) + lgamma(t - y + b) - lgamma(t + a + b);
+      const double t3 = lgamma(a + b) - lgamma(a) - lgamma(b);
+      return t1 + t2 + t3;
+    }
+    case GPL_LIK_POISSON: {                                                 // R/lik.R:355-366
+      const double mu = response_dev(l, f);
+      return xlogy_dev(y, mu) - mu - lgamma(y + 1.0);
+    }
+  }
+  return 0.0;
+}
+
+__device__ __forceinline__ double loglik_d_dev(const LikP& l, double f, double y, double t) {
+  const double mu = response_dev(l, f);
+  if (l.kind == GPL_LIK_POISSON) return (y / mu - 1.0) * mu;                // R/lik.R:441
+  double dmu;
+  if (l.link == GPL_LINK_PROBIT) dmu = 0.398942280401432677939946059934 * exp(-0.5 * f * f);
+  else dmu = mu * (1.0 - mu);
+  if (l.kind == GPL_LIK_BETABINOM) {                                        // R/lik.R:400-424
+    const double phi = l.param, a = mu / phi, b = (1.0 - mu) / phi;
+    const double t2 = (dmu / phi) * (digamma_dev(y + a) - digamma_dev(t - y + b));
+    const double t3 = (dmu / phi) * (-digamma_dev(a) + digamma_dev(b));
+    return t2 + t3;
+  }
+  return dmu * (y / mu - (t - y) / (1.0 - mu));                             // R/lik.R:396
+}
+
+__global__ void pseudodata_la_kernel(LikP l, int64_t n, const double* __restrict__ f,
+                                     const double* __restrict__ y, const double* __restrict__ trials,
+                                     const double* __restrict__ offset, double* __restrict__ z,
+                                     double* __restrict__ V) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  if (l.kind == GPL_LIK_GAUSSIAN) {                                         // R/lik.R:188-192
+    z[i] = y[i];
+    V[i] = l.param * l.param * 1.0;
+    return;
+  }
+  const double t = (l.kind == GPL_LIK_BERNOULLI) ? 1.0 : (trials ? trials[i] : 1.0);
+  const double off = offset ? offset[i] : 0.0;
+  const double fi = f[i];
+  const double eps = 1e-6;                                                  // R/lik.R:449
+  const double g = loglik_d_dev(l, fi + off, y[i], t);
+  const double ge = loglik_d_dev(l, (fi + eps) + off, y[i], t);
+  double g2 = (ge - g) / eps;
+  const double sgn = (g2 > 0.0) ? 1.0 : ((g2 < 0.0) ? -1.0 : 0.0);
+  g2 = sgn * fmax(fabs(g2), 1e-12);                                         // R/lik.R:198
+  z[i] = fi - g / g2;
+  V[i] = -1.0 / g2;
+}
+
+__global__ void loglik_sum_kernel(LikP l, int64_t n, const double* __restrict__ f,
+                                  const double* __restrict__ y, const double* __restrict__ trials,
+                                  const double* __restrict__ offset, double* __restrict__ out) {
+  __shared__ double red[32];
+  double acc = 0.0;
+  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
+    const double t = (l.kind == GPL_LIK_BERNOULLI) ? 1.0 : (trials ? trials[i] : 1.0);
+    const double off = offset ? offset[i] : 0.0;
+    acc += loglik_dev(l, f[i] + off, y[i], t);
+  }
+  const double s = block_sum(acc, red);
+  if (threadIdx.x == 0) out[0] = s;
+}
+
+constexpr int MAX_QUAD = 64;
+
+__global__ void ep_sites_kernel(LikP l, int64_t n, EpSiteArgs a, const double* __restrict__ trials,
+                                const double* __restrict__ offset, int* __restrict__ flags) {
+  __shared__ double xq[MAX_QUAD], wq[MAX_QUAD];
+  if (threadIdx.x < a.quad_order) {
+    xq[threadIdx.x] = a.quad_x[threadIdx.x];
+    wq[threadIdx.x] = a.quad_w[threadIdx.x];
+  }
+  __syncthreads();
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double t = (l.kind == GPL_LIK_BERNOULLI) ? 1.0 : (trials ? trials[i] : 1.0);
+  const double off = offset ? offset[i] : 0.0;
+  const double yi = a.y[i];
+  // R/lik.R:239-240
+  const double post_prec = 1.0 / a.fvar[i];
+  const double P_old = a.P_old[i], z_old = a.z_old[i];
+  const double cav_prec = post_prec - P_old;
+  const double cav_mean = 1.0 / cav_prec * (a.fmean[i] * post_prec - z_old * P_old);
+  const double scale = sqrt(1.0 / cav_prec);
+  const int Q = a.quad_order;
+  // pass 1: log-likelihood on the grid, its max (R/lik.R:243-259, R/gp_loo.R:136-144)
+  double cmax = -INFINITY;
+  bool ok = true;
+  for (int q = 0; q < Q; ++q) {
+    const double fg = xq[q] * scale + cav_mean;
+    double ll = loglik_dev(l, fg + off, yi, t);
+    if (ll != ll) { ll = -INFINITY; ok = false; }
+    cmax = fmax(cmax, ll);
+  }
+  double sumw = 0.0, m1 = 0.0;
+  for (int q = 0; q < Q; ++q) {
+    const double fg = xq[q] * scale + cav_mean;
+    double ll = loglik_dev(l, fg + off, yi, t);
+    double lk = exp(ll);
+    if (ll != ll) { ll = -INFINITY; lk = 0.0; }
+    sumw += wq[q] * exp(ll - cmax);
+    m1 += (fg * lk) * wq[q];
+  }
+  const double logC = cmax + log(sumw);
+  const double C = exp(logC);
+  const double mean_t = (1.0 / C) * m1;
+  double m2 = 0.0;
+  for (int q = 0; q < Q; ++q) {
+    const double fg = xq[q] * scale + cav_mean;
+    double ll = loglik_dev(l, fg + off, yi, t);
+    double lk = exp(ll);
+    if (ll != ll) lk = 0.0;
+    const double dlt = fg - mean_t;
+    m2 += ((dlt * dlt) * lk) * wq[q];
+  }
+  const double s2_t = (1.0 / C) * m2;
+  const double var_cav = 1.0 / cav_prec;
+  // R/lik.R:218-226
+  double P_new = 1.0 / s2_t - 1.0 / var_cav;
+  double nu_new = mean_t / s2_t - cav_mean / var_cav;
+  const double nu_old = z_old * P_old;
+  nu_new = a.damping * nu_new + (1.0 - a.damping) * nu_old;
+  P_new = a.damping * P_new + (1.0 - a.damping) * P_old;
+  const double zi = (1.0 / P_new) * nu_new;
+  const double Vi = 1.0 / P_new;
+  a.z_new[i] = zi;
+  a.V_new[i] = Vi;
+  a.P_new[i] = 1.0 / Vi;           // fit$P = 1 / V (R/ep.R:143)
+  a.cav_mean[i] = cav_mean;
+  a.cav_var[i] = var_cav;
+  a.logZ[i] = logC;
+  int fl = 0;
+  if (!ok) fl |= 1;
+  if (zi != zi || Vi != Vi) fl |= 2;
+  else if (!(Vi > 0.0)) fl |= 4;
+  if (fl) atomicOr(flags, fl);
+}
+
+__global__ void ep_evidence_kernel(int64_t n, const double* __restrict__ logZ,
+                                   const double* __restrict__ vc, const double* __restrict__ mc,
+                                   const double* __restrict__ z, const double* __restrict__ V,
+                                   double* __restrict__ out) {
+  __shared__ double red[32];
+  double s1 = 0.0, s2 = 0.0, s3 = 0.0;
+  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
+    const double tot = vc[i] + V[i];
+    const double dm = mc[i] - z[i];
+    s1 += logZ[i];
+    s2 += log(tot);
+    s3 += dm * dm / tot;
+  }
+  const double a1 = block_sum(s1, red);
+  const double a2 = block_sum(s2, red);
+  const double a3 = block_sum(s3, red);
+  if (threadIdx.x == 0) out[0] = a1 + 0.5 * a2 + 0.5 * a3;   // R/ep.R:47-48
+}
+
+}  // namespace
+
+int build_B(Ctx* ctx, int64_t n, const double* K, int64_t ldk, const double* s, double* B,
+            int64_t ldb) {
+  if (n <= 0) return GPL_OK;
+  dim3 grid((unsigned)((n + 255) / 256), (unsigned)((n + 7) / 8));
+  build_B_kernel<<<grid, 256, 0, ctx->stream>>>(n, K, ldk, s, B, ldb);
+  GPL_LAUNCH_CHECK(ctx);
+  return GPL_OK;
+}
+
+int gemv_t(Ctx* ctx, int64_t m, int64_t n, const double* A, int64_t lda, const double* x, double* y) {
+  if (n <= 0) return GPL_OK;
+  gemv_t_kernel<<<(unsigned)((n + 7) / 8), 256, 0, ctx->stream>>>(m, n, A, lda, x, y);
+  GPL_LAUNCH_CHECK(ctx);
+  return GPL_OK;
+}
+
+template <int MODE>
+static int row_reduce(Ctx* ctx, int64_t m, int64_t n, const double* A, int64_t lda, const double* x,
+                      double* y) {
+  if (m <= 0) return GPL_OK;
+  const int64_t row_blocks = (m + 255) / 256;
+  int64_t nsplit = (4 * (int64_t)ctx->sm_count + row_blocks - 1) / row_blocks;
+  if (nsplit < 1) nsplit = 1;
+  if (nsplit > (n + 63) / 64) nsplit = (n + 63) / 64;
+  if (nsplit < 1) nsplit = 1;
+  const int64_t cps = (n + nsplit - 1) / nsplit;
+  DevBuf part;
+  GPL_TRY(part.alloc(ctx, sizeof(double) * nsplit * m));
+  dim3 grid((unsigned)row_blocks, (unsigned)nsplit);
+  row_reduce_kernel<MODE><<<grid, 256, 0, ctx->stream>>>(m, n, A, lda, x, part.d(), cps);
+  GPL_LAUNCH_CHECK(ctx);
+  sum_partials_kernel<<<(unsigned)row_blocks, 256, 0, ctx->stream>>>(m, (int)nsplit, part.d(), y);
+  GPL_LAUNCH_CHECK(ctx);
+  return GPL_OK;
+}
+
+int gemv_n(Ctx* ctx, int64_t m, int64_t n, const double* A, int64_t lda, const double* x, double* y) {
+  return row_reduce<0>(ctx, m, n, A, lda, x, y);
+}
+
+int rowsumsq(Ctx* ctx, int64_t m, int64_t n, const double* A, int64_t lda, double* out) {
+  return row_reduce<1>(ctx, m, n, A, lda, nullptr, out);
+}
+
+int trsv_lower(Ctx* ctx, const double* dinv, bool trans, int64_t n, const double* L, int64_t ldl,
+               double* b, double* x) {
+  if (n <= 0) return GPL_OK;
+  if (b == x) {
+    set_error("trsv_lower: work vector and solution must be distinct buffers");
+    return GPL_ERR_BAD_ARG;
+  }
+  const int64_t nblk = (n + NB - 1) / NB;
+  if (!trans) {
+    for (int64_t kb = 0; kb < nblk; ++kb) {
+      const int64_t k0 = kb * NB;
+      const int nbk = (int)((n - k0) < NB ? (n - k0) : NB);
+      const int64_t rest = n - k0 - nbk;
+      const unsigned grid = (unsigned)(rest > 0 ? (rest + 255) / 256 : 1);
+      trsv_fwd_step_kernel<<<grid, 256, 0, ctx->stream>>>(n, k0, nbk, L, ldl, dinv + kb * NB * NB,
+                                                          b, x);
+      GPL_LAUNCH_CHECK(ctx);
+    }
+  } else {
+    for (int64_t kb = nblk - 1; kb >= 0; --kb) {
+      const int64_t k0 = kb * NB;
+      const int nbk = (int)((n - k0) < NB ? (n - k0) : NB);
+      const unsigned grid = (unsigned)(k0 > 0 ? (k0 + 7) / 8 : 1);
+      trsv_bwd_step_kernel<<<grid, 256, 0, ctx->stream>>>(k0, nbk, L, ldl, dinv + kb * NB * NB, b,
+                                                          x);
+      GPL_LAUNCH_CHECK(ctx);
+    }
+  }
+  return GPL_OK;
+}
+
+int lower_colsumsq(Ctx* ctx, int64_t n, const double* X, int64_t ldx, double* out) {
+  if (n <= 0) return GPL_OK;
+  lower_colsumsq_kernel<<<(unsigned)((n + 7) / 8), 256, 0, ctx->stream>>>(n, X, ldx, out);
+  GPL_LAUNCH_CHECK(ctx);
+  return GPL_OK;
+}
+
+int scale_cols(Ctx* ctx, int64_t m, int64_t n, double* A, int64_t lda, const double* s) {
+  if (m <= 0 || n <= 0) return GPL_OK;
+  dim3 grid((unsigned)((m + 255) / 256), (unsigned)n);
+  scale_kernel<<<grid, 256, 0, ctx->stream>>>(m, n, A, lda, s, 1);
+  GPL_LAUNCH_CHECK(ctx);
+  return GPL_OK;
+}
+
+int scale_rows(Ctx* ctx, int64_t m, int64_t n, double* A, int64_t lda, const double* s) {
+  if (m <= 0 || n <= 0) return GPL_OK;
+  dim3 grid((unsigned)((m + 255) / 256), (unsigned)n);
+  scale_kernel<<<grid, 256, 0, ctx->stream>>>(m, n, A, lda, s, 0);
+  GPL_LAUNCH_CHECK(ctx);
+  return GPL_OK;
+}
+
+int vec_op(Ctx* ctx, VecOp op, int64_t n, const double* a, const double* b, double* out,
+           double alpha, double beta) {
+  if (n <= 0) return GPL_OK;
+  vec_op_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>((int)op, n, a, b, out, alpha,
+                                                                     beta);
+  GPL_LAUNCH_CHECK(ctx);
+  return GPL_OK;
+}
+
+int reduce(Ctx* ctx, RedOp op, int64_t n, const double* a, const double* b, int slot) {
+  reduce_kernel<<<1, 1024, 0, ctx->stream>>>((int)op, n, a, b, ctx->d_scal + slot);
+  GPL_LAUNCH_CHECK(ctx);
+  return GPL_OK;
+}
+
+int fetch_scalars(Ctx* ctx, int count, double* host_out) {
+  GPL_CUDA(cudaMemcpyAsync(ctx->h_scal, ctx->d_scal, sizeof(double) * count, cudaMemcpyDeviceToHost,
+                           ctx->stream));
+  GPL_CUDA(cudaStreamSynchronize(ctx->stream));
+  for (int i = 0; i < count; ++i) host_out[i] = ctx->h_scal[i];
+  return GPL_OK;
+}
+
+int lik_pseudodata_la(Ctx* ctx, const LikDev& lik, int64_t n, const double* f, const double* y,
+                      double* z, double* V) {
+  if (n <= 0) return GPL_OK;
+  LikP l{lik.kind, lik.link, lik.param};
+  pseudodata_la_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(
+      l, n, f, y, lik.trials, lik.offset, z, V);
+  GPL_LAUNCH_CHECK(ctx);
+  return GPL_OK;
+}
+
+int lik_loglik_sum(Ctx* ctx, const LikDev& lik, int64_t n, const double* f, const double* y,
+                   int slot) {
+  LikP l{lik.kind, lik.link, lik.param};
+  loglik_sum_kernel<<<1, 1024, 0, ctx->stream>>>(l, n, f, y, lik.trials, lik.offset,
+                                                 ctx->d_scal + slot);
+  GPL_LAUNCH_CHECK(ctx);
+  return GPL_OK;
+}
+
+int lik_ep_sites(Ctx* ctx, const LikDev& lik, int64_t n, const EpSiteArgs& a, int* d_flags) {
+  if (a.quad_order > MAX_QUAD || a.quad_order < 1) {
+    set_error("EP quadrature order %d outside [1, %d]", a.quad_order, MAX_QUAD);
+    return GPL_ERR_BAD_ARG;
+  }
+  LikP l{lik.kind, lik.link, lik.param};
+  GPL_CUDA(cudaMemsetAsync(d_flags, 0, sizeof(int), ctx->stream));
+  ep_sites_kernel<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(l, n, a, lik.trials,
+                                                                        lik.offset, d_flags);
+  GPL_LAUNCH_CHECK(ctx);
+  return GPL_OK;
+}
+
+int ep_evidence_terms(Ctx* ctx, int64_t n, const double* logZ, const double* vc, const double* mc,
+                      const double* z, const double* V, int slot) {
+  ep_evidence_kernel<<<1, 1024, 0, ctx->stream>>>(n, logZ, vc, mc, z, V, ctx->d_scal + slot);
+  GPL_LAUNCH_CHECK(ctx);
+  return GPL_OK;
+}
+
+}  // namespace gpl

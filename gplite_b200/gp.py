@@ -1,0 +1,442 @@
+"""gp_init / gp_fit / gp_energy / gp_optim / gp_pred: gplite's public API
+(NAMESPACE:13-46) over the CUDA library.  All n x n work happens inside libgplite_b200.so;
+this file mirrors the R control flow that stays on the host (R/gp.R, R/gp_fit.R:54-88,
+R/gp_optim.R:63-160, R/gp_pred.R:88-122).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+import warnings
+
+import numpy as np
+
+from . import _lib
+from . import model as M
+from .quadrature import gauss_hermite_points
+
+
+class GP:
+    def __init__(self, cfs, lik, method, approx):
+        self.cfs = cfs
+        self.lik = lik
+        self.method = method
+        self.approx = approx
+        self.fitted = False
+        self.fit = None
+        self.x = None
+        self._handle = None      # device-resident gp$fit members (C_chol, Kxz ...)
+        self._ctx = None
+
+    def __repr__(self):
+        return f"GP(cfs={self.cfs}, lik={self.lik}, {self.method}, {self.approx})"
+
+    def _release(self):
+        if self._handle is not None and self._ctx is not None and self._ctx.h:
+            self._ctx.lib.gpl_fit_free(self._ctx.h, self._handle)
+        self._handle = None
+
+    def __del__(self):
+        try:
+            self._release()
+        except Exception:
+            pass
+
+
+def gp_init(cfs=None, lik=None, method=None, approx=None):
+    """R/gp.R:52-71."""
+    cfs = M.cf_sexp() if cfs is None else cfs
+    lik = M.lik_gaussian() if lik is None else lik
+    method = M.method_full() if method is None else method
+    approx = M.approx_laplace() if approx is None else approx
+    if lik.name == "lik_gaussian" and approx.name == "ep":
+        raise ValueError("approx_ep disabled for lik_gaussian: use approx_laplace instead, because "
+                         "it gives exact results")
+    if not isinstance(cfs, (list, tuple)):
+        cfs = [cfs]
+    return GP(list(cfs), lik, method, approx)
+
+
+# ------------------------------------------------------------------------------- parameters
+def get_param(gp):
+    """Named vector of log-parameters, R/gp.R:150-155."""
+    items = M.get_param_objs(gp.cfs, gp.lik)
+    return {name: math.log(getattr(owner, attr)) for name, owner, attr in items}
+
+
+def get_param_vector(gp):
+    return np.array(list(get_param(gp).values()), dtype=np.float64)
+
+
+def set_param(gp, param):
+    """R/gp.R:158-165: unpack log-parameters in get_param order; marks the model stale."""
+    items = M.get_param_objs(gp.cfs, gp.lik)
+    if isinstance(param, dict):
+        if list(param.keys()) != [n for n, _, _ in items]:
+            raise ValueError("parameter names do not match get_param(gp)")
+        values = list(param.values())
+    else:
+        values = list(np.asarray(param, dtype=np.float64).ravel())
+        if len(values) != len(items):
+            raise ValueError(f"expected {len(items)} parameters, got {len(values)}")
+    for (_, owner, attr), v in zip(items, values):
+        setattr(owner, attr, math.exp(float(v)))
+    gp.fitted = False
+    return gp
+
+
+def lpdf_prior(gp):
+    return sum(M.lpdf_prior_one(owner.priors[attr], math.log(getattr(owner, attr)))
+               for _, owner, attr in M.get_param_objs(gp.cfs, gp.lik))
+
+
+def is_fitted(gp, type="analytic"):
+    """R/gp.R:191-205."""
+    found = isinstance(gp.fit, dict) and gp.fit.get("type") == type
+    if found and not gp.fitted:
+        raise RuntimeError(
+            "The GP object seems to contain a posterior fit, but is not refitted after setting new "
+            "hyperparameter values. Please refit using gp_fit after calling set_param.")
+    return found
+
+
+# ------------------------------------------------------------------------------- packing
+def _as_matrix(x):
+    x = np.asarray(x, dtype=np.float64)
+    if x.ndim == 1:
+        x = x[:, None]
+    return np.asfortranarray(x)
+
+
+def _pack_lik(lik):
+    param = getattr(lik, "sigma", getattr(lik, "phi", 0.0))
+    return _lib.Lik(_lib.LIK_KINDS[lik.name], _lib.LINKS[lik.link], float(param))
+
+
+def _pack_approx(gp, fitc=False):
+    a = gp.approx
+    keep = []
+    if a.name == "laplace":
+        ap = _lib.Approx(0, int(a.maxiter), float(a.tol), 0.0, 0.0, 0, 0, None, None)
+    else:
+        xq, wq = gauss_hermite_points(int(a.quad_order))
+        xq = np.ascontiguousarray(xq)
+        wq = np.ascontiguousarray(wq)
+        keep = [xq, wq]
+        tol = 1e-3 if fitc else 1e-4                         # R/ep.R:286,335
+        ap = _lib.Approx(1, int(a.maxiter), tol, float(a.damping), 0.1, int(a.quad_order), 0,
+                         xq.ctypes.data_as(C.POINTER(C.c_double)),
+                         wq.ctypes.data_as(C.POINTER(C.c_double)))
+    return ap, keep
+
+
+def _vec(v, n):
+    if v is None:
+        return None
+    v = np.ascontiguousarray(np.broadcast_to(np.asarray(v, dtype=np.float64), (n,)))
+    return v
+
+
+def _term_mask(gp, cfind):
+    if cfind is None:
+        return 0
+    mask = 0
+    for k in np.atleast_1d(cfind):
+        mask |= 1 << int(k)
+    return mask
+
+
+# ------------------------------------------------------------------------------- eval_cf
+def eval_cf(cfs, x1, x2=None, cfind=None, diag_only=False, jitter=0.0, ctx=None):
+    """eval_cf.list (R/cf.R:402-411) on the GPU.  x2=None means x2 is x1 (symmetric fast path)."""
+    ctx = ctx or _lib.default_context()
+    if not isinstance(cfs, (list, tuple)):
+        cfs = [cfs]
+    x1 = _as_matrix(x1)
+    same = x2 is None
+    x2m = x1 if same else _as_matrix(x2)
+    if x1.shape[1] != x2m.shape[1]:
+        raise ValueError("x1 and x2 must have the same number of columns")
+    factors, _ = M.flatten_cfs(cfs)
+    pm = _lib.PackedModel(factors)
+    mask = 0
+    if cfind is not None:
+        for k in np.atleast_1d(cfind):
+            mask |= 1 << int(k)
+    n1, n2 = x1.shape[0], x2m.shape[0]
+    if diag_only:
+        out = np.empty(min(n1, n2), dtype=np.float64)
+    else:
+        out = np.empty((n1, n2), dtype=np.float64, order="F")
+    _lib.check(ctx.lib.gpl_cf_eval(ctx.h, pm.ref(), _lib._ptr(x1), n1, _lib._ptr(x2m), n2,
+                                   x1.shape[1], 1 if same else 0, mask, 1 if diag_only else 0,
+                                   float(jitter), _lib._ptr(out)))
+    return out
+
+
+# ------------------------------------------------------------------------------- gp_fit
+def gp_fit(gp, x, y, trials=None, offset=None, jitter=None, ctx=None):
+    """R/gp_fit.R:54-60 -> fit_laplace / fit_ep .method_full / .method_fitc."""
+    ctx = ctx or _lib.default_context()
+    x = _as_matrix(x)
+    y = np.ascontiguousarray(np.asarray(y, dtype=np.float64).ravel())
+    n, d = x.shape
+    if len(y) != n:
+        raise ValueError("x and y have different numbers of observations")
+    for cf in gp.cfs:
+        M.learn_scales(cf, x)
+    jit = 1e-6 if jitter is None else float(jitter)          # R/gp.R:276-281
+    factors, _ = M.flatten_cfs(gp.cfs)
+    pm = _lib.PackedModel(factors)
+    lik = _pack_lik(gp.lik)
+    meth = gp.method.name
+    if meth not in ("full", "fitc"):
+        raise NotImplementedError(f"method_{meth} is outside the GPU hot path (SURVEY section 2)")
+    ap, keep = _pack_approx(gp, fitc=(meth == "fitc"))
+    tr = _vec(trials, n)
+    off = _vec(offset, n)
+    out = _lib.FitOut()
+    vec = {k: np.empty(n) for k in ("fmean", "z", "V", "alpha", "fvar", "cavity_mean", "cavity_var")}
+    handle = C.c_void_p()
+    gp._release()
+    gp._ctx = ctx
+    args_tail = [jit, C.byref(out)] + [_lib._ptr(vec[k]) for k in
+                                       ("fmean", "z", "V", "alpha", "fvar", "cavity_mean", "cavity_var")] \
+        + [C.byref(handle)]
+    if meth == "full":
+        status = ctx.lib.gpl_fit_full(ctx.h, pm.ref(), C.byref(lik), C.byref(ap), _lib._ptr(x), n, d,
+                                      _lib._ptr(y), _lib._ptr(tr), _lib._ptr(off), *args_tail)
+        if status == _lib.GPL_ERR_NONFINITE:
+            gp.fit = dict(log_evidence=-math.inf)
+        else:
+            _lib.check(status)                                # non-PD aborts (R/gp_fit.R:95-97)
+    else:
+        zind = gp.method.inducing
+        if zind is None:
+            raise NotImplementedError(
+                "method_fitc needs explicit inducing points here (inducing=...): the reference's "
+                "k-means selection uses R's RNG (R/gp_fit.R:192-234) and is outside the hot path")
+        zind = _as_matrix(zind)
+        m = zind.shape[0]
+        status = ctx.lib.gpl_fit_fitc(ctx.h, pm.ref(), C.byref(lik), C.byref(ap), _lib._ptr(x), n, d,
+                                      _lib._ptr(zind), m, _lib._ptr(y), _lib._ptr(tr),
+                                      _lib._ptr(off), *args_tail)
+        if status in (_lib.GPL_ERR_NOT_PD, _lib.GPL_ERR_NONFINITE):
+            # R/gp_fit.R:113-121: errors are swallowed into log_evidence = -Inf
+            print(_lib.load().gpl_last_error().decode())
+            gp.fit = dict(log_evidence=-math.inf)
+        else:
+            _lib.check(status)
+    if status == _lib.GPL_OK:
+        fit = dict(fmean=vec["fmean"], z=vec["z"], V=vec["V"], alpha=vec["alpha"],
+                   log_evidence=out.log_evidence, iters=out.iters, converged=bool(out.converged))
+        if gp.approx.name == "ep":
+            fit.update(fvar=vec["fvar"], cavity_mean=vec["cavity_mean"], cavity_var=vec["cavity_var"],
+                       P=1.0 / vec["V"], quad_ok=bool(out.quad_ok))
+        if gp.approx.name == "laplace" and gp.approx.maxiter > 1 and not out.converged \
+                and gp.lik.name != "lik_gaussian":
+            warnings.warn("Maximum number of iterations in Laplace reached")
+        if gp.approx.name == "ep" and not out.converged:
+            warnings.warn("Maximum number of iterations in EP reached")
+        gp.fit = fit
+        gp._handle = handle
+    gp.x = x
+    gp.fit["type"] = "analytic"
+    gp.fitted = True
+    return gp
+
+
+def fit_member(gp, what):
+    """Materialise a device-resident member of gp$fit on demand ("C_chol", "alpha")."""
+    n = gp.x.shape[0]
+    shape = {"C_chol": (n, n), "alpha": (n,)}[what]
+    out = np.empty(shape, dtype=np.float64, order="F")
+    _lib.check(gp._ctx.lib.gpl_fit_get(gp._ctx.h, gp._handle, what.encode(), _lib._ptr(out)))
+    return out
+
+
+# ------------------------------------------------------------------------------- energy
+def gp_energy(gp, include_prior=True):
+    """R/gp.R:138-147."""
+    if not is_fitted(gp, "analytic"):
+        raise RuntimeError("The GP must be fitted. Call gp_fit first.")
+    e = -gp.fit["log_evidence"]
+    if include_prior:
+        e -= lpdf_prior(gp)
+    return e
+
+
+def gp_energy_grad(gp, x, y, jitter=None, include_prior=True, ctx=None, device_ptrs=None):
+    """Energy and its gradient w.r.t. get_param(gp) -- the new capability (the reference's
+    gp_optim is derivative-free).  lik_gaussian + method_full.
+
+    device_ptrs=(x_ptr, y_ptr, n, d): use data already resident in HBM (bench.py's `value`)."""
+    ctx = ctx or _lib.default_context()
+    items = M.get_param_objs(gp.cfs, gp.lik)
+    if device_ptrs is None:
+        x = _as_matrix(x)
+        y = np.ascontiguousarray(np.asarray(y, dtype=np.float64).ravel())
+        n, d = x.shape
+        for cf in gp.cfs:
+            M.learn_scales(cf, x)
+        xp, yp, on_dev = _lib._ptr(x), _lib._ptr(y), 0
+    else:
+        xp, yp, n, d = device_ptrs
+        xp, yp, on_dev = C.c_void_p(xp), C.c_void_p(yp), 1
+    factors, where = M.flatten_cfs(gp.cfs)
+    pm = _lib.PackedModel(factors)
+    lik = _pack_lik(gp.lik)
+    pf = np.empty(len(items), dtype=np.int32)
+    ps = np.empty(len(items), dtype=np.int32)
+    for j, (_, owner, attr) in enumerate(items):
+        if owner is gp.lik:
+            pf[j], ps[j] = -1, 0
+        else:
+            pf[j], ps[j] = where[(id(owner), attr)]
+    energy = C.c_double()
+    grad = np.zeros(len(items), dtype=np.float64)
+    jit = 1e-6 if jitter is None else float(jitter)
+    _lib.check(ctx.lib.gpl_energy_grad(ctx.h, pm.ref(), C.byref(lik), xp, n, d, yp, on_dev, jit,
+                                       len(items), _lib._ptr(pf), _lib._ptr(ps), C.byref(energy),
+                                       _lib._ptr(grad), None))
+    e = energy.value
+    if include_prior:
+        for j, (_, owner, attr) in enumerate(items):
+            lp = math.log(getattr(owner, attr))
+            e -= M.lpdf_prior_one(owner.priors[attr], lp)
+            grad[j] -= M.dlpdf_prior_one(owner.priors[attr], lp)
+    return e, grad
+
+
+# ------------------------------------------------------------------------------- gp_optim
+def gp_optim(gp, x, y, tol=1e-4, tol_param=1e-1, maxiter=500, restarts=1, verbose=True,
+             warn=True, method="Nelder-Mead", **fit_args):
+    """R/gp_optim.R:63-125.  method="Nelder-Mead" reproduces the reference's derivative-free
+    search (scipy's simplex in place of stats::optim, fnscale = n); method="L-BFGS-B" uses the
+    analytic gradient (lik_gaussian + method_full only)."""
+    from scipy.optimize import minimize
+    names = list(get_param(gp).keys())
+    n = len(np.asarray(y).ravel())
+    it = [0]
+
+    def energy(p):
+        set_param(gp, p)
+        gp_fit(gp, x, y, **fit_args)
+        e = gp_energy(gp)
+        if verbose:
+            print(" ".join(f"{v:8.2f}" for v in p), f"{e:10.2f}", f"{it[0]:9d}")
+        it[0] += 1
+        return e
+
+    if verbose:
+        print("Optimizing parameters")
+        print("\n".join(f"p{i + 1}: log {nm}" for i, nm in enumerate(names)))
+    p0 = get_param_vector(gp)
+    if method == "Nelder-Mead":
+        res = minimize(lambda p: energy(p) / n, p0, method="Nelder-Mead",
+                       options=dict(fatol=tol, xatol=np.inf, maxiter=maxiter))
+        e_opt = res.fun * n
+    else:
+        def eg(p):
+            set_param(gp, p)
+            e, g = gp_energy_grad(gp, x, y, **fit_args)
+            if verbose:
+                print(" ".join(f"{v:8.2f}" for v in p), f"{e:10.2f}", f"{it[0]:9d}")
+            it[0] += 1
+            return e / n, g / n
+        res = minimize(eg, p0, jac=True, method="L-BFGS-B", options=dict(maxiter=maxiter, ftol=tol))
+        e_opt = res.fun * n
+    if not res.success and warn and res.get("nit", 0) >= maxiter:
+        warnings.warn("Maximum number of iterations reached, optimization may not have converged.")
+    set_param(gp, res.x)
+    gp_fit(gp, x, y, **fit_args)
+    if warn:
+        converged, msg = _check_convergence(energy, e_opt, res.x, delta=tol_param)
+        if not converged:
+            if restarts > 0:
+                if verbose:
+                    print("Parameters not yet converged, restarting...\n")
+                return gp_optim(gp, x, y, tol=tol, tol_param=tol_param, maxiter=maxiter,
+                                restarts=restarts - 1, verbose=verbose, warn=warn, method=method,
+                                **fit_args)
+            warnings.warn(msg)
+        elif verbose:
+            print(msg)
+        set_param(gp, res.x)
+        gp_fit(gp, x, y, **fit_args)
+    return gp
+
+
+def _check_convergence(lossfun, loss_opt, param_opt, delta=1e-1, tol=1e-2):
+    """R/gp_optim.R:127-160."""
+    for k in range(len(param_opt)):
+        dp = np.zeros(len(param_opt))
+        dp[k] = delta
+        l1 = lossfun(param_opt + dp)
+        l2 = lossfun(param_opt - dp)
+        if loss_opt - min(l1, l2) > tol:
+            return False, (f"Not all hyperparameters have reached convergence within tolerance "
+                           f"tol_param = {delta:f}. Try increasing the number of restarts, or "
+                           f"reducing tol.")
+    return True, "Optimization converged."
+
+
+# ------------------------------------------------------------------------------- gp_pred
+def _norm_ppf(q, mean, sd):
+    from scipy.special import ndtri
+    return mean + sd * ndtri(q)
+
+
+def _get_response(lik, f):
+    """R/lik.R:458-498 (host side: only used on nt-sized vectors)."""
+    if lik.name == "lik_gaussian":
+        return f
+    if lik.name == "lik_poisson":
+        return np.exp(f)
+    if lik.link == "probit":
+        from scipy.special import ndtr
+        return ndtr(f)
+    return 1.0 / (1.0 + np.exp(-f))
+
+
+def gp_pred(gp, xnew, var=False, quantiles=None, transform=False, cfind=None, jitter=None,
+            quad_order=15, offset=None, ctx=None):
+    """R/gp_pred.R:88-122."""
+    if quantiles is not None or transform:
+        var = True
+    xnew = _as_matrix(xnew)
+    nt = xnew.shape[0]
+    if not is_fitted(gp, "analytic"):
+        # prior prediction, R/gp_pred.R:142-156
+        pred = dict(mean=np.zeros(nt))
+        if var:
+            pred["var"] = eval_cf(gp.cfs, xnew, xnew, cfind=cfind, diag_only=True, ctx=ctx)
+    else:
+        if "alpha" not in gp.fit:
+            raise RuntimeError("the fit failed (log_evidence = -Inf); cannot predict")
+        c = gp._ctx
+        factors, _ = M.flatten_cfs(gp.cfs)
+        pm = _lib.PackedModel(factors)
+        mean = np.empty(nt)
+        v = np.empty(nt) if var else None
+        fn = c.lib.gpl_pred_full if gp.method.name == "full" else c.lib.gpl_pred_fitc
+        if xnew.shape[1] != gp.x.shape[1]:
+            raise ValueError("xnew has a different number of columns than the training inputs")
+        _lib.check(fn(c.h, gp._handle, pm.ref(), _lib._ptr(xnew), nt, _term_mask(gp, cfind),
+                      _lib._ptr(mean), _lib._ptr(v)))
+        pred = dict(mean=mean)
+        if var:
+            pred["var"] = v
+    if offset is not None:
+        pred["mean"] = pred["mean"] + offset
+    if quantiles is not None:
+        q = np.stack([_norm_ppf(qq, pred["mean"], np.sqrt(pred["var"])) for qq in quantiles], axis=1)
+        pred["quantiles"] = _get_response(gp.lik, q) if transform else q
+    if transform:
+        xq, wq = gauss_hermite_points(quad_order)
+        fgrid = xq[None, :] * np.sqrt(pred["var"])[:, None] + pred["mean"][:, None]
+        ft = _get_response(gp.lik, fgrid)
+        mt = ft @ wq
+        pred["var"] = ((ft - mt[:, None]) ** 2) @ wq
+        pred["mean"] = mt
+    return pred

@@ -1,0 +1,245 @@
+/*
+ * gplite_b200.h -- C ABI of libgplite_b200.so: the B200 (sm_100a) implementation of the
+ * dense-GP hot path of the R package gplite (jpiironen/gplite v0.13.0).
+ *
+ * This is the drop-in boundary.  Everything here is `extern "C"`, plain pointers, sizes and
+ * POD structs: no R, Rcpp, torch or C++ types cross it.  R glue (.Call stubs, see
+ * INTEGRATION.md) or any FFI (the repo's own host layer uses Python ctypes) binds these
+ * symbols directly.  All matrices are IEEE fp64, COLUMN-MAJOR (R layout), dense, with the
+ * leading dimension equal to the row count unless an explicit `ld` argument says otherwise.
+ *
+ * What each entry point replaces in the reference (paths relative to the gplite repo):
+ *   gpl_cf_eval / gpl_cf_eval_dev     eval_cf.*            R/cf.R:402-497  and the native loops
+ *                                     cf_sexp_c/cf_matern32_c/cf_matern52_c/cf_nn_c
+ *                                     src/cf.cpp:9,48,86,125 (bound in src/RcppExports.cpp:16-87,
+ *                                     R/RcppExports.R:4-18); prepare_inputmat R/misc.R:17-31
+ *   gpl_cf_{sexp,matern32,matern52,nn}_c   the four .Call targets, same argument meaning
+ *   gpl_fit_full                      fit_laplace.method_full R/gp_fit.R:91-99 + laplace.method_full
+ *                                     R/laplace.R:13-38,274-297; fit_ep.method_full R/gp_fit.R:150-161
+ *                                     + ep.method_full R/ep.R:16-49,286-330
+ *   gpl_fit_fitc                      fit_laplace.method_fitc R/gp_fit.R:101-123, fit_ep.method_fitc
+ *                                     :163-188, laplace/ep .method_fitc R/laplace.R:122-152,299-325,
+ *                                     R/ep.R:148-185,333-374, inv_lemma_* R/linear_algebra.R:3-126
+ *   gpl_energy_grad                   gp_energy R/gp.R:138-147 evaluated through gp_fit, PLUS the
+ *                                     analytic gradient (new capability: the reference's gp_optim is
+ *                                     derivative-free, R/gp_optim.R:94)
+ *   gpl_pred_full / gpl_pred_fitc     gp_pred_post.method_full/fitc R/gp_pred.R:202-296
+ *   gpl_dpotrf_dev, gpl_dgemm_dev ... base-R chol()/forwardsolve()/backsolve()/%*% call sites
+ *                                     (R/laplace.R:27-30, R/ep.R:38-42, R/gp_pred.R:218)
+ *
+ * Error model: every function returns a gpl_status.  A failure message for the calling thread
+ * is available from gpl_last_error().  Non-positive-definite factorisations return
+ * GPL_ERR_NOT_PD (R's chol() error); the glue decides whether that aborts (method_full,
+ * R/gp_fit.R:95-97) or becomes log_evidence = -Inf (FITC, R/gp_fit.R:113-121).
+ * There is NO CPU fallback: without a CUDA device every compute entry returns GPL_ERR_CUDA.
+ */
+#ifndef GPLITE_B200_H
+#define GPLITE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GPL_ABI_VERSION 1
+
+typedef enum gpl_status {
+  GPL_OK = 0,
+  GPL_ERR_BAD_ARG = 1,
+  GPL_ERR_NOT_PD = 2,       /* Cholesky pivot <= 0 or NaN; gpl_last_error() names the pivot */
+  GPL_ERR_NONFINITE = 3,    /* NaN pseudo-data in EP (R/ep.R:30-32) */
+  GPL_ERR_CUDA = 4,
+  GPL_ERR_NCCL = 5,
+  GPL_ERR_NOMEM = 6,
+  GPL_ERR_NOT_LOGCONCAVE = 7 /* some pseudo-variance V <= 0: the reference's bad-site branch
+                                (R/laplace.R:40-117, R/ep.R:50-138) is outside this library */
+} gpl_status;
+
+/* ---- model descriptors ---------------------------------------------------------------- */
+
+typedef enum gpl_cf_kind {
+  GPL_CF_CONST = 0,     /* p = {magn}                      R/cf.R:413-424 */
+  GPL_CF_LIN = 1,       /* p = {magn}                      R/cf.R:426-435 */
+  GPL_CF_SEXP = 2,      /* p = {lscale, magn}              src/cf.cpp:9-42 */
+  GPL_CF_MATERN32 = 3,  /* p = {lscale, magn}              src/cf.cpp:48-80 */
+  GPL_CF_MATERN52 = 4,  /* p = {lscale, magn}              src/cf.cpp:86-119 */
+  GPL_CF_NN = 5         /* p = {sigma0, sigma, magn}       src/cf.cpp:125-162 */
+} gpl_cf_kind;
+
+/* One multiplicative factor of one summand.  gp$cfs (a list, summed: R/cf.R:402-411) whose
+ * members may be cf_prod (multiplied: R/cf.R:491-497) flattens to a list of factors, each
+ * tagged with the index `term` of the summand it multiplies into. */
+typedef struct gpl_cf_factor {
+  int32_t kind;          /* gpl_cf_kind of the (base) covariance function */
+  int32_t term;          /* 0-based index of the summand in gp$cfs */
+  int32_t periodic;      /* 1: cf_periodic -- the kind is applied to cbind(sin(w x), cos(w x)),
+                            w = 2*pi/period (R/cf.R:478-489); never normalised (R/cf.R:852-855) */
+  int32_t normalize;     /* 1: inputs are (x - means) / scales (R/misc.R:25-29) */
+  int32_t nvars;         /* number of selected input columns; 0 = all d columns (vars = NULL) */
+  int32_t reserved;
+  const int32_t* vars;   /* nvars 0-based column indices, or NULL */
+  const double* means;   /* per selected column, used iff normalize (learn_scales, R/cf.R:836-845) */
+  const double* scales;
+  double p[3];           /* parameters on the natural (not log) scale, see gpl_cf_kind */
+  double period;
+} gpl_cf_factor;
+
+typedef struct gpl_cf_model {
+  int32_t nfactors;
+  int32_t nterms;
+  const gpl_cf_factor* factors;   /* ordered by term */
+} gpl_cf_model;
+
+typedef enum gpl_lik_kind {
+  GPL_LIK_GAUSSIAN = 0,   /* param = sigma                   R/lik.R:188-192,301-308 */
+  GPL_LIK_BERNOULLI = 1,  /*                                 R/lik.R:310-312,372-374 */
+  GPL_LIK_BINOMIAL = 2,   /* needs trials                    R/lik.R:314-330,376-397 */
+  GPL_LIK_BETABINOM = 3,  /* param = phi, needs trials       R/lik.R:332-353,400-424 */
+  GPL_LIK_POISSON = 4     /* log link                        R/lik.R:355-366,426-443 */
+} gpl_lik_kind;
+
+typedef enum gpl_link { GPL_LINK_IDENTITY = 0, GPL_LINK_LOGIT = 1, GPL_LINK_PROBIT = 2,
+                        GPL_LINK_LOG = 3 } gpl_link;
+
+typedef struct gpl_lik {
+  int32_t kind;
+  int32_t link;
+  double param;           /* sigma (gaussian) or phi (betabinom) */
+} gpl_lik;
+
+typedef enum gpl_approx_kind { GPL_APPROX_LAPLACE = 0, GPL_APPROX_EP = 1 } gpl_approx_kind;
+
+typedef struct gpl_approx {
+  int32_t kind;
+  int32_t maxiter;        /* approx_laplace: 30; approx_ep: 100       R/approx.R:60,68 */
+  double tol;             /* laplace: 1e-4; EP full 1e-4, EP fitc 1e-3 R/ep.R:286,335 */
+  double damping;         /* EP, default 0.9 */
+  double damping_min;     /* EP, 0.1 (R/gp_fit.R:158) */
+  int32_t quad_order;     /* EP Gauss-Hermite order, default 11 */
+  int32_t reserved;
+  const double* quad_x;   /* quad_order nodes of probabilists' He_p (R/quadrature.R:28-34) */
+  const double* quad_w;   /* quad_order weights, summing to 1 */
+} gpl_approx;
+
+/* ---- context and handles --------------------------------------------------------------- */
+
+typedef struct gpl_ctx gpl_ctx;   /* one per (process, device): stream, workspaces */
+typedef struct gpl_fit gpl_fit;   /* device-resident result of a fit (C_chol, alpha, Kxz ...) */
+
+int gpl_abi_version(void);
+const char* gpl_last_error(void);
+int gpl_device_count(void);
+
+/* stream: 0 -> the library creates its own; otherwise a cudaStream_t cast to uintptr_t
+ * (e.g. torch.cuda.current_stream().cuda_stream) on which all work is enqueued. */
+int gpl_ctx_create(int device, uint64_t stream, gpl_ctx** out);
+int gpl_ctx_destroy(gpl_ctx* ctx);
+int gpl_ctx_sync(gpl_ctx* ctx);
+/* number of kernels this context has launched so far (for bench.py's gpu_launches) */
+int64_t gpl_ctx_launch_count(gpl_ctx* ctx);
+/* plain device memory helpers so that an FFI without its own CUDA binding can stage data */
+int gpl_dev_alloc(gpl_ctx* ctx, uint64_t bytes, void** dptr);
+int gpl_dev_free(gpl_ctx* ctx, void* dptr);
+int gpl_memcpy_h2d(gpl_ctx* ctx, void* dst, const void* src, uint64_t bytes);
+int gpl_memcpy_d2h(gpl_ctx* ctx, void* dst, const void* src, uint64_t bytes);
+
+/* ---- covariance matrices -------------------------------------------- */
+
+/* K = eval_cf(cfs, x1, x2, cfind)  [+ jitter on the diagonal when `same` != 0].
+ * Host buffers.  x1: n1 x d, x2: n2 x d (ignored when same != 0: x2 := x1 and the symmetric
+ * fast path is used), out: n1 x n2, or min(n1,n2) when diag_only.  term_mask bit k selects
+ * summand k (cfind); pass 0 for all. */
+int gpl_cf_eval(gpl_ctx* ctx, const gpl_cf_model* cf, const double* x1, int64_t n1,
+                const double* x2, int64_t n2, int32_t d, int32_t same, uint64_t term_mask,
+                int32_t diag_only, double jitter, double* out);
+
+/* Same on device-resident buffers; K has leading dimension ldk >= n1 (ldk even). */
+int gpl_cf_eval_dev(gpl_ctx* ctx, const gpl_cf_model* cf, const double* d_x1, int64_t n1,
+                    const double* d_x2, int64_t n2, int32_t d, int32_t same, uint64_t term_mask,
+                    int32_t diag_only, double jitter, double* d_out, int64_t ldk);
+
+/* The reference's four .Call targets with their argument meaning (src/RcppExports.cpp:16-74):
+ * x1 (n1 x d), x2 (n2 x d) host column-major, out n1 x n2 (or min(n1,n2) if diag_only). */
+int gpl_cf_sexp_c(gpl_ctx* ctx, const double* x1, int64_t n1, const double* x2, int64_t n2,
+                  int32_t d, double lscale, double magn, int32_t diag_only, double* out);
+int gpl_cf_matern32_c(gpl_ctx* ctx, const double* x1, int64_t n1, const double* x2, int64_t n2,
+                      int32_t d, double lscale, double magn, int32_t diag_only, double* out);
+int gpl_cf_matern52_c(gpl_ctx* ctx, const double* x1, int64_t n1, const double* x2, int64_t n2,
+                      int32_t d, double lscale, double magn, int32_t diag_only, double* out);
+int gpl_cf_nn_c(gpl_ctx* ctx, const double* x1, int64_t n1, const double* x2, int64_t n2,
+                int32_t d, double sigma0, double sigma, double magn, int32_t diag_only,
+                double* out);
+
+/* ---- dense fp64 linear algebra on device buffers (SURVEY "library calls that act as kernels")
+ * op(A): 0 = A, 1 = A^T.  Column-major, leading dimensions must be even. ------------------ */
+
+/* C = alpha op(A) op(B) + beta C;  lower != 0: only the lower triangle of (square) C is
+ * computed/written (SYRK-shaped trailing update). */
+int gpl_dgemm_dev(gpl_ctx* ctx, int32_t transa, int32_t transb, int64_t m, int64_t n, int64_t k,
+                  double alpha, const double* A, int64_t lda, const double* B, int64_t ldb,
+                  double beta, double* C, int64_t ldc, int32_t lower);
+/* In-place lower Cholesky A = L L^T (R: t(chol(A))).  Strict upper triangle is scratch.
+ * On GPL_ERR_NOT_PD *info is the 1-based failing pivot.  logdet (may be NULL) receives
+ * 2*sum(log(diag(L))). */
+int gpl_dpotrf_dev(gpl_ctx* ctx, int64_t n, double* A, int64_t lda, int32_t* info, double* logdet);
+/* B <- B L^-T (trans=1) or B L^-1 (trans=0), B is m x n, L from gpl_dpotrf_dev on the same ctx
+ * (uses the diagonal-block inverses cached by the factorisation). */
+int gpl_dtrsm_right_dev(gpl_ctx* ctx, int32_t trans, int64_t m, int64_t n, const double* L,
+                        int64_t ldl, double* B, int64_t ldb);
+/* A <- (L L^T)^-1 given L from gpl_dpotrf_dev, lower triangle (dpotri). */
+int gpl_dpotri_dev(gpl_ctx* ctx, int64_t n, double* A, int64_t lda);
+
+/* ---- fits ---------------------------------------------------------- */
+
+typedef struct gpl_fit_out {
+  double log_evidence;    /* gp$fit$log_evidence; -inf when EP hit maxiter / quad not ok */
+  int32_t iters;          /* Newton iterations / EP sweeps performed */
+  int32_t converged;
+  int32_t quad_ok;
+  int32_t reserved;
+} gpl_fit_out;
+
+/* method_full.  x: n x d host, y: n, trials/offset: n or NULL.  n-vectors are returned eagerly
+ * into the caller's buffers (any may be NULL): fmean, z, V, alpha, and for EP fvar,
+ * cavity_mean, cavity_var.  The n x n factor stays on the device behind *fit. */
+int gpl_fit_full(gpl_ctx* ctx, const gpl_cf_model* cf, const gpl_lik* lik, const gpl_approx* approx,
+                 const double* x, int64_t n, int32_t d, const double* y, const double* trials,
+                 const double* offset, double jitter, gpl_fit_out* out, double* fmean, double* z,
+                 double* V, double* alpha, double* fvar, double* cavity_mean, double* cavity_var,
+                 gpl_fit** fit);
+
+/* method_fitc with explicit inducing points zind (m x d). */
+int gpl_fit_fitc(gpl_ctx* ctx, const gpl_cf_model* cf, const gpl_lik* lik, const gpl_approx* approx,
+                 const double* x, int64_t n, int32_t d, const double* zind, int64_t m,
+                 const double* y, const double* trials, const double* offset, double jitter,
+                 gpl_fit_out* out, double* fmean, double* z, double* V, double* alpha, double* fvar,
+                 double* cavity_mean, double* cavity_var, gpl_fit** fit);
+
+/* Energy (= -log_evidence, without the prior term, which stays on the host: R/gp.R:142-146)
+ * and its gradient w.r.t. the LOG of the listed parameters, lik_gaussian + method_full.
+ * Parameter j is identified by (param_factor[j], param_slot[j]): factor index into cf->factors
+ * and slot into p[] (slot 3 = period); param_factor[j] = -1 selects the likelihood sigma.
+ * d_x / d_y are DEVICE pointers when on_device != 0, host pointers otherwise. */
+int gpl_energy_grad(gpl_ctx* ctx, const gpl_cf_model* cf, const gpl_lik* lik, const void* x,
+                    int64_t n, int32_t d, const void* y, int32_t on_device, double jitter,
+                    int32_t nparam, const int32_t* param_factor, const int32_t* param_slot,
+                    double* energy, double* grad, gpl_fit** fit /* may be NULL */);
+
+/* ---- prediction ---------------------------------------------------- */
+
+/* mean[nt] (and var[nt] if var != NULL) of the latent at xt (nt x d host). */
+int gpl_pred_full(gpl_ctx* ctx, const gpl_fit* fit, const gpl_cf_model* cf, const double* xt,
+                  int64_t nt, uint64_t term_mask, double* mean, double* var);
+int gpl_pred_fitc(gpl_ctx* ctx, const gpl_fit* fit, const gpl_cf_model* cf, const double* xt,
+                  int64_t nt, uint64_t term_mask, double* mean, double* var);
+
+/* Materialise members of gp$fit on demand: what = "C_chol" (n x n), "Kxz" (n x m),
+ * "Kz_chol" (m x m), "alpha" (n).  out must hold rows*cols doubles. */
+int gpl_fit_get(gpl_ctx* ctx, const gpl_fit* fit, const char* what, double* out);
+int gpl_fit_free(gpl_ctx* ctx, gpl_fit* fit);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GPLITE_B200_H */

@@ -1,0 +1,43 @@
+"""Shared data / model-grid builders for the tests (seeded numpy stand-ins for the R test data:
+tests/testthat/test_basic.R:6-11, test_pred.R:6-12, test_normalization.R:6-13)."""
+import itertools
+import warnings
+
+import numpy as np
+
+import gplite_b200 as g
+
+CF_MAKERS = [lambda: g.cf_const(), lambda: g.cf_lin(), lambda: g.cf_sexp(), lambda: g.cf_matern32(),
+             lambda: g.cf_matern52(), lambda: g.cf_nn(), lambda: g.cf_periodic()]
+
+
+def model_grid(triples=True):
+    mk = CF_MAKERS
+    grid = [[m()] for m in mk]
+    grid += [[mk[i](), mk[j]()] for i, j in itertools.combinations(range(7), 2)]
+    if triples:
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            grid += [[mk[i]() * mk[j]() * mk[k]()] for i, j, k in itertools.combinations(range(7), 3)]
+    return grid
+
+
+def basic_data(seed=1234, n=20, nt=30):
+    rng = np.random.default_rng(seed)
+    x = rng.normal(size=n)
+    xt = rng.normal(size=nt)
+    y = x ** 2 + 0.2 * rng.normal(size=n)
+    return x, xt, y
+
+
+def rel_err(a, b):
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    return float(np.max(np.abs(a - b) / np.maximum(np.abs(b), 1e-300))) if a.size else 0.0
+
+
+def scaled_err(a, b):
+    """max |a-b| / max|b|: the relative error norm used for vectors with entries near zero."""
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    return float(np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-300)) if a.size else 0.0

@@ -1,0 +1,153 @@
+"""CPU: pins the oracle (oracle/gplite_oracle.py) against the reference's own compiled code, the
+committed golden vectors, and the known-answer formulas the reference's tests use."""
+import copy
+import os
+import warnings
+
+import numpy as np
+import pytest
+import scipy.linalg as sla
+
+import gplite_b200 as g
+from oracle import gplite_oracle as o
+from helpers import model_grid, basic_data, rel_err, scaled_err
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def test_numpy_restatement_matches_reference_golden():
+    z = np.load(os.path.join(GOLD, "cf_native.npz"))
+    for d in (1, 3, 8):
+        x1, x2 = z[f"x1_d{d}"], z[f"x2_d{d}"]
+        for kind in ("cf_sexp", "cf_matern32", "cf_matern52", "cf_nn"):
+            p = z[f"{kind}_d{d}_p"]
+            assert rel_err(o.cf_native_np(kind, x1, x2, *p), z[f"{kind}_d{d}_full"]) < 5e-14
+            assert rel_err(o.cf_native_np(kind, x1, x1, *p), z[f"{kind}_d{d}_sym"]) < 5e-14
+            assert rel_err(o.cf_native_np(kind, x1, x2, *p, diag_only=True), z[f"{kind}_d{d}_diag"]) < 5e-14
+
+
+@pytest.mark.skipif(not o.ref_available(), reason="oracle/_ref not built (no /root/reference here)")
+def test_reference_binary_matches_golden():
+    z = np.load(os.path.join(GOLD, "cf_native.npz"))
+    x1, x2 = z["x1_d3"], z["x2_d3"]
+    for kind in ("cf_sexp", "cf_matern32", "cf_matern52", "cf_nn"):
+        p = z[f"{kind}_d3_p"]
+        assert np.array_equal(o.cf_native_ref(kind, x1, x2, *p), z[f"{kind}_d3_full"])
+
+
+def test_gaussian_fit_matches_textbook_kat():
+    """tests/testthat/test_basic.R:64-94 and :99-132 re-expressed on the golden fixture."""
+    z = np.load(os.path.join(GOLD, "gaussian_kat.npz"))
+    x, xt, y = z["x"], z["xt"], z["y"]
+    grid = model_grid()
+    for mi, j in z["index"]:
+        gp = g.gp_init(cfs=copy.deepcopy(grid[mi]), lik=g.lik_gaussian())
+        g.set_param(gp, z[f"m{mi}_{j}_param"])
+        o.gp_fit(gp, x, y)
+        assert abs(gp.fit["log_evidence"] - z[f"m{mi}_{j}_le"]) <= 1e-3 * abs(z[f"m{mi}_{j}_le"])
+        pred = o.gp_pred(gp, xt, var=True, jitter=1e-6)
+        assert scaled_err(pred["mean"], z[f"m{mi}_{j}_mean"]) < 1e-3
+        assert scaled_err(np.sqrt(pred["var"]), z[f"m{mi}_{j}_sd"]) < 1e-3
+
+
+def test_literal_laplace_equals_textbook_with_jitter():
+    # with the jitter folded into the textbook formula the restatement is exact to rounding
+    x, xt, y = basic_data()
+    gp = g.gp_init(cfs=g.cf_matern52(lscale=0.7), lik=g.lik_gaussian(sigma=0.3))
+    o.gp_fit(gp, x, y)
+    n = len(y)
+    K = o.eval_cf(gp.cfs, x, x) + (1e-6 + 0.3 ** 2) * np.eye(n)
+    L = sla.cholesky(K, lower=True)
+    a = sla.solve_triangular(L, y, lower=True)
+    le = -0.5 * a @ a - np.sum(np.log(np.diag(L))) - n / 2 * np.log(2 * np.pi)
+    assert abs(gp.fit["log_evidence"] - le) < 1e-10 * abs(le)
+
+
+def test_normalization_semantics():
+    """tests/testthat/test_normalization.R:81-141: normalize=TRUE on raw x == plain cf on scale(x)."""
+    rng = np.random.default_rng(1234)
+    n, nt = 20, 30
+    x = 5 * (rng.normal(size=n) - 1)
+    xn = (x - x.mean()) / x.std(ddof=1)
+    xt = 5 * (rng.normal(size=nt) - 1)
+    xtn = (xt - x.mean()) / x.std(ddof=1)
+    y = 0.1 * x ** 2 + 0.2 * rng.normal(size=n)
+    for mk in (g.cf_lin, g.cf_sexp, g.cf_matern32, g.cf_matern52, g.cf_nn):
+        gp_a = o.gp_fit(g.gp_init(cfs=mk(normalize=False), lik=g.lik_gaussian()), xn, y)
+        gp_b = o.gp_fit(g.gp_init(cfs=mk(normalize=True), lik=g.lik_gaussian()), x, y)
+        assert abs(gp_a.fit["log_evidence"] - gp_b.fit["log_evidence"]) < 1e-8
+        pa = o.gp_pred(gp_a, xtn, var=True)
+        pb = o.gp_pred(gp_b, xt, var=True)
+        assert scaled_err(pa["mean"], pb["mean"]) < 1e-8
+        assert scaled_err(pa["var"], pb["var"]) < 1e-6
+
+
+def test_gradient_oracle_vs_central_differences():
+    x, xt, y = basic_data(n=25)
+    X = np.stack([x, np.cos(x)], axis=1)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        models = [
+            [g.cf_sexp(lscale=0.8)], [g.cf_matern32(lscale=0.9)], [g.cf_matern52(lscale=1.1)],
+            [g.cf_nn()], [g.cf_lin(), g.cf_const(magn=0.5)],
+            [g.cf_sexp(vars=[0], lscale=0.7) * g.cf_lin(vars=[1], prior_magn=g.prior_fixed())],
+            [g.cf_periodic(vars=[0], period=1.7), g.cf_matern52(prior_lscale=g.prior_lognormal())],
+            [g.cf_sexp(normalize=True) * g.cf_matern32() * g.cf_const(prior_magn=g.prior_fixed())],
+        ]
+    for cfs in models:
+        gp = g.gp_init(cfs=cfs, lik=g.lik_gaussian(sigma=0.4))
+        e, grad = o.energy_grad_gaussian_full(gp, X, y)
+        p0 = g.get_param_vector(gp)
+        h = 1e-5
+        num = np.zeros_like(p0)
+        for k in range(len(p0)):
+            es = []
+            for sgn in (+1, -1):
+                p = p0.copy()
+                p[k] += sgn * h
+                g.set_param(gp, p)
+                o.gp_fit(gp, X, y)
+                es.append(o.gp_energy(gp))
+            num[k] = (es[0] - es[1]) / (2 * h)
+        g.set_param(gp, p0)
+        assert np.max(np.abs(grad - num)) < 2e-6 * max(1.0, np.max(np.abs(num))), (cfs, grad, num)
+
+
+def test_laplace_fixed_point_and_ep_consistency():
+    rng = np.random.default_rng(7)
+    n = 60
+    x = rng.normal(size=(n, 2))
+    f = 2 * x[:, 0] - x[:, 1]
+    y = (rng.uniform(size=n) < 1 / (1 + np.exp(-f))).astype(float)
+    for link in ("logit", "probit"):
+        gp = g.gp_init(cfs=g.cf_sexp(lscale=1.0), lik=g.lik_bernoulli(link), approx=g.approx_laplace())
+        o.gp_fit(gp, x, y)
+        fit = gp.fit
+        # Newton fixed point: alpha = d loglik / d f at the mode (R&W eq. 3.17)
+        grad = o.get_loglik_d(gp.lik, fit["fmean"], y)
+        assert np.max(np.abs(fit["alpha"] - grad)) < 5e-3
+        gpe = g.gp_init(cfs=g.cf_sexp(lscale=1.0), lik=g.lik_bernoulli(link), approx=g.approx_ep())
+        o.gp_fit(gpe, x, y)
+        assert np.isfinite(gpe.fit["log_evidence"])
+        assert abs(gpe.fit["log_evidence"] - fit["log_evidence"]) < 1.5
+        # EP marginal variances equal the diagonal identity V - V^2 diag(C^-1)
+        C = o.eval_cf(gpe.cfs, x, x) + 1e-6 * np.eye(n) + np.diag(1 / gpe.fit["P"])
+        V = 1 / gpe.fit["P"]
+        alt = V - V ** 2 * np.diag(np.linalg.inv(C))
+        assert scaled_err(alt, gpe.fit["fvar"]) < 1e-8
+
+
+def test_fitc_oracle_reduces_to_full_when_inducing_equal_training():
+    rng = np.random.default_rng(3)
+    n = 40
+    x = rng.normal(size=(n, 1))
+    y = np.sin(2 * x[:, 0]) + 0.1 * rng.normal(size=n)
+    full = o.gp_fit(g.gp_init(cfs=g.cf_sexp(lscale=0.8), lik=g.lik_gaussian(0.2)), x, y)
+    fitc = o.gp_fit(g.gp_init(cfs=g.cf_sexp(lscale=0.8), lik=g.lik_gaussian(0.2),
+                              method=g.method_fitc(inducing=x)), x, y)
+    assert abs(full.fit["log_evidence"] - fitc.fit["log_evidence"]) < 1e-3 * abs(full.fit["log_evidence"])
+    xt = np.linspace(-2, 2, 17)[:, None]
+    pf = o.gp_pred(full, xt, var=True)
+    pc = o.gp_pred(fitc, xt, var=True)
+    assert scaled_err(pc["mean"], pf["mean"]) < 1e-3
+    assert scaled_err(pc["var"], pf["var"]) < 1e-2
