@@ -74,6 +74,8 @@ SIGNATURES = {
     "gpl_ctx_destroy": (C.c_int, [_P]),
     "gpl_ctx_sync": (C.c_int, [_P]),
     "gpl_ctx_launch_count": (_I64, [_P]),
+    "gpl_ctx_profile": (C.c_int, [_P, _I32]),
+    "gpl_ctx_profile_read": (C.c_int, [_P, C.POINTER(_D), C.POINTER(_D), C.POINTER(_I64)]),
     "gpl_dev_alloc": (C.c_int, [_P, _U64, C.POINTER(_P)]),
     "gpl_dev_free": (C.c_int, [_P, _P]),
     "gpl_memcpy_h2d": (C.c_int, [_P, _P, _P, _U64]),
@@ -167,6 +169,28 @@ class Context:
 
     def launch_count(self):
         return int(self.lib.gpl_ctx_launch_count(self.h))
+
+    def profile(self, enable=True):
+        check(self.lib.gpl_ctx_profile(self.h, 1 if enable else 0))
+
+    def profile_read(self):
+        ms, fl, nl = C.c_double(), C.c_double(), C.c_int64()
+        check(self.lib.gpl_ctx_profile_read(self.h, C.byref(ms), C.byref(fl), C.byref(nl)))
+        return dict(gemm_ms=ms.value, gemm_flops=fl.value, gemm_launches=nl.value)
+
+    def alloc(self, nbytes):
+        p = _P()
+        check(self.lib.gpl_dev_alloc(self.h, int(nbytes), C.byref(p)))
+        return p
+
+    def free(self, p):
+        check(self.lib.gpl_dev_free(self.h, p))
+
+    def h2d(self, dptr, arr):
+        check(self.lib.gpl_memcpy_h2d(self.h, dptr, _ptr(arr), arr.nbytes))
+
+    def d2h(self, arr, dptr):
+        check(self.lib.gpl_memcpy_d2h(self.h, _ptr(arr), dptr, arr.nbytes))
 
 
 _default_ctx = {}

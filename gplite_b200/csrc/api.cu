@@ -111,6 +111,7 @@ int gpl_ctx_destroy(gpl_ctx* h) {
   if (c->d_info) cudaFree(c->d_info);
   if (c->d_scal) cudaFree(c->d_scal);
   if (c->h_scal) cudaFreeHost(c->h_scal);
+  for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
   if (c->own_stream) cudaStreamDestroy(c->stream);
   delete c;
   return GPL_OK;
@@ -123,6 +124,32 @@ int gpl_ctx_sync(gpl_ctx* h) {
 }
 
 int64_t gpl_ctx_launch_count(gpl_ctx* h) { return reinterpret_cast<Ctx*>(h)->launches; }
+
+int gpl_ctx_profile(gpl_ctx* h, int32_t enable) {
+  Ctx* c = reinterpret_cast<Ctx*>(h);
+  GPL_CUDA(cudaStreamSynchronize(c->stream));
+  c->profile = enable != 0;
+  c->ev_used = 0;
+  c->prof_flops = 0.0;
+  c->prof_ms = 0.0;
+  c->prof_launches = 0;
+  return GPL_OK;
+}
+
+int gpl_ctx_profile_read(gpl_ctx* h, double* gemm_ms, double* gemm_flops, int64_t* gemm_launches) {
+  Ctx* c = reinterpret_cast<Ctx*>(h);
+  GPL_CUDA(cudaStreamSynchronize(c->stream));
+  for (size_t i = 0; i + 1 < c->ev_used; i += 2) {
+    float ms = 0.f;
+    GPL_CUDA(cudaEventElapsedTime(&ms, c->ev_pool[i], c->ev_pool[i + 1]));
+    c->prof_ms += ms;
+  }
+  c->ev_used = 0;
+  if (gemm_ms) *gemm_ms = c->prof_ms;
+  if (gemm_flops) *gemm_flops = c->prof_flops;
+  if (gemm_launches) *gemm_launches = c->prof_launches;
+  return GPL_OK;
+}
 
 int gpl_dev_alloc(gpl_ctx* h, uint64_t bytes, void** dptr) {
   Ctx* c = reinterpret_cast<Ctx*>(h);

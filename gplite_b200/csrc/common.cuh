@@ -27,6 +27,14 @@ struct Ctx {
   int32_t* d_info = nullptr;    // device int[4]
   double* d_scal = nullptr;     // device double[64] for small reductions
   double* h_scal = nullptr;     // pinned host mirror
+  // optional per-launch timing of the DMMA GEMM kernel (bench.py's roofline leg): one event
+  // pair per launch on the launching stream, harvested by gpl_ctx_profile_read
+  bool profile = false;
+  std::vector<cudaEvent_t> ev_pool;
+  size_t ev_used = 0;
+  double prof_flops = 0.0;
+  double prof_ms = 0.0;
+  int64_t prof_launches = 0;
 };
 
 #define GPL_CUDA(call)                                                              \

@@ -192,8 +192,24 @@ int launch(Ctx* ctx, const GemmArgs& a, int grid) {
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     configured = true;
   }
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  if (ctx->profile) {
+    while (ctx->ev_pool.size() < ctx->ev_used + 2) {
+      cudaEvent_t e;
+      GPL_CUDA(cudaEventCreate(&e));
+      ctx->ev_pool.push_back(e);
+    }
+    e0 = ctx->ev_pool[ctx->ev_used++];
+    e1 = ctx->ev_pool[ctx->ev_used++];
+    GPL_CUDA(cudaEventRecord(e0, ctx->stream));
+  }
   gemm_f64_kernel<TA, TB><<<grid, THREADS, SMEM_BYTES, ctx->stream>>>(a);
   GPL_LAUNCH_CHECK(ctx);
+  if (ctx->profile) {
+    GPL_CUDA(cudaEventRecord(e1, ctx->stream));
+    ctx->prof_flops += 2.0 * a.M * a.N * (double)a.K * (a.lower ? 0.5 : 1.0);
+    ctx->prof_launches++;
+  }
   return GPL_OK;
 }
 

@@ -138,6 +138,12 @@ int gpl_ctx_destroy(gpl_ctx* ctx);
 int gpl_ctx_sync(gpl_ctx* ctx);
 /* number of kernels this context has launched so far (for bench.py's gpu_launches) */
 int64_t gpl_ctx_launch_count(gpl_ctx* ctx);
+/* Optional per-launch CUDA-event timing of the FP64 tensor-core GEMM/SYRK kernel (the dominant
+ * kernel of every factorisation).  enable != 0 starts a fresh accumulation; _read harvests the
+ * events recorded so far: summed kernel milliseconds, executed flops (2mnk, halved for
+ * lower-only updates) and launch count. */
+int gpl_ctx_profile(gpl_ctx* ctx, int32_t enable);
+int gpl_ctx_profile_read(gpl_ctx* ctx, double* gemm_ms, double* gemm_flops, int64_t* gemm_launches);
 /* plain device memory helpers so that an FFI without its own CUDA binding can stage data */
 int gpl_dev_alloc(gpl_ctx* ctx, uint64_t bytes, void** dptr);
 int gpl_dev_free(gpl_ctx* ctx, void* dptr);
