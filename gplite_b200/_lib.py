@@ -83,6 +83,7 @@ SIGNATURES = {
     "gpl_cf_eval": (C.c_int, [_P, C.POINTER(CfModel), _P, _I64, _P, _I64, _I32, _I32, _U64, _I32, _D, _P]),
     "gpl_cf_eval_dev": (C.c_int, [_P, C.POINTER(CfModel), _P, _I64, _P, _I64, _I32, _I32, _U64, _I32,
                                   _D, _P, _I64]),
+    "gpl_cf_eval_block_dev": (C.c_int, [_P, C.POINTER(CfModel), _P, _I64, _I64, _P, _I64, _I64, _I32, _P, _I64]),
     "gpl_cf_sexp_c": (C.c_int, [_P, _P, _I64, _P, _I64, _I32, _D, _D, _I32, _P]),
     "gpl_cf_matern32_c": (C.c_int, [_P, _P, _I64, _P, _I64, _I32, _D, _D, _I32, _P]),
     "gpl_cf_matern52_c": (C.c_int, [_P, _P, _I64, _P, _I64, _I32, _D, _D, _I32, _P]),
@@ -92,6 +93,10 @@ SIGNATURES = {
     "gpl_dpotrf_dev": (C.c_int, [_P, _I64, _P, _I64, C.POINTER(_I32), C.POINTER(_D)]),
     "gpl_dtrsm_right_dev": (C.c_int, [_P, _I32, _I64, _I64, _P, _I64, _P, _I64]),
     "gpl_dpotri_dev": (C.c_int, [_P, _I64, _P, _I64]),
+    "gpl_dpotrf_get_dinv_dev": (C.c_int, [_P, _I64, _P]),
+    "gpl_dtrsv_dev": (C.c_int, [_P, _I32, _I64, _P, _I64, _P, _P, _P]),
+    "gpl_dgemv_dev": (C.c_int, [_P, _I32, _I64, _I64, _P, _I64, _P, _P]),
+    "gpl_scale_block_dev": (C.c_int, [_P, _I64, _I64, _P, _I64, _P, _P, _D, _D, _I64]),
     "gpl_fit_full": (C.c_int, [_P, C.POINTER(CfModel), C.POINTER(Lik), C.POINTER(Approx), _P, _I64,
                                _I32, _P, _P, _P, _D, C.POINTER(FitOut), _P, _P, _P, _P, _P, _P, _P,
                                C.POINTER(_P)]),

@@ -238,6 +238,17 @@ int gpl_cf_eval(gpl_ctx* h, const gpl_cf_model* cf, const double* x1, int64_t n1
   return rc;
 }
 
+int gpl_cf_eval_block_dev(gpl_ctx* h, const gpl_cf_model* cf, const double* d_x1, int64_t n1,
+                          int64_t ldx1, const double* d_x2, int64_t n2, int64_t ldx2, int32_t d,
+                          double* d_out, int64_t ldk) {
+  Ctx* c = reinterpret_cast<Ctx*>(h);
+  if (n1 < 0 || n2 < 0 || d <= 0 || !d_out || ldk < n1 || ldx1 < n1 || ldx2 < n2) {
+    set_error("gpl_cf_eval_block_dev: bad dimensions");
+    return GPL_ERR_BAD_ARG;
+  }
+  return cf_eval_dev(c, cf, d_x1, n1, ldx1, d_x2, n2, ldx2, d, false, 0, false, 0.0, d_out, ldk);
+}
+
 static int native_cf(gpl_ctx* h, int kind, const double* x1, int64_t n1, const double* x2,
                      int64_t n2, int32_t d, double p0, double p1, double p2, int32_t diag_only,
                      double* out) {
@@ -284,6 +295,35 @@ int gpl_dtrsm_right_dev(gpl_ctx* h, int32_t trans, int64_t m, int64_t n, const d
 
 int gpl_dpotri_dev(gpl_ctx* h, int64_t n, double* A, int64_t lda) {
   return dpotri(reinterpret_cast<Ctx*>(h), n, A, lda);
+}
+
+int gpl_dpotrf_get_dinv_dev(gpl_ctx* h, int64_t n, double* d_out) {
+  Ctx* c = reinterpret_cast<Ctx*>(h);
+  const int64_t nblk = (n + NB - 1) / NB;
+  if (nblk > c->dinv_blocks || !d_out) {
+    set_error("gpl_dpotrf_get_dinv_dev: no factorisation of that size cached");
+    return GPL_ERR_BAD_ARG;
+  }
+  GPL_CUDA(cudaMemcpyAsync(d_out, c->dinv, sizeof(double) * nblk * NB * NB, cudaMemcpyDeviceToDevice,
+                           c->stream));
+  return GPL_OK;
+}
+
+int gpl_dtrsv_dev(gpl_ctx* h, int32_t trans, int64_t n, const double* L, int64_t ldl,
+                  const double* d_dinv, double* b, double* x) {
+  Ctx* c = reinterpret_cast<Ctx*>(h);
+  return trsv_lower(c, d_dinv ? d_dinv : c->dinv, trans != 0, n, L, ldl, b, x);
+}
+
+int gpl_dgemv_dev(gpl_ctx* h, int32_t trans, int64_t m, int64_t n, const double* A, int64_t lda,
+                  const double* x, double* y) {
+  Ctx* c = reinterpret_cast<Ctx*>(h);
+  return trans ? gemv_t(c, m, n, A, lda, x, y) : gemv_n(c, m, n, A, lda, x, y);
+}
+
+int gpl_scale_block_dev(gpl_ctx* h, int64_t m, int64_t n, double* A, int64_t lda, const double* r,
+                        const double* cs, double alpha, double diag_add, int64_t diag_offset) {
+  return scale_block(reinterpret_cast<Ctx*>(h), m, n, A, lda, r, cs, alpha, diag_add, diag_offset);
 }
 
 }  // extern "C"

@@ -67,6 +67,8 @@ pair_kernel(const __grid_constant__ CfPlan plan, const PairArgs a) {
   }
   const int i0 = bi * TILE, j0 = bj * TILE;
   const bool mirror = a.same && (bi != bj);
+  const bool diag_tile = a.same && (bi == bj);
+  const bool interior = (i0 + TILE <= a.n1) && (j0 + TILE <= a.n2);
 
   for (int idx = tid; idx < F * TILE; idx += PAIR_THREADS) {
     const int f = idx >> 7, r = idx & (TILE - 1);
@@ -182,17 +184,25 @@ pair_kernel(const __grid_constant__ CfPlan plan, const PairArgs a) {
       }
     }
 
-    // direct store: lanes -> consecutive rows of one column
+    // direct store: lanes -> consecutive rows of one column (256 contiguous bytes per warp store)
+    if (interior && !diag_tile) {
+      double* Kp = a.K + (int64_t)(j0 + jl0) * a.ldk + i0 + lane;
 #pragma unroll
-    for (int c = 0; c < CJ; ++c) {
-      const int gj = j0 + jl0 + c;
+      for (int c = 0; c < CJ; ++c)
 #pragma unroll
-      for (int r = 0; r < 4; ++r) {
-        const int gi = i0 + lane + 32 * r;
-        double v = out[r][c];
-        if (a.same && gi == gj) v += a.jitter;
-        out[r][c] = v;
-        if (gi < a.n1 && gj < a.n2) a.K[(int64_t)gj * a.ldk + gi] = v;
+        for (int r = 0; r < 4; ++r) Kp[(int64_t)c * a.ldk + 32 * r] = out[r][c];
+    } else {
+#pragma unroll
+      for (int c = 0; c < CJ; ++c) {
+        const int gj = j0 + jl0 + c;
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          const int gi = i0 + lane + 32 * r;
+          double v = out[r][c];
+          if (a.same && gi == gj) v += a.jitter;
+          out[r][c] = v;
+          if (gi < a.n1 && gj < a.n2) a.K[(int64_t)gj * a.ldk + gi] = v;
+        }
       }
     }
     if (mirror) {
@@ -203,14 +213,24 @@ pair_kernel(const __grid_constant__ CfPlan plan, const PairArgs a) {
 #pragma unroll
         for (int r = 0; r < 4; ++r) T[(warp * CJ + c) * TLD + lane + 32 * r] = out[r][c];
       __syncthreads();
-      for (int il = warp; il < TILE; il += PAIR_THREADS / 32) {
-        const int gcol = i0 + il;            // column of the mirrored tile
-        if (gcol >= a.n1) break;
+      if (interior) {
+        double* Kp = a.K + (int64_t)i0 * a.ldk + j0 + pass * PASSCOLS + lane;
+#pragma unroll 4
+        for (int il = warp; il < TILE; il += PAIR_THREADS / 32) {
 #pragma unroll
-        for (int h = 0; h < PASSCOLS / 32; ++h) {
-          const int cl = lane + 32 * h;
-          const int grow = j0 + pass * PASSCOLS + cl;
-          if (grow < a.n2) a.K[(int64_t)gcol * a.ldk + grow] = T[cl * TLD + il];
+          for (int h = 0; h < PASSCOLS / 32; ++h)
+            Kp[(int64_t)il * a.ldk + 32 * h] = T[(lane + 32 * h) * TLD + il];
+        }
+      } else {
+        for (int il = warp; il < TILE; il += PAIR_THREADS / 32) {
+          const int gcol = i0 + il;            // column of the mirrored tile
+          if (gcol >= a.n1) break;
+#pragma unroll
+          for (int h = 0; h < PASSCOLS / 32; ++h) {
+            const int cl = lane + 32 * h;
+            const int grow = j0 + pass * PASSCOLS + cl;
+            if (grow < a.n2) a.K[(int64_t)gcol * a.ldk + grow] = T[cl * TLD + il];
+          }
         }
       }
       __syncthreads();
@@ -351,6 +371,7 @@ int make_plan(const gpl_cf_model* cf, int d, uint64_t term_mask, HostPlan* out, 
         fd.c0 = sqrt(5.0) / f.p[0];
         fd.c1 = 5.0 / (3.0 * (f.p[0] * f.p[0]));
         fd.magn2 = f.p[1] * f.p[1];
+        fd.c2 = fd.magn2 * fd.c1;
         break;
       case GPL_CF_NN:
         fd.c0 = f.p[0] * f.p[0] * f.p[1] * f.p[1];

@@ -20,21 +20,33 @@ namespace gpl {
 namespace {
 
 constexpr int PLD = NB + 1;
-constexpr int POTF2_THREADS = 1024;
-constexpr int POTF2_SMEM = NB * PLD * (int)sizeof(double);
+constexpr int PW = 16;                 // panel width of the in-CTA factorisation
+constexpr int NPANEL = NB / PW;
+constexpr int POTF2_THREADS = 512;
+constexpr int POTF2_SMEM = (NB * PLD + NB) * (int)sizeof(double);
+
+__device__ __forceinline__ double shfl_d(double v, int src) {
+  return __shfl_sync(0xffffffffu, v, src);
+}
 
 // Factor one nb x nb (nb <= 128) diagonal block in shared memory and emit its inverse.
 //   A    : in/out, lower triangle replaced by L
 //   Linv : out, 128 x 128 (ld 128), lower = L^-1, strict upper = 0, identity padding beyond nb
 //   info : device int; set to the smallest 1-based global pivot index that was not > 0
+//
+// Blocked by 16-column panels so that every flop outside the 16 x 16 diagonal blocks is a
+// register-tiled rank-16 update (a rank-1 formulation needs 3 shared-memory accesses per FMA and
+// ran at ~250 us per block).  Per panel: (A) warp 0 factors the 16 x 16 diagonal block in
+// registers with shuffles, (B) one thread per row below solves its 16 unknowns by substitution,
+// (C) all 16 warps apply the rank-16 update: warp <-> 8 columns, lane <-> rows {lane + 32 r},
+// so panel reads are conflict-free (rows) or broadcasts (columns).  The inverse uses the same
+// three primitives on the block recurrence X_IJ = -X_II sum_K L_IK X_KJ.
 __global__ void __launch_bounds__(POTF2_THREADS, 1)
 potf2_inv_kernel(double* __restrict__ A, int64_t lda, int nb, double* __restrict__ Linv,
                  int* __restrict__ info, int pivot_base) {
-  extern __shared__ double S[];
-  const int tid = threadIdx.x;
-  const int ti = tid & (NB - 1);      // row owned in the sweeps
-  const int tc = tid >> 7;            // column phase 0..7
-  constexpr int TC = POTF2_THREADS / NB;
+  extern __shared__ double S[];          // S[c * PLD + r] = element (r, c)
+  double* rdiag = S + NB * PLD;          // 1 / L_jj
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
   for (int idx = tid; idx < NB * NB; idx += POTF2_THREADS) {
     const int i = idx & (NB - 1), c = idx >> 7;
@@ -44,68 +56,182 @@ potf2_inv_kernel(double* __restrict__ A, int64_t lda, int nb, double* __restrict
   }
   __syncthreads();
 
-  // Right-looking elimination on unscaled columns: after step j column j holds a_ij (not yet
-  // divided by sqrt(d_j)); the update uses a_ij * a_kj / d_j == l_ij * l_kj.
-  for (int j = 0; j < NB - 1; ++j) {
-    const double d = S[j * PLD + j];
-    if (tid == 0 && !(d > 0.0) && j < nb) atomicMin(info, pivot_base + j + 1);
-    if (ti > j) {
-      const double w = S[j * PLD + ti] / d;
-      for (int k = j + 1 + tc; k <= ti; k += TC) S[k * PLD + ti] -= w * S[j * PLD + k];
+  // ------------------------------------------------------------------ factorisation
+  for (int p = 0; p < NPANEL; ++p) {
+    const int c0 = p * PW;
+    // (A) diagonal block, one warp, lane r (mod 16) owns row r
+    if (warp == 0) {
+      const int r = lane & 15;
+      double a[PW];
+#pragma unroll
+      for (int k = 0; k < PW; ++k) a[k] = S[(c0 + k) * PLD + c0 + r];
+#pragma unroll
+      for (int j = 0; j < PW; ++j) {
+        const double djj = shfl_d(a[j], j);
+        if (lane == 0 && !(djj > 0.0) && c0 + j < nb) atomicMin(info, pivot_base + c0 + j + 1);
+        const double rinv = rsqrt(djj);
+        a[j] = (r == j) ? djj * rinv : a[j] * rinv;
+        if (lane == 0) rdiag[c0 + j] = rinv;
+#pragma unroll
+        for (int k = j + 1; k < PW; ++k) {
+          const double lkj = shfl_d(a[j], k);
+          a[k] = fma(-a[j], lkj, a[k]);
+        }
+      }
+      if (lane < PW) {
+#pragma unroll
+        for (int k = 0; k < PW; ++k)
+          if (k <= r) S[(c0 + k) * PLD + c0 + r] = a[k];
+      }
+    }
+    __syncthreads();
+    // (B) rows below the diagonal block: x L_D^T = a, one thread per row
+    {
+      const int i = c0 + PW + tid;
+      if (i < NB) {
+        double x[PW];
+#pragma unroll
+        for (int j = 0; j < PW; ++j) {
+          double sacc = S[(c0 + j) * PLD + i];
+#pragma unroll
+          for (int k = 0; k < j; ++k) sacc = fma(-x[k], S[(c0 + k) * PLD + c0 + j], sacc);
+          x[j] = sacc * rdiag[c0 + j];
+        }
+#pragma unroll
+        for (int j = 0; j < PW; ++j) S[(c0 + j) * PLD + i] = x[j];
+      }
+    }
+    __syncthreads();
+    // (C) trailing update S[i][k] -= sum_c P[i][c] P[k][c], lower triangle
+    {
+      const int kc0 = c0 + PW + 8 * warp;
+      if (kc0 < NB) {
+        double acc[4][8];
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+          for (int q = 0; q < 8; ++q) acc[r][q] = 0.0;
+#pragma unroll 4
+        for (int c = 0; c < PW; ++c) {
+          const double* col = S + (c0 + c) * PLD;
+          double ai[4], ak[8];
+#pragma unroll
+          for (int r = 0; r < 4; ++r) ai[r] = col[lane + 32 * r];
+#pragma unroll
+          for (int q = 0; q < 8; ++q) ak[q] = col[kc0 + q];
+#pragma unroll
+          for (int r = 0; r < 4; ++r)
+#pragma unroll
+            for (int q = 0; q < 8; ++q) acc[r][q] = fma(ai[r], ak[q], acc[r][q]);
+        }
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+#pragma unroll
+          for (int r = 0; r < 4; ++r) {
+            const int i = lane + 32 * r;
+            if (i >= kc0 + q) S[(kc0 + q) * PLD + i] -= acc[r][q];
+          }
+      }
     }
     __syncthreads();
   }
-  if (tid == 0 && !(S[(NB - 1) * PLD + NB - 1] > 0.0) && NB - 1 < nb)
-    atomicMin(info, pivot_base + NB);
 
-  // scale columns: L_ij = a_ij / sqrt(d_j)
-  {
-    double v[NB * NB / POTF2_THREADS];
+  // L back to global
+  for (int idx = tid; idx < NB * NB; idx += POTF2_THREADS) {
+    const int i = idx & (NB - 1), c = idx >> 7;
+    if (i < nb && c < nb && i >= c) A[(int64_t)c * lda + i] = S[c * PLD + i];
+  }
+  __syncthreads();
+
+  // ------------------------------------------------------------------ inverse
+  // (A') all eight 16 x 16 diagonal blocks at once, one warp each: lane c owns column c of the
+  // inverse, L[i][k] comes by shuffle from the lane that owns row i.
+  if (warp < NPANEL) {
+    const int c0 = warp * PW;
+    const int r = lane & 15;
+    double a[PW], x[PW];
 #pragma unroll
-    for (int q = 0; q < NB * NB / POTF2_THREADS; ++q) {
-      const int c = tc + q * TC;
-      const double l = sqrt(S[c * PLD + c]);
-      const double a = S[c * PLD + ti];
-      v[q] = (ti == c) ? l : ((ti > c) ? a / l : 0.0);
+    for (int k = 0; k < PW; ++k) a[k] = S[(c0 + k) * PLD + c0 + r];
+#pragma unroll
+    for (int i = 0; i < PW; ++i) {
+      double sacc = (i == r) ? 1.0 : 0.0;
+#pragma unroll
+      for (int k = 0; k < i; ++k) {
+        const double lik = shfl_d(a[k], i);
+        sacc = fma(-lik, x[k], sacc);
+      }
+      x[i] = sacc * rdiag[c0 + i];
     }
-    __syncthreads();
+    __syncwarp();
+    if (lane < PW) {
 #pragma unroll
-    for (int q = 0; q < NB * NB / POTF2_THREADS; ++q) {
-      const int c = tc + q * TC;
-      S[c * PLD + ti] = v[q];
-      if (ti < nb && c < nb && ti >= c) A[(int64_t)c * lda + ti] = v[q];
+      for (int i = 0; i < PW; ++i)
+        if (i >= r) S[(c0 + r) * PLD + c0 + i] = x[i];
     }
   }
   __syncthreads();
 
-  // In-place inverse by forward substitution on unscaled rows U: at step k every row i > k does
-  // U[i][c] -= (L[i][k] / L[k][k]) * U[k][c] (c < k) and U[i][k] = -(L[i][k] / L[k][k]).
-  // Column k+1 of L is prefetched before the barrier, so the overwrite of column k is safe.
-  double l_next = (ti > 0) ? S[0 * PLD + ti] : 0.0;
-  double d_next = S[0];
-  for (int k = 0; k < NB - 1; ++k) {
-    const double lx = l_next / d_next;
-    if (ti > k) {
-      for (int c = tc; c < k; c += TC) S[c * PLD + ti] -= lx * S[c * PLD + k];
+  for (int K = 0; K < NPANEL; ++K) {
+    const int k0 = K * PW;
+    // (B') finalise block row K: X_KJ = -X_KK R_KJ for the columns left of the diagonal block
+    if (tid < k0) {
+      double* col = S + tid * PLD + k0;
+      double rv[PW], ov[PW];
+#pragma unroll
+      for (int c = 0; c < PW; ++c) rv[c] = col[c];
+#pragma unroll
+      for (int r = 0; r < PW; ++r) {
+        double sacc = 0.0;
+#pragma unroll
+        for (int c = 0; c <= r; ++c) sacc = fma(S[(k0 + c) * PLD + k0 + r], rv[c], sacc);
+        ov[r] = -sacc;
+      }
+#pragma unroll
+      for (int r = 0; r < PW; ++r) col[r] = ov[r];
     }
-    l_next = (ti > k + 1) ? S[(k + 1) * PLD + ti] : 0.0;
-    d_next = S[(k + 1) * PLD + k + 1];
-    if (ti > k && tc == (k & (TC - 1))) S[k * PLD + ti] = -lx;
+    __syncthreads();
+    // (C') rows below block row K: R_IJ += L_IK X_KJ (J < K) and R_IK = L_IK X_KK.  The second
+    // overwrites its own input, so everything is accumulated first and written after a barrier.
+    const int kc0 = 8 * warp;                       // this warp's 8 columns
+    const bool active = (kc0 < k0 + PW) && (k0 + PW < NB);
+    double acc[4][8];
+    if (active) {
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int q = 0; q < 8; ++q) acc[r][q] = 0.0;
+#pragma unroll 4
+      for (int c = 0; c < PW; ++c) {
+        double ai[4], xk[8];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) ai[r] = S[(k0 + c) * PLD + lane + 32 * r];      // L[i][k0 + c]
+#pragma unroll
+        for (int q = 0; q < 8; ++q) xk[q] = (kc0 + q <= k0 + c) ? S[(kc0 + q) * PLD + k0 + c] : 0.0;
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+          for (int q = 0; q < 8; ++q) acc[r][q] = fma(ai[r], xk[q], acc[r][q]);
+      }
+    }
+    __syncthreads();
+    if (active) {
+#pragma unroll
+      for (int q = 0; q < 8; ++q)
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          const int i = lane + 32 * r;
+          if (i >= k0 + PW) {
+            double* dst = S + (kc0 + q) * PLD + i;
+            *dst = (kc0 + q >= k0) ? acc[r][q] : *dst + acc[r][q];
+          }
+        }
+    }
     __syncthreads();
   }
-  {
-    double v[NB * NB / POTF2_THREADS];
-    const double dii = S[ti * PLD + ti];
-#pragma unroll
-    for (int q = 0; q < NB * NB / POTF2_THREADS; ++q) {
-      const int c = tc + q * TC;
-      v[q] = (ti == c) ? 1.0 / dii : ((ti > c) ? S[c * PLD + ti] / dii : 0.0);
-    }
-#pragma unroll
-    for (int q = 0; q < NB * NB / POTF2_THREADS; ++q) {
-      const int c = tc + q * TC;
-      Linv[c * NB + ti] = v[q];
-    }
+
+  for (int idx = tid; idx < NB * NB; idx += POTF2_THREADS) {
+    const int i = idx & (NB - 1), c = idx >> 7;
+    Linv[c * NB + i] = (i >= c) ? S[c * PLD + i] : 0.0;
   }
 }
 
@@ -162,7 +288,7 @@ int trsm_right_rec(const Fac& f, bool trans, int64_t m, int64_t n, const double*
   if (m <= 0 || n <= 0) return GPL_OK;
   if (n <= NB) {
     return dgemm(f.ctx, false, trans, m, n, n, 1.0, B, ldb, f.dinv + blk0 * NB * NB, NB, 0.0, B,
-                 ldb, false);
+                 ldb, false, 1);
   }
   const int64_t n1 = split(n), n2 = n - n1;
   const double* L21 = L + n1;
@@ -196,7 +322,7 @@ int potrf_rec(const Fac& f, double* A, int64_t lda, int64_t n, int64_t blk0) {
 int trmm_right_lower(const Fac& f, int64_t m, int64_t n, const double* X, int64_t ldx, double* B,
                      int64_t ldb) {
   if (m <= 0 || n <= 0) return GPL_OK;
-  if (n <= NB) return dgemm(f.ctx, false, false, m, n, n, 1.0, B, ldb, X, ldx, 0.0, B, ldb, false);
+  if (n <= NB) return dgemm(f.ctx, false, false, m, n, n, 1.0, B, ldb, X, ldx, 0.0, B, ldb, false, 1);
   const int64_t n1 = split(n), n2 = n - n1;
   double* B2 = B + n1 * ldb;
   GPL_TRY(trmm_right_lower(f, m, n1, X, ldx, B, ldb));
@@ -209,7 +335,7 @@ int trmm_right_lower(const Fac& f, int64_t m, int64_t n, const double* X, int64_
 int trmm_left_lower(const Fac& f, double alpha, int64_t n, int64_t m, const double* X, int64_t ldx,
                     double* B, int64_t ldb) {
   if (m <= 0 || n <= 0) return GPL_OK;
-  if (n <= NB) return dgemm(f.ctx, false, false, n, m, n, alpha, X, ldx, B, ldb, 0.0, B, ldb, false);
+  if (n <= NB) return dgemm(f.ctx, false, false, n, m, n, alpha, X, ldx, B, ldb, 0.0, B, ldb, false, 2);
   const int64_t n1 = split(n), n2 = n - n1;
   double* B2 = B + n1;
   GPL_TRY(trmm_left_lower(f, alpha, n2, m, X + n1 * ldx + n1, ldx, B2, ldb));
@@ -222,7 +348,7 @@ int trmm_left_lower(const Fac& f, double alpha, int64_t n, int64_t m, const doub
 int trmm_left_lowerT(const Fac& f, int64_t n, int64_t m, const double* X, int64_t ldx, double* B,
                      int64_t ldb) {
   if (m <= 0 || n <= 0) return GPL_OK;
-  if (n <= NB) return dgemm(f.ctx, true, false, n, m, n, 1.0, X, ldx, B, ldb, 0.0, B, ldb, false);
+  if (n <= NB) return dgemm(f.ctx, true, false, n, m, n, 1.0, X, ldx, B, ldb, 0.0, B, ldb, false, 2);
   const int64_t n1 = split(n), n2 = n - n1;
   double* B2 = B + n1;
   GPL_TRY(trmm_left_lowerT(f, n1, m, X, ldx, B, ldb));
@@ -251,7 +377,7 @@ int trtri_rec(const Fac& f, double* L, int64_t ldl, int64_t n, int64_t blk0) {
 
 // X (n x n lower) <- X^T X (lower triangle; diagonal blocks come out full)
 int lauum_rec(const Fac& f, double* X, int64_t ldx, int64_t n) {
-  if (n <= NB) return dgemm(f.ctx, true, false, n, n, n, 1.0, X, ldx, X, ldx, 0.0, X, ldx, false);
+  if (n <= NB) return dgemm(f.ctx, true, false, n, n, n, 1.0, X, ldx, X, ldx, 0.0, X, ldx, false, 3);
   const int64_t n1 = split(n), n2 = n - n1;
   double* X21 = X + n1;
   double* X22 = X + n1 * ldx + n1;

@@ -69,7 +69,9 @@ inline int64_t round_up(int64_t a, int64_t b) { return (a + b - 1) / b * b; }
 // ---- gemm_f64.cu ----
 int dgemm(Ctx* ctx, bool ta, bool tb, int64_t m, int64_t n, int64_t k, double alpha,
           const double* A, int64_t lda, const double* B, int64_t ldb, double beta, double* C,
-          int64_t ldc, bool lower);
+          int64_t ldc, bool lower, int alias = 0);
+// alias: 0 = C distinct from A and B; 1 = C is A (needs n <= 128); 2 = C is B (needs m <= 128);
+// 3 = both (single tile)
 
 // ---- chol.cu ----
 int ensure_dinv(Ctx* ctx, int64_t n);

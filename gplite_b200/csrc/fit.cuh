@@ -45,6 +45,9 @@ int rowsumsq(Ctx* ctx, int64_t m, int64_t n, const double* A, int64_t lda, doubl
 int scale_cols(Ctx* ctx, int64_t m, int64_t n, double* A, int64_t lda, const double* s);
 // A[i, :] *= s_i
 int scale_rows(Ctx* ctx, int64_t m, int64_t n, double* A, int64_t lda, const double* s);
+// A[i, j] <- alpha r_i A[i, j] c_j (+ diag_add where i == j + diag_offset)
+int scale_block(Ctx* ctx, int64_t m, int64_t n, double* A, int64_t lda, const double* r,
+                const double* c, double alpha, double diag_add, int64_t diag_offset);
 
 enum VecOp {
   VOP_DIV = 0,        // out = a / b

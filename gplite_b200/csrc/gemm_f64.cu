@@ -12,15 +12,38 @@
 // R/ep.R:38-42, R/linear_algebra.R:24, R/gp_pred.R:218).
 #include "common.cuh"
 
+#include <stdlib.h>
+
 namespace gpl {
 
 namespace {
 
-constexpr int BM = 128, BN = 128, BK = 16, STAGES = 4, THREADS = 256;
-constexpr int LDM = 132;            // smem row stride of the [k][mn] layout (== 4 mod 16)
-constexpr int LDK = 20;             // smem row stride of the [mn][k] layout (== 4 mod 16)
-constexpr int OPER = 128 * LDK;     // doubles per operand per stage (>= 16*LDM)
-constexpr int SMEM_BYTES = STAGES * 2 * OPER * (int)sizeof(double);
+
+// CTA tile BM x BN, warp tile WM x WN.  Three configurations: L (128x128, 8 warps of 32x64) for
+// large updates, M (64x64, 4 warps of 32x32) and S (32x32, 4 warps of 16x16) so that the small
+// GEMMs near the diagonal of the recursive factorisation still spread over many SMs -- one SM
+// only issues 64 fp64 FMA/clk, so a 128^3 product on a single CTA costs ~17 us.
+template <int BM_, int BN_, int WM_, int WN_, int BK_, int STAGES_>
+struct Cfg {
+  static constexpr int BM = BM_, BN = BN_, WM = WM_, WN = WN_, BK = BK_, STAGES = STAGES_;
+  static constexpr int LDK = BK + 4;                   // [mn][k] stride (== 4 mod 16)
+  static constexpr int WARPS_M = BM / WM, WARPS_N = BN / WN;
+  static constexpr int THREADS = WARPS_M * WARPS_N * 32;
+  static constexpr int MI = WM / 8, NI = WN / 8;
+  static constexpr int LDA = BM + 4, LDB = BN + 4;     // [k][mn] strides (== 4 mod 16)
+  static constexpr int OPER_A = (BM * LDK > BK * LDA) ? BM * LDK : BK * LDA;
+  static constexpr int OPER_B = (BN * LDK > BK * LDB) ? BN * LDK : BK * LDB;
+  static constexpr int SMEM_BYTES = STAGES * (OPER_A + OPER_B) * (int)sizeof(double);
+};
+using CfgL = Cfg<128, 128, 32, 64, 32, 3>;
+using CfgL16 = Cfg<128, 128, 32, 32, 32, 3>;   // same CTA tile, 16 warps (4 per scheduler) of 32x32
+using CfgM = Cfg<64, 64, 32, 32, 16, 4>;
+using CfgS = Cfg<32, 32, 16, 16, 16, 4>;
+// In-place products (C aliases an operand) are only race-free when one CTA owns the whole
+// K-extent of what it overwrites: full-width row panels (C aliases A, N <= 128) or full-height
+// column panels (C aliases B, M <= 128).
+using CfgR = Cfg<32, 128, 16, 32, 16, 4>;
+using CfgC = Cfg<128, 32, 32, 16, 16, 4>;
 
 __device__ __forceinline__ void cp_async16(double* smem_dst, const double* gsrc, int nbytes) {
   unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
@@ -39,40 +62,74 @@ __device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b)
                : "d"(a), "d"(b));
 }
 
-// Stage one 128 x 16 operand tile.  KCONTIG: global is contiguous along k (element (mn,k) at
-// g[k + mn*ld]) -> smem [mn][k].  Otherwise contiguous along mn (g[mn + k*ld]) -> smem [k][mn].
-// Out-of-range parts are zero-filled by cp.async's src-size.
-template <bool KCONTIG>
-__device__ __forceinline__ void load_tile(double* s, const double* __restrict__ g, int64_t ld,
-                                          int mn0, int mn_lim, int k0, int k_lim, int tid) {
-  if (KCONTIG) {
-    const int k2 = tid & 7;
-    const int k = k0 + 2 * k2;
-    int kb = (k_lim - k) * 8;
-    kb = kb < 0 ? 0 : (kb > 16 ? 16 : kb);
+// Per-thread cp.async plan for one R x BK operand tile (NT threads).  KCONTIG: global is
+// contiguous along k (element (mn,k) at g[k + mn*ld]) -> smem [mn][k], row stride BK + 4.
+// Otherwise contiguous along mn (g[mn + k*ld]) -> smem [k][mn], row stride R + 4.  All address
+// arithmetic that does not depend on the k-tile is done once in init(); per k-tile a chunk
+// costs one 64-bit add.  Out-of-range parts are zero-filled by cp.async's src-size.
+template <bool KCONTIG, int R, int NT, int BK>
+struct TileLoader {
+  static constexpr int CPR = KCONTIG ? BK / 2 : R / 2;      // 16-byte chunks per smem row
+  static constexpr int ROWS = KCONTIG ? R : BK;             // smem rows
+  static constexpr int RSTEP = NT / CPR;                    // rows covered per iteration
+  static constexpr int ITERS = ROWS / RSTEP;
+  static constexpr int LDS_ = KCONTIG ? BK + 4 : R + 4;
+  static_assert(NT % CPR == 0 && ROWS % RSTEP == 0, "tile/thread mismatch");
+  const double* base;
+  const double* p;        // this thread's chunk of iteration 0 in the current k-tile
+  int64_t step;           // doubles between iterations
+  int64_t kadv;           // doubles per k-tile
+  int soff;               // smem offset (doubles) of iteration 0
+  int r0, c2;             // first row, chunk column (in doubles)
+  int fixed_bytes;        // !KCONTIG: valid bytes along mn (constant)
+  unsigned rowmask;       // KCONTIG: bit i set iff row of iteration i is inside the matrix
+
+  __device__ __forceinline__ void init(const double* g, int64_t ld, int mn0, int mn_lim, int tid) {
+    base = g;
+    r0 = tid / CPR;
+    c2 = 2 * (tid % CPR);
+    soff = r0 * LDS_ + c2;
+    if (KCONTIG) {
+      p = g + (int64_t)(mn0 + r0) * ld + c2;
+      step = (int64_t)RSTEP * ld;
+      kadv = BK;
+      rowmask = 0;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int r = (tid >> 3) + 32 * i;
-      const int mn = mn0 + r;
-      const int nb = (mn < mn_lim) ? kb : 0;
-      const double* src = nb ? (g + (int64_t)mn * ld + k) : g;
-      cp_async16(s + r * LDK + 2 * k2, src, nb);
-    }
-  } else {
-    const int m2 = tid & 63;
-    const int mn = mn0 + 2 * m2;
-    int mb = (mn_lim - mn) * 8;
-    mb = mb < 0 ? 0 : (mb > 16 ? 16 : mb);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int kr = (tid >> 6) + 4 * i;
-      const int k = k0 + kr;
-      const int nb = (k < k_lim) ? mb : 0;
-      const double* src = nb ? (g + (int64_t)k * ld + mn) : g;
-      cp_async16(s + kr * LDM + 2 * m2, src, nb);
+      for (int i = 0; i < ITERS; ++i)
+        if (mn0 + r0 + RSTEP * i < mn_lim) rowmask |= 1u << i;
+      fixed_bytes = 0;
+    } else {
+      p = g + (int64_t)r0 * ld + mn0 + c2;
+      step = (int64_t)RSTEP * ld;
+      kadv = (int64_t)BK * ld;
+      int mb = (mn_lim - (mn0 + c2)) * 8;
+      fixed_bytes = mb < 0 ? 0 : (mb > 16 ? 16 : mb);
+      rowmask = 0;
     }
   }
-}
+  // krem = K - k0 (> 0): number of valid k in this tile onwards
+  __device__ __forceinline__ void issue(double* s, int krem) {
+    const double* q = p;
+    if (KCONTIG) {
+      int kb = (krem - c2) * 8;
+      kb = kb < 0 ? 0 : (kb > 16 ? 16 : kb);
+#pragma unroll
+      for (int i = 0; i < ITERS; ++i) {
+        const int nb = ((rowmask >> i) & 1u) ? kb : 0;
+        cp_async16(s + soff + i * RSTEP * LDS_, nb ? q : base, nb);
+        q += step;
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < ITERS; ++i) {
+        const int nb = (r0 + RSTEP * i < krem) ? fixed_bytes : 0;
+        cp_async16(s + soff + i * RSTEP * LDS_, nb ? q : base, nb);
+        q += step;
+      }
+    }
+    p += kadv;
+  }
+};
 
 struct GemmArgs {
   int M, N, K;
@@ -87,13 +144,17 @@ struct GemmArgs {
   int tiles_m, tiles_n;
 };
 
-template <bool TA, bool TB>
-__global__ void __launch_bounds__(THREADS, 1) gemm_f64_kernel(const GemmArgs p) {
+template <bool TA, bool TB, class CF>
+__global__ void __launch_bounds__(CF::THREADS) gemm_f64_kernel(const GemmArgs p) {
   extern __shared__ __align__(16) double smem[];
+  constexpr int BM = CF::BM, BN = CF::BN, MI = CF::MI, NI = CF::NI;
+  constexpr int BK = CF::BK, STAGES = CF::STAGES, LDK = CF::LDK;
+  constexpr int LDA = CF::LDA, LDB = CF::LDB;
+  constexpr int STAGE = CF::OPER_A + CF::OPER_B;
   const int tid = threadIdx.x;
   const int lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, t = lane & 3;
-  const int wm = warp & 3, wn = warp >> 2;
+  const int wm = warp % CF::WARPS_M, wn = warp / CF::WARPS_M;
 
   int bm, bn;
   if (p.lower) {
@@ -109,21 +170,24 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_f64_kernel(const GemmArgs p) 
   }
   const int m0 = bm * BM, n0 = bn * BN;
 
-  double acc[4][8][2];
+  double acc[MI][NI][2];
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
+  for (int i = 0; i < MI; ++i)
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+    for (int j = 0; j < NI; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
   const int ktiles = (p.K + BK - 1) / BK;
 
+  // A operand: TA -> stored K x M, contiguous along k.  The B operand of the product is
+  // op(B)(k,n): !TB -> stored K x N, contiguous along k.
+  TileLoader<TA, BM, CF::THREADS, BK> ldA;
+  TileLoader<!TB, BN, CF::THREADS, BK> ldB;
+  ldA.init(p.A, p.lda, m0, p.M, tid);
+  ldB.init(p.B, p.ldb, n0, p.N, tid);
   auto issue = [&](int kt) {
-    double* sA = smem + (kt % STAGES) * 2 * OPER;
-    double* sB = sA + OPER;
-    // A operand: TA -> stored K x M, contiguous along k
-    load_tile<TA>(sA, p.A, p.lda, m0, p.M, kt * BK, p.K, tid);
-    // B operand of the product is op(B)(k,n): !TB -> stored K x N, contiguous along k
-    load_tile<!TB>(sB, p.B, p.ldb, n0, p.N, kt * BK, p.K, tid);
+    double* sA = smem + (kt % STAGES) * STAGE;
+    ldA.issue(sA, p.K - kt * BK);
+    ldB.issue(sA + CF::OPER_A, p.K - kt * BK);
   };
 
 #pragma unroll
@@ -138,26 +202,26 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_f64_kernel(const GemmArgs p) 
     if (kt + STAGES - 1 < ktiles) issue(kt + STAGES - 1);
     cp_async_commit();
 
-    const double* sA = smem + (kt % STAGES) * 2 * OPER;
-    const double* sB = sA + OPER;
+    const double* sA = smem + (kt % STAGES) * STAGE;
+    const double* sB = sA + CF::OPER_A;
 #pragma unroll
     for (int ks = 0; ks < BK / 4; ++ks) {
       const int kk = ks * 4 + t;
-      double a[4], b[8];
+      double a[MI], b[NI];
 #pragma unroll
-      for (int im = 0; im < 4; ++im) {
-        const int m = wm * 32 + im * 8 + g;
-        a[im] = TA ? sA[m * LDK + kk] : sA[kk * LDM + m];
+      for (int im = 0; im < MI; ++im) {
+        const int m = wm * CF::WM + im * 8 + g;
+        a[im] = TA ? sA[m * LDK + kk] : sA[kk * LDA + m];
       }
 #pragma unroll
-      for (int in = 0; in < 8; ++in) {
-        const int n = wn * 64 + in * 8 + g;
-        b[in] = TB ? sB[kk * LDM + n] : sB[n * LDK + kk];
+      for (int in = 0; in < NI; ++in) {
+        const int n = wn * CF::WN + in * 8 + g;
+        b[in] = TB ? sB[kk * LDB + n] : sB[n * LDK + kk];
       }
 #pragma unroll
-      for (int im = 0; im < 4; ++im)
+      for (int im = 0; im < MI; ++im)
 #pragma unroll
-        for (int in = 0; in < 8; ++in) dmma(acc[im][in][0], acc[im][in][1], a[im], b[in]);
+        for (int in = 0; in < NI; ++in) dmma(acc[im][in][0], acc[im][in][1], a[im], b[in]);
     }
   }
   cp_async_wait<0>();
@@ -165,14 +229,14 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_f64_kernel(const GemmArgs p) 
   // epilogue: thread owns C[row = .. + g][col = .. + 2t, 2t+1] of each 8x8 sub-tile
   const bool diag_tile = p.lower && (bm == bn);
 #pragma unroll
-  for (int im = 0; im < 4; ++im) {
-    const int row = m0 + wm * 32 + im * 8 + g;
+  for (int im = 0; im < MI; ++im) {
+    const int row = m0 + wm * CF::WM + im * 8 + g;
     if (row >= p.M) continue;
 #pragma unroll
-    for (int in = 0; in < 8; ++in) {
+    for (int in = 0; in < NI; ++in) {
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
-        const int col = n0 + wn * 64 + in * 8 + 2 * t + c;
+        const int col = n0 + wn * CF::WN + in * 8 + 2 * t + c;
         if (col >= p.N) continue;
         if (diag_tile && col > row) continue;
         double* dst = p.C + (int64_t)col * p.ldc + row;
@@ -184,14 +248,17 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_f64_kernel(const GemmArgs p) 
   }
 }
 
-template <bool TA, bool TB>
-int launch(Ctx* ctx, const GemmArgs& a, int grid) {
+template <bool TA, bool TB, class CF>
+int launch(Ctx* ctx, GemmArgs a) {
   static bool configured = false;
   if (!configured) {
-    GPL_CUDA(cudaFuncSetAttribute(gemm_f64_kernel<TA, TB>,
-                                  cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    GPL_CUDA(cudaFuncSetAttribute(gemm_f64_kernel<TA, TB, CF>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, CF::SMEM_BYTES));
     configured = true;
   }
+  a.tiles_m = (a.M + CF::BM - 1) / CF::BM;
+  a.tiles_n = (a.N + CF::BN - 1) / CF::BN;
+  const int grid = a.lower ? a.tiles_m * (a.tiles_m + 1) / 2 : a.tiles_m * a.tiles_n;
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   if (ctx->profile) {
     while (ctx->ev_pool.size() < ctx->ev_used + 2) {
@@ -203,7 +270,7 @@ int launch(Ctx* ctx, const GemmArgs& a, int grid) {
     e1 = ctx->ev_pool[ctx->ev_used++];
     GPL_CUDA(cudaEventRecord(e0, ctx->stream));
   }
-  gemm_f64_kernel<TA, TB><<<grid, THREADS, SMEM_BYTES, ctx->stream>>>(a);
+  gemm_f64_kernel<TA, TB, CF><<<grid, CF::THREADS, CF::SMEM_BYTES, ctx->stream>>>(a);
   GPL_LAUNCH_CHECK(ctx);
   if (ctx->profile) {
     GPL_CUDA(cudaEventRecord(e1, ctx->stream));
@@ -213,11 +280,35 @@ int launch(Ctx* ctx, const GemmArgs& a, int grid) {
   return GPL_OK;
 }
 
+template <bool TA, bool TB>
+int dispatch(Ctx* ctx, const GemmArgs& a, int alias) {
+  if (alias) {
+    if (((alias & 1) && a.N > 128) || ((alias & 2) && a.M > 128)) {
+      set_error("dgemm: in-place product needs the aliased extent <= 128");
+      return GPL_ERR_BAD_ARG;
+    }
+    if (alias == 3) return launch<TA, TB, CfgL>(ctx, a);
+    if (alias == 1)
+      return (a.M >= 64 * ctx->sm_count) ? launch<TA, TB, CfgL>(ctx, a) : launch<TA, TB, CfgR>(ctx, a);
+    return (a.N >= 64 * ctx->sm_count) ? launch<TA, TB, CfgL>(ctx, a) : launch<TA, TB, CfgC>(ctx, a);
+  }
+  auto ntiles = [&](int bm, int bn) {
+    const int64_t tm = (a.M + bm - 1) / bm, tn = (a.N + bn - 1) / bn;
+    return a.lower ? tm * (tm + 1) / 2 : tm * tn;
+  };
+  const int64_t sms = ctx->sm_count;
+  static const int use_l16 = getenv("GPL_GEMM_L16") ? atoi(getenv("GPL_GEMM_L16")) : 0;
+  if (ntiles(128, 128) >= sms)
+    return use_l16 ? launch<TA, TB, CfgL16>(ctx, a) : launch<TA, TB, CfgL>(ctx, a);
+  if (ntiles(64, 64) >= sms) return launch<TA, TB, CfgM>(ctx, a);
+  return launch<TA, TB, CfgS>(ctx, a);
+}
+
 }  // namespace
 
 int dgemm(Ctx* ctx, bool ta, bool tb, int64_t m, int64_t n, int64_t k, double alpha,
           const double* A, int64_t lda, const double* B, int64_t ldb, double beta, double* C,
-          int64_t ldc, bool lower) {
+          int64_t ldc, bool lower, int alias) {
   if (m <= 0 || n <= 0) return GPL_OK;
   if ((lda & 1) || (ldb & 1) || ((uintptr_t)A & 15) || ((uintptr_t)B & 15)) {
     set_error("dgemm: operands must be 16-byte aligned with even leading dimensions "
@@ -232,16 +323,14 @@ int dgemm(Ctx* ctx, bool ta, bool tb, int64_t m, int64_t n, int64_t k, double al
   a.M = (int)m; a.N = (int)n; a.K = (int)k;
   a.A = A; a.lda = lda; a.B = B; a.ldb = ldb; a.C = C; a.ldc = ldc;
   a.alpha = alpha; a.beta = beta; a.lower = lower ? 1 : 0;
-  a.tiles_m = (int)((m + BM - 1) / BM);
-  a.tiles_n = (int)((n + BN - 1) / BN);
-  int grid = lower ? a.tiles_m * (a.tiles_m + 1) / 2 : a.tiles_m * a.tiles_n;
+  a.tiles_m = a.tiles_n = 0;
   if (ta && tb) {
     set_error("dgemm: TT product not implemented (never needed on the hot path)");
     return GPL_ERR_BAD_ARG;
   }
-  if (!ta && !tb) return launch<false, false>(ctx, a, grid);
-  if (!ta && tb) return launch<false, true>(ctx, a, grid);
-  return launch<true, false>(ctx, a, grid);
+  if (!ta && !tb) return dispatch<false, false>(ctx, a, alias);
+  if (!ta && tb) return dispatch<false, true>(ctx, a, alias);
+  return dispatch<true, false>(ctx, a, alias);
 }
 
 }  // namespace gpl

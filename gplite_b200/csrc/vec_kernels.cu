@@ -135,22 +135,35 @@ __global__ void trsv_fwd_step_kernel(int64_t n, int64_t k0, int nbk, const doubl
   if (tid < NB) bk[tid] = (tid < nbk) ? b[k0 + tid] : 0.0;
   __syncthreads();
   if (tid < NB) {
-    double s = 0.0;
-    for (int c = 0; c <= tid; ++c) s = fma(Linv[c * NB + tid], bk[c], s);
+    // Linv is stored as a full 128 x 128 tile with a zero upper triangle: run the whole row so the
+    // loads pipeline (fixed trip count, 4 independent accumulators)
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+#pragma unroll 8
+    for (int c = 0; c < NB; c += 4) {
+      s0 = fma(Linv[(c + 0) * NB + tid], bk[c + 0], s0);
+      s1 = fma(Linv[(c + 1) * NB + tid], bk[c + 1], s1);
+      s2 = fma(Linv[(c + 2) * NB + tid], bk[c + 2], s2);
+      s3 = fma(Linv[(c + 3) * NB + tid], bk[c + 3], s3);
+    }
+    const double s = (s0 + s1) + (s2 + s3);
     w[tid] = s;
     if (blockIdx.x == 0 && tid < nbk) x[k0 + tid] = s;
   }
   __syncthreads();
   const int64_t i = k0 + nbk + (int64_t)blockIdx.x * blockDim.x + tid;
   if (i >= n) return;
-  double s0 = 0.0, s1 = 0.0;
+  double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
   const double* Lp = L + k0 * ldl + i;
-  for (int c = 0; c + 1 < nbk; c += 2) {
-    s0 = fma(Lp[(int64_t)c * ldl], w[c], s0);
+  int c = 0;
+#pragma unroll 4
+  for (; c + 3 < nbk; c += 4) {
+    s0 = fma(Lp[(int64_t)(c + 0) * ldl], w[c + 0], s0);
     s1 = fma(Lp[(int64_t)(c + 1) * ldl], w[c + 1], s1);
+    s2 = fma(Lp[(int64_t)(c + 2) * ldl], w[c + 2], s2);
+    s3 = fma(Lp[(int64_t)(c + 3) * ldl], w[c + 3], s3);
   }
-  if (nbk & 1) s0 = fma(Lp[(int64_t)(nbk - 1) * ldl], w[nbk - 1], s0);
-  b[i] -= s0 + s1;
+  for (; c < nbk; ++c) s0 = fma(Lp[(int64_t)c * ldl], w[c], s0);
+  b[i] -= (s0 + s1) + (s2 + s3);
 }
 
 // one block-step of the backward solve L^T v = w: v_k = Linv_kk^T w_k, then every column
@@ -160,17 +173,24 @@ __global__ void trsv_bwd_step_kernel(int64_t k0, int nbk, const double* __restri
                                      double* __restrict__ b, double* __restrict__ x) {
   __shared__ double bk[NB], v[NB];
   const int tid = threadIdx.x;
+  const int lane = tid & 31, wid = tid >> 5;
   if (tid < NB) bk[tid] = (tid < nbk) ? b[k0 + tid] : 0.0;
   __syncthreads();
-  if (tid < NB) {
-    double s = 0.0;
-    for (int r = tid; r < NB; ++r) s = fma(Linv[tid * NB + r], bk[r], s);
-    v[tid] = s;
-    if (blockIdx.x == 0 && tid < nbk) x[k0 + tid] = s;
+  // v_c = sum_r Linv[r][c] bk[r]: one warp per column c (coalesced along r), 8 warps x 16 columns
+  for (int c = wid; c < NB; c += (blockDim.x >> 5)) {
+    const double* col = Linv + c * NB;
+    double s = fma(col[lane], bk[lane], 0.0);
+    s = fma(col[lane + 32], bk[lane + 32], s);
+    s = fma(col[lane + 64], bk[lane + 64], s);
+    s = fma(col[lane + 96], bk[lane + 96], s);
+    s = warp_sum(s);
+    if (lane == 0) {
+      v[c] = s;
+      if (blockIdx.x == 0 && c < nbk) x[k0 + c] = s;
+    }
   }
   __syncthreads();
-  const int lane = tid & 31;
-  const int64_t j = (int64_t)blockIdx.x * (blockDim.x >> 5) + (tid >> 5);
+  const int64_t j = (int64_t)blockIdx.x * (blockDim.x >> 5) + wid;
   if (j >= k0) return;
   const double* col = L + j * ldl + k0;
   double s = 0.0;
@@ -203,6 +223,20 @@ __global__ void scale_kernel(int64_t m, int64_t n, double* __restrict__ A, int64
   const int64_t j = blockIdx.y;
   if (i >= m || j >= n) return;
   A[j * lda + i] *= by_col ? s[j] : s[i];
+}
+
+__global__ void scale_block_kernel(int64_t m, int64_t n, double* __restrict__ A, int64_t lda,
+                                   const double* __restrict__ r, const double* __restrict__ c,
+                                   double alpha, double diag_add, int64_t diag_offset) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t j = blockIdx.y;
+  if (i >= m || j >= n) return;
+  double v = A[j * lda + i];
+  if (c) v *= c[j];
+  if (r) v *= r[i];
+  v *= alpha;
+  if (i == j + diag_offset) v += diag_add;
+  A[j * lda + i] = v;
 }
 
 __global__ void vec_op_kernel(int op, int64_t n, const double* __restrict__ a,
@@ -575,6 +609,15 @@ int scale_rows(Ctx* ctx, int64_t m, int64_t n, double* A, int64_t lda, const dou
   if (m <= 0 || n <= 0) return GPL_OK;
   dim3 grid((unsigned)((m + 255) / 256), (unsigned)n);
   scale_kernel<<<grid, 256, 0, ctx->stream>>>(m, n, A, lda, s, 0);
+  GPL_LAUNCH_CHECK(ctx);
+  return GPL_OK;
+}
+
+int scale_block(Ctx* ctx, int64_t m, int64_t n, double* A, int64_t lda, const double* r,
+                const double* c, double alpha, double diag_add, int64_t diag_offset) {
+  if (m <= 0 || n <= 0) return GPL_OK;
+  dim3 grid((unsigned)((m + 255) / 256), (unsigned)n);
+  scale_block_kernel<<<grid, 256, 0, ctx->stream>>>(m, n, A, lda, r, c, alpha, diag_add, diag_offset);
   GPL_LAUNCH_CHECK(ctx);
   return GPL_OK;
 }

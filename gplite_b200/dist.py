@@ -1,0 +1,258 @@
+"""Multi-GPU full GP (BASELINE config 5: n = 200k, lik_gaussian, method_full): K is built and
+factorised across the GPUs of one box, one process per GPU.
+
+Layout: 1-D block-cyclic by block COLUMNS (block b of width nb lives on rank b % P, stored as a
+local column-major slab of full height).  On NVSwitch every peer is equally far, so a 1-D layout
+costs nothing in link contention and makes the panel step entirely local to one rank:
+
+  step k:  owner(k): potrf(diag block) + TRSM of the rows below        (DMMA, local)
+           broadcast the (n - k0) x nb panel to all ranks                (NCCL over NVLink)
+           every rank: A[:, j] -= P[j-rows] P[j-block]^T for its own block columns j > k  (DMMA GEMM)
+
+Panel traffic is n^2/2 * 8 bytes in total (160 GB at n = 200k, received by every rank) against
+n^3/3 / P flops per rank: ~2-3 % of the step time at P = 8 even without overlap.  The triangular
+solves for alpha run block by block with an 8 KB all-reduce / broadcast per block.
+
+All n x n arithmetic goes through the C ABI (`ops`); torch.distributed is only the transport.
+`TorchOps`-style stand-ins used by the CPU (gloo) tests live in tests/, not here: this module has
+no CPU compute path.
+
+Reference semantics: fit_laplace.method_full (R/gp_fit.R:91-99) + laplace_iter.method_full
+(R/laplace.R:13-38) for lik_gaussian, with f = K alpha evaluated as z - V alpha (the two are
+identical because (K + V) alpha = z).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+
+import numpy as np
+
+from . import _lib
+from . import model as M
+
+
+class BlockCyclic:
+    """Ownership / index maps of the 1-D block-cyclic column layout."""
+
+    def __init__(self, n, nb, world, rank):
+        self.n, self.nb, self.world, self.rank = n, nb, world, rank
+        self.nblk = (n + nb - 1) // nb
+        self.owned = [b for b in range(self.nblk) if b % world == rank]
+        self.width = [min(nb, n - b * nb) for b in range(self.nblk)]
+        self.local_col0 = {}
+        c = 0
+        for b in self.owned:
+            self.local_col0[b] = c
+            c += self.width[b]
+        self.nloc = c
+
+    def owner(self, b):
+        return b % self.world
+
+    def col0(self, b):
+        return b * self.nb
+
+
+class GpuOps:
+    """The C-ABI calls used by the distributed driver, on torch CUDA tensors (column-major slabs:
+    tensor[l, i] is element (row i, local column l))."""
+
+    def __init__(self, ctx):
+        self.ctx = ctx
+        self.lib = ctx.lib
+
+    @staticmethod
+    def _p(t, offset_elems=0):
+        return C.c_void_p(t.data_ptr() + 8 * offset_elems)
+
+    def kblock(self, pm, X_t, n, d, r0, nrows, c0, ncols, A_t, lc0):
+        ld = A_t.shape[1]
+        _lib.check(self.lib.gpl_cf_eval_block_dev(self.ctx.h, pm.ref(), self._p(X_t, r0), nrows, n,
+                                                  self._p(X_t, c0), ncols, n, d,
+                                                  self._p(A_t, lc0 * ld + r0), ld))
+
+    def scale_block(self, A_t, lc0, ncols, r0, nrows, alpha, diag_add, diag_offset):
+        ld = A_t.shape[1]
+        _lib.check(self.lib.gpl_scale_block_dev(self.ctx.h, nrows, ncols, self._p(A_t, lc0 * ld + r0), ld,
+                                                None, None, float(alpha), float(diag_add), diag_offset))
+
+    def potrf(self, A_t, lc0, r0, nbk):
+        ld = A_t.shape[1]
+        info = C.c_int32()
+        logdet = C.c_double()
+        st = self.lib.gpl_dpotrf_dev(self.ctx.h, nbk, self._p(A_t, lc0 * ld + r0), ld, C.byref(info),
+                                     C.byref(logdet))
+        return st, info.value, logdet.value
+
+    def save_dinv(self, nbk, out_t):
+        _lib.check(self.lib.gpl_dpotrf_get_dinv_dev(self.ctx.h, nbk, self._p(out_t)))
+
+    def trsm_below(self, A_t, lc0, r0, nbk, m):
+        """rows r0+nbk .. r0+nbk+m of the block column <- (those rows) L^-T, L = diag block"""
+        ld = A_t.shape[1]
+        _lib.check(self.lib.gpl_dtrsm_right_dev(self.ctx.h, 1, m, nbk, self._p(A_t, lc0 * ld + r0), ld,
+                                                self._p(A_t, lc0 * ld + r0 + nbk), ld))
+
+    def update(self, P_t, ldp, nbk, off_rows, m, off_cols, ncols, A_t, lc0, r0):
+        """A[r0:r0+m, lc0:lc0+ncols] -= P[off_rows:off_rows+m, :] P[off_cols:off_cols+ncols, :]^T"""
+        ld = A_t.shape[1]
+        _lib.check(self.lib.gpl_dgemm_dev(self.ctx.h, 0, 1, m, ncols, nbk, -1.0, self._p(P_t, off_rows), ldp,
+                                          self._p(P_t, off_cols), ldp, 1.0, self._p(A_t, lc0 * ld + r0), ld, 0))
+
+    def trsv(self, trans, nbk, A_t, lc0, r0, dinv_t, b_t, x_t):
+        ld = A_t.shape[1]
+        _lib.check(self.lib.gpl_dtrsv_dev(self.ctx.h, trans, nbk, self._p(A_t, lc0 * ld + r0), ld,
+                                          self._p(dinv_t), self._p(b_t), self._p(x_t)))
+
+    def gemv(self, trans, m, ncols, A_t, lc0, r0, x_t, x_off, y_t, y_off):
+        ld = A_t.shape[1]
+        _lib.check(self.lib.gpl_dgemv_dev(self.ctx.h, trans, m, ncols, self._p(A_t, lc0 * ld + r0), ld,
+                                          self._p(x_t, x_off), self._p(y_t, y_off)))
+
+    def sync(self):
+        self.ctx.sync()
+
+
+def dist_fit_gaussian(gp, x, y, jitter=None, nb=1024, ops=None, dist=None, device="cuda", timings=None):
+    """Distributed gp_fit for lik_gaussian + method_full + approx_laplace.  Every rank passes the
+    same (replicated) x, y; returns dict(log_evidence, alpha (replicated torch tensor), fmean).
+
+    `dist` is torch.distributed (initialised by the caller: NCCL on GPUs); `ops` defaults to the
+    C-ABI GpuOps on the calling process's default context."""
+    import torch
+    if gp.lik.name != "lik_gaussian" or gp.method.name != "full":
+        raise NotImplementedError("the multi-GPU path covers lik_gaussian + method_full")
+    if dist is None:
+        import torch.distributed as dist
+    rank, world = dist.get_rank(), dist.get_world_size()
+    x = np.asarray(x, dtype=np.float64)
+    if x.ndim == 1:
+        x = x[:, None]
+    y = np.asarray(y, dtype=np.float64).ravel()
+    n, d = x.shape
+    if nb % 128 or n % 2:
+        raise ValueError("nb must be a multiple of 128 and n even")
+    for cf in gp.cfs:
+        M.learn_scales(cf, x)
+    jit = 1e-6 if jitter is None else float(jitter)
+    sigma2 = gp.lik.sigma ** 2
+    factors, _ = M.flatten_cfs(gp.cfs)
+    pm = _lib.PackedModel(factors)
+    if ops is None:
+        # same stream as torch: kernels, copies and NCCL collectives are then ordered without
+        # host synchronisation
+        ops = GpuOps(_lib.Context(torch.cuda.current_device(), torch.cuda.current_stream().cuda_stream))
+    lay = BlockCyclic(n, nb, world, rank)
+    ld = (n + 15) // 16 * 16
+    t_mark = {}
+
+    def mark(name):
+        if timings is not None:
+            ops.sync()
+            if device == "cuda":
+                torch.cuda.synchronize()
+            import time
+            t_mark[name] = time.perf_counter()
+
+    X_t = torch.from_numpy(np.ascontiguousarray(x.T)).to(device)          # (d, n): column-major n x d
+    y_t = torch.from_numpy(y).to(device)
+    A_t = torch.empty((max(lay.nloc, 1), ld), dtype=torch.float64, device=device)
+    dinv = {b: torch.empty(((lay.width[b] + 127) // 128) * 128 * 128, dtype=torch.float64, device=device)
+            for b in lay.owned}
+    mark("start")
+
+    # ---- K (owned block columns, rows at and below the diagonal block), then B = I + K / sigma^2 in place
+    for b in lay.owned:
+        c0, w, lc0 = lay.col0(b), lay.width[b], lay.local_col0[b]
+        ops.kblock(pm, X_t, n, d, c0, n - c0, c0, w, A_t, lc0)
+        ops.scale_block(A_t, lc0, w, c0, n - c0, 1.0 / sigma2, 1.0 + jit / sigma2, 0)
+    mark("kbuild")
+
+    # ---- right-looking factorisation with panel broadcasts
+    panel = torch.empty(nb * ld, dtype=torch.float64, device=device)
+    logdet_local = 0.0
+    fail = 0
+    for k in range(lay.nblk):
+        k0, w = lay.col0(k), lay.width[k]
+        m_below = n - k0 - w
+        mp = n - k0                                    # panel rows
+        ldp = mp                                       # mp is even because n, nb are
+        P_t = panel[: w * ldp].view(w, ldp)
+        if lay.owner(k) == rank:
+            lc0 = lay.local_col0[k]
+            st, info, ld_k = ops.potrf(A_t, lc0, k0, w)
+            if st != _lib.GPL_OK:
+                fail = max(fail, k0 + info if st == _lib.GPL_ERR_NOT_PD else -1)
+            else:
+                ops.save_dinv(w, dinv[k])
+                logdet_local += ld_k
+                if m_below > 0:
+                    ops.trsm_below(A_t, lc0, k0, w, m_below)
+            P_t.copy_(A_t[lc0:lc0 + w, k0:n])
+        dist.broadcast(P_t, src=lay.owner(k))
+        if m_below > 0:
+            for j in lay.owned:
+                if j <= k:
+                    continue
+                j0, wj = lay.col0(j), lay.width[j]
+                ops.update(P_t, ldp, w, j0 - k0, n - j0, j0 - k0, wj, A_t, lay.local_col0[j], j0)
+    flag = torch.tensor([float(fail)], dtype=torch.float64, device=device)
+    dist.all_reduce(flag, op=dist.ReduceOp.MAX)
+    if flag.item() != 0:
+        raise _lib.NotPositiveDefinite(_lib.GPL_ERR_NOT_PD,
+                                       f"the leading minor of order {int(flag.item())} is not positive definite")
+    mark("factor")
+
+    # ---- alpha = C^-1 z, C = diag(sqrtV) L L^T diag(sqrtV), V = sigma^2  (R/laplace.R:29)
+    sq = math.sqrt(sigma2)
+    rhs = y_t / sq
+    u = torch.zeros(n, dtype=torch.float64, device=device)      # local partial sums  sum_j L[:, j] w_j
+    wv = torch.zeros(n, dtype=torch.float64, device=device)     # forward solution (owned blocks)
+    tmp = torch.empty(nb, dtype=torch.float64, device=device)
+    tmp2 = torch.empty(nb, dtype=torch.float64, device=device)
+    for k in range(lay.nblk):
+        k0, w = lay.col0(k), lay.width[k]
+        blk = u[k0:k0 + w].clone()
+        dist.all_reduce(blk)
+        if lay.owner(k) == rank:
+            lc0 = lay.local_col0[k]
+            tmp[:w] = rhs[k0:k0 + w] - blk
+            ops.trsv(0, w, A_t, lc0, k0, dinv[k], tmp, tmp2)
+            wv[k0:k0 + w] = tmp2[:w]
+            if n - k0 - w > 0:
+                upd = torch.empty(n - k0 - w, dtype=torch.float64, device=device)
+                ops.gemv(0, n - k0 - w, w, A_t, lc0, k0 + w, tmp2, 0, upd, 0)
+                u[k0 + w:] += upd
+    xv = torch.zeros(n, dtype=torch.float64, device=device)     # backward solution, replicated
+    for k in reversed(range(lay.nblk)):
+        k0, w = lay.col0(k), lay.width[k]
+        blk = torch.zeros(w, dtype=torch.float64, device=device)
+        if lay.owner(k) == rank:
+            lc0 = lay.local_col0[k]
+            tmp[:w] = wv[k0:k0 + w]
+            if n - k0 - w > 0:
+                dot = torch.empty(w, dtype=torch.float64, device=device)
+                ops.gemv(1, n - k0 - w, w, A_t, lc0, k0 + w, xv, k0 + w, dot, 0)
+                tmp[:w] -= dot
+            ops.trsv(1, w, A_t, lc0, k0, dinv[k], tmp, tmp2)
+            blk.copy_(tmp2[:w])
+        dist.broadcast(blk, src=lay.owner(k))
+        xv[k0:k0 + w] = blk
+    alpha = xv / sq
+    mark("solve")
+
+    # ---- log evidence (R/laplace.R:33-38); C_logdet - V_logdet = logdet(B)
+    ldt = torch.tensor([logdet_local], dtype=torch.float64, device=device)
+    dist.all_reduce(ldt)
+    fmean = y_t - sigma2 * alpha                                  # == K alpha
+    resid = y_t - fmean
+    log_lik = float(-0.5 * n * math.log(2 * math.pi * sigma2) - 0.5 * torch.sum(resid * resid).item() / sigma2)
+    f_invK_f = float(torch.dot(fmean, alpha).item())
+    log_evidence = log_lik - 0.5 * f_invK_f - 0.5 * float(ldt.item())
+    mark("done")
+    if timings is not None:
+        names = ["start", "kbuild", "factor", "solve", "done"]
+        for a, b in zip(names[:-1], names[1:]):
+            timings[b] = t_mark[b] - t_mark[a]
+    return dict(log_evidence=log_evidence, alpha=alpha, fmean=fmean, layout=lay)

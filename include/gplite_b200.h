@@ -165,6 +165,13 @@ int gpl_cf_eval_dev(gpl_ctx* ctx, const gpl_cf_model* cf, const double* d_x1, in
                     const double* d_x2, int64_t n2, int32_t d, int32_t same, uint64_t term_mask,
                     int32_t diag_only, double jitter, double* d_out, int64_t ldk);
 
+/* Rectangular block of K on device buffers whose row counts differ from their leading dimensions
+ * (sub-blocks of a replicated x): out[i, j] = k(x1_i, x2_j), i < n1, j < n2.  Used by the
+ * multi-GPU path, where each rank builds only the block columns it owns. */
+int gpl_cf_eval_block_dev(gpl_ctx* ctx, const gpl_cf_model* cf, const double* d_x1, int64_t n1,
+                          int64_t ldx1, const double* d_x2, int64_t n2, int64_t ldx2, int32_t d,
+                          double* d_out, int64_t ldk);
+
 /* The reference's four .Call targets with their argument meaning (src/RcppExports.cpp:16-74):
  * x1 (n1 x d), x2 (n2 x d) host column-major, out n1 x n2 (or min(n1,n2) if diag_only). */
 int gpl_cf_sexp_c(gpl_ctx* ctx, const double* x1, int64_t n1, const double* x2, int64_t n2,
@@ -195,6 +202,20 @@ int gpl_dtrsm_right_dev(gpl_ctx* ctx, int32_t trans, int64_t m, int64_t n, const
                         int64_t ldl, double* B, int64_t ldb);
 /* A <- (L L^T)^-1 given L from gpl_dpotrf_dev, lower triangle (dpotri). */
 int gpl_dpotri_dev(gpl_ctx* ctx, int64_t n, double* A, int64_t lda);
+/* Copy out the diagonal-block inverses cached by the last gpl_dpotrf_dev on this ctx
+ * (ceil(n/128) blocks of 128 x 128 doubles) so that several factors can be kept alive. */
+int gpl_dpotrf_get_dinv_dev(gpl_ctx* ctx, int64_t n, double* d_dinv_out);
+/* x <- L^-1 b (trans = 0) or L^-T b (trans = 1) for one right-hand side; dinv from
+ * gpl_dpotrf_get_dinv_dev (NULL: the ctx cache).  b is destroyed, x must not alias b. */
+int gpl_dtrsv_dev(gpl_ctx* ctx, int32_t trans, int64_t n, const double* L, int64_t ldl,
+                  const double* d_dinv, double* b, double* x);
+/* y = A x (trans = 0, A is m x n) or y = A^T x (trans = 1, y has n entries). */
+int gpl_dgemv_dev(gpl_ctx* ctx, int32_t trans, int64_t m, int64_t n, const double* A, int64_t lda,
+                  const double* x, double* y);
+/* A[i, j] <- alpha * r_i * A[i, j] * c_j  (+ diag_add where i == j + diag_offset); r, c may be NULL.
+ * Builds B = I + V^-1/2 K V^-1/2 (R/laplace.R:27) in place on a block of columns. */
+int gpl_scale_block_dev(gpl_ctx* ctx, int64_t m, int64_t n, double* A, int64_t lda, const double* r,
+                        const double* c, double alpha, double diag_add, int64_t diag_offset);
 
 /* ---- fits ---------------------------------------------------------- */
 

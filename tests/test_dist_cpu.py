@@ -1,0 +1,127 @@
+"""CPU, world_size 2 over gloo: the multi-GPU driver's host logic (block-cyclic ownership, panel
+broadcast schedule, distributed triangular solves, evidence assembly) with the C-ABI calls replaced
+by a torch-CPU stand-in that lives only here.  The result must equal the oracle's gp_fit."""
+import copy
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+class TorchOps:
+    """Stand-in for gplite_b200.dist.GpuOps on CPU tensors (test-only)."""
+
+    def __init__(self, gp):
+        self.gp = gp
+
+    def kblock(self, pm, X_t, n, d, r0, nrows, c0, ncols, A_t, lc0):
+        import torch
+        from oracle import gplite_oracle as o
+        x = X_t.numpy().T
+        K = o.eval_cf(self.gp.cfs, x[r0:r0 + nrows], x[c0:c0 + ncols])
+        A_t[lc0:lc0 + ncols, r0:r0 + nrows] = torch.from_numpy(np.ascontiguousarray(K.T))
+
+    def scale_block(self, A_t, lc0, ncols, r0, nrows, alpha, diag_add, diag_offset):
+        A_t[lc0:lc0 + ncols, r0:r0 + nrows] *= alpha
+        for j in range(ncols):
+            i = j + diag_offset
+            if 0 <= i < nrows:
+                A_t[lc0 + j, r0 + i] += diag_add
+
+    def potrf(self, A_t, lc0, r0, nbk):
+        import torch
+        blk = A_t[lc0:lc0 + nbk, r0:r0 + nbk].T
+        sym = torch.tril(blk) + torch.tril(blk, -1).T
+        L = torch.linalg.cholesky(sym)
+        A_t[lc0:lc0 + nbk, r0:r0 + nbk] = L.T
+        return 0, 0, float(2 * torch.log(torch.diagonal(L)).sum())
+
+    def save_dinv(self, nbk, out_t):
+        pass
+
+    def trsm_below(self, A_t, lc0, r0, nbk, m):
+        import torch
+        L = torch.tril(A_t[lc0:lc0 + nbk, r0:r0 + nbk].T)
+        B = A_t[lc0:lc0 + nbk, r0 + nbk:r0 + nbk + m].T          # m x nbk
+        X = torch.linalg.solve_triangular(L, B.T, upper=False).T
+        A_t[lc0:lc0 + nbk, r0 + nbk:r0 + nbk + m] = X.T
+
+    def update(self, P_t, ldp, nbk, off_rows, m, off_cols, ncols, A_t, lc0, r0):
+        Pm = P_t.T                                                # (panel rows) x nbk
+        A_t[lc0:lc0 + ncols, r0:r0 + m] -= (Pm[off_rows:off_rows + m] @ Pm[off_cols:off_cols + ncols].T).T
+
+    def trsv(self, trans, nbk, A_t, lc0, r0, dinv_t, b_t, x_t):
+        import torch
+        L = torch.tril(A_t[lc0:lc0 + nbk, r0:r0 + nbk].T)
+        M = L.T if trans else L
+        x_t[:nbk] = torch.linalg.solve_triangular(M, b_t[:nbk, None], upper=bool(trans))[:, 0]
+
+    def gemv(self, trans, m, ncols, A_t, lc0, r0, x_t, x_off, y_t, y_off):
+        A = A_t[lc0:lc0 + ncols, r0:r0 + m].T                     # m x ncols
+        if trans:
+            y_t[y_off:y_off + ncols] = A.T @ x_t[x_off:x_off + m]
+        else:
+            y_t[y_off:y_off + m] = A @ x_t[x_off:x_off + ncols]
+
+    def sync(self):
+        pass
+
+
+def _worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    import torch.distributed as dist
+    import gplite_b200 as g
+    from gplite_b200.dist import dist_fit_gaussian, BlockCyclic
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        lay = BlockCyclic(1000, 128, world, rank)
+        assert lay.nblk == 8 and lay.owned == list(range(rank, 8, world))
+        assert sum(lay.width) == 1000 and lay.width[-1] == 104
+        rng = np.random.default_rng(3)
+        n = 600
+        X = rng.normal(size=(n, 3))
+        y = np.sin(X[:, 0]) + 0.4 * X[:, 1] + 0.3 * rng.normal(size=n)
+        gp = g.gp_init(cfs=[g.cf_matern52(lscale=1.1), g.cf_lin(magn=0.3)], lik=g.lik_gaussian(sigma=0.4))
+        res = dist_fit_gaussian(gp, X, y, nb=128, ops=TorchOps(gp), dist=dist, device="cpu")
+        q.put((rank, res["log_evidence"], res["alpha"].numpy().copy()))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_distributed_driver_world2_matches_oracle():
+    import torch.multiprocessing as mp
+    import gplite_b200 as g
+    from oracle import gplite_oracle as o
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    out = [q.get(timeout=180) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    rng = np.random.default_rng(3)
+    n = 600
+    X = rng.normal(size=(n, 3))
+    y = np.sin(X[:, 0]) + 0.4 * X[:, 1] + 0.3 * rng.normal(size=n)
+    gpo = g.gp_init(cfs=[g.cf_matern52(lscale=1.1), g.cf_lin(magn=0.3)], lik=g.lik_gaussian(sigma=0.4))
+    o.gp_fit(gpo, X, y)
+    for rank, le, alpha in out:
+        assert abs(le - gpo.fit["log_evidence"]) < 1e-9 * abs(gpo.fit["log_evidence"])
+        assert np.max(np.abs(alpha - gpo.fit["alpha"])) < 1e-7 * np.max(np.abs(gpo.fit["alpha"]))

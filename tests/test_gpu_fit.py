@@ -183,3 +183,57 @@ def test_non_pd_aborts_full_gp(ctx):
     gp = g.gp_init(cfs=g.cf_sexp(), lik=g.lik_gaussian())
     with pytest.raises(g.GplError):
         g.gp_fit(gp, X, y, ctx=ctx)
+
+
+# ------------------------------------------------------------------------------ method_fitc
+def _fitc_data(n, m, d, seed):
+    rng = np.random.default_rng(seed)
+    X = rng.uniform(-3, 3, size=(n, d))
+    y = np.sin(X[:, 0]) + 0.3 * X[:, 1] + 0.5 * rng.normal(size=n)
+    Zi = X[rng.permutation(n)[:m]].copy()
+    return X, y, Zi
+
+
+@pytest.mark.parametrize("n,m", [(500, 37), (1500, 200)])
+def test_fitc_gaussian(ctx, n, m):
+    """FITC fit + prediction vs the oracle restatement of
+    R/gp_fit.R:101-123, R/laplace.R:122-152, R/linear_algebra.R:3-126, R/gp_pred.R:234-296."""
+    X, y, Zi = _fitc_data(n, m, 2, 4)
+    for cfs in ([g.cf_sexp(lscale=1.0)], [g.cf_matern32(lscale=1.5), g.cf_const(magn=0.3)]):
+        gp = g.gp_init(cfs=cfs, lik=g.lik_gaussian(sigma=0.5), method=g.method_fitc(inducing=Zi))
+        gpo = copy.deepcopy(gp)
+        g.gp_fit(gp, X, y, ctx=ctx)
+        o.gp_fit(gpo, X, y)
+        assert abs(gp.fit["log_evidence"] - gpo.fit["log_evidence"]) < TOL * abs(gpo.fit["log_evidence"])
+        assert scaled_err(gp.fit["fmean"], gpo.fit["fmean"]) < TOL
+        assert scaled_err(gp.fit["alpha"], gpo.fit["alpha"]) < 1e-6
+        Xt = np.random.default_rng(9).uniform(-3.5, 3.5, size=(60, 2))
+        p = g.gp_pred(gp, Xt, var=True)
+        po = o.gp_pred(gpo, Xt, var=True)
+        assert scaled_err(p["mean"], po["mean"]) < TOL
+        assert scaled_err(p["var"], po["var"]) < 1e-7     # reference formula cancels ~1e-9 itself
+
+
+def test_fitc_laplace_and_ep_bernoulli(ctx):
+    rng = np.random.default_rng(12)
+    n, m = 600, 50
+    X = rng.normal(size=(n, 2))
+    f = 2 * X[:, 0] - X[:, 1]
+    y = (rng.uniform(size=n) < 1 / (1 + np.exp(-f))).astype(float)
+    Zi = X[rng.permutation(n)[:m]].copy()
+    for approx in (g.approx_laplace(), g.approx_ep()):
+        gp = g.gp_init(cfs=g.cf_sexp(lscale=1.2), lik=g.lik_bernoulli(), method=g.method_fitc(inducing=Zi),
+                       approx=approx)
+        gpo = copy.deepcopy(gp)
+        g.gp_fit(gp, X, y, ctx=ctx)
+        o.gp_fit(gpo, X, y)
+        assert gp.fit["iters"] == gpo.fit["iters"], approx
+        assert abs(gp.fit["log_evidence"] - gpo.fit["log_evidence"]) < TOL * abs(gpo.fit["log_evidence"]), approx
+        assert scaled_err(gp.fit["fmean"], gpo.fit["fmean"]) < TOL, approx
+        if approx.name == "ep":
+            assert scaled_err(gp.fit["fvar"], gpo.fit["fvar"]) < 1e-7
+        Xt = rng.normal(size=(30, 2))
+        p = g.gp_pred(gp, Xt, var=True)
+        po = o.gp_pred(gpo, Xt, var=True)
+        assert scaled_err(p["mean"], po["mean"]) < TOL
+        assert scaled_err(p["var"], po["var"]) < 1e-7

@@ -1,0 +1,90 @@
+"""Multi-GPU full GP (BASELINE config 5) -- launch with torchrun, one rank per GPU:
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+        --master-port 29511 tools/dist_fit_bench.py --n 200000 [--nb 1024] [--check]
+
+--check : first run n = 6000 both ways (distributed vs the single-GPU gp_fit) and compare.
+Prints one JSON line from rank 0: seconds per phase (max over ranks), aggregate TFLOP/s of the
+factorisation (n^3/3 flops), log evidence.
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import gplite_b200 as g                                 # noqa: E402
+from gplite_b200.dist import dist_fit_gaussian          # noqa: E402
+
+
+def data(n, d, seed):
+    rng = np.random.default_rng(seed)
+    X = rng.normal(size=(n, d))
+    y = np.sin(X[:, 0]) + 0.5 * X[:, 1] ** 2 + X[:, 2] + 0.5 * rng.normal(size=n)
+    return X, y
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--n", type=int, default=65536)
+    ap.add_argument("--d", type=int, default=8)
+    ap.add_argument("--nb", type=int, default=1024)
+    ap.add_argument("--kind", default="matern32")
+    ap.add_argument("--check", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    mk = {"matern32": g.cf_matern32, "matern52": g.cf_matern52, "sexp": g.cf_sexp}[args.kind]
+
+    if args.check:
+        X, y = data(6000, args.d, 5)
+        gp = g.gp_init(cfs=mk(lscale=1.3), lik=g.lik_gaussian(sigma=0.5))
+        res = dist_fit_gaussian(gp, X, y, nb=256)
+        out = {"check_n": 6000, "dist_log_evidence": res["log_evidence"]}
+        if rank == 0:
+            gp1 = g.gp_init(cfs=mk(lscale=1.3), lik=g.lik_gaussian(sigma=0.5))
+            g.gp_fit(gp1, X, y)
+            le1 = gp1.fit["log_evidence"]
+            a1 = gp1.fit["alpha"]
+            out.update(single_log_evidence=le1, rel_diff=abs(res["log_evidence"] - le1) / abs(le1),
+                       alpha_scaled_err=float(np.max(np.abs(res["alpha"].cpu().numpy() - a1)) / np.max(np.abs(a1))))
+            print(json.dumps(out), flush=True)
+        dist.barrier()
+
+    X, y = data(args.n, args.d, 5)
+    gp = g.gp_init(cfs=mk(lscale=1.3), lik=g.lik_gaussian(sigma=0.5))
+    tm = {}
+    torch.cuda.synchronize()
+    dist.barrier()
+    t0 = time.perf_counter()
+    res = dist_fit_gaussian(gp, X, y, nb=args.nb, timings=tm)
+    torch.cuda.synchronize()
+    total = time.perf_counter() - t0
+    vals = torch.tensor([tm["kbuild"], tm["factor"], tm["solve"], total], dtype=torch.float64, device="cuda")
+    dist.all_reduce(vals, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        kb, fa, so, tot = [float(v) for v in vals]
+        n = args.n
+        print(json.dumps({"workload": f"cfg5-style: full GP n={n}, d={args.d}, cf_{args.kind} + lik_gaussian, "
+                                      f"1-D block-cyclic (nb={args.nb}) over {world} GPU(s)",
+                          "n_gpus": world, "kbuild_s": kb, "factor_s": fa, "solve_s": so, "total_s": tot,
+                          "factor_tflops_aggregate": n ** 3 / 3 / fa / 1e12,
+                          "factor_tflops_per_gpu": n ** 3 / 3 / fa / 1e12 / world,
+                          "kbuild_gbs_aggregate": 8.0 * n * n / 2 / kb / 1e9,
+                          "log_evidence": res["log_evidence"],
+                          "matrix_gb_per_gpu": 8.0 * n * n / world / 1e9}), flush=True)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
