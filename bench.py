@@ -1,7 +1,7 @@
 """Headline benchmark: gp_energy + gradient evaluations / second at n = 32768, d = 8, fp64
 (BASELINE.json configs[1]: synthetic regression, cf_matern52 + lik_gaussian, method_full).
 
-    python bench.py --gpus N --steps K --warmup W [--impl reference] [--n 32768]
+    python bench.py --gpus N --steps K --warmup W [--impl reference] [--size 32768]
 
 A "step" is ONE complete energy + gradient evaluation of the full GP: K build (+jitter) ->
 B = I + K/sigma^2 -> blocked DMMA Cholesky -> alpha, f = K alpha, log evidence -> (K+V)^-1 via
@@ -168,7 +168,9 @@ def run_ours(args, rank, world, local_rank):
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    stream = torch.cuda.current_stream().cuda_stream
+    # torch's default stream has handle 0 ("create your own" for gpl_ctx_create): use
+    # cudaStreamLegacy (1) so that torch.cuda.Event timing sees the library's kernels
+    stream = torch.cuda.current_stream().cuda_stream or 1
     ctx = _lib.Context(local_rank, stream)
     n, d = args.n, D_FULL
     X, y = synth(n, d, seed=2)
@@ -288,7 +290,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--n", type=int, default=N_FULL)
+    ap.add_argument("--size", dest="n", type=int, default=N_FULL)
     ap.add_argument("--cpu-n", type=int, default=3072, help="sample size of the CPU reference arm")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -302,7 +304,7 @@ def main():
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
                "--master-addr", "127.0.0.1", "--master-port", str(29500 + os.getpid() % 1000), __file__,
                "--gpus", str(args.gpus), "--steps", str(args.steps), "--warmup", str(args.warmup),
-               "--n", str(args.n), "--cpu-n", str(args.cpu_n)]
+               "--size", str(args.n), "--cpu-n", str(args.cpu_n)]
         sys.exit(subprocess.call(cmd))
     run_ours(args, rank, world, local_rank)
 

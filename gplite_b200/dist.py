@@ -142,7 +142,9 @@ def dist_fit_gaussian(gp, x, y, jitter=None, nb=1024, ops=None, dist=None, devic
     if ops is None:
         # same stream as torch: kernels, copies and NCCL collectives are then ordered without
         # host synchronisation
-        ops = GpuOps(_lib.Context(torch.cuda.current_device(), torch.cuda.current_stream().cuda_stream))
+        # (torch's default stream has handle 0, which the C ABI reads as "create your own": pass
+        # cudaStreamLegacy = 1 for it)
+        ops = GpuOps(_lib.Context(torch.cuda.current_device(), torch.cuda.current_stream().cuda_stream or 1))
     lay = BlockCyclic(n, nb, world, rank)
     ld = (n + 15) // 16 * 16
     t_mark = {}

@@ -131,8 +131,9 @@ int gpl_abi_version(void);
 const char* gpl_last_error(void);
 int gpl_device_count(void);
 
-/* stream: 0 -> the library creates its own; otherwise a cudaStream_t cast to uintptr_t
- * (e.g. torch.cuda.current_stream().cuda_stream) on which all work is enqueued. */
+/* stream: 0 -> the library creates its own (non-blocking) stream; otherwise a cudaStream_t cast to
+ * uintptr_t on which all work is enqueued.  To share the legacy default stream (what
+ * torch.cuda.current_stream().cuda_stream == 0 denotes) pass cudaStreamLegacy, i.e. 1. */
 int gpl_ctx_create(int device, uint64_t stream, gpl_ctx** out);
 int gpl_ctx_destroy(gpl_ctx* ctx);
 int gpl_ctx_sync(gpl_ctx* ctx);

@@ -237,3 +237,101 @@ def test_fitc_laplace_and_ep_bernoulli(ctx):
         po = o.gp_pred(gpo, Xt, var=True)
         assert scaled_err(p["mean"], po["mean"]) < TOL
         assert scaled_err(p["var"], po["var"]) < 1e-7
+
+
+# ------------------------------------------------------------------------------ wider coverage
+def test_pred_with_cfind_subset(ctx):
+    """gp_pred(..., cfind=) predicts with a subset of the summed cfs but the full-model alpha / C_chol
+    (R/gp_pred.R:206-207, R/cf.R:402-411)."""
+    rng = np.random.default_rng(21)
+    n = 300
+    X = rng.normal(size=(n, 2))
+    y = np.sin(2 * X[:, 0]) + 0.5 * X[:, 1] + 0.2 * rng.normal(size=n)
+    cfs = [g.cf_sexp(vars=[0], lscale=0.7), g.cf_lin(vars=[1], magn=0.8), g.cf_const(magn=0.5)]
+    gp = g.gp_init(cfs=cfs, lik=g.lik_gaussian(sigma=0.3))
+    gpo = copy.deepcopy(gp)
+    g.gp_fit(gp, X, y, ctx=ctx)
+    o.gp_fit(gpo, X, y)
+    Xt = rng.normal(size=(40, 2))
+    for cfind in ([0], [1, 2], [0, 1, 2]):
+        p = g.gp_pred(gp, Xt, var=True, cfind=cfind)
+        po = o.gp_pred(gpo, Xt, var=True, cfind=cfind)
+        assert scaled_err(p["mean"], po["mean"]) < TOL
+        assert np.max(np.abs(p["var"] - po["var"])) < TOL * max(1e-2, np.max(np.abs(po["var"])))
+    q = g.gp_pred(gp, Xt, quantiles=[0.05, 0.95])
+    qo = o.gp_pred(gpo, Xt, quantiles=[0.05, 0.95])
+    assert scaled_err(q["quantiles"], qo["quantiles"]) < 1e-7
+
+
+def test_laplace_betabinom_and_ep_counts(ctx):
+    rng = np.random.default_rng(31)
+    n = 200
+    X = rng.normal(size=(n, 2))
+    f = X[:, 0] - 0.5 * X[:, 1]
+    trials = rng.integers(2, 15, size=n).astype(float)
+    yb = rng.binomial(trials.astype(int), 1 / (1 + np.exp(-f))).astype(float)
+    yp = rng.poisson(np.exp(0.5 * f + 0.5)).astype(float)
+    # beta-binomial is not log-concave everywhere: either both sides fit, or both refuse the bad-site branch
+    gp = g.gp_init(cfs=g.cf_sexp(lscale=1.0), lik=g.lik_betabinom(phi=0.05))
+    gpo = copy.deepcopy(gp)
+    try:
+        o.gp_fit(gpo, X, yb, trials=trials)
+        ok = True
+    except o.NonLogConcave:
+        ok = False
+    if ok:
+        g.gp_fit(gp, X, yb, trials=trials, ctx=ctx)
+        assert abs(gp.fit["log_evidence"] - gpo.fit["log_evidence"]) < 1e-7 * abs(gpo.fit["log_evidence"])
+        assert scaled_err(gp.fit["fmean"], gpo.fit["fmean"]) < 1e-7
+    else:
+        with pytest.raises(g.GplError):
+            g.gp_fit(gp, X, yb, trials=trials, ctx=ctx)
+    for lik, y, extra in ((g.lik_binomial(), yb, dict(trials=trials)), (g.lik_poisson(), yp, dict())):
+        gp = g.gp_init(cfs=g.cf_matern32(lscale=1.2), lik=lik, approx=g.approx_ep(damping=0.8))
+        gpo = copy.deepcopy(gp)
+        g.gp_fit(gp, X, y, ctx=ctx, **extra)
+        o.gp_fit(gpo, X, y, **extra)
+        assert gp.fit["iters"] == gpo.fit["iters"], lik
+        assert abs(gp.fit["log_evidence"] - gpo.fit["log_evidence"]) < TOL * abs(gpo.fit["log_evidence"]), lik
+        assert scaled_err(gp.fit["fvar"], gpo.fit["fvar"]) < TOL, lik
+
+
+def test_gp_optim_runs_both_optimisers(ctx):
+    """gp_optim (R/gp_optim.R:63-125): derivative-free search as in the reference, and the
+    gradient-based option built on gpl_energy_grad; both must lower the energy to a similar optimum."""
+    rng = np.random.default_rng(41)
+    n = 150
+    x = rng.normal(size=n)
+    y = np.sin(3 * x) * np.exp(-np.abs(x)) + 0.1 * rng.normal(size=n)
+    res = {}
+    for method in ("Nelder-Mead", "L-BFGS-B"):
+        gp = g.gp_init(cfs=g.cf_sexp(), lik=g.lik_gaussian())
+        g.gp_fit(gp, x, y, ctx=ctx)
+        e0 = g.gp_energy(gp)
+        g.gp_optim(gp, x, y, verbose=False, warn=False, method=method, maxiter=300, ctx=ctx)
+        res[method] = g.gp_energy(gp)
+        assert res[method] < e0 - 1.0
+    assert abs(res["Nelder-Mead"] - res["L-BFGS-B"]) < 0.05 * abs(res["L-BFGS-B"]) + 0.5
+
+
+def test_energy_grad_at_scale_property(ctx):
+    """Full-size style check without an O(n^3) CPU oracle: at n = 4096 the analytic gradient must
+    match central differences of the library's own energy (size-independent property)."""
+    rng = np.random.default_rng(2)
+    n, d = 4096, 8
+    X = rng.normal(size=(n, d))
+    y = np.sin(X[:, 0]) + 0.5 * X[:, 1] ** 2 + X[:, 2] + 0.5 * rng.normal(size=n)
+    gp = g.gp_init(cfs=g.cf_matern52(lscale=1.3), lik=g.lik_gaussian(sigma=0.5))
+    e, grad = g.gp_energy_grad(gp, X, y, ctx=ctx)
+    p0 = g.get_param_vector(gp)
+    h = 1e-4
+    for k in range(len(p0)):
+        es = []
+        for sgn in (1, -1):
+            p = p0.copy()
+            p[k] += sgn * h
+            g.set_param(gp, p)
+            es.append(g.gp_energy_grad(gp, X, y, ctx=ctx)[0])
+        num = (es[0] - es[1]) / (2 * h)
+        assert abs(num - grad[k]) < 1e-5 * max(1.0, abs(grad[k])), (k, num, grad[k])
+    g.set_param(gp, p0)

@@ -1,7 +1,7 @@
 """Multi-GPU full GP (BASELINE config 5) -- launch with torchrun, one rank per GPU:
 
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
-        --master-port 29511 tools/dist_fit_bench.py --n 200000 [--nb 1024] [--check]
+        --master-port 29511 tools/dist_fit_bench.py --size 200000 [--nb 1024] [--check]
 
 --check : first run n = 6000 both ways (distributed vs the single-GPU gp_fit) and compare.
 Prints one JSON line from rank 0: seconds per phase (max over ranks), aggregate TFLOP/s of the
@@ -32,7 +32,7 @@ def data(n, d, seed):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--n", type=int, default=65536)
+    ap.add_argument("--size", dest="n", type=int, default=65536)
     ap.add_argument("--d", type=int, default=8)
     ap.add_argument("--nb", type=int, default=1024)
     ap.add_argument("--kind", default="matern32")

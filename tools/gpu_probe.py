@@ -44,8 +44,8 @@ def ev_time(fn, ctx=None, reps=3, warm=1):
 def pipes():
     lib = C.CDLL(os.path.join(ROOT, "tools", "libprobe_fp64.so"))
     lib.probe_fp64.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double)]
-    for mode, name in ((0, "DMMA.8x8x4"), (1, "DFMA")):
-        for threads, bps in ((256, 1), (512, 1), (1024, 1), (512, 2)):
+    for mode, name in ((0, "DMMA.8x8x4"), (2, "DMMA 4x8 tile pattern"), (1, "DFMA")):
+        for threads, bps in ((256, 1), (512, 1), (256, 2)):
             tf = C.c_double()
             rc = lib.probe_fp64(mode, threads, bps, 4000, C.byref(tf))
             emit(section="pipes", op=name, threads=threads, blocks_per_sm=bps, rc=rc, tflops=round(tf.value, 2))
