@@ -51,6 +51,8 @@ pair_kernel(const __grid_constant__ CfPlan plan, const PairArgs a) {
   double* Zs2 = sm + F * TILE;      // [F][128]
   double* T = sm + 2 * F * TILE;    // [8*CJ][129], only used on the mirrored path
   constexpr int PASSCOLS = 8 * CJ;
+  __shared__ double etab[64];       // 2^(j/64) for exp_neg_fast
+  if (threadIdx.x < 64) etab[threadIdx.x] = kExpTab[threadIdx.x];
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   int bi, bj;
@@ -126,7 +128,7 @@ pair_kernel(const __grid_constant__ CfPlan plan, const PairArgs a) {
 #pragma unroll
       for (int r = 0; r < 4; ++r)
 #pragma unroll
-        for (int c = 0; c < CJ; ++c) out[r][c] = factor_value(fk, s[r][c], sb[r], sc[c]);
+        for (int c = 0; c < CJ; ++c) out[r][c] = factor_value(fk, s[r][c], sb[r], sc[c], etab);
     } else {
       double prod[4][CJ];
 #pragma unroll
@@ -177,7 +179,7 @@ pair_kernel(const __grid_constant__ CfPlan plan, const PairArgs a) {
         for (int r = 0; r < 4; ++r)
 #pragma unroll
           for (int c = 0; c < CJ; ++c) {
-            const double v = factor_value(f, s[r][c], sb[r], sc[c]);
+            const double v = factor_value(f, s[r][c], sb[r], sc[c], etab);
             prod[r][c] = first ? v : prod[r][c] * v;
             if (last) out[r][c] += prod[r][c];
           }

@@ -14,6 +14,8 @@
 
 #include <stdlib.h>
 
+#include <type_traits>
+
 namespace gpl {
 
 namespace {
@@ -107,28 +109,24 @@ struct TileLoader {
       rowmask = 0;
     }
   }
-  // krem = K - k0 (> 0): number of valid k in this tile onwards
-  __device__ __forceinline__ void issue(double* s, int krem) {
-    const double* q = p;
-    if (KCONTIG) {
-      int kb = (krem - c2) * 8;
-      kb = kb < 0 ? 0 : (kb > 16 ? 16 : kb);
-#pragma unroll
-      for (int i = 0; i < ITERS; ++i) {
-        const int nb = ((rowmask >> i) & 1u) ? kb : 0;
-        cp_async16(s + soff + i * RSTEP * LDS_, nb ? q : base, nb);
-        q += step;
-      }
-    } else {
-#pragma unroll
-      for (int i = 0; i < ITERS; ++i) {
-        const int nb = (r0 + RSTEP * i < krem) ? fixed_bytes : 0;
-        cp_async16(s + soff + i * RSTEP * LDS_, nb ? q : base, nb);
-        q += step;
+  // Chunk i of the current k-tile.  FAST: the CTA's tile is interior and K is a multiple of BK, so
+  // no bounds logic is needed (one LDGSTS + one 64-bit add).  krem = K - k0 (> 0).
+  template <bool FAST>
+  __device__ __forceinline__ void issue_chunk(double* s, int krem, int i, const double*& q) const {
+    int nb = 16;
+    if (!FAST) {
+      if (KCONTIG) {
+        int kb = (krem - c2) * 8;
+        kb = kb < 0 ? 0 : (kb > 16 ? 16 : kb);
+        nb = ((rowmask >> i) & 1u) ? kb : 0;
+      } else {
+        nb = (r0 + RSTEP * i < krem) ? fixed_bytes : 0;
       }
     }
-    p += kadv;
+    cp_async16(s + soff + i * RSTEP * LDS_, (FAST || nb) ? q : base, nb);
+    q += step;
   }
+  __device__ __forceinline__ void advance() { p += kadv; }
 };
 
 struct GemmArgs {
@@ -184,46 +182,85 @@ __global__ void __launch_bounds__(CF::THREADS) gemm_f64_kernel(const GemmArgs p)
   TileLoader<!TB, BN, CF::THREADS, BK> ldB;
   ldA.init(p.A, p.lda, m0, p.M, tid);
   ldB.init(p.B, p.ldb, n0, p.N, tid);
-  auto issue = [&](int kt) {
+  // interior tile and K a multiple of BK: no bounds logic in the loads (CTA-uniform)
+  const bool fast = (m0 + BM <= p.M) && (n0 + BN <= p.N) && (p.K % BK == 0);
+  constexpr int KS = BK / 4;                       // k4 steps per tile
+  constexpr int ITA = decltype(ldA)::ITERS, ITB = decltype(ldB)::ITERS;
+
+  // whole-tile issue (prologue)
+  auto issue_tile = [&](int kt) {
     double* sA = smem + (kt % STAGES) * STAGE;
-    ldA.issue(sA, p.K - kt * BK);
-    ldB.issue(sA + CF::OPER_A, p.K - kt * BK);
+    double* sB = sA + CF::OPER_A;
+    const int krem = p.K - kt * BK;
+    const double* qa = ldA.p;
+    const double* qb = ldB.p;
+#pragma unroll
+    for (int i = 0; i < ITA; ++i) ldA.template issue_chunk<false>(sA, krem, i, qa);
+#pragma unroll
+    for (int i = 0; i < ITB; ++i) ldB.template issue_chunk<false>(sB, krem, i, qb);
+    ldA.advance();
+    ldB.advance();
   };
 
 #pragma unroll
   for (int s = 0; s < STAGES - 1; ++s) {
-    if (s < ktiles) issue(s);
+    if (s < ktiles) issue_tile(s);
     cp_async_commit();
   }
 
-  for (int kt = 0; kt < ktiles; ++kt) {
-    cp_async_wait<STAGES - 2>();
-    __syncthreads();
-    if (kt + STAGES - 1 < ktiles) issue(kt + STAGES - 1);
-    cp_async_commit();
+  // main loop: the cp.async chunks of tile kt + STAGES - 1 are spread over the k4 steps of tile kt,
+  // so that the two warps of a scheduler do not both leave the DMMA pipe idle after the barrier
+  auto mainloop = [&](auto fast_tag) {
+    constexpr bool FAST = decltype(fast_tag)::value;
+    for (int kt = 0; kt < ktiles; ++kt) {
+      cp_async_wait<STAGES - 2>();
+      __syncthreads();
+      const int ktn = kt + STAGES - 1;
+      const bool do_load = ktn < ktiles;
+      double* nA = smem + (ktn % STAGES) * STAGE;
+      double* nB = nA + CF::OPER_A;
+      const int krem = p.K - ktn * BK;
+      const double* qa = ldA.p;
+      const double* qb = ldB.p;
 
-    const double* sA = smem + (kt % STAGES) * STAGE;
-    const double* sB = sA + CF::OPER_A;
+      const double* sA = smem + (kt % STAGES) * STAGE;
+      const double* sB = sA + CF::OPER_A;
 #pragma unroll
-    for (int ks = 0; ks < BK / 4; ++ks) {
-      const int kk = ks * 4 + t;
-      double a[MI], b[NI];
+      for (int ks = 0; ks < KS; ++ks) {
+        if (do_load) {
 #pragma unroll
-      for (int im = 0; im < MI; ++im) {
-        const int m = wm * CF::WM + im * 8 + g;
-        a[im] = TA ? sA[m * LDK + kk] : sA[kk * LDA + m];
+          for (int i = 0; i < ITA; ++i)
+            if (i * KS / ITA == ks) ldA.template issue_chunk<FAST>(nA, krem, i, qa);
+#pragma unroll
+          for (int i = 0; i < ITB; ++i)
+            if (i * KS / ITB == ks) ldB.template issue_chunk<FAST>(nB, krem, i, qb);
+        }
+        const int kk = ks * 4 + t;
+        double a[MI], b[NI];
+#pragma unroll
+        for (int im = 0; im < MI; ++im) {
+          const int m = wm * CF::WM + im * 8 + g;
+          a[im] = TA ? sA[m * LDK + kk] : sA[kk * LDA + m];
+        }
+#pragma unroll
+        for (int in = 0; in < NI; ++in) {
+          const int n = wn * CF::WN + in * 8 + g;
+          b[in] = TB ? sB[kk * LDB + n] : sB[n * LDK + kk];
+        }
+#pragma unroll
+        for (int im = 0; im < MI; ++im)
+#pragma unroll
+          for (int in = 0; in < NI; ++in) dmma(acc[im][in][0], acc[im][in][1], a[im], b[in]);
       }
-#pragma unroll
-      for (int in = 0; in < NI; ++in) {
-        const int n = wn * CF::WN + in * 8 + g;
-        b[in] = TB ? sB[kk * LDB + n] : sB[n * LDK + kk];
+      if (do_load) {
+        ldA.advance();
+        ldB.advance();
       }
-#pragma unroll
-      for (int im = 0; im < MI; ++im)
-#pragma unroll
-        for (int in = 0; in < NI; ++in) dmma(acc[im][in][0], acc[im][in][1], a[im], b[in]);
+      cp_async_commit();
     }
-  }
+  };
+  if (fast) mainloop(std::true_type{});
+  else mainloop(std::false_type{});
   cp_async_wait<0>();
 
   // epilogue: thread owns C[row = .. + g][col = .. + 2t, 2t+1] of each 8x8 sub-tile

@@ -67,7 +67,8 @@ __global__ void build_B_kernel(int64_t n, const double* __restrict__ K, int64_t 
 }
 
 __global__ void gemv_t_kernel(int64_t m, int64_t n, const double* __restrict__ A, int64_t lda,
-                              const double* __restrict__ x, double* __restrict__ y) {
+                              const double* __restrict__ x, double* __restrict__ y, double alpha,
+                              double beta) {
   const int lane = threadIdx.x & 31;
   const int64_t j = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (j >= n) return;
@@ -82,7 +83,7 @@ __global__ void gemv_t_kernel(int64_t m, int64_t n, const double* __restrict__ A
   }
   for (; i < m; i += 32) s0 = fma(col[i], x[i], s0);
   const double s = warp_sum((s0 + s1) + (s2 + s3));
-  if (lane == 0) y[j] = s;
+  if (lane == 0) y[j] = (beta != 0.0) ? beta * y[j] + alpha * s : alpha * s;
 }
 
 // partial[split][m]: row-wise reduction over a column range. MODE 0: sum A_ij x_j, 1: sum A_ij^2
@@ -115,88 +116,46 @@ __global__ void row_reduce_kernel(int64_t m, int64_t n, const double* __restrict
 }
 
 __global__ void sum_partials_kernel(int64_t m, int nsplit, const double* __restrict__ partial,
-                                    double* __restrict__ y) {
+                                    double* __restrict__ y, double alpha, double beta) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= m) return;
   double s = 0.0;
   for (int k = 0; k < nsplit; ++k) s += partial[(int64_t)k * m + i];
-  y[i] = s;
+  y[i] = (beta != 0.0) ? beta * y[i] + alpha * s : alpha * s;
 }
 
-// one block-step of the forward solve L w = b.  Every CTA recomputes w_k = Linv_kk b_k in
-// shared memory; CTA 0 publishes it into x, all CTAs update their rows of b below the block.
-__global__ void trsv_fwd_step_kernel(int64_t n, int64_t k0, int nbk, const double* __restrict__ L,
-                                     int64_t ldl, const double* __restrict__ Linv,
-                                     double* __restrict__ b, double* __restrict__ x) {
-  // b: work vector (rows below the block are updated), x: solution (distinct buffer -- other
-  // CTAs still read b_k while CTA 0 publishes w_k)
-  __shared__ double bk[NB], w[NB];
-  const int tid = threadIdx.x;
-  if (tid < NB) bk[tid] = (tid < nbk) ? b[k0 + tid] : 0.0;
+// x <- Linv b (trans = 0) or Linv^T b (trans = 1) for one <= 128 base block, in place.  Linv is the
+// full 128 x 128 tile with a zero upper triangle, so fixed trip counts keep the loads pipelined.
+__global__ void trsv_block_kernel(int nbk, const double* __restrict__ Linv, double* __restrict__ b,
+                                  int trans) {
+  __shared__ double bk[NB];
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  if (tid < NB) bk[tid] = (tid < nbk) ? b[tid] : 0.0;
   __syncthreads();
-  if (tid < NB) {
-    // Linv is stored as a full 128 x 128 tile with a zero upper triangle: run the whole row so the
-    // loads pipeline (fixed trip count, 4 independent accumulators)
-    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+  if (!trans) {
+    if (tid < NB) {
+      double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
 #pragma unroll 8
-    for (int c = 0; c < NB; c += 4) {
-      s0 = fma(Linv[(c + 0) * NB + tid], bk[c + 0], s0);
-      s1 = fma(Linv[(c + 1) * NB + tid], bk[c + 1], s1);
-      s2 = fma(Linv[(c + 2) * NB + tid], bk[c + 2], s2);
-      s3 = fma(Linv[(c + 3) * NB + tid], bk[c + 3], s3);
+      for (int c = 0; c < NB; c += 4) {
+        s0 = fma(Linv[(c + 0) * NB + tid], bk[c + 0], s0);
+        s1 = fma(Linv[(c + 1) * NB + tid], bk[c + 1], s1);
+        s2 = fma(Linv[(c + 2) * NB + tid], bk[c + 2], s2);
+        s3 = fma(Linv[(c + 3) * NB + tid], bk[c + 3], s3);
+      }
+      if (tid < nbk) b[tid] = (s0 + s1) + (s2 + s3);
     }
-    const double s = (s0 + s1) + (s2 + s3);
-    w[tid] = s;
-    if (blockIdx.x == 0 && tid < nbk) x[k0 + tid] = s;
-  }
-  __syncthreads();
-  const int64_t i = k0 + nbk + (int64_t)blockIdx.x * blockDim.x + tid;
-  if (i >= n) return;
-  double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-  const double* Lp = L + k0 * ldl + i;
-  int c = 0;
-#pragma unroll 4
-  for (; c + 3 < nbk; c += 4) {
-    s0 = fma(Lp[(int64_t)(c + 0) * ldl], w[c + 0], s0);
-    s1 = fma(Lp[(int64_t)(c + 1) * ldl], w[c + 1], s1);
-    s2 = fma(Lp[(int64_t)(c + 2) * ldl], w[c + 2], s2);
-    s3 = fma(Lp[(int64_t)(c + 3) * ldl], w[c + 3], s3);
-  }
-  for (; c < nbk; ++c) s0 = fma(Lp[(int64_t)c * ldl], w[c], s0);
-  b[i] -= (s0 + s1) + (s2 + s3);
-}
-
-// one block-step of the backward solve L^T v = w: v_k = Linv_kk^T w_k, then every column
-// j < k0 gets w_j -= L[k0:k0+nbk, j] . v_k (one warp per column, 1 KB contiguous reads)
-__global__ void trsv_bwd_step_kernel(int64_t k0, int nbk, const double* __restrict__ L,
-                                     int64_t ldl, const double* __restrict__ Linv,
-                                     double* __restrict__ b, double* __restrict__ x) {
-  __shared__ double bk[NB], v[NB];
-  const int tid = threadIdx.x;
-  const int lane = tid & 31, wid = tid >> 5;
-  if (tid < NB) bk[tid] = (tid < nbk) ? b[k0 + tid] : 0.0;
-  __syncthreads();
-  // v_c = sum_r Linv[r][c] bk[r]: one warp per column c (coalesced along r), 8 warps x 16 columns
-  for (int c = wid; c < NB; c += (blockDim.x >> 5)) {
-    const double* col = Linv + c * NB;
-    double s = fma(col[lane], bk[lane], 0.0);
-    s = fma(col[lane + 32], bk[lane + 32], s);
-    s = fma(col[lane + 64], bk[lane + 64], s);
-    s = fma(col[lane + 96], bk[lane + 96], s);
-    s = warp_sum(s);
-    if (lane == 0) {
-      v[c] = s;
-      if (blockIdx.x == 0 && c < nbk) x[k0 + c] = s;
+  } else {
+    // x_c = sum_r Linv[r][c] b_r: one warp per column (coalesced along r)
+    for (int c = wid; c < nbk; c += (blockDim.x >> 5)) {
+      const double* col = Linv + c * NB;
+      double s = fma(col[lane], bk[lane], 0.0);
+      s = fma(col[lane + 32], bk[lane + 32], s);
+      s = fma(col[lane + 64], bk[lane + 64], s);
+      s = fma(col[lane + 96], bk[lane + 96], s);
+      s = warp_sum(s);
+      if (lane == 0) b[c] = s;
     }
   }
-  __syncthreads();
-  const int64_t j = (int64_t)blockIdx.x * (blockDim.x >> 5) + wid;
-  if (j >= k0) return;
-  const double* col = L + j * ldl + k0;
-  double s = 0.0;
-  for (int r = lane; r < nbk; r += 32) s = fma(col[r], v[r], s);
-  s = warp_sum(s);
-  if (lane == 0) b[j] -= s;
 }
 
 __global__ void lower_colsumsq_kernel(int64_t n, const double* __restrict__ X, int64_t ldx,
@@ -524,16 +483,21 @@ int build_B(Ctx* ctx, int64_t n, const double* K, int64_t ldk, const double* s, 
   return GPL_OK;
 }
 
-int gemv_t(Ctx* ctx, int64_t m, int64_t n, const double* A, int64_t lda, const double* x, double* y) {
+int gemv_t_ab(Ctx* ctx, int64_t m, int64_t n, const double* A, int64_t lda, const double* x,
+              double* y, double alpha, double beta) {
   if (n <= 0) return GPL_OK;
-  gemv_t_kernel<<<(unsigned)((n + 7) / 8), 256, 0, ctx->stream>>>(m, n, A, lda, x, y);
+  gemv_t_kernel<<<(unsigned)((n + 7) / 8), 256, 0, ctx->stream>>>(m, n, A, lda, x, y, alpha, beta);
   GPL_LAUNCH_CHECK(ctx);
   return GPL_OK;
 }
 
+int gemv_t(Ctx* ctx, int64_t m, int64_t n, const double* A, int64_t lda, const double* x, double* y) {
+  return gemv_t_ab(ctx, m, n, A, lda, x, y, 1.0, 0.0);
+}
+
 template <int MODE>
 static int row_reduce(Ctx* ctx, int64_t m, int64_t n, const double* A, int64_t lda, const double* x,
-                      double* y) {
+                      double* y, double alpha = 1.0, double beta = 0.0) {
   if (m <= 0) return GPL_OK;
   const int64_t row_blocks = (m + 255) / 256;
   int64_t nsplit = (4 * (int64_t)ctx->sm_count + row_blocks - 1) / row_blocks;
@@ -546,7 +510,8 @@ static int row_reduce(Ctx* ctx, int64_t m, int64_t n, const double* A, int64_t l
   dim3 grid((unsigned)row_blocks, (unsigned)nsplit);
   row_reduce_kernel<MODE><<<grid, 256, 0, ctx->stream>>>(m, n, A, lda, x, part.d(), cps);
   GPL_LAUNCH_CHECK(ctx);
-  sum_partials_kernel<<<(unsigned)row_blocks, 256, 0, ctx->stream>>>(m, (int)nsplit, part.d(), y);
+  sum_partials_kernel<<<(unsigned)row_blocks, 256, 0, ctx->stream>>>(m, (int)nsplit, part.d(), y,
+                                                                      alpha, beta);
   GPL_LAUNCH_CHECK(ctx);
   return GPL_OK;
 }
@@ -555,8 +520,38 @@ int gemv_n(Ctx* ctx, int64_t m, int64_t n, const double* A, int64_t lda, const d
   return row_reduce<0>(ctx, m, n, A, lda, x, y);
 }
 
+int gemv_n_ab(Ctx* ctx, int64_t m, int64_t n, const double* A, int64_t lda, const double* x,
+              double* y, double alpha, double beta) {
+  return row_reduce<0>(ctx, m, n, A, lda, x, y, alpha, beta);
+}
+
 int rowsumsq(Ctx* ctx, int64_t m, int64_t n, const double* A, int64_t lda, double* out) {
   return row_reduce<1>(ctx, m, n, A, lda, nullptr, out);
+}
+
+// recursive in-place triangular solve: the block products are plain GEMVs over L21 (HBM-bound,
+// n^2/2 * 8 bytes in total), the 128-blocks use the factor's cached block inverses
+static int trsv_rec(Ctx* ctx, const double* dinv, bool trans, int64_t n, const double* L,
+                    int64_t ldl, double* x, int64_t blk0) {
+  if (n <= NB) {
+    trsv_block_kernel<<<1, 256, 0, ctx->stream>>>((int)n, dinv + blk0 * NB * NB, x, trans ? 1 : 0);
+    GPL_LAUNCH_CHECK(ctx);
+    return GPL_OK;
+  }
+  const int64_t nblk = (n + NB - 1) / NB;
+  const int64_t n1 = (nblk / 2) * NB, n2 = n - n1;
+  const double* L21 = L + n1;
+  const double* L22 = L + n1 * ldl + n1;
+  if (!trans) {
+    GPL_TRY(trsv_rec(ctx, dinv, false, n1, L, ldl, x, blk0));
+    GPL_TRY(gemv_n_ab(ctx, n2, n1, L21, ldl, x, x + n1, -1.0, 1.0));
+    GPL_TRY(trsv_rec(ctx, dinv, false, n2, L22, ldl, x + n1, blk0 + n1 / NB));
+  } else {
+    GPL_TRY(trsv_rec(ctx, dinv, true, n2, L22, ldl, x + n1, blk0 + n1 / NB));
+    GPL_TRY(gemv_t_ab(ctx, n2, n1, L21, ldl, x + n1, x, -1.0, 1.0));
+    GPL_TRY(trsv_rec(ctx, dinv, true, n1, L, ldl, x, blk0));
+  }
+  return GPL_OK;
 }
 
 int trsv_lower(Ctx* ctx, const double* dinv, bool trans, int64_t n, const double* L, int64_t ldl,
@@ -566,28 +561,8 @@ int trsv_lower(Ctx* ctx, const double* dinv, bool trans, int64_t n, const double
     set_error("trsv_lower: work vector and solution must be distinct buffers");
     return GPL_ERR_BAD_ARG;
   }
-  const int64_t nblk = (n + NB - 1) / NB;
-  if (!trans) {
-    for (int64_t kb = 0; kb < nblk; ++kb) {
-      const int64_t k0 = kb * NB;
-      const int nbk = (int)((n - k0) < NB ? (n - k0) : NB);
-      const int64_t rest = n - k0 - nbk;
-      const unsigned grid = (unsigned)(rest > 0 ? (rest + 255) / 256 : 1);
-      trsv_fwd_step_kernel<<<grid, 256, 0, ctx->stream>>>(n, k0, nbk, L, ldl, dinv + kb * NB * NB,
-                                                          b, x);
-      GPL_LAUNCH_CHECK(ctx);
-    }
-  } else {
-    for (int64_t kb = nblk - 1; kb >= 0; --kb) {
-      const int64_t k0 = kb * NB;
-      const int nbk = (int)((n - k0) < NB ? (n - k0) : NB);
-      const unsigned grid = (unsigned)(k0 > 0 ? (k0 + 7) / 8 : 1);
-      trsv_bwd_step_kernel<<<grid, 256, 0, ctx->stream>>>(k0, nbk, L, ldl, dinv + kb * NB * NB, b,
-                                                          x);
-      GPL_LAUNCH_CHECK(ctx);
-    }
-  }
-  return GPL_OK;
+  GPL_CUDA(cudaMemcpyAsync(x, b, sizeof(double) * n, cudaMemcpyDeviceToDevice, ctx->stream));
+  return trsv_rec(ctx, dinv, trans, n, L, ldl, x, 0);
 }
 
 int lower_colsumsq(Ctx* ctx, int64_t n, const double* X, int64_t ldx, double* out) {
