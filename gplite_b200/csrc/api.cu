@@ -86,6 +86,13 @@ int gpl_ctx_create(int device, uint64_t stream, gpl_ctx** out) {
     GPL_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     c->own_stream = true;
   }
+  {
+    int lo = 0, hi = 0;
+    GPL_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    GPL_CUDA(cudaStreamCreateWithPriority(&c->panel_stream, cudaStreamNonBlocking, hi));
+    GPL_CUDA(cudaEventCreateWithFlags(&c->ev_col, cudaEventDisableTiming));
+    GPL_CUDA(cudaEventCreateWithFlags(&c->ev_diag, cudaEventDisableTiming));
+  }
   cudaDeviceProp prop;
   GPL_CUDA(cudaGetDeviceProperties(&prop, device));
   c->sm_count = prop.multiProcessorCount;
@@ -112,6 +119,9 @@ int gpl_ctx_destroy(gpl_ctx* h) {
   if (c->d_scal) cudaFree(c->d_scal);
   if (c->h_scal) cudaFreeHost(c->h_scal);
   for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
+  if (c->panel_stream) cudaStreamDestroy(c->panel_stream);
+  if (c->ev_col) cudaEventDestroy(c->ev_col);
+  if (c->ev_diag) cudaEventDestroy(c->ev_diag);
   if (c->own_stream) cudaStreamDestroy(c->stream);
   delete c;
   return GPL_OK;

@@ -14,6 +14,7 @@
 #include "common.cuh"
 
 #include <math.h>
+#include <stdlib.h>
 
 namespace gpl {
 
@@ -388,6 +389,59 @@ int lauum_rec(const Fac& f, double* X, int64_t ldx, int64_t n) {
   return GPL_OK;
 }
 
+// Blocked right-looking factorisation with one step of look-ahead for large n.  Block columns of
+// LA_NB: after panel k has been solved, block column k+1 is updated first and its diagonal block is
+// factored (the recursive routine: a latency-bound chain of small kernels) on a high-priority side
+// stream while the main stream applies panel k to the rest of the trailing matrix -- so the
+// small-kernel chain leaves the critical path.
+constexpr int64_t LA_NB = 2048;
+
+int potrf_lookahead(const Fac& f, double* A, int64_t lda, int64_t n) {
+  Ctx* ctx = f.ctx;
+  cudaStream_t main = ctx->stream, side = ctx->panel_stream;
+  const int64_t nblk = (n + LA_NB - 1) / LA_NB;
+  // order the side stream after whatever produced A on the main stream
+  GPL_CUDA(cudaEventRecord(ctx->ev_col, main));
+  GPL_CUDA(cudaStreamWaitEvent(side, ctx->ev_col, 0));
+  ctx->stream = side;
+  int rc = potrf_rec(f, A, lda, LA_NB < n ? LA_NB : n, 0);
+  ctx->stream = main;
+  GPL_TRY(rc);
+  GPL_CUDA(cudaEventRecord(ctx->ev_diag, side));
+  for (int64_t k = 0; k < nblk; ++k) {
+    const int64_t k0 = k * LA_NB;
+    const int64_t w = (n - k0) < LA_NB ? (n - k0) : LA_NB;
+    const int64_t k1 = k0 + w;
+    if (k1 >= n) {
+      GPL_CUDA(cudaStreamWaitEvent(main, ctx->ev_diag, 0));
+      break;
+    }
+    double* Akk = A + k0 * lda + k0;
+    double* P = A + k0 * lda + k1;                    // panel rows k1.., columns k0..k1
+    const int64_t mp = n - k1;
+    GPL_CUDA(cudaStreamWaitEvent(main, ctx->ev_diag, 0));
+    GPL_TRY(trsm_right_rec(f, true, mp, w, Akk, lda, P, lda, k0 / NB));
+    const int64_t w1 = (n - k1) < LA_NB ? (n - k1) : LA_NB;
+    const int64_t k2 = k1 + w1;
+    // block column k+1 (rows k1.., columns k1..k2): its diagonal block is needed first
+    GPL_TRY(dgemm(ctx, false, true, mp, w1, w, -1.0, P, lda, P, lda, 1.0, A + k1 * lda + k1, lda, false));
+    GPL_CUDA(cudaEventRecord(ctx->ev_col, main));
+    GPL_CUDA(cudaStreamWaitEvent(side, ctx->ev_col, 0));
+    ctx->stream = side;
+    rc = potrf_rec(f, A + k1 * lda + k1, lda, w1, k1 / NB);
+    ctx->stream = main;
+    GPL_TRY(rc);
+    GPL_CUDA(cudaEventRecord(ctx->ev_diag, side));
+    // rest of the trailing matrix (lower triangle), concurrently with the side stream
+    if (k2 < n) {
+      double* P2 = A + k0 * lda + k2;
+      GPL_TRY(dgemm(ctx, false, true, n - k2, n - k2, w, -1.0, P2, lda, P2, lda, 1.0,
+                    A + k2 * lda + k2, lda, true));
+    }
+  }
+  return GPL_OK;
+}
+
 }  // namespace
 
 int ensure_dinv(Ctx* ctx, int64_t n) {
@@ -416,7 +470,12 @@ int dpotrf_with(Ctx* ctx, double* dinv, int64_t n, double* A, int64_t lda, int32
   const int32_t big = 0x7fffffff;
   GPL_CUDA(cudaMemcpyAsync(ctx->d_info, &big, sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
   Fac f{ctx, dinv};
-  GPL_TRY(potrf_rec(f, A, lda, n, 0));
+  static const int lookahead_off = getenv("GPL_NO_LOOKAHEAD") ? 1 : 0;
+  if (n >= 4 * LA_NB && ctx->panel_stream && !lookahead_off && !ctx->profile) {
+    GPL_TRY(potrf_lookahead(f, A, lda, n));
+  } else {
+    GPL_TRY(potrf_rec(f, A, lda, n, 0));
+  }
   diag_logsum_kernel<<<1, 1024, 0, ctx->stream>>>(A, lda, n, ctx->d_scal);
   GPL_LAUNCH_CHECK(ctx);
   int32_t info = 0;

@@ -19,6 +19,10 @@ struct Ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
   bool own_stream = false;
+  // high-priority side stream + events for the look-ahead Cholesky (diagonal-block factorisation
+  // of step k+1 overlaps the trailing update of step k)
+  cudaStream_t panel_stream = nullptr;
+  cudaEvent_t ev_col = nullptr, ev_diag = nullptr;
   int sm_count = 148;
   int64_t launches = 0;
   // scratch: diagonal-block inverses of the most recent factorisation living in this ctx

@@ -171,34 +171,53 @@ def dist_fit_gaussian(gp, x, y, jitter=None, nb=1024, ops=None, dist=None, devic
         ops.scale_block(A_t, lc0, w, c0, n - c0, 1.0 / sigma2, 1.0 + jit / sigma2, 0)
     mark("kbuild")
 
-    # ---- right-looking factorisation with panel broadcasts
-    panel = torch.empty(nb * ld, dtype=torch.float64, device=device)
+    # ---- right-looking factorisation with panel broadcasts and one step of look-ahead:
+    # the owner of panel k+1 updates that block column first, factors it and starts its broadcast
+    # (async, NCCL stream) while every rank is still applying panel k to its other columns, so the
+    # panel factorisation and the NVLink transfer leave the critical path.
+    panels = [torch.empty(nb * ld, dtype=torch.float64, device=device) for _ in range(2)]
     logdet_local = 0.0
     fail = 0
-    for k in range(lay.nblk):
+
+    def panel_view(k):
+        w, mp = lay.width[k], n - lay.col0(k)
+        return panels[k % 2][: w * mp].view(w, mp)
+
+    def factor_panel(k):
+        """owner only: potrf of the diagonal block, TRSM of the rows below, pack for broadcast"""
+        nonlocal logdet_local, fail
+        k0, w, lc0 = lay.col0(k), lay.width[k], lay.local_col0[k]
+        st, info, ld_k = ops.potrf(A_t, lc0, k0, w)
+        if st != _lib.GPL_OK:
+            fail = max(fail, k0 + info if st == _lib.GPL_ERR_NOT_PD else 1)
+        else:
+            ops.save_dinv(w, dinv[k])
+            logdet_local += ld_k
+            if n - k0 - w > 0:
+                ops.trsm_below(A_t, lc0, k0, w, n - k0 - w)
+        panel_view(k).copy_(A_t[lc0:lc0 + w, k0:n])
+
+    def apply_panel(k, j):
         k0, w = lay.col0(k), lay.width[k]
-        m_below = n - k0 - w
-        mp = n - k0                                    # panel rows
-        ldp = mp                                       # mp is even because n, nb are
-        P_t = panel[: w * ldp].view(w, ldp)
-        if lay.owner(k) == rank:
-            lc0 = lay.local_col0[k]
-            st, info, ld_k = ops.potrf(A_t, lc0, k0, w)
-            if st != _lib.GPL_OK:
-                fail = max(fail, k0 + info if st == _lib.GPL_ERR_NOT_PD else -1)
-            else:
-                ops.save_dinv(w, dinv[k])
-                logdet_local += ld_k
-                if m_below > 0:
-                    ops.trsm_below(A_t, lc0, k0, w, m_below)
-            P_t.copy_(A_t[lc0:lc0 + w, k0:n])
-        dist.broadcast(P_t, src=lay.owner(k))
-        if m_below > 0:
-            for j in lay.owned:
-                if j <= k:
-                    continue
-                j0, wj = lay.col0(j), lay.width[j]
-                ops.update(P_t, ldp, w, j0 - k0, n - j0, j0 - k0, wj, A_t, lay.local_col0[j], j0)
+        j0, wj = lay.col0(j), lay.width[j]
+        ops.update(panel_view(k), n - k0, w, j0 - k0, n - j0, j0 - k0, wj, A_t, lay.local_col0[j], j0)
+
+    if lay.owner(0) == rank:
+        factor_panel(0)
+    work = dist.broadcast(panel_view(0), src=lay.owner(0), async_op=True)
+    for k in range(lay.nblk):
+        if work is not None:
+            work.wait()
+        nxt = k + 1
+        work = None
+        if nxt < lay.nblk:
+            if lay.owner(nxt) == rank:
+                apply_panel(k, nxt)
+                factor_panel(nxt)
+            work = dist.broadcast(panel_view(nxt), src=lay.owner(nxt), async_op=True)
+        for j in lay.owned:
+            if j > k and not (j == nxt):
+                apply_panel(k, j)
     flag = torch.tensor([float(fail)], dtype=torch.float64, device=device)
     dist.all_reduce(flag, op=dist.ReduceOp.MAX)
     if flag.item() != 0:

@@ -31,7 +31,7 @@ class OneRank:
         return 1
 
     @staticmethod
-    def broadcast(t, src=0):
+    def broadcast(t, src=0, async_op=False):
         return None
 
     @staticmethod

@@ -112,3 +112,31 @@ def test_dpotrf_reports_non_pd(ctx):
     assert st == _lib.GPL_ERR_NOT_PD
     assert info.value == 201
     assert b"201" in ctx.lib.gpl_last_error()
+
+
+@pytest.mark.parametrize("n", [8192, 8500])
+def test_dpotrf_lookahead_path_large(ctx, n):
+    """n >= 8192 takes the blocked look-ahead path (side stream); check against cuSOLVER through
+    torch on the device, plus the solve/inverse built on the same factor."""
+    gen = torch.Generator(device="cuda").manual_seed(n)
+    Q = torch.randn(n, 96, dtype=torch.float64, device="cuda", generator=gen)
+    A = Q @ Q.T / 96 + 0.5 * torch.eye(n, dtype=torch.float64, device="cuda")
+    ld = (n + 15) // 16 * 16
+    dA = torch.zeros(n, ld, dtype=torch.float64, device="cuda")
+    dA[:, :n] = A                                   # symmetric: row-major copy == column-major
+    info = C.c_int32(-1)
+    logdet = C.c_double()
+    torch.cuda.synchronize()
+    _lib.check(ctx.lib.gpl_dpotrf_dev(ctx.h, n, ptr(dA), ld, C.byref(info), C.byref(logdet)))
+    sync(ctx)
+    Lw = torch.linalg.cholesky(A)
+    L = torch.tril(dA[:, :n].T)
+    assert info.value == 0
+    assert float((L - Lw).abs().max()) < 1e-11 * float(Lw.abs().max()) * 50
+    assert abs(logdet.value - 2 * float(torch.log(torch.diagonal(Lw)).sum())) < 1e-9 * abs(logdet.value)
+    torch.cuda.synchronize()
+    _lib.check(ctx.lib.gpl_dpotri_dev(ctx.h, n, ptr(dA), ld))
+    sync(ctx)
+    Ainv = torch.tril(dA[:, :n].T)
+    want = torch.tril(torch.cholesky_inverse(Lw))
+    assert float((Ainv - want).abs().max()) < 1e-8 * float(want.abs().max())
