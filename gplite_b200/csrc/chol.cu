@@ -470,8 +470,11 @@ int dpotrf_with(Ctx* ctx, double* dinv, int64_t n, double* A, int64_t lda, int32
   const int32_t big = 0x7fffffff;
   GPL_CUDA(cudaMemcpyAsync(ctx->d_info, &big, sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
   Fac f{ctx, dinv};
-  static const int lookahead_off = getenv("GPL_NO_LOOKAHEAD") ? 1 : 0;
-  if (n >= 4 * LA_NB && ctx->panel_stream && !lookahead_off && !ctx->profile) {
+  // Measured on B200 (profiles/r01_probe_v8_lookahead.jsonl): 409 ms vs 403 ms for the plain
+  // recursion at n = 32768 -- the K = 2048 blocked updates lose what the overlap gains -- so the
+  // look-ahead path is opt-in (GPL_LOOKAHEAD=1) until the side-stream chain is shortened.
+  static const int lookahead_on = getenv("GPL_LOOKAHEAD") ? atoi(getenv("GPL_LOOKAHEAD")) : 0;
+  if (n >= 4 * LA_NB && ctx->panel_stream && lookahead_on && !ctx->profile) {
     GPL_TRY(potrf_lookahead(f, A, lda, n));
   } else {
     GPL_TRY(potrf_rec(f, A, lda, n, 0));
@@ -520,6 +523,11 @@ int dpotri_with(Ctx* ctx, double* dinv, int64_t n, double* A, int64_t lda) {
 int dtrtri_with(Ctx* ctx, double* dinv, int64_t n, double* A, int64_t lda) {
   Fac f{ctx, dinv};
   return trtri_rec(f, A, lda, n, 0);
+}
+
+int lauum_oop(Ctx* ctx, int64_t n, const double* X, int64_t ldx, double* Y, int64_t ldy) {
+  // Y_ij = sum_{k >= i} X_ki X_kj (i >= j): rows k < i of column-block i are zero
+  return dgemm(ctx, true, false, n, n, n, 1.0, X, ldx, X, ldx, 0.0, Y, ldy, true, 0, 1);
 }
 
 int dpotri(Ctx* ctx, int64_t n, double* A, int64_t lda) {

@@ -372,13 +372,17 @@ int energy_grad_impl(Ctx* ctx, const gpl_cf_model* cf, const gpl_lik* lik, const
       GPL_TRY(keep.alloc(ctx, sizeof(double) * st.ld * n));
       GPL_TRY(copy_lower(ctx, n, st.B.d(), st.ld, keep.d(), st.ld));
     }
-    GPL_TRY(dpotri_with(ctx, st.dinv.d(), n, st.B.d(), st.ld));           // B <- B^-1 (lower)
+    // B^-1 = X^T X with X = L_B^-1: trtri in place, then ONE triangular-aware SYRK into the K
+    // buffer (K is dead from here on: the trace kernel regenerates dK/dtheta from the features)
+    GPL_TRY(dtrtri_with(ctx, st.dinv.d(), n, st.B.d(), st.ld));
+    GPL_TRY(lauum_oop(ctx, n, st.B.d(), st.ld, st.K.d(), st.ld));
+    const double* Binv = st.K.d();
     DevBuf gout;
     GPL_TRY(gout.alloc(ctx, sizeof(double) * (MAX_GRAD_PARAMS + 8)));
-    GPL_TRY(grad_trace(ctx, st.hp.plan, st.Z.d(), n, st.Zaux.d(), n, st.B.d(), st.ld,
+    GPL_TRY(grad_trace(ctx, st.hp.plan, st.Z.d(), n, st.Zaux.d(), n, Binv, st.ld,
                        st.v[V_S].d(), st.v[V_ALPHA].d(), ncf, gp, gout.d()));
     // sigma: dC/dlog sigma = 2 sigma^2 I  ->  tr(W) = sum alpha^2 - sum s_i^2 Binv_ii
-    GPL_TRY(diag_extract(ctx, n, st.B.d(), st.ld, st.v[V_T1].d()));
+    GPL_TRY(diag_extract(ctx, n, Binv, st.ld, st.v[V_T1].d()));
     GPL_TRY(vec_op(ctx, VOP_MUL, n, st.v[V_S].d(), st.v[V_S].d(), st.v[V_T2].d()));
     GPL_TRY(reduce(ctx, RED_DOT, n, st.v[V_T1].d(), st.v[V_T2].d(), 5));
     GPL_TRY(fetch_scalars(ctx, 6, sc));

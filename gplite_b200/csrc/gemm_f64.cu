@@ -139,6 +139,8 @@ struct GemmArgs {
   int64_t ldc;
   double alpha, beta;
   int lower;
+  int kskip;      // 0: full k range; 1: k starts at the tile's first row (A^T lower-triangular in k);
+                  // 2: k starts at the tile's first column (B lower-triangular)
   int tiles_m, tiles_n;
 };
 
@@ -175,6 +177,8 @@ __global__ void __launch_bounds__(CF::THREADS) gemm_f64_kernel(const GemmArgs p)
     for (int j = 0; j < NI; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
   const int ktiles = (p.K + BK - 1) / BK;
+  // triangular operands: the leading k-tiles of this output tile only multiply stored zeros
+  const int kt0 = p.kskip == 1 ? m0 / BK : (p.kskip == 2 ? n0 / BK : 0);
 
   // A operand: TA -> stored K x M, contiguous along k.  The B operand of the product is
   // op(B)(k,n): !TB -> stored K x N, contiguous along k.
@@ -182,6 +186,8 @@ __global__ void __launch_bounds__(CF::THREADS) gemm_f64_kernel(const GemmArgs p)
   TileLoader<!TB, BN, CF::THREADS, BK> ldB;
   ldA.init(p.A, p.lda, m0, p.M, tid);
   ldB.init(p.B, p.ldb, n0, p.N, tid);
+  ldA.p += (int64_t)kt0 * ldA.kadv;
+  ldB.p += (int64_t)kt0 * ldB.kadv;
   // interior tile and K a multiple of BK: no bounds logic in the loads (CTA-uniform)
   const bool fast = (m0 + BM <= p.M) && (n0 + BN <= p.N) && (p.K % BK == 0);
   constexpr int KS = BK / 4;                       // k4 steps per tile
@@ -189,7 +195,7 @@ __global__ void __launch_bounds__(CF::THREADS) gemm_f64_kernel(const GemmArgs p)
 
   // whole-tile issue (prologue)
   auto issue_tile = [&](int kt) {
-    double* sA = smem + (kt % STAGES) * STAGE;
+    double* sA = smem + ((kt - kt0) % STAGES) * STAGE;
     double* sB = sA + CF::OPER_A;
     const int krem = p.K - kt * BK;
     const double* qa = ldA.p;
@@ -204,7 +210,7 @@ __global__ void __launch_bounds__(CF::THREADS) gemm_f64_kernel(const GemmArgs p)
 
 #pragma unroll
   for (int s = 0; s < STAGES - 1; ++s) {
-    if (s < ktiles) issue_tile(s);
+    if (kt0 + s < ktiles) issue_tile(kt0 + s);
     cp_async_commit();
   }
 
@@ -212,18 +218,18 @@ __global__ void __launch_bounds__(CF::THREADS) gemm_f64_kernel(const GemmArgs p)
   // so that the two warps of a scheduler do not both leave the DMMA pipe idle after the barrier
   auto mainloop = [&](auto fast_tag) {
     constexpr bool FAST = decltype(fast_tag)::value;
-    for (int kt = 0; kt < ktiles; ++kt) {
+    for (int kt = kt0; kt < ktiles; ++kt) {
       cp_async_wait<STAGES - 2>();
       __syncthreads();
       const int ktn = kt + STAGES - 1;
       const bool do_load = ktn < ktiles;
-      double* nA = smem + (ktn % STAGES) * STAGE;
+      double* nA = smem + ((ktn - kt0) % STAGES) * STAGE;
       double* nB = nA + CF::OPER_A;
       const int krem = p.K - ktn * BK;
       const double* qa = ldA.p;
       const double* qb = ldB.p;
 
-      const double* sA = smem + (kt % STAGES) * STAGE;
+      const double* sA = smem + ((kt - kt0) % STAGES) * STAGE;
       const double* sB = sA + CF::OPER_A;
 #pragma unroll
       for (int ks = 0; ks < KS; ++ks) {
@@ -311,7 +317,7 @@ int launch(Ctx* ctx, GemmArgs a) {
   GPL_LAUNCH_CHECK(ctx);
   if (ctx->profile) {
     GPL_CUDA(cudaEventRecord(e1, ctx->stream));
-    ctx->prof_flops += 2.0 * a.M * a.N * (double)a.K * (a.lower ? 0.5 : 1.0);
+    ctx->prof_flops += 2.0 * a.M * a.N * (double)a.K * (a.lower ? 0.5 : 1.0) * (a.kskip ? 2.0 / 3.0 : 1.0);
     ctx->prof_launches++;
   }
   return GPL_OK;
@@ -345,7 +351,7 @@ int dispatch(Ctx* ctx, const GemmArgs& a, int alias) {
 
 int dgemm(Ctx* ctx, bool ta, bool tb, int64_t m, int64_t n, int64_t k, double alpha,
           const double* A, int64_t lda, const double* B, int64_t ldb, double beta, double* C,
-          int64_t ldc, bool lower, int alias) {
+          int64_t ldc, bool lower, int alias, int kskip) {
   if (m <= 0 || n <= 0) return GPL_OK;
   if ((lda & 1) || (ldb & 1) || ((uintptr_t)A & 15) || ((uintptr_t)B & 15)) {
     set_error("dgemm: operands must be 16-byte aligned with even leading dimensions "
@@ -360,6 +366,7 @@ int dgemm(Ctx* ctx, bool ta, bool tb, int64_t m, int64_t n, int64_t k, double al
   a.M = (int)m; a.N = (int)n; a.K = (int)k;
   a.A = A; a.lda = lda; a.B = B; a.ldb = ldb; a.C = C; a.ldc = ldc;
   a.alpha = alpha; a.beta = beta; a.lower = lower ? 1 : 0;
+  a.kskip = kskip;
   a.tiles_m = a.tiles_n = 0;
   if (ta && tb) {
     set_error("dgemm: TT product not implemented (never needed on the hot path)");

@@ -115,9 +115,10 @@ def test_dpotrf_reports_non_pd(ctx):
 
 
 @pytest.mark.parametrize("n", [8192, 8500])
-def test_dpotrf_lookahead_path_large(ctx, n):
-    """n >= 8192 takes the blocked look-ahead path (side stream); check against cuSOLVER through
-    torch on the device, plus the solve/inverse built on the same factor."""
+def test_dpotrf_large(ctx, n):
+    """Large n (all three GEMM tile configurations, deep recursion; with GPL_LOOKAHEAD=1 also the
+    blocked look-ahead path): check against cuSOLVER through torch on the device, plus the inverse
+    built on the same factor."""
     gen = torch.Generator(device="cuda").manual_seed(n)
     Q = torch.randn(n, 96, dtype=torch.float64, device="cuda", generator=gen)
     A = Q @ Q.T / 96 + 0.5 * torch.eye(n, dtype=torch.float64, device="cuda")
