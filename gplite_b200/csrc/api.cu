@@ -24,26 +24,22 @@ int cf_eval_dev(Ctx* ctx, const gpl_cf_model* cf, const double* d_x1, int64_t n1
   HostPlan hp;
   GPL_TRY(make_plan(cf, d, term_mask, &hp));
   const int F = hp.plan.nfeat;
-  double *z1 = nullptr, *z2 = nullptr;
+  DevBuf z1, z2;                       // freed (stream-ordered) on every return path
   const int64_t ldz1 = n1 > 0 ? n1 : 1, ldz2 = n2 > 0 ? n2 : 1;
   if (F > 0) {
-    GPL_CUDA(cudaMallocAsync(&z1, sizeof(double) * ldz1 * F, ctx->stream));
-    GPL_TRY(prep_features(ctx, hp, d_x1, n1, ldx1, z1, ldz1));
+    GPL_TRY(z1.alloc(ctx, sizeof(double) * ldz1 * F));
+    GPL_TRY(prep_features(ctx, hp, d_x1, n1, ldx1, z1.d(), ldz1));
     if (!same) {
-      GPL_CUDA(cudaMallocAsync(&z2, sizeof(double) * ldz2 * F, ctx->stream));
-      GPL_TRY(prep_features(ctx, hp, d_x2, n2, ldx2, z2, ldz2));
+      GPL_TRY(z2.alloc(ctx, sizeof(double) * ldz2 * F));
+      GPL_TRY(prep_features(ctx, hp, d_x2, n2, ldx2, z2.d(), ldz2));
     }
   }
-  int rc;
   if (diag_only) {
     const int64_t n = same ? n1 : (n1 < n2 ? n1 : n2);
-    rc = cf_diag(ctx, hp.plan, z1, ldz1, same ? z1 : z2, same ? ldz1 : ldz2, n, jitter, d_out);
-  } else {
-    rc = cf_pairwise(ctx, hp.plan, z1, n1, ldz1, z2, n2, ldz2, same, jitter, d_out, ldk);
+    return cf_diag(ctx, hp.plan, z1.d(), ldz1, same ? z1.d() : z2.d(), same ? ldz1 : ldz2, n, jitter,
+                   d_out);
   }
-  if (z1) GPL_CUDA(cudaFreeAsync(z1, ctx->stream));
-  if (z2) GPL_CUDA(cudaFreeAsync(z2, ctx->stream));
-  return rc;
+  return cf_pairwise(ctx, hp.plan, z1.d(), n1, ldz1, z2.d(), n2, ldz2, same, jitter, d_out, ldk);
 }
 
 }  // namespace gpl
@@ -219,44 +215,20 @@ int gpl_cf_eval(gpl_ctx* h, const gpl_cf_model* cf, const double* x1, int64_t n1
   }
   const int64_t nout = diag_only ? (n1 < n2 ? n1 : n2) : n1 * n2;
   if (nout == 0) return GPL_OK;
-  double *dx1 = nullptr, *dx2 = nullptr, *dk = nullptr;
+  DevBuf dx1, dx2, dk;
   cudaStream_t s = c->stream;
-  GPL_CUDA(cudaMallocAsync(&dx1, sizeof(double) * n1 * d, s));
-  GPL_CUDA(cudaMemcpyAsync(dx1, x1, sizeof(double) * n1 * d, cudaMemcpyHostToDevice, s));
+  GPL_TRY(dx1.alloc(c, sizeof(double) * n1 * d));
+  GPL_CUDA(cudaMemcpyAsync(dx1.p, x1, sizeof(double) * n1 * d, cudaMemcpyHostToDevice, s));
   if (!same) {
-    GPL_CUDA(cudaMallocAsync(&dx2, sizeof(double) * n2 * d, s));
-    GPL_CUDA(cudaMemcpyAsync(dx2, x2, sizeof(double) * n2 * d, cudaMemcpyHostToDevice, s));
+    GPL_TRY(dx2.alloc(c, sizeof(double) * n2 * d));
+    GPL_CUDA(cudaMemcpyAsync(dx2.p, x2, sizeof(double) * n2 * d, cudaMemcpyHostToDevice, s));
   }
-  {
-    cudaError_t e = cudaMallocAsync(&dk, sizeof(double) * nout, s);
-    if (e == cudaErrorMemoryAllocation) {
-      cudaGetLastError();
-      set_error("gpl_cf_eval: cannot allocate %lld bytes for K", (long long)(nout * 8));
-      return GPL_ERR_NOMEM;
-    }
-    GPL_CUDA(e);
-  }
-  int rc = cf_eval_dev(c, cf, dx1, n1, n1, same ? dx1 : dx2, n2, n2, d, same != 0, term_mask,
-                       diag_only != 0, jitter, dk, n1);
-  if (rc == GPL_OK) {
-    GPL_CUDA(cudaMemcpyAsync(out, dk, sizeof(double) * nout, cudaMemcpyDeviceToHost, s));
-  }
-  GPL_CUDA(cudaFreeAsync(dx1, s));
-  if (dx2) GPL_CUDA(cudaFreeAsync(dx2, s));
-  GPL_CUDA(cudaFreeAsync(dk, s));
+  GPL_TRY(dk.alloc(c, sizeof(double) * nout));
+  GPL_TRY(cf_eval_dev(c, cf, dx1.d(), n1, n1, same ? dx1.d() : dx2.d(), n2, n2, d, same != 0, term_mask,
+                      diag_only != 0, jitter, dk.d(), n1));
+  GPL_CUDA(cudaMemcpyAsync(out, dk.p, sizeof(double) * nout, cudaMemcpyDeviceToHost, s));
   GPL_CUDA(cudaStreamSynchronize(s));
-  return rc;
-}
-
-int gpl_cf_eval_block_dev(gpl_ctx* h, const gpl_cf_model* cf, const double* d_x1, int64_t n1,
-                          int64_t ldx1, const double* d_x2, int64_t n2, int64_t ldx2, int32_t d,
-                          double* d_out, int64_t ldk) {
-  Ctx* c = reinterpret_cast<Ctx*>(h);
-  if (n1 < 0 || n2 < 0 || d <= 0 || !d_out || ldk < n1 || ldx1 < n1 || ldx2 < n2) {
-    set_error("gpl_cf_eval_block_dev: bad dimensions");
-    return GPL_ERR_BAD_ARG;
-  }
-  return cf_eval_dev(c, cf, d_x1, n1, ldx1, d_x2, n2, ldx2, d, false, 0, false, 0.0, d_out, ldk);
+  return GPL_OK;
 }
 
 static int native_cf(gpl_ctx* h, int kind, const double* x1, int64_t n1, const double* x2,

@@ -77,7 +77,8 @@ int dgemm(Ctx* ctx, bool ta, bool tb, int64_t m, int64_t n, int64_t k, double al
 // alias: 0 = C distinct from A and B; 1 = C is A (needs n <= 128); 2 = C is B (needs m <= 128);
 // 3 = both (single tile)
 // kskip: 1 = skip the k-tiles above each output tile's first ROW (op(A) = A^T with A lower
-// triangular in k), 2 = above its first COLUMN (B lower triangular); the skipped tiles are zeros.
+// triangular in k), 2 = above its first COLUMN (B lower triangular), 3 = beyond its last row (A lower
+// triangular); the skipped tiles are zeros (or never-written scratch above the diagonal).
 
 // ---- chol.cu ----
 int ensure_dinv(Ctx* ctx, int64_t n);

@@ -6,11 +6,38 @@
 #include "fit.cuh"
 
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
+
+#include <chrono>
 
 namespace gpl {
 
 namespace {
+
+// GPL_TIMING=1: per-phase wall times of gpl_energy_grad on stderr (each phase fenced by a stream
+// synchronise, so only meaningful for profiling runs)
+struct PhaseTimer {
+  Ctx* ctx;
+  bool on;
+  std::chrono::steady_clock::time_point t0;
+  explicit PhaseTimer(Ctx* c) : ctx(c) {
+    static const int env = getenv("GPL_TIMING") ? atoi(getenv("GPL_TIMING")) : 0;
+    on = env != 0;
+    if (on) {
+      cudaStreamSynchronize(ctx->stream);
+      t0 = std::chrono::steady_clock::now();
+    }
+  }
+  void mark(const char* what) {
+    if (!on) return;
+    cudaStreamSynchronize(ctx->stream);
+    auto t1 = std::chrono::steady_clock::now();
+    fprintf(stderr, "[gpl timing] %-28s %9.3f ms\n", what,
+            std::chrono::duration<double, std::milli>(t1 - t0).count());
+    t0 = t1;
+  }
+};
 
 __global__ void diag_extract_kernel(int64_t n, const double* __restrict__ A, int64_t lda,
                                     double* __restrict__ out) {
@@ -336,7 +363,9 @@ int energy_grad_impl(Ctx* ctx, const gpl_cf_model* cf, const gpl_lik* lik, const
   for (int j = 0; j < nparam; ++j)
     if (param_factor[j] >= 0 && param_slot[j] == 3) want_aux = true;
   FullState st;
+  PhaseTimer tm(ctx);
   GPL_TRY(full_setup(ctx, st, cf, lik, x, n, d, y, nullptr, nullptr, on_device, jitter, want_aux));
+  tm.mark("upload + features + K build");
   // map model factor indices to plan factor indices (identical: term_mask == 0 keeps all)
   GradParam gp[MAX_GRAD_PARAMS];
   int ncf = 0;
@@ -361,6 +390,7 @@ int energy_grad_impl(Ctx* ctx, const gpl_cf_model* cf, const gpl_lik* lik, const
   double sc[8];
   GPL_TRY(lik_pseudodata_la(ctx, st.lik, n, st.v[V_F].d(), st.y.d(), st.v[V_Z].d(), st.v[V_V].d()));
   GPL_TRY(factor_and_solve(ctx, st));
+  tm.mark("B build + potrf + alpha + K alpha");
   GPL_TRY(reduce(ctx, RED_SUMLOG_PROD, n, st.v[V_SQRTV].d(), st.v[V_DIAG].d(), 0));
   GPL_TRY(reduce(ctx, RED_SUMLOG, n, st.v[V_V].d(), nullptr, 1));
   GPL_TRY(reduce(ctx, RED_DOT, n, st.v[V_FNEW].d(), st.v[V_ALPHA].d(), 2));
@@ -375,7 +405,9 @@ int energy_grad_impl(Ctx* ctx, const gpl_cf_model* cf, const gpl_lik* lik, const
     // B^-1 = X^T X with X = L_B^-1: trtri in place, then ONE triangular-aware SYRK into the K
     // buffer (K is dead from here on: the trace kernel regenerates dK/dtheta from the features)
     GPL_TRY(dtrtri_with(ctx, st.dinv.d(), n, st.B.d(), st.ld));
+    tm.mark("trtri");
     GPL_TRY(lauum_oop(ctx, n, st.B.d(), st.ld, st.K.d(), st.ld));
+    tm.mark("lauum (single SYRK)");
     const double* Binv = st.K.d();
     DevBuf gout;
     GPL_TRY(gout.alloc(ctx, sizeof(double) * (MAX_GRAD_PARAMS + 8)));
@@ -390,6 +422,7 @@ int energy_grad_impl(Ctx* ctx, const gpl_cf_model* cf, const gpl_lik* lik, const
     GPL_CUDA(cudaMemcpyAsync(hg, gout.p, sizeof(double) * (ncf > 0 ? ncf : 1),
                              cudaMemcpyDeviceToHost, ctx->stream));
     GPL_CUDA(cudaStreamSynchronize(ctx->stream));
+    tm.mark("gradient trace + reductions");
     for (int q = 0; q < ncf; ++q) grad[cf_pos[q]] = -0.5 * hg[q];
     const double sigma2 = lik->param * lik->param;
     for (int j = 0; j < nparam; ++j)

@@ -140,7 +140,8 @@ struct GemmArgs {
   double alpha, beta;
   int lower;
   int kskip;      // 0: full k range; 1: k starts at the tile's first row (A^T lower-triangular in k);
-                  // 2: k starts at the tile's first column (B lower-triangular)
+                  // 2: k starts at the tile's first column (B lower-triangular);
+                  // 3: k ends at the tile's last row (A lower-triangular: A[m][k] = 0 for k > m)
   int tiles_m, tiles_n;
 };
 
@@ -176,9 +177,13 @@ __global__ void __launch_bounds__(CF::THREADS) gemm_f64_kernel(const GemmArgs p)
 #pragma unroll
     for (int j = 0; j < NI; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
-  const int ktiles = (p.K + BK - 1) / BK;
-  // triangular operands: the leading k-tiles of this output tile only multiply stored zeros
+  int ktiles = (p.K + BK - 1) / BK;
+  // triangular operands: the leading (or trailing) k-tiles of this output tile only multiply zeros
   const int kt0 = p.kskip == 1 ? m0 / BK : (p.kskip == 2 ? n0 / BK : 0);
+  if (p.kskip == 3) {
+    const int kend = (m0 + BM + BK - 1) / BK;
+    ktiles = kend < ktiles ? kend : ktiles;
+  }
 
   // A operand: TA -> stored K x M, contiguous along k.  The B operand of the product is
   // op(B)(k,n): !TB -> stored K x N, contiguous along k.
@@ -317,7 +322,8 @@ int launch(Ctx* ctx, GemmArgs a) {
   GPL_LAUNCH_CHECK(ctx);
   if (ctx->profile) {
     GPL_CUDA(cudaEventRecord(e1, ctx->stream));
-    ctx->prof_flops += 2.0 * a.M * a.N * (double)a.K * (a.lower ? 0.5 : 1.0) * (a.kskip ? 2.0 / 3.0 : 1.0);
+    ctx->prof_flops += 2.0 * a.M * a.N * (double)a.K * (a.lower ? 0.5 : 1.0) *
+                       (a.kskip ? (a.lower ? 1.0 / 3.0 : 0.5) : 1.0);
     ctx->prof_launches++;
   }
   return GPL_OK;

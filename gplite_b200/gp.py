@@ -440,3 +440,66 @@ def gp_pred(gp, xnew, var=False, quantiles=None, transform=False, cfind=None, ji
         pred["var"] = ((ft - mt[:, None]) ** 2) @ wq
         pred["mean"] = mt
     return pred
+
+
+# ------------------------------------------------------------------------------- gp_loo
+def _get_loglik_grid(lik, fgrid, y, trials=None, offset=None):
+    """get_loglik(..., sum = FALSE) on an n x q grid (R/lik.R:297-366).  Host side: n*q values."""
+    from scipy.special import gammaln, xlogy, xlog1py
+    f = fgrid if offset is None else fgrid + np.asarray(offset, dtype=np.float64)[:, None]
+    yb = np.asarray(y, dtype=np.float64)[:, None]
+    if lik.name == "lik_gaussian":
+        s = lik.sigma
+        return -0.5 * math.log(2 * math.pi) - math.log(s) - 0.5 * ((yb - f) / s) ** 2
+    if lik.name == "lik_poisson":
+        mu = np.exp(f)
+        return xlogy(yb, mu) - mu - gammaln(yb + 1)
+    t = np.ones_like(yb) if lik.name == "lik_bernoulli" else np.asarray(trials, dtype=np.float64)[:, None]
+    mu = _get_response(lik, f)
+    if lik.name == "lik_betabinom":
+        a, b = mu / lik.phi, (1 - mu) / lik.phi
+        return ((gammaln(t + 1) - gammaln(yb + 1) - gammaln(t - yb + 1))
+                + (gammaln(yb + a) + gammaln(t - yb + b) - gammaln(t + a + b))
+                + (gammaln(a + b) - gammaln(a) - gammaln(b)))
+    lch = gammaln(t + 1) - gammaln(yb + 1) - gammaln(t - yb + 1)
+    return lch + xlogy(yb, mu) + xlog1py(t - yb, -mu)
+
+
+def gp_loo(gp, x, y, quad_order=11, trials=None, offset=None):
+    """Leave-one-out predictive densities, R/gp_loo.R:73-133 (quadrature = TRUE branch), for
+    method_full.  The O(n^3) part -- the posterior variances at the training points for the
+    Laplace approximation -- runs on the GPU through gp_pred; the n x q quadrature is host side."""
+    if not is_fitted(gp, "analytic"):
+        raise RuntimeError("The provied GP model is not fitted. Please call gp_fit (or gp_optim) first.")
+    if gp.method.name != "full":
+        raise NotImplementedError("gp_loo is implemented for method_full")
+    y = np.asarray(y, dtype=np.float64).ravel()
+    n = len(y)
+    if gp.approx.name == "ep":                                     # R/gp_loo.R:131-133
+        loo_mean, loo_var = gp.fit["cavity_mean"], gp.fit["cavity_var"]
+    else:                                                          # R/gp_loo.R:119-129
+        fhat, z, V = gp.fit["fmean"], gp.fit["z"], gp.fit["V"]
+        grad = (z - fhat) / V
+        post_var = gp_pred(gp, x, var=True)["var"]
+        loo_var = 1.0 / (1.0 / post_var - 1.0 / V)
+        loo_mean = fhat - loo_var * grad
+    xq, wq = gauss_hermite_points(quad_order)
+    fgrid = xq[None, :] * np.sqrt(loo_var)[:, None] + loo_mean[:, None]
+    loglik = _get_loglik_grid(gp.lik, fgrid, y, trials=trials, offset=offset)
+    c = loglik.max(axis=1, keepdims=True)
+    loos = (c + np.log(np.sum(wq[None, :] * np.exp(loglik - c), axis=1, keepdims=True)))[:, 0]
+    return dict(loo=float(loos.sum()), sd=float(n * (loos.std(ddof=1) / math.sqrt(n))), loos=loos)
+
+
+def gp_compare(*loos, ref=None):
+    """R/gp_loo.R:147-175."""
+    vals = [l["loo"] for l in loos]
+    if ref is None:
+        ref = int(np.argmax(vals))
+    n = len(loos[0]["loos"])
+    out = np.zeros((len(loos), 2))
+    for i, l in enumerate(loos):
+        dlt = l["loos"] - loos[ref]["loos"]
+        out[i, 0] = n * dlt.mean()
+        out[i, 1] = n * (dlt.std(ddof=1) / math.sqrt(n))
+    return out

@@ -847,6 +847,25 @@ def gp_pred(gp, xnew, var=False, cfind=None, jitter=None, offset=None, transform
     return pred
 
 
+def gp_loo(gp, x, y, quad_order=11, trials=None, offset=None):
+    """R/gp_loo.R:73-133, quadrature = TRUE branch, method_full."""
+    y = np.asarray(y, dtype=np.float64)
+    if gp.approx.name == "ep":
+        loo_mean, loo_var = gp.fit["cavity_mean"], gp.fit["cavity_var"]
+    else:
+        fhat, z, V = gp.fit["fmean"], gp.fit["z"], gp.fit["V"]
+        grad = (z - fhat) / V
+        post_var = gp_pred_post_full(gp, _as_matrix(x), var=True)["var"]
+        loo_var = 1 / (1 / post_var - 1 / V)
+        loo_mean = fhat - loo_var * grad
+    xq, wq = gauss_hermite_points(quad_order)
+    fgrid = xq[None, :] * np.sqrt(loo_var)[:, None] + loo_mean[:, None]
+    loglik = get_loglik(gp.lik, fgrid, y, sum=False, trials=trials, offset=offset)
+    loos = logsumexp_w(loglik, wq)
+    n = len(y)
+    return dict(loo=float(np.sum(loos)), sd=float(n * (np.std(loos, ddof=1) / math.sqrt(n))), loos=loos)
+
+
 # --------------------------------------------------------------------------------------
 # gradient oracle (NOT in the reference -- derived; see module docstring)
 # --------------------------------------------------------------------------------------

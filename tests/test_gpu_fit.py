@@ -335,3 +335,22 @@ def test_energy_grad_at_scale_property(ctx):
         num = (es[0] - es[1]) / (2 * h)
         assert abs(num - grad[k]) < 1e-5 * max(1.0, abs(grad[k])), (k, num, grad[k])
     g.set_param(gp, p0)
+
+
+def test_gp_loo_laplace_and_ep(ctx):
+    """gp_loo (R/gp_loo.R:73-133) for method_full: Laplace needs the posterior variances at the
+    training inputs (GPU prediction path), EP reuses the cavity moments."""
+    X, y = _classification(250, 2, 9)
+    res = {}
+    for approx in (g.approx_laplace(), g.approx_ep()):
+        gp = g.gp_init(cfs=g.cf_sexp(lscale=1.0), lik=g.lik_bernoulli(), approx=approx)
+        gpo = copy.deepcopy(gp)
+        g.gp_fit(gp, X, y, ctx=ctx)
+        o.gp_fit(gpo, X, y)
+        l = g.gp_loo(gp, X, y)
+        lo = o.gp_loo(gpo, X, y)
+        assert abs(l["loo"] - lo["loo"]) < 1e-7 * abs(lo["loo"])
+        assert scaled_err(l["loos"], lo["loos"]) < 1e-6
+        res[approx.name] = l
+    cmp = g.gp_compare(res["laplace"], res["ep"])
+    assert cmp.shape == (2, 2) and np.min(np.abs(cmp[:, 0])) == 0.0
