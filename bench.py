@@ -264,8 +264,17 @@ def run_ours(args, rank, world, local_rank):
             best = min(best, t0.elapsed_time(t1))
         peak = 2 * 8192.0 ** 3 / (best * 1e-3) / 1e12
         del a, b
+        traffic = None
+        try:      # DRAM bytes of all GEMM launches of one step, from the committed ncu capture
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r01_gemm_traffic_egrad32768.json")))
+            if n == N_FULL:
+                traffic = tj["dram_bytes_total"]
+        except Exception:
+            pass
         line["roofline"] = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                            "frac": achieved / peak, "traffic": None,
+                            "frac": achieved / peak, "traffic": traffic,
+                            "traffic_note": "bytes per step over all launches of the kernel (ncu dram__bytes_read+write, "
+                                            "profiles/r01_gemm_traffic_egrad32768.json); achieved is per step likewise",
                             "kernel": "gemm_f64_kernel (DMMA.8x8x4 FP64 tensor path)",
                             "peak_source": "cuBLAS DGEMM 8192^3 burst measured in this run (no fp64 entry in "
                                            "MEASURED_PEAKS.json); nominal B200 FP64 tensor 37-40 TFLOP/s",

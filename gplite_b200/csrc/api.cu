@@ -231,6 +231,17 @@ int gpl_cf_eval(gpl_ctx* h, const gpl_cf_model* cf, const double* x1, int64_t n1
   return GPL_OK;
 }
 
+int gpl_cf_eval_block_dev(gpl_ctx* h, const gpl_cf_model* cf, const double* d_x1, int64_t n1,
+                          int64_t ldx1, const double* d_x2, int64_t n2, int64_t ldx2, int32_t d,
+                          double* d_out, int64_t ldk) {
+  Ctx* c = reinterpret_cast<Ctx*>(h);
+  if (n1 < 0 || n2 < 0 || d <= 0 || !d_out || ldk < n1 || ldx1 < n1 || ldx2 < n2) {
+    set_error("gpl_cf_eval_block_dev: bad dimensions");
+    return GPL_ERR_BAD_ARG;
+  }
+  return cf_eval_dev(c, cf, d_x1, n1, ldx1, d_x2, n2, ldx2, d, false, 0, false, 0.0, d_out, ldk);
+}
+
 static int native_cf(gpl_ctx* h, int kind, const double* x1, int64_t n1, const double* x2,
                      int64_t n2, int32_t d, double p0, double p1, double p2, int32_t diag_only,
                      double* out) {
