@@ -515,9 +515,13 @@ int dpotrf_with(Ctx* ctx, double* dinv, int64_t n, double* A, int64_t lda, int32
   // look-ahead path is opt-in (GPL_LOOKAHEAD=1) until the side-stream chain is shortened.
   static const int lookahead_on = getenv("GPL_LOOKAHEAD") ? atoi(getenv("GPL_LOOKAHEAD")) : 0;
   static const int ll_off = getenv("GPL_NO_LEFTLOOKING") ? 1 : 0;
+  // Left-looking potrf measured 436 ms vs 403 ms for the recursion at n = 32768 (its panel TRSMs and
+  // 1024-block factorisations are exposed), so it is opt-in; left-looking trtri is a win (370 vs 411 ms)
+  // and is the default.
+  static const int potrf_ll_on = getenv("GPL_POTRF_LL") ? atoi(getenv("GPL_POTRF_LL")) : 0;
   if (n >= 4 * LA_NB && ctx->panel_stream && lookahead_on && !ctx->profile) {
     GPL_TRY(potrf_lookahead(f, A, lda, n));
-  } else if (n >= 4 * LL_NB && !ll_off) {
+  } else if (n >= 4 * LL_NB && !ll_off && potrf_ll_on) {
     GPL_TRY(potrf_ll(f, A, lda, n));
   } else {
     GPL_TRY(potrf_rec(f, A, lda, n, 0));
