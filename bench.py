@@ -300,7 +300,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--size", dest="n", type=int, default=N_FULL)
-    ap.add_argument("--cpu-n", type=int, default=3072, help="sample size of the CPU reference arm")
+    ap.add_argument("--cpu-n", type=int, default=5120, help="sample size of the CPU reference arm")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
