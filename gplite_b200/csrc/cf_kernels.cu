@@ -15,6 +15,7 @@
 #include "cf.cuh"
 
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 namespace gpl {
@@ -240,6 +241,177 @@ pair_kernel(const __grid_constant__ CfPlan plan, const PairArgs a) {
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Stationary single-factor fast path: squared distances through the FP64 tensor pipe.
+//   r2_ij = |a_i|^2 + |b_j|^2 - 2 a_i . b_j,  a . b by DMMA.8x8x4 (a Gram contraction over features)
+// which halves the fp64-pipe time of the distance part (one FMA per feature instead of a subtract
+// and an FMA) and removes it from the issue stream (2 DMMA per 8 x 8 entries at d = 8).  All rows
+// are first shifted by one common reference row (distances are translation invariant) and a tile
+// whose |a|^2 + |b|^2 is still so large that the cancellation could cost more than ~5e-13 relative
+// in K falls back to direct differences (CTA-uniform branch).  Warp tile 32 x 32 per 64-column pass;
+// the accumulator layout (row g, columns 2t, 2t+1) makes the mirrored store a 16-byte vector store
+// and the direct stores 64-byte row segments, so no shared-memory transpose is needed.
+constexpr int GLD = TILE + 4;       // smem row stride, == 4 mod 16: conflict-free fragment loads
+
+__device__ __forceinline__ void dmma_k4(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
+}
+
+template <int KIND>
+__global__ void __launch_bounds__(PAIR_THREADS, 2)
+pair_gram_kernel(const __grid_constant__ CfPlan plan, const PairArgs a) {
+  extern __shared__ double sm[];
+  const int F = plan.nfeat, F4 = (F + 3) & ~3;
+  double* Zs1 = sm;                      // [F4][GLD]
+  double* Zs2 = sm + F4 * GLD;
+  double* nrm1 = sm + 2 * F4 * GLD;      // [TILE]
+  double* nrm2 = nrm1 + TILE;
+  __shared__ double etab[64];
+  __shared__ int s_bad;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  const int wm = warp & 3, wn = warp >> 2;
+  if (tid < 64) etab[tid] = kExpTab[tid];
+  if (tid == 0) s_bad = 0;
+
+  int bi, bj;
+  if (a.same) {
+    const int L = blockIdx.x;
+    int b = (int)((sqrt(8.0 * (double)L + 1.0) - 1.0) * 0.5);
+    while ((int64_t)b * (b + 1) / 2 > L) --b;
+    while ((int64_t)(b + 1) * (b + 2) / 2 <= L) ++b;
+    bi = b;
+    bj = L - b * (b + 1) / 2;
+  } else {
+    bi = blockIdx.x % a.tiles_i;
+    bj = blockIdx.x / a.tiles_i;
+  }
+  const int i0 = bi * TILE, j0 = bj * TILE;
+  const bool mirror = a.same && (bi != bj);
+  const bool diag_tile = a.same && (bi == bj);
+  const bool interior = (i0 + TILE <= a.n1) && (j0 + TILE <= a.n2);
+  const bool vec_ok = ((a.ldk & 1) == 0) && ((reinterpret_cast<uintptr_t>(a.K) & 15) == 0);
+
+  for (int idx = tid; idx < F4 * TILE; idx += PAIR_THREADS) {
+    const int f = idx >> 7, r = idx & (TILE - 1);
+    const int gi = i0 + r, gj = j0 + r;
+    double v1 = 0.0, v2 = 0.0;
+    if (f < F) {
+      const double ref = a.z1[(int64_t)f * a.ldz1];
+      if (gi < a.n1) v1 = a.z1[(int64_t)f * a.ldz1 + gi] - ref;
+      if (gj < a.n2) v2 = a.z2[(int64_t)f * a.ldz2 + gj] - ref;
+    }
+    Zs1[f * GLD + r] = v1;
+    Zs2[f * GLD + r] = v2;
+  }
+  __syncthreads();
+  FactorDev fk = plan.f[0];
+  fk.kind = KIND;
+  {
+    const double* Zs = (tid < TILE) ? Zs1 : Zs2;
+    const int r = tid & (TILE - 1);
+    double sacc = 0.0;
+    for (int f = 0; f < F4; ++f) {
+      const double v = Zs[f * GLD + r];
+      sacc = fma(v, v, sacc);
+    }
+    ((tid < TILE) ? nrm1 : nrm2)[r] = sacc;
+    // cancellation guard: relative error of K ~ cs * 4 eps (|a|^2 + |b|^2), cs ~ 1 / lscale^2
+    const double cs = (KIND == GPL_CF_SEXP) ? fabs(fk.c0) : fk.c0 * fk.c0;
+    if (!(2.0 * sacc * cs < 500.0)) s_bad = 1;       // also catches NaN
+  }
+  __syncthreads();
+  const bool bad = s_bad != 0;
+
+#pragma unroll 1
+  for (int pass = 0; pass < 2; ++pass) {
+    double acc[4][4][2];
+#pragma unroll
+    for (int im = 0; im < 4; ++im)
+#pragma unroll
+      for (int in = 0; in < 4; ++in) acc[im][in][0] = acc[im][in][1] = 0.0;
+    const int cbase = pass * 64 + wn * 32;
+    if (!bad) {
+      for (int ks = 0; ks < F4; ks += 4) {
+        const int kk = ks + t;
+        double av[4], bv[4];
+#pragma unroll
+        for (int im = 0; im < 4; ++im) av[im] = Zs1[kk * GLD + wm * 32 + im * 8 + g];
+#pragma unroll
+        for (int in = 0; in < 4; ++in) bv[in] = Zs2[kk * GLD + cbase + in * 8 + g];
+#pragma unroll
+        for (int im = 0; im < 4; ++im)
+#pragma unroll
+          for (int in = 0; in < 4; ++in) dmma_k4(acc[im][in][0], acc[im][in][1], av[im], bv[in]);
+      }
+    }
+#pragma unroll
+    for (int im = 0; im < 4; ++im) {
+      const int row = wm * 32 + im * 8 + g;
+      const int gi = i0 + row;
+      const double n1v = nrm1[row];
+#pragma unroll
+      for (int in = 0; in < 4; ++in) {
+        const int col = cbase + in * 8 + 2 * t;
+        const int gj = j0 + col;
+        double v[2];
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          double r2;
+          if (!bad) {
+            r2 = fma(-2.0, acc[im][in][c], n1v + nrm2[col + c]);
+            r2 = 0.5 * (r2 + fabs(r2));                       // clamp at 0, NaN stays NaN
+          } else {
+            r2 = 0.0;
+            for (int f = 0; f < F; ++f) {
+              const double dlt = Zs1[f * GLD + row] - Zs2[f * GLD + col + c];
+              r2 = fma(dlt, dlt, r2);
+            }
+          }
+          if (diag_tile && gi == gj + c) r2 = 0.0;
+          double val = factor_value(fk, r2, 0.0, 0.0, etab);
+          if (diag_tile && gi == gj + c) val += a.jitter;
+          v[c] = val;
+        }
+        if (interior) {
+          a.K[(int64_t)gj * a.ldk + gi] = v[0];
+          a.K[(int64_t)(gj + 1) * a.ldk + gi] = v[1];
+          if (mirror) {
+            double* dst = a.K + (int64_t)gi * a.ldk + gj;
+            if (vec_ok) {
+              *reinterpret_cast<double2*>(dst) = make_double2(v[0], v[1]);
+            } else {
+              dst[0] = v[0];
+              dst[1] = v[1];
+            }
+          }
+        } else {
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            if (gi < a.n1 && gj + c < a.n2) {
+              a.K[(int64_t)(gj + c) * a.ldk + gi] = v[c];
+              if (mirror) a.K[(int64_t)gi * a.ldk + gj + c] = v[c];
+            }
+          }
+        }
+      }
+    }
+  }
+}
+
+template <int KIND>
+int launch_pair_gram(Ctx* ctx, const CfPlan& plan, const PairArgs& a, int grid) {
+  const int F4 = (plan.nfeat + 3) & ~3;
+  const int smem = (2 * F4 * GLD + 2 * TILE) * (int)sizeof(double);
+  GPL_CUDA(cudaFuncSetAttribute(pair_gram_kernel<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                smem));
+  pair_gram_kernel<KIND><<<grid, PAIR_THREADS, smem, ctx->stream>>>(plan, a);
+  GPL_LAUNCH_CHECK(ctx);
+  return GPL_OK;
+}
+
 struct DiagArgs {
   const double* z1;
   const double* z2;
@@ -454,6 +626,15 @@ int cf_pairwise(Ctx* ctx, const CfPlan& plan, const double* z1, int64_t n1, int6
   a.tiles_j = (int)((a.n2 + TILE - 1) / TILE);
   a.jitter = same ? jitter : 0.0;
   const int grid = same ? a.tiles_i * (a.tiles_i + 1) / 2 : a.tiles_i * a.tiles_j;
+  static const int direct_only = getenv("GPL_KBUILD_DIRECT") ? atoi(getenv("GPL_KBUILD_DIRECT")) : 0;
+  if (plan.nfactors == 1 && plan.nfeat >= 1 && plan.nfeat <= 32 && !direct_only) {
+    switch (plan.f[0].kind) {
+      case GPL_CF_SEXP: return launch_pair_gram<GPL_CF_SEXP>(ctx, plan, a, grid);
+      case GPL_CF_MATERN32: return launch_pair_gram<GPL_CF_MATERN32>(ctx, plan, a, grid);
+      case GPL_CF_MATERN52: return launch_pair_gram<GPL_CF_MATERN52>(ctx, plan, a, grid);
+      default: break;
+    }
+  }
   if (plan.nfactors == 1) {
     switch (plan.f[0].kind) {
       case GPL_CF_SEXP: return launch_pair<8, GPL_CF_SEXP>(ctx, plan, a, grid);

@@ -354,3 +354,38 @@ def test_gp_loo_laplace_and_ep(ctx):
         res[approx.name] = l
     cmp = g.gp_compare(res["laplace"], res["ep"])
     assert cmp.shape == (2, 2) and np.min(np.abs(cmp[:, 0])) == 0.0
+
+
+def test_full_size_config2_properties(ctx):
+    """BASELINE config 2 at FULL size (n = 32768, d = 8, cf_matern52 + lik_gaussian): no O(n^3) CPU
+    oracle can run here, so check size-independent properties -- the analytic gradient against a
+    central difference of the library's own energy along a random direction, alpha against the
+    defining equation (K + (jitter + sigma^2) I) alpha = y on sampled rows (K rows from the oracle),
+    and predictions at training points reproducing y - sigma^2 alpha."""
+    rng = np.random.default_rng(2)
+    n, d = 32768, 8
+    X = rng.normal(size=(n, d))
+    y = np.sin(X[:, 0]) + 0.5 * X[:, 1] ** 2 + X[:, 2] + 0.5 * rng.normal(size=n)
+    gp = g.gp_init(cfs=g.cf_matern52(lscale=1.3), lik=g.lik_gaussian(sigma=0.5))
+    e0, grad = g.gp_energy_grad(gp, X, y, ctx=ctx)
+    p0 = g.get_param_vector(gp)
+    u = rng.normal(size=len(p0))
+    u /= np.linalg.norm(u)
+    h = 1e-4
+    es = []
+    for sgn in (1, -1):
+        g.set_param(gp, p0 + sgn * h * u)
+        es.append(g.gp_energy_grad(gp, X, y, ctx=ctx)[0])
+    g.set_param(gp, p0)
+    num = (es[0] - es[1]) / (2 * h)
+    assert abs(num - grad @ u) < 1e-5 * max(1.0, abs(grad @ u)), (num, grad @ u)
+    g.gp_fit(gp, X, y, ctx=ctx)
+    assert abs(-gp.fit["log_evidence"] - e0 + g.lpdf_prior(gp)) < 1e-9 * abs(e0)
+    alpha = gp.fit["alpha"]
+    idx = rng.choice(n, size=64, replace=False)
+    Krows = o.cf_native_np("cf_matern52", X[idx], X, 1.3, 1.0)
+    lhs = Krows @ alpha + (1e-6 + 0.25) * alpha[idx]
+    assert np.max(np.abs(lhs - y[idx])) < 1e-8 * np.max(np.abs(y))
+    p = g.gp_pred(gp, X[idx], var=True)
+    assert np.max(np.abs(p["mean"] - (y[idx] - (0.25 + 1e-6) * alpha[idx]))) < 1e-8
+    assert np.all(p["var"] > 0) and np.all(p["var"] < 1.0)
