@@ -93,6 +93,8 @@ SIGNATURES = {
     "gpl_dpotrf_dev": (C.c_int, [_P, _I64, _P, _I64, C.POINTER(_I32), C.POINTER(_D)]),
     "gpl_dtrsm_right_dev": (C.c_int, [_P, _I32, _I64, _I64, _P, _I64, _P, _I64]),
     "gpl_dpotri_dev": (C.c_int, [_P, _I64, _P, _I64]),
+    "gpl_dtrsm_right_dinv_dev": (C.c_int, [_P, _I32, _I64, _I64, _P, _I64, _P, _P, _I64]),
+    "gpl_rowsumsq_dev": (C.c_int, [_P, _I64, _I64, _P, _I64, _P]),
     "gpl_dpotrf_get_dinv_dev": (C.c_int, [_P, _I64, _P]),
     "gpl_dtrsv_dev": (C.c_int, [_P, _I32, _I64, _P, _I64, _P, _P, _P]),
     "gpl_dgemv_dev": (C.c_int, [_P, _I32, _I64, _I64, _P, _I64, _P, _P]),

@@ -286,6 +286,16 @@ int gpl_dtrsm_right_dev(gpl_ctx* h, int32_t trans, int64_t m, int64_t n, const d
   return dtrsm_right(reinterpret_cast<Ctx*>(h), trans != 0, m, n, L, ldl, B, ldb, 0);
 }
 
+int gpl_dtrsm_right_dinv_dev(gpl_ctx* h, int32_t trans, int64_t m, int64_t n, const double* L,
+                             int64_t ldl, const double* d_dinv, double* B, int64_t ldb) {
+  return dtrsm_right_with(reinterpret_cast<Ctx*>(h), const_cast<double*>(d_dinv), trans != 0, m, n, L,
+                          ldl, B, ldb);
+}
+
+int gpl_rowsumsq_dev(gpl_ctx* h, int64_t m, int64_t n, const double* A, int64_t lda, double* out) {
+  return rowsumsq(reinterpret_cast<Ctx*>(h), m, n, A, lda, out);
+}
+
 int gpl_dpotri_dev(gpl_ctx* h, int64_t n, double* A, int64_t lda) {
   return dpotri(reinterpret_cast<Ctx*>(h), n, A, lda);
 }

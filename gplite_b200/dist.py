@@ -277,3 +277,181 @@ def dist_fit_gaussian(gp, x, y, jitter=None, nb=1024, ops=None, dist=None, devic
         for a, b in zip(names[:-1], names[1:]):
             timings[b] = t_mark[b] - t_mark[a]
     return dict(log_evidence=log_evidence, alpha=alpha, fmean=fmean, layout=lay)
+
+
+# ================================================================================================
+# FITC across GPUs ("shards naturally, one reduction")
+# ================================================================================================
+
+class FitcOps:
+    """C-ABI calls of the row-sharded FITC driver on torch CUDA tensors.  Matrices are column-major
+    slabs: a (rows x cols) matrix is a tensor of shape (cols, ld), element (i, j) at t[j, i]."""
+
+    def __init__(self, ctx):
+        self.ctx = ctx
+        self.lib = ctx.lib
+
+    _p = staticmethod(GpuOps._p)
+
+    def ksym(self, pm, Z_t, m, d, jitter, out_t):
+        """out (m x m) = K(z, z) + jitter I"""
+        _lib.check(self.lib.gpl_cf_eval_dev(self.ctx.h, pm.ref(), self._p(Z_t), m, self._p(Z_t), m, d, 1, 0, 0,
+                                            float(jitter), self._p(out_t), out_t.shape[1]))
+
+    def kblock(self, pm, X_t, nr, ldx, Z_t, m, d, out_t):
+        """out (nr x m) = K(x_local, z)"""
+        _lib.check(self.lib.gpl_cf_eval_block_dev(self.ctx.h, pm.ref(), self._p(X_t), nr, ldx, self._p(Z_t), m, m,
+                                                  d, self._p(out_t), out_t.shape[1]))
+
+    def kdiag(self, pm, X_t, nr, d, jitter, out_t):
+        _lib.check(self.lib.gpl_cf_eval_dev(self.ctx.h, pm.ref(), self._p(X_t), nr, self._p(X_t), nr, d, 1, 0, 1,
+                                            float(jitter), self._p(out_t), nr))
+
+    def potrf(self, A_t, m, dinv_t):
+        info = C.c_int32()
+        logdet = C.c_double()
+        st = self.lib.gpl_dpotrf_dev(self.ctx.h, m, self._p(A_t), A_t.shape[1], C.byref(info), C.byref(logdet))
+        if st == _lib.GPL_OK:
+            _lib.check(self.lib.gpl_dpotrf_get_dinv_dev(self.ctx.h, m, self._p(dinv_t)))
+        return st, info.value, logdet.value
+
+    def rownorms_after_solve(self, W_t, rows, m, L_t, dinv_t, out_t, out_off):
+        """out[off:off+rows] = row sums of squares of W L^-T  (W is destroyed)"""
+        _lib.check(self.lib.gpl_dtrsm_right_dinv_dev(self.ctx.h, 1, rows, m, self._p(L_t), L_t.shape[1],
+                                                     self._p(dinv_t), self._p(W_t), W_t.shape[1]))
+        _lib.check(self.lib.gpl_rowsumsq_dev(self.ctx.h, rows, m, self._p(W_t), W_t.shape[1], self._p(out_t, out_off)))
+
+    def scale_rows(self, W_t, rows, m, s_t, s_off):
+        _lib.check(self.lib.gpl_scale_block_dev(self.ctx.h, rows, m, self._p(W_t), W_t.shape[1], self._p(s_t, s_off),
+                                                None, 1.0, 0.0, -(1 << 40)))
+
+    def syrk_acc(self, W_t, rows, m, A_t):
+        """A (lower) += W^T W"""
+        _lib.check(self.lib.gpl_dgemm_dev(self.ctx.h, 1, 0, m, m, rows, 1.0, self._p(W_t), W_t.shape[1],
+                                          self._p(W_t), W_t.shape[1], 1.0, self._p(A_t), A_t.shape[1], 1))
+
+    def gemv(self, trans, rows, m, K_t, x_t, y_t):
+        _lib.check(self.lib.gpl_dgemv_dev(self.ctx.h, trans, rows, m, self._p(K_t), K_t.shape[1], self._p(x_t),
+                                          self._p(y_t)))
+
+    def trsv(self, trans, m, L_t, dinv_t, b_t, x_t):
+        _lib.check(self.lib.gpl_dtrsv_dev(self.ctx.h, trans, m, self._p(L_t), L_t.shape[1], self._p(dinv_t),
+                                          self._p(b_t), self._p(x_t)))
+
+    def sync(self):
+        self.ctx.sync()
+
+
+def dist_fit_fitc_gaussian(gp, x, y, jitter=None, ops=None, dist=None, device="cuda", chunk_rows=None):
+    """Row-sharded FITC fit for lik_gaussian (R/gp_fit.R:101-123 + R/laplace.R:122-152 +
+    R/linear_algebra.R:3-43): rank r owns rows [r n/P, (r+1) n/P) of x; Kz and the m x m
+    factorisations are replicated; the only data-path collectives are one all-reduce of the m x m
+    matrix Kzx S^-1 Kxz and a few m-vectors / scalars.  Every rank passes the full x, y."""
+    import torch
+    if gp.lik.name != "lik_gaussian" or gp.method.name != "fitc":
+        raise NotImplementedError("dist_fit_fitc_gaussian covers lik_gaussian + method_fitc")
+    if dist is None:
+        import torch.distributed as dist
+    rank, world = dist.get_rank(), dist.get_world_size()
+    x = np.asarray(x, dtype=np.float64)
+    if x.ndim == 1:
+        x = x[:, None]
+    y = np.asarray(y, dtype=np.float64).ravel()
+    zind = np.asarray(gp.method.inducing, dtype=np.float64)
+    if zind.ndim == 1:
+        zind = zind[:, None]
+    n, d = x.shape
+    m = zind.shape[0]
+    for cf in gp.cfs:
+        M.learn_scales(cf, x)                       # training means / scales use ALL rows
+    jit = 1e-6 if jitter is None else float(jitter)
+    sigma2 = gp.lik.sigma ** 2
+    factors, _ = M.flatten_cfs(gp.cfs)
+    pm = _lib.PackedModel(factors)
+    if ops is None:
+        ops = FitcOps(_lib.Context(torch.cuda.current_device(), torch.cuda.current_stream().cuda_stream or 1))
+    lo = (n * rank) // world
+    hi = (n * (rank + 1)) // world
+    nr = hi - lo
+    f64 = dict(dtype=torch.float64, device=device)
+    ldr = (max(nr, 1) + 15) // 16 * 16
+    ldm = (m + 15) // 16 * 16
+    X_t = torch.from_numpy(np.ascontiguousarray(x[lo:hi].T)).to(device)          # (d, nr)
+    Z_t = torch.from_numpy(np.ascontiguousarray(zind.T)).to(device)              # (d, m)
+    y_t = torch.from_numpy(y[lo:hi].copy()).to(device)
+    nblk = (m + 127) // 128
+    Kz = torch.zeros((m, ldm), **f64)
+    Lz = torch.zeros((m, ldm), **f64)
+    A = torch.zeros((m, ldm), **f64)
+    dinv_z = torch.empty(nblk * 128 * 128, **f64)
+    dinv_a = torch.empty(nblk * 128 * 128, **f64)
+    Kxz = torch.zeros((m, ldr), **f64)
+    ops.ksym(pm, Z_t, m, d, jit, Kz)
+    Lz.copy_(Kz)
+    st, info, logdet_z = ops.potrf(Lz, m, dinv_z)
+    if st != _lib.GPL_OK:
+        raise _lib.NotPositiveDefinite(st, "Kz is not positive definite")
+    ops.kblock(pm, X_t, nr, nr, Z_t, m, d, Kxz)
+    Kdiag = torch.empty(max(nr, 1), **f64)
+    ops.kdiag(pm, X_t, nr, d, jit, Kdiag)
+    # D = K_diag - |Lz^-1 k_zi|^2, streamed through a row-chunk workspace
+    if chunk_rows is None:
+        chunk_rows = max(1024, int(2.0e9 / (8.0 * m)) // 128 * 128)
+    chunk_rows = min(chunk_rows, max(nr, 1))
+    ldw = (chunk_rows + 15) // 16 * 16
+    W = torch.empty((m, ldw), **f64)
+    q = torch.empty(max(nr, 1), **f64)
+    for r0 in range(0, nr, chunk_rows):
+        c = min(chunk_rows, nr - r0)
+        W[:, :c].copy_(Kxz[:, r0:r0 + c])
+        ops.rownorms_after_solve(W, c, m, Lz, dinv_z, q, r0)
+    D = Kdiag[:nr] - q[:nr]
+    S = D + sigma2
+    rs = torch.rsqrt(S).contiguous()
+    # A = Kz + sum over ranks of Kzx S^-1 Kxz  (lower triangle)
+    part = torch.zeros((m, ldm), **f64)
+    for r0 in range(0, nr, chunk_rows):
+        c = min(chunk_rows, nr - r0)
+        W[:, :c].copy_(Kxz[:, r0:r0 + c])
+        ops.scale_rows(W, c, m, rs, r0)
+        ops.syrk_acc(W, c, m, part)
+    dist.all_reduce(part)
+    A.copy_(Kz + part)
+    st, info, logdet_a = ops.potrf(A, m, dinv_a)
+    if st != _lib.GPL_OK:
+        raise _lib.NotPositiveDefinite(st, "Kz + Kzx S^-1 Kxz is not positive definite")
+    # alpha = z/S - S^-1 Kxz A^-1 Kzx (z/S)
+    t = (y_t / S).contiguous()
+    u = torch.zeros(m, **f64)
+    if nr > 0:
+        ops.gemv(1, nr, m, Kxz, t, u)
+    dist.all_reduce(u)
+    w1 = torch.empty(m, **f64)
+    v = torch.empty(m, **f64)
+    ops.trsv(0, m, A, dinv_a, u.clone(), w1)
+    ops.trsv(1, m, A, dinv_a, w1.clone(), v)
+    kv = torch.zeros(max(nr, 1), **f64)
+    if nr > 0:
+        ops.gemv(0, nr, m, Kxz, v, kv)
+    alpha = t - kv[:nr] / S
+    # f = Kxz Kz^-1 Kzx alpha + D alpha
+    u2 = torch.zeros(m, **f64)
+    if nr > 0:
+        ops.gemv(1, nr, m, Kxz, alpha.contiguous(), u2)
+    dist.all_reduce(u2)
+    beta = torch.empty(m, **f64)
+    ops.trsv(0, m, Lz, dinv_z, u2.clone(), w1)
+    ops.trsv(1, m, Lz, dinv_z, w1.clone(), beta)
+    kb = torch.zeros(max(nr, 1), **f64)
+    if nr > 0:
+        ops.gemv(0, nr, m, Kxz, beta, kb)
+    fmean = kb[:nr] + D * alpha
+    resid = y_t - fmean
+    sc = torch.stack([torch.log(S).sum(), torch.dot(fmean, alpha), (resid * resid).sum()])
+    dist.all_reduce(sc)
+    sum_log_S, f_invK_f, rss = [float(vv) for vv in sc]
+    log_lik = -0.5 * n * math.log(2 * math.pi * sigma2) - 0.5 * rss / sigma2
+    C_logdet = sum_log_S - logdet_z + logdet_a                                # R/linear_algebra.R:32
+    V_logdet = n * math.log(sigma2)
+    log_evidence = log_lik - 0.5 * f_invK_f + 0.5 * (V_logdet - C_logdet)     # R/laplace.R:143-150
+    return dict(log_evidence=log_evidence, alpha_local=alpha, fmean_local=fmean, rows=(lo, hi), beta=beta)

@@ -201,6 +201,12 @@ int gpl_dpotrf_dev(gpl_ctx* ctx, int64_t n, double* A, int64_t lda, int32_t* inf
  * (uses the diagonal-block inverses cached by the factorisation). */
 int gpl_dtrsm_right_dev(gpl_ctx* ctx, int32_t trans, int64_t m, int64_t n, const double* L,
                         int64_t ldl, double* B, int64_t ldb);
+/* Same with an explicit block-inverse buffer (from gpl_dpotrf_get_dinv_dev), so that several
+ * factors can be alive on one context (FITC keeps chol(Kz) and chol(Kz + Kzx S^-1 Kxz)). */
+int gpl_dtrsm_right_dinv_dev(gpl_ctx* ctx, int32_t trans, int64_t m, int64_t n, const double* L,
+                             int64_t ldl, const double* d_dinv, double* B, int64_t ldb);
+/* out_i = sum_j A_ij^2 (A is m x n): column norms of forwardsolve(L, t(A)) once A <- A L^-T. */
+int gpl_rowsumsq_dev(gpl_ctx* ctx, int64_t m, int64_t n, const double* A, int64_t lda, double* out);
 /* A <- (L L^T)^-1 given L from gpl_dpotrf_dev, lower triangle (dpotri). */
 int gpl_dpotri_dev(gpl_ctx* ctx, int64_t n, double* A, int64_t lda);
 /* Copy out the diagonal-block inverses cached by the last gpl_dpotrf_dev on this ctx

@@ -53,3 +53,22 @@ def test_driver_single_rank_matches_oracle(n, nb):
     assert np.max(np.abs(a - gpo.fit["alpha"])) < 1e-6 * np.max(np.abs(gpo.fit["alpha"]))
     f = res["fmean"].cpu().numpy()
     assert np.max(np.abs(f - gpo.fit["fmean"])) < 1e-8 * np.max(np.abs(gpo.fit["fmean"]))
+
+
+def test_fitc_driver_single_rank_matches_oracle():
+    from gplite_b200.dist import dist_fit_fitc_gaussian
+    rng = np.random.default_rng(8)
+    n, m = 1203, 150
+    X = rng.uniform(-3, 3, size=(n, 2))
+    y = np.sin(X[:, 0]) + 0.3 * X[:, 1] + 0.4 * rng.normal(size=n)
+    Zi = X[rng.permutation(n)[:m]].copy()
+    gp = g.gp_init(cfs=[g.cf_sexp(lscale=1.1), g.cf_const(magn=0.2)], lik=g.lik_gaussian(sigma=0.4),
+                   method=g.method_fitc(inducing=Zi))
+    gpo = copy.deepcopy(gp)
+    res = dist_fit_fitc_gaussian(gp, X, y, dist=OneRank, chunk_rows=512)
+    o.gp_fit(gpo, X, y)
+    assert abs(res["log_evidence"] - gpo.fit["log_evidence"]) < 1e-8 * abs(gpo.fit["log_evidence"])
+    a = res["alpha_local"].cpu().numpy()
+    assert np.max(np.abs(a - gpo.fit["alpha"])) < 1e-6 * np.max(np.abs(gpo.fit["alpha"]))
+    f = res["fmean_local"].cpu().numpy()
+    assert np.max(np.abs(f - gpo.fit["fmean"])) < 1e-8 * np.max(np.abs(gpo.fit["fmean"]))
