@@ -271,11 +271,11 @@ struct Fac {
 };
 
 int potf2(const Fac& f, double* A, int64_t lda, int64_t n, int64_t blk0) {
-  static bool configured = false;
-  if (!configured) {
+  static bool configured[64] = {false};
+  if (!configured[f.ctx->device & 63]) {
     GPL_CUDA(cudaFuncSetAttribute(potf2_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   POTF2_SMEM));
-    configured = true;
+    configured[f.ctx->device & 63] = true;
   }
   potf2_inv_kernel<<<1, POTF2_THREADS, POTF2_SMEM, f.ctx->stream>>>(
       A, lda, (int)n, f.dinv + blk0 * NB * NB, f.ctx->d_info, (int)(blk0 * NB));

@@ -508,6 +508,20 @@ int fit_get_impl(Ctx* ctx, const Fit* fit, const char* what, double* out) {
     GPL_CUDA(cudaStreamSynchronize(ctx->stream));
     return GPL_OK;
   }
+  if (fit->method == 1 && (!strcmp(what, "Kxz") || !strcmp(what, "Kz_chol"))) {
+    const bool kxz = !strcmp(what, "Kxz");
+    const int64_t rows = kxz ? fit->n : fit->m, cols = fit->m;
+    const double* src = kxz ? fit->Kxz.d() : fit->Kz_chol.d();
+    const int64_t lds = kxz ? fit->ldkxz : fit->ldm;
+    GPL_CUDA(cudaMemcpy2DAsync(out, sizeof(double) * rows, src, sizeof(double) * lds,
+                               sizeof(double) * rows, cols, cudaMemcpyDeviceToHost, ctx->stream));
+    GPL_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (!kxz) {          // the strict upper triangle of the factor buffer is scratch: return zeros
+      for (int64_t j = 1; j < cols; ++j)
+        for (int64_t i = 0; i < j; ++i) out[j * rows + i] = 0.0;
+    }
+    return GPL_OK;
+  }
   set_error("gpl_fit_get: unknown member '%s'", what);
   return GPL_ERR_BAD_ARG;
 }

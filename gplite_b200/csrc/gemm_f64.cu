@@ -303,11 +303,11 @@ __global__ void __launch_bounds__(CF::THREADS) gemm_f64_kernel(const GemmArgs p)
 
 template <bool TA, bool TB, class CF>
 int launch(Ctx* ctx, GemmArgs a) {
-  static bool configured = false;
-  if (!configured) {
+  static bool configured[64] = {false};      // per device: the attribute is per-context
+  if (!configured[ctx->device & 63]) {
     GPL_CUDA(cudaFuncSetAttribute(gemm_f64_kernel<TA, TB, CF>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, CF::SMEM_BYTES));
-    configured = true;
+    configured[ctx->device & 63] = true;
   }
   a.tiles_m = (a.M + CF::BM - 1) / CF::BM;
   a.tiles_n = (a.N + CF::BN - 1) / CF::BN;
@@ -350,11 +350,18 @@ int dispatch(Ctx* ctx, const GemmArgs& a, int alias) {
     const int64_t tm = (a.M + bm - 1) / bm, tn = (a.N + bn - 1) / bn;
     return a.lower ? tm * (tm + 1) / 2 : tm * tn;
   };
+  // Wave-quantisation cost model (units: one full wave of L tiles).  L runs 1 CTA/SM at full DMMA
+  // rate; an M tile is a quarter of the work at ~83 % of that rate with 2 CTAs/SM; an S tile a
+  // sixteenth at ~50 % with 8 CTAs/SM.  Mid-size updates (a few hundred L tiles) otherwise lose up
+  // to half a wave: 100 such launches were 14 % of a n = 32768 factorisation.
   const int64_t sms = ctx->sm_count;
+  const double cost_l = (double)((ntiles(128, 128) + sms - 1) / sms);
+  const double cost_m = (double)((ntiles(64, 64) + 2 * sms - 1) / (2 * sms)) * 0.30;
+  const double cost_s = (double)((ntiles(32, 32) + 8 * sms - 1) / (8 * sms)) * 0.125;
   static const int use_l16 = getenv("GPL_GEMM_L16") ? atoi(getenv("GPL_GEMM_L16")) : 0;
-  if (ntiles(128, 128) >= sms)
+  if (ntiles(128, 128) >= sms && cost_l <= cost_m && cost_l <= cost_s)
     return use_l16 ? launch<TA, TB, CfgL16>(ctx, a) : launch<TA, TB, CfgL>(ctx, a);
-  if (ntiles(64, 64) >= sms) return launch<TA, TB, CfgM>(ctx, a);
+  if (cost_m <= cost_s) return launch<TA, TB, CfgM>(ctx, a);
   return launch<TA, TB, CfgS>(ctx, a);
 }
 

@@ -249,7 +249,8 @@ def gp_fit(gp, x, y, trials=None, offset=None, jitter=None, ctx=None):
 def fit_member(gp, what):
     """Materialise a device-resident member of gp$fit on demand ("C_chol", "alpha")."""
     n = gp.x.shape[0]
-    shape = {"C_chol": (n, n), "alpha": (n,)}[what]
+    m = gp.method.inducing.shape[0] if gp.method.name == "fitc" else 0
+    shape = {"C_chol": (n, n), "alpha": (n,), "Kxz": (n, m), "Kz_chol": (m, m)}[what]
     out = np.empty(shape, dtype=np.float64, order="F")
     _lib.check(gp._ctx.lib.gpl_fit_get(gp._ctx.h, gp._handle, what.encode(), _lib._ptr(out)))
     return out

@@ -207,6 +207,8 @@ def test_fitc_gaussian(ctx, n, m):
         assert abs(gp.fit["log_evidence"] - gpo.fit["log_evidence"]) < TOL * abs(gpo.fit["log_evidence"])
         assert scaled_err(gp.fit["fmean"], gpo.fit["fmean"]) < TOL
         assert scaled_err(gp.fit["alpha"], gpo.fit["alpha"]) < 1e-6
+        assert scaled_err(g.fit_member(gp, "Kxz"), gpo.fit["Kxz"]) < 1e-12
+        assert scaled_err(g.fit_member(gp, "Kz_chol"), gpo.fit["Kz_chol"]) < 1e-9
         Xt = np.random.default_rng(9).uniform(-3.5, 3.5, size=(60, 2))
         p = g.gp_pred(gp, Xt, var=True)
         po = o.gp_pred(gpo, Xt, var=True)
