@@ -75,6 +75,7 @@ SIGNATURES = {
     "gpl_ctx_sync": (C.c_int, [_P]),
     "gpl_ctx_launch_count": (_I64, [_P]),
     "gpl_ctx_profile": (C.c_int, [_P, _I32]),
+    "gpl_ctx_gemm_config": (C.c_int, [_P, _I32]),
     "gpl_ctx_profile_read": (C.c_int, [_P, C.POINTER(_D), C.POINTER(_D), C.POINTER(_I64)]),
     "gpl_dev_alloc": (C.c_int, [_P, _U64, C.POINTER(_P)]),
     "gpl_dev_free": (C.c_int, [_P, _P]),

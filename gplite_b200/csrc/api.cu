@@ -139,18 +139,37 @@ int gpl_ctx_profile(gpl_ctx* h, int32_t enable) {
   c->prof_flops = 0.0;
   c->prof_ms = 0.0;
   c->prof_launches = 0;
+  c->prof_recs.clear();
+  return GPL_OK;
+}
+
+int gpl_ctx_gemm_config(gpl_ctx* h, int32_t cfg) {
+  if (cfg < 0 || cfg > 3) {
+    set_error("gpl_ctx_gemm_config: cfg must be 0 (auto), 1 (128x128), 2 (64x64) or 3 (32x32)");
+    return GPL_ERR_BAD_ARG;
+  }
+  reinterpret_cast<Ctx*>(h)->gemm_force = cfg;
   return GPL_OK;
 }
 
 int gpl_ctx_profile_read(gpl_ctx* h, double* gemm_ms, double* gemm_flops, int64_t* gemm_launches) {
   Ctx* c = reinterpret_cast<Ctx*>(h);
   GPL_CUDA(cudaStreamSynchronize(c->stream));
+  // GPL_GEMM_LOG=path: append one CSV line per profiled launch (shape, tile, milliseconds)
+  const char* log_path = getenv("GPL_GEMM_LOG");
+  FILE* log = (log_path && c->ev_used) ? fopen(log_path, "a") : nullptr;
   for (size_t i = 0; i + 1 < c->ev_used; i += 2) {
     float ms = 0.f;
     GPL_CUDA(cudaEventElapsedTime(&ms, c->ev_pool[i], c->ev_pool[i + 1]));
     c->prof_ms += ms;
+    if (log && i / 2 < c->prof_recs.size()) {
+      const Ctx::GemmRec& r = c->prof_recs[i / 2];
+      fprintf(log, "%d,%d,%d,%d,%d,%d,%.5f\n", r.m, r.n, r.k, r.lower, r.kskip, r.tile, ms);
+    }
   }
+  if (log) fclose(log);
   c->ev_used = 0;
+  c->prof_recs.clear();
   if (gemm_ms) *gemm_ms = c->prof_ms;
   if (gemm_flops) *gemm_flops = c->prof_flops;
   if (gemm_launches) *gemm_launches = c->prof_launches;

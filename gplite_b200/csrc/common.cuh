@@ -34,11 +34,14 @@ struct Ctx {
   // optional per-launch timing of the DMMA GEMM kernel (bench.py's roofline leg): one event
   // pair per launch on the launching stream, harvested by gpl_ctx_profile_read
   bool profile = false;
+  int gemm_force = 0;   // tuning knob: 0 = automatic tile choice, 1/2/3 = force the 128/64/32 tile
   std::vector<cudaEvent_t> ev_pool;
   size_t ev_used = 0;
   double prof_flops = 0.0;
   double prof_ms = 0.0;
   int64_t prof_launches = 0;
+  struct GemmRec { int m, n, k, lower, kskip, tile; };
+  std::vector<GemmRec> prof_recs;   // one per profiled launch (GPL_GEMM_LOG=path dumps them with times)
 };
 
 #define GPL_CUDA(call)                                                              \

@@ -279,23 +279,42 @@ __global__ void __launch_bounds__(CF::THREADS) gemm_f64_kernel(const GemmArgs p)
   else mainloop(std::false_type{});
   cp_async_wait<0>();
 
-  // epilogue: thread owns C[row = .. + g][col = .. + 2t, 2t+1] of each 8x8 sub-tile
+  // epilogue: thread owns C[row = .. + g][col = .. + 2t, 2t+1] of each 8x8 sub-tile.  The C values of
+  // a batch of sub-tiles are all loaded before the first store: interleaved load/store pairs cannot
+  // be reordered by the compiler (possible aliasing), which serialised 64 L2 round trips per thread
+  // (~16 us per 128x128 tile, as much as 7 k-tiles of the main loop).
   const bool diag_tile = p.lower && (bm == bn);
+  const bool rmw = p.beta != 0.0;
+  constexpr int IMB = (MI % 2 == 0) ? 2 : 1;
 #pragma unroll
-  for (int im = 0; im < MI; ++im) {
-    const int row = m0 + wm * CF::WM + im * 8 + g;
-    if (row >= p.M) continue;
+  for (int im0 = 0; im0 < MI; im0 += IMB) {
+    double cv[IMB][NI][2];
+    unsigned ok = 0;
 #pragma unroll
-    for (int in = 0; in < NI; ++in) {
+    for (int ii = 0; ii < IMB; ++ii) {
+      const int row = m0 + wm * CF::WM + (im0 + ii) * 8 + g;
 #pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        const int col = n0 + wn * CF::WN + in * 8 + 2 * t + c;
-        if (col >= p.N) continue;
-        if (diag_tile && col > row) continue;
-        double* dst = p.C + (int64_t)col * p.ldc + row;
-        double v = p.alpha * acc[im][in][c];
-        if (p.beta != 0.0) v += p.beta * (*dst);
-        *dst = v;
+      for (int in = 0; in < NI; ++in) {
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          const int col = n0 + wn * CF::WN + in * 8 + 2 * t + c;
+          const bool v = row < p.M && col < p.N && !(diag_tile && col > row);
+          if (v) ok |= 1u << ((ii * NI + in) * 2 + c);
+          cv[ii][in][c] = (v && rmw) ? p.C[(int64_t)col * p.ldc + row] : 0.0;
+        }
+      }
+    }
+#pragma unroll
+    for (int ii = 0; ii < IMB; ++ii) {
+      const int row = m0 + wm * CF::WM + (im0 + ii) * 8 + g;
+#pragma unroll
+      for (int in = 0; in < NI; ++in) {
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          const int col = n0 + wn * CF::WN + in * 8 + 2 * t + c;
+          if ((ok >> ((ii * NI + in) * 2 + c)) & 1u)
+            p.C[(int64_t)col * p.ldc + row] = p.alpha * acc[im0 + ii][in][c] + p.beta * cv[ii][in][c];
+        }
       }
     }
   }
@@ -330,6 +349,7 @@ int launch(Ctx* ctx, GemmArgs a) {
     ctx->prof_flops += 2.0 * a.M * a.N * (double)a.K * (a.lower ? 0.5 : 1.0) *
                        (a.kskip ? (a.lower ? 1.0 / 3.0 : 0.5) : 1.0);
     ctx->prof_launches++;
+    ctx->prof_recs.push_back({a.M, a.N, a.K, a.lower, a.kskip, CF::BM * 1000 + CF::BN});
   }
   return GPL_OK;
 }
@@ -350,16 +370,33 @@ int dispatch(Ctx* ctx, const GemmArgs& a, int alias) {
     const int64_t tm = (a.M + bm - 1) / bm, tn = (a.N + bn - 1) / bn;
     return a.lower ? tm * (tm + 1) / 2 : tm * tn;
   };
-  // Wave-quantisation cost model (units: one full wave of L tiles).  L runs 1 CTA/SM at full DMMA
-  // rate; an M tile is a quarter of the work at ~83 % of that rate with 2 CTAs/SM; an S tile a
-  // sixteenth at ~50 % with 8 CTAs/SM.  Mid-size updates (a few hundred L tiles) otherwise lose up
-  // to half a wave: 100 such launches were 14 % of a n = 32768 factorisation.
+  // Tile choice by a small analytical cost model, fitted to a measured table of 480 shapes x 3 tiles
+  // (tools/gemm_tune.py, tools/gemm_model.py; regret vs the per-shape best: 0.4 %).  Per config:
+  // r co-resident CTAs per SM, s1 = us per unit of k for one CTA alone on an SM, rate = flop/us per
+  // SM at full residency, t0 = prologue + epilogue that nothing overlaps.  A single wave spreads
+  // breadth-first over the SMs; after that, slots free up r at a time, so L and M run in waves of
+  // r * SMs tiles while the many small S CTAs de-synchronise into a near-continuous refill.
   const int64_t sms = ctx->sm_count;
-  const double cost_l = (double)((ntiles(128, 128) + sms - 1) / sms);
-  const double cost_m = (double)((ntiles(64, 64) + 2 * sms - 1) / (2 * sms)) * 0.30;
-  const double cost_s = (double)((ntiles(32, 32) + 8 * sms - 1) / (8 * sms)) * 0.125;
+  if (ctx->gemm_force == 1) return launch<TA, TB, CfgL>(ctx, a);
+  if (ctx->gemm_force == 2) return launch<TA, TB, CfgM>(ctx, a);
+  if (ctx->gemm_force == 3) return launch<TA, TB, CfgS>(ctx, a);
+  const double k = a.kskip ? 0.5 * a.K : (double)a.K;
+  auto cost = [&](int b, int r, double s1, double rate, double t0, bool continuous) {
+    const int64_t T = ntiles(b, b);
+    const double w = 2.0 * b * b;
+    if (T <= r * sms) {
+      const double q = (double)((T + sms - 1) / sms);
+      return t0 + k * fmax(s1, q * w / rate);
+    }
+    if (continuous) return t0 + k * (double)((T + sms - 1) / sms) * w / rate;
+    const double waves = (double)((T + r * sms - 1) / (r * sms));
+    return t0 + waves * k * r * w / rate + (r == 1 ? t0 * (waves - 1.0) : 0.0);
+  };
+  const double cost_l = cost(128, 1, 0.139, 234e3, 9.0, false);
+  const double cost_m = cost(64, 2, 0.044, 231e3, 4.5, false);
+  const double cost_s = cost(32, 5, 0.016, 220e3, 3.0, true);
   static const int use_l16 = getenv("GPL_GEMM_L16") ? atoi(getenv("GPL_GEMM_L16")) : 0;
-  if (ntiles(128, 128) >= sms && cost_l <= cost_m && cost_l <= cost_s)
+  if (cost_l <= cost_m && cost_l <= cost_s)
     return use_l16 ? launch<TA, TB, CfgL16>(ctx, a) : launch<TA, TB, CfgL>(ctx, a);
   if (cost_m <= cost_s) return launch<TA, TB, CfgM>(ctx, a);
   return launch<TA, TB, CfgS>(ctx, a);

@@ -145,6 +145,9 @@ int64_t gpl_ctx_launch_count(gpl_ctx* ctx);
  * lower-only updates) and launch count. */
 int gpl_ctx_profile(gpl_ctx* ctx, int32_t enable);
 int gpl_ctx_profile_read(gpl_ctx* ctx, double* gemm_ms, double* gemm_flops, int64_t* gemm_launches);
+/* Tuning knob for the GEMM tile choice of gpl_dgemm_dev and everything built on it: 0 = automatic
+ * (default), 1 / 2 / 3 = force the 128x128 / 64x64 / 32x32 CTA tile (tools/gemm_tune.py). */
+int gpl_ctx_gemm_config(gpl_ctx* ctx, int32_t cfg);
 /* plain device memory helpers so that an FFI without its own CUDA binding can stage data */
 int gpl_dev_alloc(gpl_ctx* ctx, uint64_t bytes, void** dptr);
 int gpl_dev_free(gpl_ctx* ctx, void* dptr);
