@@ -56,7 +56,7 @@ class Approx(C.Structure):
 
 class FitOut(C.Structure):
     _fields_ = [("log_evidence", C.c_double), ("iters", C.c_int32), ("converged", C.c_int32),
-                ("quad_ok", C.c_int32), ("reserved", C.c_int32)]
+                ("quad_ok", C.c_int32), ("n_bad", C.c_int32)]
 
 
 _P = C.c_void_p

@@ -49,6 +49,19 @@ int scale_rows(Ctx* ctx, int64_t m, int64_t n, double* A, int64_t lda, const dou
 int scale_block(Ctx* ctx, int64_t m, int64_t n, double* A, int64_t lda, const double* r,
                 const double* c, double alpha, double diag_add, int64_t diag_offset);
 
+// ---- helpers of the non-log-concave ("bad site") branch (R/laplace.R:40-117, R/ep.R:50-138) ----
+int gather_vec(Ctx* ctx, int64_t n, const double* src, const int32_t* perm, double* dst);   // dst_i = src[perm_i]
+int scatter_vec(Ctx* ctx, int64_t n, const double* src, const int32_t* perm, double* dst);  // dst[perm_i] = src_i
+int gather_rows(Ctx* ctx, int64_t n, int64_t ncols, const double* src, int64_t lds,
+                const int32_t* perm, double* dst, int64_t ldd);
+int transpose(Ctx* ctx, int64_t m, int64_t n, const double* A, int64_t lda, double* B, int64_t ldb);
+// out = tril(L) with rows scaled by r (r may be null)
+int tril_scale(Ctx* ctx, int64_t n, const double* L, int64_t ldl, const double* r, double* out,
+               int64_t ldo);
+// out_i = sum_j A_ij^2 w_j
+int rowsumsq_w(Ctx* ctx, int64_t m, int64_t n, const double* A, int64_t lda, const double* w,
+               double* out);
+
 enum VecOp {
   VOP_DIV = 0,        // out = a / b
   VOP_MUL = 1,        // out = a * b
@@ -107,6 +120,10 @@ int lik_ep_sites(Ctx* ctx, const LikDev& lik, int64_t n, const EpSiteArgs& a, in
 int ep_evidence_terms(Ctx* ctx, int64_t n, const double* logZ, const double* vc, const double* mc,
                       const double* z, const double* V, int slot);
 
+// same with log((vc + V) / V) in the middle term (bad sites, R/ep.R:112-114)
+int ep_evidence_terms_bad(Ctx* ctx, int64_t n, const double* logZ, const double* vc,
+                          const double* mc, const double* z, const double* V, int slot);
+
 // ---- gradient trace (new capability; see gpl_energy_grad) -----------------------------------
 struct GradParam {
   int factor;   // index into plan.f, or -1 for the likelihood sigma (handled outside)
@@ -138,6 +155,20 @@ struct Fit {
   int64_t ldm = 0;
   DevBuf S;              // D + V
   DevBuf Dg;             // FITC diagonal correction D
+  // Non-log-concave fit (some pseudo-variances <= 0; the reference keeps an LU of K + diag(V),
+  // R/laplace.R:113, R/ep.R:122).  Here: sites permuted good-first; Lb/dinv/sqrtV factor the good
+  // block (size ng); the bad block is eliminated through its nb x nb Schur complement
+  // S = pred_cov + V_bad with pred_cov = Lk Lk^T and A = I + Lk^T V_bad^-1 Lk = Ac Ac^T.
+  int64_t ng = 0, nb = 0;
+  DevBuf perm;           // int32[n]: permuted position -> original index
+  DevBuf xp;             // n x d inputs, permuted
+  DevBuf alpha_p;        // n, permuted
+  DevBuf W;              // nb x ng: K_bg C_chol_gg^-T
+  int64_t ldw = 0;
+  DevBuf Lk, Lk_dinv;    // nb x nb (clean lower triangle), ld ldp
+  DevBuf Ac, Ac_dinv;    // nb x nb factor of A
+  int64_t ldp = 0;
+  DevBuf invVb;          // nb: 1 / V_bad
 };
 
 }  // namespace gpl

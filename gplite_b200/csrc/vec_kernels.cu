@@ -472,6 +472,86 @@ __global__ void ep_evidence_kernel(int64_t n, const double* __restrict__ logZ,
   if (threadIdx.x == 0) out[0] = a1 + 0.5 * a2 + 0.5 * a3;   // R/ep.R:47-48
 }
 
+// ---- small helpers of the non-log-concave ("bad site") branch ---------------------------------
+__global__ void gather_vec_kernel(int64_t n, const double* __restrict__ src,
+                                  const int32_t* __restrict__ perm, double* __restrict__ dst) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = src[perm[i]];
+}
+
+__global__ void scatter_vec_kernel(int64_t n, const double* __restrict__ src,
+                                   const int32_t* __restrict__ perm, double* __restrict__ dst) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[perm[i]] = src[i];
+}
+
+__global__ void gather_rows_kernel(int64_t n, const double* __restrict__ src, int64_t lds,
+                                   const int32_t* __restrict__ perm, double* __restrict__ dst,
+                                   int64_t ldd) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t j = blockIdx.y;
+  if (i < n) dst[j * ldd + i] = src[j * lds + perm[i]];
+}
+
+// B (n x m) = A^T, A m x n; 32 x 32 tiles through shared memory
+__global__ void transpose_kernel(int64_t m, int64_t n, const double* __restrict__ A, int64_t lda,
+                                 double* __restrict__ B, int64_t ldb) {
+  __shared__ double tile[32][33];
+  const int64_t i0 = (int64_t)blockIdx.x * 32, j0 = (int64_t)blockIdx.y * 32;
+  for (int jj = threadIdx.y; jj < 32; jj += blockDim.y) {
+    const int64_t i = i0 + threadIdx.x, j = j0 + jj;
+    tile[jj][threadIdx.x] = (i < m && j < n) ? A[j * lda + i] : 0.0;
+  }
+  __syncthreads();
+  for (int ii = threadIdx.y; ii < 32; ii += blockDim.y) {
+    const int64_t j = j0 + threadIdx.x, i = i0 + ii;
+    if (i < m && j < n) B[i * ldb + j] = tile[threadIdx.x][ii];
+  }
+}
+
+// out(i,j) = (i >= j) ? r_i L(i,j) : 0   (clean lower-triangular copy, optional row scaling)
+__global__ void tril_scale_kernel(int64_t n, const double* __restrict__ L, int64_t ldl,
+                                  const double* __restrict__ r, double* __restrict__ out,
+                                  int64_t ldo) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t j = blockIdx.y;
+  if (i >= n) return;
+  out[j * ldo + i] = (i >= j) ? (r ? r[i] : 1.0) * L[j * ldl + i] : 0.0;
+}
+
+// out_i = sum_j A_ij^2 w_j   (one warp per row; A m x n with small n)
+__global__ void rowsumsq_w_kernel(int64_t m, int64_t n, const double* __restrict__ A, int64_t lda,
+                                  const double* __restrict__ w, double* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= m) return;
+  double s = 0.0;
+  for (int64_t j = 0; j < n; ++j) {
+    const double a = A[j * lda + i];
+    s += a * a * w[j];
+  }
+  out[i] = s;
+}
+
+// bad-site EP evidence terms (R/ep.R:112-114): sum logZ + 0.5 sum log((vc+V)/V) + 0.5 sum (mc-z)^2/(vc+V)
+__global__ void ep_evidence_bad_kernel(int64_t n, const double* __restrict__ logZ,
+                                       const double* __restrict__ vc, const double* __restrict__ mc,
+                                       const double* __restrict__ z, const double* __restrict__ V,
+                                       double* __restrict__ out) {
+  __shared__ double red[32];
+  double s1 = 0.0, s2 = 0.0, s3 = 0.0;
+  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
+    const double tot = vc[i] + V[i];
+    const double dm = mc[i] - z[i];
+    s1 += logZ[i];
+    s2 += log(tot / V[i]);
+    s3 += dm * dm / tot;
+  }
+  const double a1 = block_sum(s1, red);
+  const double a2 = block_sum(s2, red);
+  const double a3 = block_sum(s3, red);
+  if (threadIdx.x == 0) out[0] = a1 + 0.5 * a2 + 0.5 * a3;
+}
+
 }  // namespace
 
 int build_B(Ctx* ctx, int64_t n, const double* K, int64_t ldk, const double* s, double* B,
@@ -655,6 +735,61 @@ int lik_ep_sites(Ctx* ctx, const LikDev& lik, int64_t n, const EpSiteArgs& a, in
 int ep_evidence_terms(Ctx* ctx, int64_t n, const double* logZ, const double* vc, const double* mc,
                       const double* z, const double* V, int slot) {
   ep_evidence_kernel<<<1, 1024, 0, ctx->stream>>>(n, logZ, vc, mc, z, V, ctx->d_scal + slot);
+  GPL_LAUNCH_CHECK(ctx);
+  return GPL_OK;
+}
+
+int gather_vec(Ctx* ctx, int64_t n, const double* src, const int32_t* perm, double* dst) {
+  if (n <= 0) return GPL_OK;
+  gather_vec_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(n, src, perm, dst);
+  GPL_LAUNCH_CHECK(ctx);
+  return GPL_OK;
+}
+
+int scatter_vec(Ctx* ctx, int64_t n, const double* src, const int32_t* perm, double* dst) {
+  if (n <= 0) return GPL_OK;
+  scatter_vec_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(n, src, perm, dst);
+  GPL_LAUNCH_CHECK(ctx);
+  return GPL_OK;
+}
+
+int gather_rows(Ctx* ctx, int64_t n, int64_t ncols, const double* src, int64_t lds,
+                const int32_t* perm, double* dst, int64_t ldd) {
+  if (n <= 0 || ncols <= 0) return GPL_OK;
+  dim3 grid((unsigned)((n + 255) / 256), (unsigned)ncols);
+  gather_rows_kernel<<<grid, 256, 0, ctx->stream>>>(n, src, lds, perm, dst, ldd);
+  GPL_LAUNCH_CHECK(ctx);
+  return GPL_OK;
+}
+
+int transpose(Ctx* ctx, int64_t m, int64_t n, const double* A, int64_t lda, double* B, int64_t ldb) {
+  if (m <= 0 || n <= 0) return GPL_OK;
+  dim3 grid((unsigned)((m + 31) / 32), (unsigned)((n + 31) / 32));
+  transpose_kernel<<<grid, dim3(32, 8), 0, ctx->stream>>>(m, n, A, lda, B, ldb);
+  GPL_LAUNCH_CHECK(ctx);
+  return GPL_OK;
+}
+
+int tril_scale(Ctx* ctx, int64_t n, const double* L, int64_t ldl, const double* r, double* out,
+               int64_t ldo) {
+  if (n <= 0) return GPL_OK;
+  dim3 grid((unsigned)((n + 255) / 256), (unsigned)n);
+  tril_scale_kernel<<<grid, 256, 0, ctx->stream>>>(n, L, ldl, r, out, ldo);
+  GPL_LAUNCH_CHECK(ctx);
+  return GPL_OK;
+}
+
+int rowsumsq_w(Ctx* ctx, int64_t m, int64_t n, const double* A, int64_t lda, const double* w,
+               double* out) {
+  if (m <= 0) return GPL_OK;
+  rowsumsq_w_kernel<<<(unsigned)((m + 255) / 256), 256, 0, ctx->stream>>>(m, n, A, lda, w, out);
+  GPL_LAUNCH_CHECK(ctx);
+  return GPL_OK;
+}
+
+int ep_evidence_terms_bad(Ctx* ctx, int64_t n, const double* logZ, const double* vc,
+                          const double* mc, const double* z, const double* V, int slot) {
+  ep_evidence_bad_kernel<<<1, 1024, 0, ctx->stream>>>(n, logZ, vc, mc, z, V, ctx->d_scal + slot);
   GPL_LAUNCH_CHECK(ctx);
   return GPL_OK;
 }

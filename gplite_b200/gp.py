@@ -229,7 +229,11 @@ def gp_fit(gp, x, y, trials=None, offset=None, jitter=None, ctx=None):
             _lib.check(status)
     if status == _lib.GPL_OK:
         fit = dict(fmean=vec["fmean"], z=vec["z"], V=vec["V"], alpha=vec["alpha"],
-                   log_evidence=out.log_evidence, iters=out.iters, converged=bool(out.converged))
+                   log_evidence=out.log_evidence, iters=out.iters, converged=bool(out.converged),
+                   n_bad=int(out.n_bad))
+        if out.n_bad > 500:                                   # R/laplace.R:48-50, R/ep.R:59-61
+            warnings.warn("More than 500 data points with pseudo-variance < 0 (outliers), computation "
+                          "getting slow. Check that the model and hyperparameter values are sensible.")
         if gp.approx.name == "ep":
             fit.update(fvar=vec["fvar"], cavity_mean=vec["cavity_mean"], cavity_var=vec["cavity_var"],
                        P=1.0 / vec["V"], quad_ok=bool(out.quad_ok))

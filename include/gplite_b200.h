@@ -52,8 +52,9 @@ typedef enum gpl_status {
   GPL_ERR_CUDA = 4,
   GPL_ERR_NCCL = 5,
   GPL_ERR_NOMEM = 6,
-  GPL_ERR_NOT_LOGCONCAVE = 7 /* some pseudo-variance V <= 0: the reference's bad-site branch
-                                (R/laplace.R:40-117, R/ep.R:50-138) is outside this library */
+  GPL_ERR_NOT_LOGCONCAVE = 7 /* FITC only: some pseudo-variance V <= 0 and the reference's FITC
+                                bad-site branch (R/laplace.R:153-232, R/ep.R:186-272) is not
+                                implemented; method_full handles V <= 0 (gpl_fit_out.n_bad) */
 } gpl_status;
 
 /* ---- model descriptors ---------------------------------------------------------------- */
@@ -234,7 +235,8 @@ typedef struct gpl_fit_out {
   int32_t iters;          /* Newton iterations / EP sweeps performed */
   int32_t converged;
   int32_t quad_ok;
-  int32_t reserved;
+  int32_t n_bad;          /* sites with pseudo-variance <= 0 in the returned fit (0: C_chol; > 0: the
+                           * reference's C_lu case, R/laplace.R:40-117, R/ep.R:50-138) */
 } gpl_fit_out;
 
 /* method_full.  x: n x d host, y: n, trials/offset: n or NULL.  n-vectors are returned eagerly

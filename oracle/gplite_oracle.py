@@ -468,7 +468,67 @@ def laplace_iter_full(gp, K, y, fhat_old, trials=None, offset=None):
     z, V = get_pseudodata_la(gp.lik, fhat_old, y, trials=trials, offset=offset)
     n = len(z)
     if not np.all(V > 0):
-        raise NonLogConcave("V <= 0 branch (R/laplace.R:40-117) is out of scope")
+        return _laplace_iter_full_bad(gp, K, y, fhat_old, z, V, trials, offset)
+    return _laplace_iter_full_good(gp, K, y, z, V, trials, offset)
+
+
+def _sub(v, idx):
+    return None if v is None else np.asarray(v, dtype=np.float64)[idx]
+
+
+def _lu_solve_full(K, V, rhs):
+    """alpha = solve(U, solve(L, solve(P, rhs))) with Matrix::lu(K + diag(V)) (partial pivoting),
+    R/laplace.R:113-114, R/ep.R:128-129."""
+    lu, piv = sla.lu_factor(K + np.diag(V))
+    return sla.lu_solve((lu, piv), rhs), (lu, piv)
+
+
+def _bad_site_common(K, z, V, good, bad, fit1):
+    """Shared linear algebra of R/laplace.R:63-83 and R/ep.R:81-101: predictive 'prior' of the bad
+    sites given the good ones, and the factor of A = I + Lk^T diag(1/V_bad) Lk."""
+    K21 = K[np.ix_(bad, good)]
+    K22 = K[np.ix_(bad, bad)]
+    pred_mean = K21 @ fit1["alpha"]
+    aux = _fsolve(fit1["C_chol"], K21.T)
+    pred_cov = K22 - aux.T @ aux
+    Lk = _chol_lower(pred_cov)                       # failure = improper posterior: error propagates
+    A = np.eye(len(bad)) + Lk.T @ ((1 / V[bad])[:, None] * Lk)
+    try:
+        A_chol = _chol_lower(A)
+    except (np.linalg.LinAlgError, sla.LinAlgError):
+        A_chol = None
+    if A_chol is not None and not np.all(np.isfinite(A_chol)):
+        A_chol = None
+    return pred_mean, pred_cov, Lk, A_chol
+
+
+def _laplace_iter_full_bad(gp, K, y, fhat_old, z, V, trials, offset):
+    """R/laplace.R:40-117 (non-log-concave sites: p(y) = p(y_good) p(y_bad | y_good), LU for the fit)."""
+    good = np.where(V > 0)[0]
+    bad = np.where(~(V > 0))[0]
+    fit1 = _laplace_iter_full_good(gp, K[np.ix_(good, good)], y[good], z[good], V[good],
+                                   _sub(trials, good), _sub(offset, good))
+    pred_mean, pred_cov, Lk, A_chol = _bad_site_common(K, z, V, good, bad, fit1)
+    if A_chol is None:
+        return dict(fmean=fhat_old, log_evidence=-np.inf)                      # :78-80
+    Q = lambda v: _bsolve_t(Lk, _bsolve_t(A_chol, _fsolve(A_chol, Lk.T @ v)))
+    alpha2 = Q(z[bad] / V[bad])                                                # :81
+    aux = _bsolve_t(Lk, _fsolve(Lk, pred_mean))                                # :83
+    aux = Q(aux)                                                               # :84
+    f2hat = pred_cov @ (alpha2 + aux)                                          # :85
+    invC2_V2_logdet = 2 * np.sum(np.log(np.diag(A_chol)))                      # :88
+    df2 = np.sum(_fsolve(Lk, f2hat - pred_mean) ** 2)                          # :90
+    log_lik2 = get_loglik(gp.lik, f2hat, y[bad], trials=_sub(trials, bad), offset=_sub(offset, bad))
+    log_evidence = fit1["log_evidence"] + float(log_lik2 - 0.5 * df2 + 0.5 * invC2_V2_logdet)
+    alpha, C_lu = _lu_solve_full(K, V, z)                                      # :113-114
+    fhat_new = K @ alpha
+    return dict(fmean=fhat_new, z=z, V=V, C_lu=C_lu, alpha=alpha, log_evidence=log_evidence,
+                n_bad=len(bad))
+
+
+def _laplace_iter_full_good(gp, K, y, z, V, trials, offset):
+    """R/laplace.R:23-38 (all pseudo-variances positive)."""
+    n = len(z)
     s = np.sqrt(1 / V)
     B = np.eye(n) + s[:, None] * (K * s[None, :])                 # :27
     C_chol = np.sqrt(V)[:, None] * _chol_lower(B)                 # :28
@@ -563,7 +623,40 @@ def ep_iter_full(gp, K, y, fmean_old, fvar_old, z_old, P_old, damping, quad_orde
     if np.any(np.isnan(V) | np.isnan(z)):
         return dict(fmean=None, log_evidence=-np.inf)
     if not np.all(V > 0):
-        raise NonLogConcave("V <= 0 branch (R/ep.R:50-138) is out of scope")
+        return _ep_iter_full_bad(gp, K, pobs)
+    return _ep_iter_full_good(K, pobs)
+
+
+def _ep_iter_full_bad(gp, K, pobs):
+    """R/ep.R:50-138."""
+    z, V = pobs["z"], pobs["var"]
+    good = np.where(V > 0)[0]
+    bad = np.where(~(V > 0))[0]
+    sub = {k: (v[good] if isinstance(v, np.ndarray) else v) for k, v in pobs.items()}
+    fit1 = _ep_iter_full_good(K[np.ix_(good, good)], sub)
+    pred_mean, pred_cov, Lk, A_chol = _bad_site_common(K, z, V, good, bad, fit1)
+    if A_chol is None:
+        return dict(fmean=None, log_evidence=-np.inf)                          # :95-97
+    Q = lambda v: _bsolve_t(Lk, _bsolve_t(A_chol, _fsolve(A_chol, Lk.T @ v)))
+    invC2_V2_logdet = 2 * np.sum(np.log(np.diag(A_chol)))
+    dz = pred_mean - z[bad]
+    df2 = dz @ Q(dz / V[bad])                                                  # :107-110
+    mc, vc, logZ = pobs["mean_cavity"], pobs["var_cavity"], pobs["log_normalizing_const"]
+    log_evidence2 = -0.5 * df2 + 0.5 * invC2_V2_logdet + np.sum(logZ[bad]) \
+        + 0.5 * np.sum(np.log((vc[bad] + V[bad]) / V[bad])) \
+        + 0.5 * np.sum((mc[bad] - z[bad]) ** 2 / (vc[bad] + V[bad]))          # :112-114
+    alpha, C_lu = _lu_solve_full(K, V, z)                                      # :122-123
+    fmean_new = K @ alpha
+    fcov_new = V[:, None] * sla.lu_solve(C_lu, K)                              # :125
+    return dict(fmean=fmean_new, fvar=np.diag(fcov_new).copy(), cavity_mean=mc, cavity_var=vc,
+                z=z, P=1 / V, C_lu=C_lu, alpha=alpha, quad_ok=pobs["quad_ok"],
+                log_evidence=float(fit1["log_evidence"] + log_evidence2), n_bad=len(bad))
+
+
+def _ep_iter_full_good(K, pobs):
+    """R/ep.R:34-49,140-145 (all pseudo-variances positive)."""
+    z, V = pobs["z"], pobs["var"]
+    n = len(z)
     s = np.sqrt(1 / V)
     B = np.eye(n) + s[:, None] * (K * s[None, :])
     C_chol = np.sqrt(V)[:, None] * _chol_lower(B)
@@ -775,8 +868,11 @@ def gp_pred_post_full(gp, xt, var=False, cov=False, cfind=None, jitter=None):
     if var or cov:
         nt = len(mean)
         jit = 1e-6 if jitter is None else jitter
-        aux = _fsolve(gp.fit["C_chol"], Kt.T)
-        pred_cov = Ktt - aux.T @ aux
+        if gp.fit.get("C_chol") is not None:
+            aux = _fsolve(gp.fit["C_chol"], Kt.T)
+            pred_cov = Ktt - aux.T @ aux
+        else:                                                     # :220-223 (LU of K + diag(V))
+            pred_cov = Ktt - Kt @ sla.lu_solve(gp.fit["C_lu"], Kt.T)
         if cov:
             return dict(mean=mean, cov=pred_cov + jit * np.eye(nt))
         return dict(mean=mean, var=np.diag(pred_cov).copy())

@@ -41,3 +41,16 @@ def scaled_err(a, b):
     a = np.asarray(a, dtype=np.float64)
     b = np.asarray(b, dtype=np.float64)
     return float(np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-300)) if a.size else 0.0
+
+
+def outlier_counts(seed, n=150, n_out=15):
+    """Beta-binomial data with gross outliers: drives some Laplace / EP pseudo-variances negative
+    (the reference's non-log-concave branch, R/laplace.R:40-117, R/ep.R:50-138)."""
+    rng = np.random.default_rng(seed)
+    X = rng.normal(size=(n, 2))
+    f = 1.5 * X[:, 0] - 1.0 * X[:, 1]
+    trials = rng.integers(10, 40, size=n).astype(float)
+    y = rng.binomial(trials.astype(int), 1 / (1 + np.exp(-f))).astype(float)
+    idx = rng.choice(n, n_out, replace=False)
+    y[idx] = np.where(f[idx] > 0, 0.0, trials[idx])
+    return X, y, trials

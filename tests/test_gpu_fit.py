@@ -12,7 +12,7 @@ pytestmark = pytest.mark.gpu
 
 import gplite_b200 as g                      # noqa: E402
 from oracle import gplite_oracle as o        # noqa: E402
-from helpers import model_grid, basic_data, rel_err, scaled_err   # noqa: E402
+from helpers import model_grid, basic_data, rel_err, scaled_err, outlier_counts   # noqa: E402
 
 GOLD = os.path.join(os.path.dirname(__file__), "golden")
 TOL = 1e-8
@@ -391,3 +391,46 @@ def test_full_size_config2_properties(ctx):
     p = g.gp_pred(gp, X[idx], var=True)
     assert np.max(np.abs(p["mean"] - (y[idx] - (0.25 + 1e-6) * alpha[idx]))) < 1e-8
     assert np.all(p["var"] > 0) and np.all(p["var"] < 1.0)
+
+
+@pytest.mark.parametrize("seed,phi", [(44, 0.3), (41, 0.3), (42, 0.05), (37, 0.05), (7, 0.3)])
+@pytest.mark.parametrize("approx", ["laplace", "ep"])
+def test_non_log_concave_sites(ctx, approx, seed, phi):
+    """pseudo-variances <= 0 (beta-binomial with gross outliers).  The reference
+    refits with a pivoted LU (R/laplace.R:40-117, R/ep.R:50-138, R/gp_pred.R:220-223); the CUDA path
+    eliminates the bad block instead.  Same evidence, alpha, fmean, fvar and predictions."""
+    if seed == 37:
+        rng = np.random.default_rng(seed)
+        n = 120
+        X = rng.normal(size=(n, 2))
+        f = X[:, 0] - 0.5 * X[:, 1]
+        trials = rng.integers(2, 15, size=n).astype(float)
+        y = rng.binomial(trials.astype(int), 1 / (1 + np.exp(-f))).astype(float)
+        idx = rng.choice(n, 6, replace=False)
+        y[idx] = np.where(f[idx] > 0, 0.0, trials[idx])
+    elif seed == 7:      # 133 bad sites: the small factors span more than one 128-block
+        X, y, trials = outlier_counts(seed, n=1200, n_out=600)
+    else:
+        X, y, trials = outlier_counts(seed)
+    mk = g.approx_laplace if approx == "laplace" else g.approx_ep
+    gp = g.gp_init(cfs=g.cf_sexp(lscale=1.0), lik=g.lik_betabinom(phi=phi), approx=mk())
+    gpo = copy.deepcopy(gp)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        o.gp_fit(gpo, X, y, trials=trials)
+        g.gp_fit(gp, X, y, trials=trials, ctx=ctx)
+    assert gpo.fit.get("n_bad", 0) >= 1, "scenario no longer exercises the bad-site branch"
+    assert gp.fit["n_bad"] == gpo.fit["n_bad"]
+    assert gp.fit["iters"] == gpo.fit["iters"]
+    assert abs(gp.fit["log_evidence"] - gpo.fit["log_evidence"]) < TOL * abs(gpo.fit["log_evidence"])
+    assert scaled_err(gp.fit["alpha"], gpo.fit["alpha"]) < TOL
+    assert scaled_err(gp.fit["fmean"], gpo.fit["fmean"]) < TOL
+    if approx == "ep":
+        assert scaled_err(gp.fit["fvar"], gpo.fit["fvar"]) < TOL
+    Xt = np.random.default_rng(seed + 1).normal(size=(37, 2))
+    p = g.gp_pred(gp, Xt, var=True)
+    po = o.gp_pred(gpo, Xt, var=True)
+    assert scaled_err(p["mean"], po["mean"]) < TOL
+    assert scaled_err(p["var"], po["var"]) < TOL
+    with pytest.raises(g.GplError):
+        g.fit_member(gp, "C_chol")

@@ -10,7 +10,7 @@ import scipy.linalg as sla
 
 import gplite_b200 as g
 from oracle import gplite_oracle as o
-from helpers import model_grid, basic_data, rel_err, scaled_err
+from helpers import model_grid, basic_data, rel_err, scaled_err, outlier_counts
 
 GOLD = os.path.join(os.path.dirname(__file__), "golden")
 
@@ -151,3 +151,40 @@ def test_fitc_oracle_reduces_to_full_when_inducing_equal_training():
     pc = o.gp_pred(fitc, xt, var=True)
     assert scaled_err(pc["mean"], pf["mean"]) < 1e-3
     assert scaled_err(pc["var"], pf["var"]) < 1e-2
+
+
+@pytest.mark.parametrize("approx", ["laplace", "ep"])
+def test_bad_site_branch_block_elimination_equals_lu(approx):
+    """The oracle follows the reference literally (pivoted LU of K + diag(V), R/laplace.R:113,
+    R/ep.R:122).  The CUDA path eliminates the bad block through its Schur complement instead; check
+    here, on the CPU, that both give the same alpha / fvar / predictive variance."""
+    X, y, trials = outlier_counts(44)
+    gp = g.gp_init(cfs=g.cf_sexp(lscale=1.0), lik=g.lik_betabinom(phi=0.3),
+                   approx=g.approx_laplace() if approx == "laplace" else g.approx_ep())
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        o.gp_fit(gp, X, y, trials=trials)
+    fit = gp.fit
+    assert fit["n_bad"] >= 3 and "C_lu" in fit and np.isfinite(fit["log_evidence"])
+    z, V = fit["z"], fit["V"] if approx == "laplace" else 1 / fit["P"]
+    n = len(y)
+    K = o.eval_cf(gp.cfs, X, X) + 1e-6 * np.eye(n)
+    good, bad = np.where(V > 0)[0], np.where(~(V > 0))[0]
+    s = 1 / np.sqrt(V[good])
+    L = np.linalg.cholesky(np.eye(len(good)) + s[:, None] * K[np.ix_(good, good)] * s[None, :])
+    W = sla.solve_triangular(L, (K[np.ix_(bad, good)] * s[None, :]).T, lower=True).T
+    a1 = s * sla.solve_triangular(L.T, sla.solve_triangular(L, s * z[good], lower=True), lower=False)
+    S = K[np.ix_(bad, bad)] - W @ W.T + np.diag(V[bad])
+    ab = np.linalg.solve(S, z[bad] - K[np.ix_(bad, good)] @ a1)
+    ag = a1 - s * sla.solve_triangular(L.T, W.T @ ab, lower=False)
+    alpha = np.zeros(n)
+    alpha[good], alpha[bad] = ag, ab
+    assert scaled_err(alpha, fit["alpha"]) < 1e-10
+    assert scaled_err(K @ alpha, fit["fmean"]) < 1e-10
+    Xt = np.random.default_rng(0).normal(size=(25, 2))
+    po = o.gp_pred_post_full(gp, Xt, var=True)
+    Kt = o.eval_cf(gp.cfs, Xt, X)
+    at = sla.solve_triangular(L, (Kt[:, good] * s[None, :]).T, lower=True).T
+    r = Kt[:, bad] - at @ W.T
+    var = np.diag(o.eval_cf(gp.cfs, Xt, Xt)) - np.sum(at * at, axis=1) - np.sum(r * np.linalg.solve(S, r.T).T, axis=1)
+    assert scaled_err(var, po["var"]) < 1e-10
