@@ -348,4 +348,27 @@ int gpl_scale_block_dev(gpl_ctx* h, int64_t m, int64_t n, double* A, int64_t lda
   return scale_block(reinterpret_cast<Ctx*>(h), m, n, A, lda, r, cs, alpha, diag_add, diag_offset);
 }
 
+int gpl_lik_pseudodata_la_dev(gpl_ctx* h, const gpl_lik* lik, int64_t n, const double* f,
+                              const double* y, const double* trials, const double* offset,
+                              double* z, double* V) {
+  if (!lik || n < 0 || !f || !y || !z || !V) {
+    set_error("gpl_lik_pseudodata_la_dev: bad arguments");
+    return GPL_ERR_BAD_ARG;
+  }
+  LikDev ld{lik->kind, lik->link, lik->param, trials, offset};
+  return lik_pseudodata_la(reinterpret_cast<Ctx*>(h), ld, n, f, y, z, V);
+}
+
+int gpl_lik_loglik_dev(gpl_ctx* h, const gpl_lik* lik, int64_t n, const double* f, const double* y,
+                       const double* trials, const double* offset, double* loglik_host) {
+  if (!lik || n < 0 || !f || !y || !loglik_host) {
+    set_error("gpl_lik_loglik_dev: bad arguments");
+    return GPL_ERR_BAD_ARG;
+  }
+  Ctx* c = reinterpret_cast<Ctx*>(h);
+  LikDev ld{lik->kind, lik->link, lik->param, trials, offset};
+  GPL_TRY(lik_loglik_sum(c, ld, n, f, y, 0));
+  return fetch_scalars(c, 1, loglik_host);
+}
+
 }  // extern "C"

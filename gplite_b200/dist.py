@@ -17,9 +17,11 @@ All n x n arithmetic goes through the C ABI (`ops`); torch.distributed is only t
 `TorchOps`-style stand-ins used by the CPU (gloo) tests live in tests/, not here: this module has
 no CPU compute path.
 
-Reference semantics: fit_laplace.method_full (R/gp_fit.R:91-99) + laplace_iter.method_full
-(R/laplace.R:13-38) for lik_gaussian, with f = K alpha evaluated as z - V alpha (the two are
-identical because (K + V) alpha = z).
+Reference semantics: fit_laplace.method_full (R/gp_fit.R:91-99) + laplace.method_full /
+laplace_iter.method_full (R/laplace.R:13-38, 274-297) for every likelihood (the Newton loop rebuilds
+B = I + V^-1/2 K V^-1/2 from x each iteration -- the K build is ~1 % of a factorisation -- and the
+site vectors f, z, V are replicated: 8n bytes), with f = K alpha evaluated as z - V alpha (the two
+are identical because (K + V) alpha = z).
 """
 from __future__ import annotations
 
@@ -72,10 +74,29 @@ class GpuOps:
                                                   self._p(X_t, c0), ncols, n, d,
                                                   self._p(A_t, lc0 * ld + r0), ld))
 
-    def scale_block(self, A_t, lc0, ncols, r0, nrows, alpha, diag_add, diag_offset):
+    def scale_block(self, A_t, lc0, ncols, r0, nrows, alpha, diag_add, diag_offset, s_t=None, c0=0):
+        """A[r0:r0+nrows, lc0:lc0+ncols] <- alpha s_i A_ij s_j (+ diag_add on the block's diagonal);
+        s_t: replicated n-vector (rows r0.., global columns c0..) or None"""
         ld = A_t.shape[1]
+        r = self._p(s_t, r0) if s_t is not None else None
+        c = self._p(s_t, c0) if s_t is not None else None
         _lib.check(self.lib.gpl_scale_block_dev(self.ctx.h, nrows, ncols, self._p(A_t, lc0 * ld + r0), ld,
-                                                None, None, float(alpha), float(diag_add), diag_offset))
+                                                r, c, float(alpha), float(diag_add), diag_offset))
+
+    def pseudodata(self, lik, f_t, y_t, tr_t, off_t, z_t, V_t):
+        """z, V <- get_pseudodata_la(lik, f, y) on replicated device n-vectors (R/lik.R:188-201)"""
+        _lib.check(self.lib.gpl_lik_pseudodata_la_dev(
+            self.ctx.h, C.byref(lik), f_t.numel(), self._p(f_t), self._p(y_t),
+            self._p(tr_t) if tr_t is not None else None, self._p(off_t) if off_t is not None else None,
+            self._p(z_t), self._p(V_t)))
+
+    def loglik(self, lik, f_t, y_t, tr_t, off_t):
+        out = C.c_double()
+        _lib.check(self.lib.gpl_lik_loglik_dev(
+            self.ctx.h, C.byref(lik), f_t.numel(), self._p(f_t), self._p(y_t),
+            self._p(tr_t) if tr_t is not None else None, self._p(off_t) if off_t is not None else None,
+            C.byref(out)))
+        return out.value
 
     def potrf(self, A_t, lc0, r0, nbk):
         ld = A_t.shape[1]
@@ -115,14 +136,25 @@ class GpuOps:
 
 
 def dist_fit_gaussian(gp, x, y, jitter=None, nb=1024, ops=None, dist=None, device="cuda", timings=None):
-    """Distributed gp_fit for lik_gaussian + method_full + approx_laplace.  Every rank passes the
-    same (replicated) x, y; returns dict(log_evidence, alpha (replicated torch tensor), fmean).
+    """lik_gaussian entry point kept for callers of the first version: see dist_fit_laplace."""
+    if gp.lik.name != "lik_gaussian":
+        raise NotImplementedError("dist_fit_gaussian is for lik_gaussian; use dist_fit_laplace")
+    return dist_fit_laplace(gp, x, y, jitter=jitter, nb=nb, ops=ops, dist=dist, device=device,
+                            timings=timings)
+
+
+def dist_fit_laplace(gp, x, y, trials=None, offset=None, jitter=None, nb=1024, ops=None, dist=None,
+                     device="cuda", timings=None):
+    """Distributed gp_fit for method_full + approx_laplace, any likelihood (log-concave sites).
+    Every rank passes the same (replicated) x, y; returns dict(log_evidence, alpha, fmean, z, V
+    (replicated torch tensors), iters, converged).
 
     `dist` is torch.distributed (initialised by the caller: NCCL on GPUs); `ops` defaults to the
     C-ABI GpuOps on the calling process's default context."""
     import torch
-    if gp.lik.name != "lik_gaussian" or gp.method.name != "full":
-        raise NotImplementedError("the multi-GPU path covers lik_gaussian + method_full")
+    from .gp import _pack_lik
+    if gp.method.name != "full" or gp.approx.name != "laplace":
+        raise NotImplementedError("the multi-GPU path covers method_full + approx_laplace")
     if dist is None:
         import torch.distributed as dist
     rank, world = dist.get_rank(), dist.get_world_size()
@@ -136,7 +168,8 @@ def dist_fit_gaussian(gp, x, y, jitter=None, nb=1024, ops=None, dist=None, devic
     for cf in gp.cfs:
         M.learn_scales(cf, x)
     jit = 1e-6 if jitter is None else float(jitter)
-    sigma2 = gp.lik.sigma ** 2
+    gaussian = gp.lik.name == "lik_gaussian"
+    lik = _pack_lik(gp.lik)
     factors, _ = M.flatten_cfs(gp.cfs)
     pm = _lib.PackedModel(factors)
     if ops is None:
@@ -148,6 +181,7 @@ def dist_fit_gaussian(gp, x, y, jitter=None, nb=1024, ops=None, dist=None, devic
     lay = BlockCyclic(n, nb, world, rank)
     ld = (n + 15) // 16 * 16
     t_mark = {}
+    t_acc = {"kbuild": 0.0, "factor": 0.0, "solve": 0.0}
 
     def mark(name):
         if timings is not None:
@@ -157,27 +191,24 @@ def dist_fit_gaussian(gp, x, y, jitter=None, nb=1024, ops=None, dist=None, devic
             import time
             t_mark[name] = time.perf_counter()
 
+    def vec(v):
+        return None if v is None else torch.from_numpy(np.asarray(v, dtype=np.float64).ravel().copy()).to(device)
+
     X_t = torch.from_numpy(np.ascontiguousarray(x.T)).to(device)          # (d, n): column-major n x d
-    y_t = torch.from_numpy(y).to(device)
+    y_t = vec(y)
+    tr_t, off_t = vec(trials), vec(offset)
+    if gp.lik.name in ("lik_binomial", "lik_betabinom") and tr_t is None:
+        raise ValueError("trials must be provided for the binomial / beta-binomial likelihood")
     A_t = torch.empty((max(lay.nloc, 1), ld), dtype=torch.float64, device=device)
     dinv = {b: torch.empty(((lay.width[b] + 127) // 128) * 128 * 128, dtype=torch.float64, device=device)
             for b in lay.owned}
-    mark("start")
-
-    # ---- K (owned block columns, rows at and below the diagonal block), then B = I + K / sigma^2 in place
-    for b in lay.owned:
-        c0, w, lc0 = lay.col0(b), lay.width[b], lay.local_col0[b]
-        ops.kblock(pm, X_t, n, d, c0, n - c0, c0, w, A_t, lc0)
-        ops.scale_block(A_t, lc0, w, c0, n - c0, 1.0 / sigma2, 1.0 + jit / sigma2, 0)
-    mark("kbuild")
-
-    # ---- right-looking factorisation with panel broadcasts and one step of look-ahead:
-    # the owner of panel k+1 updates that block column first, factors it and starts its broadcast
-    # (async, NCCL stream) while every rank is still applying panel k to its other columns, so the
-    # panel factorisation and the NVLink transfer leave the critical path.
     panels = [torch.empty(nb * ld, dtype=torch.float64, device=device) for _ in range(2)]
-    logdet_local = 0.0
-    fail = 0
+    f_t = torch.zeros(n, dtype=torch.float64, device=device)               # R/laplace.R:280
+    z_t = torch.empty(n, dtype=torch.float64, device=device)
+    V_t = torch.empty(n, dtype=torch.float64, device=device)
+    maxiter = 1 if gaussian else max(int(gp.approx.maxiter), 1)            # R/laplace.R:281-283
+    tol = float(gp.approx.tol)
+    state = {"logdet": 0.0, "fail": 0}
 
     def panel_view(k):
         w, mp = lay.width[k], n - lay.col0(k)
@@ -185,14 +216,13 @@ def dist_fit_gaussian(gp, x, y, jitter=None, nb=1024, ops=None, dist=None, devic
 
     def factor_panel(k):
         """owner only: potrf of the diagonal block, TRSM of the rows below, pack for broadcast"""
-        nonlocal logdet_local, fail
         k0, w, lc0 = lay.col0(k), lay.width[k], lay.local_col0[k]
         st, info, ld_k = ops.potrf(A_t, lc0, k0, w)
         if st != _lib.GPL_OK:
-            fail = max(fail, k0 + info if st == _lib.GPL_ERR_NOT_PD else 1)
+            state["fail"] = max(state["fail"], k0 + info if st == _lib.GPL_ERR_NOT_PD else 1)
         else:
             ops.save_dinv(w, dinv[k])
-            logdet_local += ld_k
+            state["logdet"] += ld_k
             if n - k0 - w > 0:
                 ops.trsm_below(A_t, lc0, k0, w, n - k0 - w)
         panel_view(k).copy_(A_t[lc0:lc0 + w, k0:n])
@@ -202,81 +232,118 @@ def dist_fit_gaussian(gp, x, y, jitter=None, nb=1024, ops=None, dist=None, devic
         j0, wj = lay.col0(j), lay.width[j]
         ops.update(panel_view(k), n - k0, w, j0 - k0, n - j0, j0 - k0, wj, A_t, lay.local_col0[j], j0)
 
-    if lay.owner(0) == rank:
-        factor_panel(0)
-    work = dist.broadcast(panel_view(0), src=lay.owner(0), async_op=True)
-    for k in range(lay.nblk):
-        if work is not None:
-            work.wait()
-        nxt = k + 1
-        work = None
-        if nxt < lay.nblk:
-            if lay.owner(nxt) == rank:
-                apply_panel(k, nxt)
-                factor_panel(nxt)
-            work = dist.broadcast(panel_view(nxt), src=lay.owner(nxt), async_op=True)
-        for j in lay.owned:
-            if j > k and not (j == nxt):
-                apply_panel(k, j)
-    flag = torch.tensor([float(fail)], dtype=torch.float64, device=device)
-    dist.all_reduce(flag, op=dist.ReduceOp.MAX)
-    if flag.item() != 0:
-        raise _lib.NotPositiveDefinite(_lib.GPL_ERR_NOT_PD,
-                                       f"the leading minor of order {int(flag.item())} is not positive definite")
-    mark("factor")
+    def newton_step():
+        """one laplace_iter.method_full (R/laplace.R:13-38) on the sharded matrix"""
+        ops.pseudodata(lik, f_t, y_t, tr_t, off_t, z_t, V_t)
+        if not bool((V_t > 0).all().item()):
+            raise _lib.GplError(_lib.GPL_ERR_NOT_LOGCONCAVE,
+                                "pseudo-variance <= 0: the non-log-concave branch (R/laplace.R:40-117) "
+                                "is single-GPU only")
+        s_t = torch.rsqrt(V_t)
+        mark("iter_start")
+        # ---- K (owned block columns, rows at and below the diagonal block), then
+        # B = I + V^-1/2 K V^-1/2 in place (jitter on K's diagonal)
+        for b in lay.owned:
+            c0, w, lc0 = lay.col0(b), lay.width[b], lay.local_col0[b]
+            ops.kblock(pm, X_t, n, d, c0, n - c0, c0, w, A_t, lc0)
+            ops.scale_block(A_t, lc0, w, c0, n - c0, 1.0, 0.0, 0, s_t, c0)
+        diag_add = 1.0 + jit * s_t * s_t                                   # replicated n-vector
+        for b in lay.owned:
+            c0, w, lc0 = lay.col0(b), lay.width[b], lay.local_col0[b]
+            A_t[lc0:lc0 + w, c0:c0 + w].diagonal().add_(diag_add[c0:c0 + w])
+        mark("kbuild")
 
-    # ---- alpha = C^-1 z, C = diag(sqrtV) L L^T diag(sqrtV), V = sigma^2  (R/laplace.R:29)
-    sq = math.sqrt(sigma2)
-    rhs = y_t / sq
-    u = torch.zeros(n, dtype=torch.float64, device=device)      # local partial sums  sum_j L[:, j] w_j
-    wv = torch.zeros(n, dtype=torch.float64, device=device)     # forward solution (owned blocks)
-    tmp = torch.empty(nb, dtype=torch.float64, device=device)
-    tmp2 = torch.empty(nb, dtype=torch.float64, device=device)
-    for k in range(lay.nblk):
-        k0, w = lay.col0(k), lay.width[k]
-        blk = u[k0:k0 + w].clone()
-        dist.all_reduce(blk)
-        if lay.owner(k) == rank:
-            lc0 = lay.local_col0[k]
-            tmp[:w] = rhs[k0:k0 + w] - blk
-            ops.trsv(0, w, A_t, lc0, k0, dinv[k], tmp, tmp2)
-            wv[k0:k0 + w] = tmp2[:w]
-            if n - k0 - w > 0:
-                upd = torch.empty(n - k0 - w, dtype=torch.float64, device=device)
-                ops.gemv(0, n - k0 - w, w, A_t, lc0, k0 + w, tmp2, 0, upd, 0)
-                u[k0 + w:] += upd
-    xv = torch.zeros(n, dtype=torch.float64, device=device)     # backward solution, replicated
-    for k in reversed(range(lay.nblk)):
-        k0, w = lay.col0(k), lay.width[k]
-        blk = torch.zeros(w, dtype=torch.float64, device=device)
-        if lay.owner(k) == rank:
-            lc0 = lay.local_col0[k]
-            tmp[:w] = wv[k0:k0 + w]
-            if n - k0 - w > 0:
-                dot = torch.empty(w, dtype=torch.float64, device=device)
-                ops.gemv(1, n - k0 - w, w, A_t, lc0, k0 + w, xv, k0 + w, dot, 0)
-                tmp[:w] -= dot
-            ops.trsv(1, w, A_t, lc0, k0, dinv[k], tmp, tmp2)
-            blk.copy_(tmp2[:w])
-        dist.broadcast(blk, src=lay.owner(k))
-        xv[k0:k0 + w] = blk
-    alpha = xv / sq
-    mark("solve")
+        # ---- right-looking factorisation with panel broadcasts and one step of look-ahead:
+        # the owner of panel k+1 updates that block column first, factors it and starts its broadcast
+        # (async, NCCL stream) while every rank is still applying panel k to its other columns, so the
+        # panel factorisation and the NVLink transfer leave the critical path.
+        state["logdet"], state["fail"] = 0.0, 0
+        if lay.owner(0) == rank:
+            factor_panel(0)
+        work = dist.broadcast(panel_view(0), src=lay.owner(0), async_op=True)
+        for k in range(lay.nblk):
+            if work is not None:
+                work.wait()
+            nxt = k + 1
+            work = None
+            if nxt < lay.nblk:
+                if lay.owner(nxt) == rank:
+                    apply_panel(k, nxt)
+                    factor_panel(nxt)
+                work = dist.broadcast(panel_view(nxt), src=lay.owner(nxt), async_op=True)
+            for j in lay.owned:
+                if j > k and not (j == nxt):
+                    apply_panel(k, j)
+        flag = torch.tensor([float(state["fail"])], dtype=torch.float64, device=device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MAX)
+        if flag.item() != 0:
+            raise _lib.NotPositiveDefinite(_lib.GPL_ERR_NOT_PD,
+                                           f"the leading minor of order {int(flag.item())} is not positive definite")
+        mark("factor")
 
-    # ---- log evidence (R/laplace.R:33-38); C_logdet - V_logdet = logdet(B)
-    ldt = torch.tensor([logdet_local], dtype=torch.float64, device=device)
-    dist.all_reduce(ldt)
-    fmean = y_t - sigma2 * alpha                                  # == K alpha
-    resid = y_t - fmean
-    log_lik = float(-0.5 * n * math.log(2 * math.pi * sigma2) - 0.5 * torch.sum(resid * resid).item() / sigma2)
-    f_invK_f = float(torch.dot(fmean, alpha).item())
-    log_evidence = log_lik - 0.5 * f_invK_f - 0.5 * float(ldt.item())
+        # ---- alpha = C^-1 z, C = diag(sqrtV) L L^T diag(sqrtV)  (R/laplace.R:29)
+        rhs = z_t * s_t
+        u = torch.zeros(n, dtype=torch.float64, device=device)      # local partial sums  sum_j L[:, j] w_j
+        wv = torch.zeros(n, dtype=torch.float64, device=device)     # forward solution (owned blocks)
+        tmp = torch.empty(nb, dtype=torch.float64, device=device)
+        tmp2 = torch.empty(nb, dtype=torch.float64, device=device)
+        for k in range(lay.nblk):
+            k0, w = lay.col0(k), lay.width[k]
+            blk = u[k0:k0 + w].clone()
+            dist.all_reduce(blk)
+            if lay.owner(k) == rank:
+                lc0 = lay.local_col0[k]
+                tmp[:w] = rhs[k0:k0 + w] - blk
+                ops.trsv(0, w, A_t, lc0, k0, dinv[k], tmp, tmp2)
+                wv[k0:k0 + w] = tmp2[:w]
+                if n - k0 - w > 0:
+                    upd = torch.empty(n - k0 - w, dtype=torch.float64, device=device)
+                    ops.gemv(0, n - k0 - w, w, A_t, lc0, k0 + w, tmp2, 0, upd, 0)
+                    u[k0 + w:] += upd
+        xv = torch.zeros(n, dtype=torch.float64, device=device)     # backward solution, replicated
+        for k in reversed(range(lay.nblk)):
+            k0, w = lay.col0(k), lay.width[k]
+            blk = torch.zeros(w, dtype=torch.float64, device=device)
+            if lay.owner(k) == rank:
+                lc0 = lay.local_col0[k]
+                tmp[:w] = wv[k0:k0 + w]
+                if n - k0 - w > 0:
+                    dot = torch.empty(w, dtype=torch.float64, device=device)
+                    ops.gemv(1, n - k0 - w, w, A_t, lc0, k0 + w, xv, k0 + w, dot, 0)
+                    tmp[:w] -= dot
+                ops.trsv(1, w, A_t, lc0, k0, dinv[k], tmp, tmp2)
+                blk.copy_(tmp2[:w])
+            dist.broadcast(blk, src=lay.owner(k))
+            xv[k0:k0 + w] = blk
+        alpha = xv * s_t
+        mark("solve")
+        if timings is not None:
+            for a, b in (("iter_start", "kbuild"), ("kbuild", "factor"), ("factor", "solve")):
+                t_acc[b] += t_mark[b] - t_mark[a]
+
+        # ---- log evidence (R/laplace.R:33-38); C_logdet - V_logdet = logdet(B)
+        ldt = torch.tensor([state["logdet"]], dtype=torch.float64, device=device)
+        dist.all_reduce(ldt)
+        fnew = z_t - V_t * alpha                                      # == K alpha
+        log_lik = ops.loglik(lik, fnew, y_t, tr_t, off_t)
+        f_invK_f = float(torch.dot(fnew, alpha).item())
+        return fnew, alpha, log_lik - 0.5 * f_invK_f - 0.5 * float(ldt.item())
+
+    mark("start")
+    it = 0
+    for it in range(1, maxiter + 1):                                   # R/laplace.R:285-292
+        fnew, alpha, log_evidence = newton_step()
+        diff = float(torch.max(torch.abs(f_t - fnew)).item())
+        f_t = fnew
+        if diff < tol:
+            break
     mark("done")
     if timings is not None:
-        names = ["start", "kbuild", "factor", "solve", "done"]
-        for a, b in zip(names[:-1], names[1:]):
-            timings[b] = t_mark[b] - t_mark[a]
-    return dict(log_evidence=log_evidence, alpha=alpha, fmean=fmean, layout=lay)
+        timings.update(t_acc)
+        timings["done"] = 0.0
+        timings["total"] = t_mark["done"] - t_mark["start"]
+    return dict(log_evidence=log_evidence, alpha=alpha, fmean=f_t, z=z_t, V=V_t, iters=it,
+                converged=not (maxiter > 1 and it == maxiter), layout=lay)
 
 
 # ================================================================================================

@@ -227,6 +227,14 @@ int gpl_dgemv_dev(gpl_ctx* ctx, int32_t trans, int64_t m, int64_t n, const doubl
  * Builds B = I + V^-1/2 K V^-1/2 (R/laplace.R:27) in place on a block of columns. */
 int gpl_scale_block_dev(gpl_ctx* ctx, int64_t m, int64_t n, double* A, int64_t lda, const double* r,
                         const double* c, double alpha, double diag_add, int64_t diag_offset);
+/* Site kernels on device n-vectors (the multi-GPU Newton loop keeps f, z, V replicated per rank).
+ * get_pseudodata_la (R/lik.R:188-201): z, V from f, y; trials / offset may be NULL. */
+int gpl_lik_pseudodata_la_dev(gpl_ctx* ctx, const gpl_lik* lik, int64_t n, const double* f,
+                              const double* y, const double* trials, const double* offset,
+                              double* z, double* V);
+/* sum_i log p(y_i | f_i) (get_loglik, R/lik.R:297-366) returned to the host. */
+int gpl_lik_loglik_dev(gpl_ctx* ctx, const gpl_lik* lik, int64_t n, const double* f, const double* y,
+                       const double* trials, const double* offset, double* loglik_host);
 
 /* ---- fits ---------------------------------------------------------- */
 

@@ -33,8 +33,10 @@ class TorchOps:
         K = o.eval_cf(self.gp.cfs, x[r0:r0 + nrows], x[c0:c0 + ncols])
         A_t[lc0:lc0 + ncols, r0:r0 + nrows] = torch.from_numpy(np.ascontiguousarray(K.T))
 
-    def scale_block(self, A_t, lc0, ncols, r0, nrows, alpha, diag_add, diag_offset):
+    def scale_block(self, A_t, lc0, ncols, r0, nrows, alpha, diag_add, diag_offset, s_t=None, c0=0):
         A_t[lc0:lc0 + ncols, r0:r0 + nrows] *= alpha
+        if s_t is not None:
+            A_t[lc0:lc0 + ncols, r0:r0 + nrows] *= s_t[c0:c0 + ncols, None] * s_t[None, r0:r0 + nrows]
         for j in range(ncols):
             i = j + diag_offset
             if 0 <= i < nrows:
@@ -75,8 +77,32 @@ class TorchOps:
         else:
             y_t[y_off:y_off + m] = A @ x_t[x_off:x_off + ncols]
 
+    def _lik_args(self, tr_t, off_t):
+        return dict(trials=None if tr_t is None else tr_t.numpy(), offset=None if off_t is None else off_t.numpy())
+
+    def pseudodata(self, lik, f_t, y_t, tr_t, off_t, z_t, V_t):
+        import torch
+        from oracle import gplite_oracle as o
+        z, V = o.get_pseudodata_la(self.gp.lik, f_t.numpy(), y_t.numpy(), **self._lik_args(tr_t, off_t))
+        z_t.copy_(torch.from_numpy(z))
+        V_t.copy_(torch.from_numpy(V))
+
+    def loglik(self, lik, f_t, y_t, tr_t, off_t):
+        from oracle import gplite_oracle as o
+        return float(o.get_loglik(self.gp.lik, f_t.numpy(), y_t.numpy(), **self._lik_args(tr_t, off_t)))
+
     def sync(self):
         pass
+
+
+def _bernoulli_case():
+    import gplite_b200 as g
+    rng = np.random.default_rng(11)
+    n = 500
+    X = rng.normal(size=(n, 2))
+    y = (rng.uniform(size=n) < 1 / (1 + np.exp(-(2 * X[:, 0] - X[:, 1])))).astype(float)
+    gp = g.gp_init(cfs=g.cf_sexp(lscale=0.8), lik=g.lik_bernoulli(), approx=g.approx_laplace())
+    return gp, X, y
 
 
 def _worker(rank, world, port, q):
@@ -97,7 +123,12 @@ def _worker(rank, world, port, q):
         y = np.sin(X[:, 0]) + 0.4 * X[:, 1] + 0.3 * rng.normal(size=n)
         gp = g.gp_init(cfs=[g.cf_matern52(lscale=1.1), g.cf_lin(magn=0.3)], lik=g.lik_gaussian(sigma=0.4))
         res = dist_fit_gaussian(gp, X, y, nb=128, ops=TorchOps(gp), dist=dist, device="cpu")
-        q.put((rank, res["log_evidence"], res["alpha"].numpy().copy()))
+        # Newton loop over the sharded factor (non-Gaussian likelihood)
+        from gplite_b200.dist import dist_fit_laplace
+        gpb, Xb, yb = _bernoulli_case()
+        resb = dist_fit_laplace(gpb, Xb, yb, nb=128, ops=TorchOps(gpb), dist=dist, device="cpu")
+        q.put((rank, res["log_evidence"], res["alpha"].numpy().copy(), resb["log_evidence"],
+               resb["fmean"].numpy().copy(), resb["iters"]))
     finally:
         dist.destroy_process_group()
 
@@ -122,9 +153,14 @@ def test_distributed_driver_world2_matches_oracle():
     y = np.sin(X[:, 0]) + 0.4 * X[:, 1] + 0.3 * rng.normal(size=n)
     gpo = g.gp_init(cfs=[g.cf_matern52(lscale=1.1), g.cf_lin(magn=0.3)], lik=g.lik_gaussian(sigma=0.4))
     o.gp_fit(gpo, X, y)
-    for rank, le, alpha in out:
+    gpb, Xb, yb = _bernoulli_case()
+    o.gp_fit(gpb, Xb, yb)
+    for rank, le, alpha, leb, fb, itb in out:
         assert abs(le - gpo.fit["log_evidence"]) < 1e-9 * abs(gpo.fit["log_evidence"])
         assert np.max(np.abs(alpha - gpo.fit["alpha"])) < 1e-7 * np.max(np.abs(gpo.fit["alpha"]))
+        assert itb == gpb.fit["iters"] and itb > 2
+        assert abs(leb - gpb.fit["log_evidence"]) < 1e-9 * abs(gpb.fit["log_evidence"])
+        assert np.max(np.abs(fb - gpb.fit["fmean"])) < 1e-8 * np.max(np.abs(gpb.fit["fmean"]))
 
 
 # ------------------------------------------------------------------------------ FITC row sharding

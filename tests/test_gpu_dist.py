@@ -55,6 +55,38 @@ def test_driver_single_rank_matches_oracle(n, nb):
     assert np.max(np.abs(f - gpo.fit["fmean"])) < 1e-8 * np.max(np.abs(gpo.fit["fmean"]))
 
 
+@pytest.mark.parametrize("lik", ["bernoulli", "poisson", "binomial"])
+def test_laplace_driver_single_rank_matches_oracle(lik):
+    """SURVEY 8e "Laplace site sweeps": the Newton loop over the block-cyclic factor, site kernels
+    through gpl_lik_*_dev on replicated n-vectors."""
+    from gplite_b200.dist import dist_fit_laplace
+    rng = np.random.default_rng(21)
+    n = 900
+    X = rng.normal(size=(n, 3))
+    f = 1.5 * X[:, 0] - X[:, 1]
+    kw = {}
+    if lik == "bernoulli":
+        y = (rng.uniform(size=n) < 1 / (1 + np.exp(-f))).astype(float)
+        L = g.lik_bernoulli()
+    elif lik == "poisson":
+        y = rng.poisson(np.exp(0.5 * f + 0.3)).astype(float)
+        L = g.lik_poisson()
+    else:
+        kw["trials"] = rng.integers(2, 12, size=n).astype(float)
+        y = rng.binomial(kw["trials"].astype(int), 1 / (1 + np.exp(-f))).astype(float)
+        L = g.lik_binomial(link="probit")
+    gp = g.gp_init(cfs=[g.cf_sexp(lscale=1.1), g.cf_const(magn=0.3)], lik=L, approx=g.approx_laplace())
+    gpo = copy.deepcopy(gp)
+    res = dist_fit_laplace(gp, X, y, nb=256, dist=OneRank, **kw)
+    o.gp_fit(gpo, X, y, **kw)
+    assert res["iters"] == gpo.fit["iters"] and res["iters"] > 2
+    assert abs(res["log_evidence"] - gpo.fit["log_evidence"]) < 1e-8 * abs(gpo.fit["log_evidence"])
+    a = res["alpha"].cpu().numpy()
+    assert np.max(np.abs(a - gpo.fit["alpha"])) < 1e-6 * np.max(np.abs(gpo.fit["alpha"]))
+    fm = res["fmean"].cpu().numpy()
+    assert np.max(np.abs(fm - gpo.fit["fmean"])) < 1e-8 * np.max(np.abs(gpo.fit["fmean"]))
+
+
 def test_fitc_driver_single_rank_matches_oracle():
     from gplite_b200.dist import dist_fit_fitc_gaussian
     rng = np.random.default_rng(8)
