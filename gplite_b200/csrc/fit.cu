@@ -817,6 +817,61 @@ int energy_grad_impl(Ctx* ctx, const gpl_cf_model* cf, const gpl_lik* lik, const
   return GPL_OK;
 }
 
+int grad_trace_block_impl(Ctx* ctx, const gpl_cf_model* cf, const double* x, int64_t n, int d,
+                          int64_t col0, int64_t ncols, const double* Cinv, int64_t ld,
+                          const double* s, const double* alpha, int nparam,
+                          const int32_t* param_factor, const int32_t* param_slot, double* out,
+                          double* diag_sum) {
+  if (!cf || !x || n <= 0 || d <= 0 || !Cinv || !s || !alpha || nparam < 0 ||
+      nparam > MAX_GRAD_PARAMS || !out) {
+    set_error("gpl_grad_trace_block_dev: bad arguments");
+    return GPL_ERR_BAD_ARG;
+  }
+  bool want_aux = false;
+  for (int j = 0; j < nparam; ++j)
+    if (param_factor[j] >= 0 && param_slot[j] == 3) want_aux = true;
+  HostPlan hp;
+  GPL_TRY(make_plan(cf, d, 0, &hp, want_aux));
+  const int F = hp.plan.nfeat > 0 ? hp.plan.nfeat : 1, FA = hp.plan.naux;
+  DevBuf Z, Zaux, gout, dg, s2;
+  GPL_TRY(Z.alloc(ctx, sizeof(double) * n * F));
+  if (FA > 0) GPL_TRY(Zaux.alloc(ctx, sizeof(double) * n * FA));
+  GPL_TRY(prep_features(ctx, hp, x, n, n, Z.d(), n, FA > 0 ? Zaux.d() : nullptr, n));
+  GradParam gp[MAX_GRAD_PARAMS];
+  int pos[MAX_GRAD_PARAMS], ncf = 0;
+  for (int j = 0; j < nparam; ++j) {
+    out[j] = 0.0;
+    if (param_factor[j] < 0) continue;
+    if (param_factor[j] >= hp.plan.nfactors) {
+      set_error("gpl_grad_trace_block_dev: parameter %d refers to factor %d of %d", j,
+                param_factor[j], hp.plan.nfactors);
+      return GPL_ERR_BAD_ARG;
+    }
+    gp[ncf].factor = param_factor[j];
+    gp[ncf].slot = param_slot[j];
+    pos[ncf++] = j;
+  }
+  GPL_TRY(gout.alloc(ctx, sizeof(double) * (MAX_GRAD_PARAMS + 8)));
+  GPL_TRY(grad_trace(ctx, hp.plan, Z.d(), n, Zaux.d(), n, Cinv, ld, s, alpha, ncf, gp, gout.d(),
+                     col0, ncols));
+  // diagonal of the block: element (col0 + j, j) of the slab
+  GPL_TRY(dg.alloc(ctx, sizeof(double) * ncols));
+  GPL_TRY(s2.alloc(ctx, sizeof(double) * ncols));
+  GPL_TRY(diag_extract(ctx, ncols, Cinv + col0, ld, dg.d()));
+  GPL_TRY(vec_op(ctx, VOP_MUL, ncols, s + col0, s + col0, s2.d()));
+  GPL_TRY(reduce(ctx, RED_DOT, ncols, dg.d(), s2.d(), 0));
+  double sc[1];
+  GPL_TRY(fetch_scalars(ctx, 1, sc));
+  if (diag_sum) *diag_sum = sc[0];
+  double hg[MAX_GRAD_PARAMS];
+  if (ncf > 0) {
+    GPL_CUDA(cudaMemcpyAsync(hg, gout.p, sizeof(double) * ncf, cudaMemcpyDeviceToHost, ctx->stream));
+    GPL_CUDA(cudaStreamSynchronize(ctx->stream));
+    for (int q = 0; q < ncf; ++q) out[pos[q]] = hg[q];
+  }
+  return GPL_OK;
+}
+
 int pred_full_impl(Ctx* ctx, const Fit* fit, const gpl_cf_model* cf, const double* xt, int64_t nt,
                    uint64_t term_mask, double* mean, double* var) {
   if (!fit || fit->method != 0 || nt < 0 || !mean) {
@@ -954,6 +1009,16 @@ int gpl_energy_grad(gpl_ctx* h, const gpl_cf_model* cf, const gpl_lik* lik, cons
   if (fit) *fit = reinterpret_cast<gpl_fit*>(f);
   if (rc != GPL_OK) cudaStreamSynchronize(reinterpret_cast<Ctx*>(h)->stream);
   return rc;
+}
+
+int gpl_grad_trace_block_dev(gpl_ctx* h, const gpl_cf_model* cf, const double* x, int64_t n,
+                             int32_t d, int64_t col0, int64_t ncols, const double* Cinv_blk,
+                             int64_t ld, const double* s, const double* alpha, int32_t nparam,
+                             const int32_t* param_factor, const int32_t* param_slot, double* out,
+                             double* diag_sum) {
+  return gpl::grad_trace_block_impl(reinterpret_cast<gpl::Ctx*>(h), cf, x, n, d, col0, ncols,
+                                    Cinv_blk, ld, s, alpha, nparam, param_factor, param_slot, out,
+                                    diag_sum);
 }
 
 int gpl_pred_full(gpl_ctx* h, const gpl_fit* fit, const gpl_cf_model* cf, const double* xt,

@@ -133,7 +133,10 @@ constexpr int MAX_GRAD_PARAMS = 24;
 // out[j] = sum_{i,k} (alpha_i alpha_k - s_i Binv_ik s_k) dK_ik/dlog(theta_j), Binv lower triangle
 int grad_trace(Ctx* ctx, const CfPlan& plan, const double* z, int64_t ldz, const double* zaux,
                int64_t n, const double* Binv, int64_t ldb, const double* s, const double* alpha,
-               int nparam, const GradParam* params, double* d_out /* device, nparam doubles */);
+               int nparam, const GradParam* params, double* d_out /* device, nparam doubles */,
+               int64_t col0 = -1, int64_t ncols = 0);
+// col0 >= 0: block mode -- Binv holds only the block column [col0, col0 + ncols) (all n rows, rows
+// above the block's diagonal are never read); the result is that block column's share of the sum.
 
 // ---- fit object --------------------------------------------------------------------------------
 struct Fit {

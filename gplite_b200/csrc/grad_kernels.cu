@@ -28,6 +28,11 @@ struct GradArgs {
   int64_t ldz, ldaux, ldb;
   int n;
   int nparam;
+  // block mode (multi-GPU: one block column of the inverse per call): Binv holds columns
+  // [col_tile0 * GT, ...) only, grid = (row tiles, column tiles of the block)
+  int block_mode;
+  int col_tile0;
+  int col_end;        // one past the last column this call covers
   GradParam prm[GP];
 };
 
@@ -94,12 +99,23 @@ grad_trace_kernel(const __grid_constant__ CfPlan plan, const GradArgs a) {
   __shared__ double red[GTHREADS / 32][GP];
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int L = blockIdx.x;
-  int bi = (int)((sqrt(8.0 * (double)L + 1.0) - 1.0) * 0.5);
-  while ((int64_t)bi * (bi + 1) / 2 > L) --bi;
-  while ((int64_t)(bi + 1) * (bi + 2) / 2 <= L) ++bi;
-  const int bj = L - bi * (bi + 1) / 2;
+  int bi, bj;
+  if (a.block_mode) {
+    bi = blockIdx.x;
+    bj = a.col_tile0 + blockIdx.y;
+    if (bi < bj) {                               // above the diagonal: nothing to add
+      if (tid < GP) a.partial[((int64_t)blockIdx.y * gridDim.x + blockIdx.x) * GP + tid] = 0.0;
+      return;
+    }
+  } else {
+    const int L = blockIdx.x;
+    bi = (int)((sqrt(8.0 * (double)L + 1.0) - 1.0) * 0.5);
+    while ((int64_t)bi * (bi + 1) / 2 > L) --bi;
+    while ((int64_t)(bi + 1) * (bi + 2) / 2 <= L) ++bi;
+    bj = L - bi * (bi + 1) / 2;
+  }
   const int i0 = bi * GT, j0 = bj * GT;
+  const int64_t bcol0 = a.block_mode ? (int64_t)a.col_tile0 * GT : 0;
 
   for (int idx = tid; idx < F * GT; idx += GTHREADS) {
     const int f = idx >> 7, r = idx & (GT - 1);
@@ -127,7 +143,7 @@ grad_trace_kernel(const __grid_constant__ CfPlan plan, const GradArgs a) {
   for (int c = 0; c < 16; ++c) {
     const int jl = warp * 16 + c;
     const int gj = j0 + jl;
-    if (gj >= a.n) break;
+    if (gj >= a.col_end) break;
 #pragma unroll 1
     for (int r = 0; r < 4; ++r) {
       const int il = lane + 32 * r;
@@ -135,7 +151,7 @@ grad_trace_kernel(const __grid_constant__ CfPlan plan, const GradArgs a) {
       if (gi >= a.n || gi < gj) continue;          // lower triangle only
       const double wgt = (gi == gj) ? 1.0 : 2.0;   // mirror entry
       const double W = wgt * (al1[il] * al2[jl] -
-                              sv1[il] * a.Binv[(int64_t)gj * a.ldb + gi] * sv2[jl]);
+                              sv1[il] * a.Binv[((int64_t)gj - bcol0) * a.ldb + gi] * sv2[jl]);
       // walk the terms
       int fi = 0;
       while (fi < plan.nfactors) {
@@ -208,7 +224,7 @@ grad_trace_kernel(const __grid_constant__ CfPlan plan, const GradArgs a) {
   if (tid < GP) {
     double v = 0.0;
     for (int w = 0; w < GTHREADS / 32; ++w) v += red[w][tid];
-    a.partial[(int64_t)blockIdx.x * GP + tid] = v;
+    a.partial[((int64_t)blockIdx.y * gridDim.x + blockIdx.x) * GP + tid] = v;
   }
 }
 
@@ -234,10 +250,16 @@ __global__ void sum_grad_partials_kernel(const double* __restrict__ partial, int
 
 int grad_trace(Ctx* ctx, const CfPlan& plan, const double* z, int64_t ldz, const double* zaux,
                int64_t n, const double* Binv, int64_t ldb, const double* s, const double* alpha,
-               int nparam, const GradParam* params, double* d_out) {
+               int nparam, const GradParam* params, double* d_out, int64_t col0, int64_t ncols) {
   if (nparam <= 0 || n <= 0) return GPL_OK;
   const int tiles = (int)((n + GT - 1) / GT);
-  const int grid = tiles * (tiles + 1) / 2;
+  const bool block_mode = col0 >= 0;
+  if (block_mode && (col0 % GT != 0 || ncols <= 0 || col0 + ncols > n)) {
+    set_error("grad_trace: the block column must start at a multiple of %d inside the matrix", GT);
+    return GPL_ERR_BAD_ARG;
+  }
+  const int ctiles = block_mode ? (int)((ncols + GT - 1) / GT) : 0;
+  const int grid = block_mode ? tiles * ctiles : tiles * (tiles + 1) / 2;
   const int smem = (2 * (plan.nfeat + plan.naux) * GT + 4 * GT) * (int)sizeof(double);
   if (smem > 227 * 1024) {
     set_error("grad_trace: too many feature columns (%d) for shared memory", plan.nfeat);
@@ -250,14 +272,20 @@ int grad_trace(Ctx* ctx, const CfPlan& plan, const double* z, int64_t ldz, const
   for (int p0 = 0; p0 < nparam; p0 += GP) {
     GradArgs a;
     a.z = z; a.zaux = zaux; a.Binv = Binv; a.s = s; a.alpha = alpha; a.partial = part.d();
-    a.ldz = ldz; a.ldaux = ldz; a.ldb = ldb; a.n = (int)n;
+    a.ldz = ldz; a.ldaux = ldz; a.ldb = ldb;
+    // block mode: columns beyond the block belong to other calls
+    a.n = (int)n;
+    a.block_mode = block_mode ? 1 : 0;
+    a.col_tile0 = block_mode ? (int)(col0 / GT) : 0;
+    a.col_end = block_mode ? (int)(col0 + ncols) : (int)n;
     a.nparam = nparam - p0 < GP ? nparam - p0 : GP;
     for (int p = 0; p < GP; ++p) {
       a.prm[p].factor = -2;
       a.prm[p].slot = 0;
       if (p < a.nparam) a.prm[p] = params[p0 + p];
     }
-    grad_trace_kernel<<<grid, GTHREADS, smem, ctx->stream>>>(plan, a);
+    const dim3 g = block_mode ? dim3((unsigned)tiles, (unsigned)ctiles) : dim3((unsigned)grid);
+    grad_trace_kernel<<<g, GTHREADS, smem, ctx->stream>>>(plan, a);
     GPL_LAUNCH_CHECK(ctx);
     sum_grad_partials_kernel<<<a.nparam, 256, 0, ctx->stream>>>(part.d(), grid, a.nparam,
                                                                 d_out + p0);

@@ -83,6 +83,33 @@ class GpuOps:
         _lib.check(self.lib.gpl_scale_block_dev(self.ctx.h, nrows, ncols, self._p(A_t, lc0 * ld + r0), ld,
                                                 r, c, float(alpha), float(diag_add), diag_offset))
 
+    def gemm(self, ta, tb, m, n, k, alpha, A, B, beta, Cm, lower=0):
+        """C <- alpha op(A) op(B) + beta C on column-major views given as (tensor, element offset, ld)"""
+        (At, ao, lda), (Bt, bo, ldb), (Ct, co, ldc) = A, B, Cm
+        _lib.check(self.lib.gpl_dgemm_dev(self.ctx.h, ta, tb, m, n, k, float(alpha), self._p(At, ao), lda,
+                                          self._p(Bt, bo), ldb, float(beta), self._p(Ct, co), ldc, lower))
+
+    def inv_diag(self, A_t, lc0, k0, w, dinv_t, out_t, ldo):
+        """out (w x w, ld ldo) <- L_kk^-1 for the diagonal block of block column lc0 (exact zeros above
+        the diagonal): right-solve X L_kk = I with that block's saved 128-block inverses"""
+        import torch
+        ld = A_t.shape[1]
+        blk = torch.as_strided(out_t, (w, w), (ldo, 1))
+        blk.zero_()
+        blk.diagonal().fill_(1.0)
+        _lib.check(self.lib.gpl_dtrsm_right_dinv_dev(self.ctx.h, 0, w, w, self._p(A_t, lc0 * ld + k0), ld,
+                                                     self._p(dinv_t), self._p(out_t), ldo))
+
+    def grad_trace_block(self, pm, X_t, n, d, c0, w, Y_t, lc0, s_t, alpha_t, pf, ps):
+        """block column's share of sum W_ij dK_ij/dlog(theta_p) and of sum_j s_j^2 Binv_jj"""
+        ld = Y_t.shape[1]
+        out = np.zeros(len(pf), dtype=np.float64)
+        dsum = C.c_double()
+        _lib.check(self.lib.gpl_grad_trace_block_dev(
+            self.ctx.h, pm.ref(), self._p(X_t), n, d, c0, w, self._p(Y_t, lc0 * ld), ld, self._p(s_t),
+            self._p(alpha_t), len(pf), _lib._ptr(pf), _lib._ptr(ps), _lib._ptr(out), C.byref(dsum)))
+        return out, dsum.value
+
     def pseudodata(self, lik, f_t, y_t, tr_t, off_t, z_t, V_t):
         """z, V <- get_pseudodata_la(lik, f, y) on replicated device n-vectors (R/lik.R:188-201)"""
         _lib.check(self.lib.gpl_lik_pseudodata_la_dev(
@@ -144,13 +171,16 @@ def dist_fit_gaussian(gp, x, y, jitter=None, nb=1024, ops=None, dist=None, devic
 
 
 def dist_fit_laplace(gp, x, y, trials=None, offset=None, jitter=None, nb=1024, ops=None, dist=None,
-                     device="cuda", timings=None):
+                     device="cuda", timings=None, grad_params=None):
     """Distributed gp_fit for method_full + approx_laplace, any likelihood (log-concave sites).
     Every rank passes the same (replicated) x, y; returns dict(log_evidence, alpha, fmean, z, V
     (replicated torch tensors), iters, converged).
 
     `dist` is torch.distributed (initialised by the caller: NCCL on GPUs); `ops` defaults to the
-    C-ABI GpuOps on the calling process's default context."""
+    C-ABI GpuOps on the calling process's default context.
+
+    grad_params=(param_factor, param_slot) (lik_gaussian only): also return `grad_raw`, the
+    derivative of the energy without priors w.r.t. those log-parameters -- see dist_energy_grad."""
     import torch
     from .gp import _pack_lik
     if gp.method.name != "full" or gp.approx.name != "laplace":
@@ -338,12 +368,132 @@ def dist_fit_laplace(gp, x, y, trials=None, offset=None, jitter=None, nb=1024, o
         if diff < tol:
             break
     mark("done")
+    out = dict(log_evidence=log_evidence, alpha=alpha, fmean=f_t, z=z_t, V=V_t, iters=it,
+               converged=not (maxiter > 1 and it == maxiter), layout=lay)
+
+    if grad_params is not None:
+        # ---- energy gradient (SURVEY 8e "C^-1 + trace term"): B^-1 = X^T X, X = L^-1, in the same
+        # block-cyclic layout.  Two more sweeps of panel broadcasts, each n^3/3 flops spread like the
+        # factorisation:
+        #   X sweep: panel k = [L_kk^-1 ; L[k1:, k]] goes to every rank; for its own columns j < k a
+        #            rank finishes block row k of X (X_kj = L_kk^-1 R_kj) and pushes the update down
+        #            (R[k1:, j] -= L[k1:, k] X_kj); the running right-hand side R lives in X's slab.
+        #   Y sweep: panel i = X[i0:, i]; Y_ij = X[i0:, i]^T X[i0:, j] for own columns j <= i,
+        #            written over the block row of X it no longer needs.
+        # Panels depend only on finished data, so panel k+1 is always in flight during step k.
+        if not gaussian:
+            raise NotImplementedError("the analytic gradient is implemented for lik_gaussian")
+        pf, ps = (np.ascontiguousarray(v, dtype=np.int32) for v in grad_params)
+        s_t = torch.rsqrt(V_t)
+        Xi_t = torch.zeros((max(lay.nloc, 1), ld), dtype=torch.float64, device=device)
+        tmpb = torch.empty(nb * nb, dtype=torch.float64, device=device)
+        ldn = ld
+
+        def prep_L_panel(k):
+            k0, w, lc0 = lay.col0(k), lay.width[k], lay.local_col0[k]
+            pv = panel_view(k)                                   # (w, n - k0): column-major (n-k0) x w
+            pv.copy_(A_t[lc0:lc0 + w, k0:n])
+            ops.inv_diag(A_t, lc0, k0, w, dinv[k], pv, n - k0)   # diagonal block <- L_kk^-1
+            # this rank's own column k of X:  X_kk = L_kk^-1,  R[k1:, k] = -L[k1:, k] L_kk^-1
+            Xi_t[lc0:lc0 + w, k0:k0 + w] = pv[:, :w]
+            if n - k0 - w > 0:
+                ops.gemm(0, 0, n - k0 - w, w, w, -1.0, (pv, w, n - k0), (pv, 0, n - k0), 0.0,
+                         (Xi_t, lc0 * ldn + k0 + w, ldn))
+
+        def sweep(prep, apply):
+            if lay.owner(0) == rank:
+                prep(0)
+            work = dist.broadcast(panel_view(0), src=lay.owner(0), async_op=True)
+            for k in range(lay.nblk):
+                if work is not None:
+                    work.wait()
+                work = None
+                if k + 1 < lay.nblk:
+                    if lay.owner(k + 1) == rank:
+                        prep(k + 1)
+                    work = dist.broadcast(panel_view(k + 1), src=lay.owner(k + 1), async_op=True)
+                apply(k)
+
+        def apply_L_panel(k):
+            k0, w = lay.col0(k), lay.width[k]
+            pv = panel_view(k)
+            for j in lay.owned:
+                if j >= k:
+                    break
+                wj, lcj = lay.width[j], lay.local_col0[j]
+                # X_kj = L_kk^-1 R_kj (into a scratch block, then over R_kj)
+                ops.gemm(0, 0, w, wj, w, 1.0, (pv, 0, n - k0), (Xi_t, lcj * ldn + k0, ldn), 0.0, (tmpb, 0, w))
+                if n - k0 - w > 0:
+                    ops.gemm(0, 0, n - k0 - w, wj, w, -1.0, (pv, w, n - k0), (tmpb, 0, w), 1.0,
+                             (Xi_t, lcj * ldn + k0 + w, ldn))
+                Xi_t[lcj:lcj + wj, k0:k0 + w] = torch.as_strided(tmpb, (wj, w), (w, 1))
+
+        def prep_X_panel(i):
+            i0, w, lc0 = lay.col0(i), lay.width[i], lay.local_col0[i]
+            panel_view(i).copy_(Xi_t[lc0:lc0 + w, i0:n])
+
+        def apply_X_panel(i):
+            i0, w = lay.col0(i), lay.width[i]
+            pv = panel_view(i)
+            for j in lay.owned:
+                if j > i:
+                    break
+                wj, lcj = lay.width[j], lay.local_col0[j]
+                ops.gemm(1, 0, w, wj, n - i0, 1.0, (pv, 0, n - i0), (Xi_t, lcj * ldn + i0, ldn), 0.0,
+                         (tmpb, 0, w), 1 if j == i else 0)
+                Xi_t[lcj:lcj + wj, i0:i0 + w] = torch.as_strided(tmpb, (wj, w), (w, 1))
+
+        sweep(prep_L_panel, apply_L_panel)
+        mark("trtri")
+        sweep(prep_X_panel, apply_X_panel)
+        mark("lauum")
+        g_loc = np.zeros(len(pf), dtype=np.float64)
+        dsum_loc = 0.0
+        for j in lay.owned:
+            gj, dj = ops.grad_trace_block(pm, X_t, n, d, lay.col0(j), lay.width[j], Xi_t, lay.local_col0[j],
+                                          s_t, alpha, pf, ps)
+            g_loc += gj
+            dsum_loc += dj
+        red = torch.from_numpy(np.concatenate([g_loc, [dsum_loc]])).to(device)
+        dist.all_reduce(red)
+        red = red.cpu().numpy()
+        sigma2 = gp.lik.sigma ** 2
+        tr_w = float(torch.dot(alpha, alpha).item()) - red[-1]            # tr(alpha alpha^T - C^-1)
+        graw = np.where(pf < 0, -0.5 * 2.0 * sigma2 * tr_w, -0.5 * red[:-1])
+        mark("trace")
+        out["grad_raw"] = graw
+        if timings is not None:
+            timings["trtri"] = t_mark["trtri"] - t_mark["done"]
+            timings["lauum"] = t_mark["lauum"] - t_mark["trtri"]
+            timings["trace"] = t_mark["trace"] - t_mark["lauum"]
+
     if timings is not None:
         timings.update(t_acc)
         timings["done"] = 0.0
         timings["total"] = t_mark["done"] - t_mark["start"]
-    return dict(log_evidence=log_evidence, alpha=alpha, fmean=f_t, z=z_t, V=V_t, iters=it,
-                converged=not (maxiter > 1 and it == maxiter), layout=lay)
+    return out
+
+
+def dist_energy_grad(gp, x, y, jitter=None, include_prior=True, nb=1024, ops=None, dist=None, device="cuda",
+                     timings=None):
+    """Multi-GPU gp_energy_grad (lik_gaussian + method_full): energy and its gradient w.r.t.
+    get_param(gp), same conventions as gp.gp_energy_grad; every rank returns the same values."""
+    items = M.get_param_objs(gp.cfs, gp.lik)
+    _, where = M.flatten_cfs(gp.cfs)
+    pf = np.empty(len(items), dtype=np.int32)
+    ps = np.empty(len(items), dtype=np.int32)
+    for j, (_, owner, attr) in enumerate(items):
+        pf[j], ps[j] = (-1, 0) if owner is gp.lik else where[(id(owner), attr)]
+    res = dist_fit_laplace(gp, x, y, jitter=jitter, nb=nb, ops=ops, dist=dist, device=device, timings=timings,
+                           grad_params=(pf, ps))
+    e = -res["log_evidence"]
+    grad = res["grad_raw"].copy()
+    if include_prior:
+        for j, (_, owner, attr) in enumerate(items):
+            lp = math.log(getattr(owner, attr))
+            e -= M.lpdf_prior_one(owner.priors[attr], lp)
+            grad[j] -= M.dlpdf_prior_one(owner.priors[attr], lp)
+    return e, grad
 
 
 # ================================================================================================

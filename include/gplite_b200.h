@@ -235,6 +235,18 @@ int gpl_lik_pseudodata_la_dev(gpl_ctx* ctx, const gpl_lik* lik, int64_t n, const
 /* sum_i log p(y_i | f_i) (get_loglik, R/lik.R:297-366) returned to the host. */
 int gpl_lik_loglik_dev(gpl_ctx* ctx, const gpl_lik* lik, int64_t n, const double* f, const double* y,
                        const double* trials, const double* offset, double* loglik_host);
+/* One block column's share of the gradient trace (multi-GPU energy gradient; the single-GPU path is
+ * gpl_energy_grad).  Cinv_blk: columns [col0, col0 + ncols) of the lower triangle of
+ * Binv = (I + S K S)^-1, all n rows with leading dimension ld (rows above the block's diagonal are
+ * not read); col0 a multiple of 128.  s = V^-1/2 and alpha are device n-vectors, x is n x d on the
+ * device.  out[p] = sum over the block's lower-triangular entries (mirror entries counted) of
+ * (alpha_i alpha_j - s_i Binv_ij s_j) dK_ij/dlog(theta_p); *diag_sum = sum_j s_j^2 Binv_jj.
+ * param_factor / param_slot as in gpl_energy_grad (entries with factor < 0 are skipped: out = 0). */
+int gpl_grad_trace_block_dev(gpl_ctx* ctx, const gpl_cf_model* cf, const double* x, int64_t n,
+                             int32_t d, int64_t col0, int64_t ncols, const double* Cinv_blk,
+                             int64_t ld, const double* s, const double* alpha, int32_t nparam,
+                             const int32_t* param_factor, const int32_t* param_slot, double* out,
+                             double* diag_sum);
 
 /* ---- fits ---------------------------------------------------------- */
 

@@ -77,6 +77,53 @@ class TorchOps:
         else:
             y_t[y_off:y_off + m] = A @ x_t[x_off:x_off + ncols]
 
+    @staticmethod
+    def _view(spec, rows, cols):
+        import torch
+        t, off, ld = spec
+        base = t if t.dim() == 1 and t.is_contiguous() else t.reshape(-1) if t.is_contiguous() else None
+        assert base is not None
+        return torch.as_strided(base, (rows, cols), (1, ld), base.storage_offset() + off)
+
+    def gemm(self, ta, tb, m, n, k, alpha, A, B, beta, Cm, lower=0):
+        import torch
+        a = self._view(A, k, m).T if ta else self._view(A, m, k)
+        b = self._view(B, n, k).T if tb else self._view(B, k, n)
+        c = self._view(Cm, m, n)
+        r = alpha * (a @ b) + (beta * c if beta != 0 else 0.0)
+        if lower:
+            mask = torch.tril(torch.ones(m, n, dtype=torch.bool))
+            c[mask] = r[mask]
+        else:
+            c.copy_(r)
+
+    def inv_diag(self, A_t, lc0, k0, w, dinv_t, out_t, ldo):
+        import torch
+        L = torch.tril(A_t[lc0:lc0 + w, k0:k0 + w].T)
+        Li = torch.linalg.solve_triangular(L, torch.eye(w, dtype=torch.float64), upper=False)
+        torch.as_strided(out_t, (w, w), (1, ldo)).copy_(Li)
+
+    def grad_trace_block(self, pm, X_t, n, d, c0, w, Y_t, lc0, s_t, alpha_t, pf, ps):
+        from oracle import gplite_oracle as o
+        import gplite_b200.model as M
+        x = X_t.numpy().T
+        Y = Y_t[lc0:lc0 + w, :n].numpy().T                       # n x w block column of Binv (lower valid)
+        s, a = s_t.numpy(), alpha_t.numpy()
+        rows = np.arange(n)[:, None]
+        cols = (c0 + np.arange(w))[None, :]
+        wgt = np.where(rows > cols, 2.0, np.where(rows == cols, 1.0, 0.0))
+        Wm = wgt * (np.outer(a, a[c0:c0 + w]) - s[:, None] * Y * s[None, c0:c0 + w])
+        Wm[wgt == 0] = 0.0
+        items = M.get_param_objs(self.gp.cfs, self.gp.lik)
+        out = np.zeros(len(pf))
+        for p, (_, owner, attr) in enumerate(items):
+            if pf[p] < 0:
+                continue
+            dK = o._dK_dlogparam(self.gp.cfs, owner, attr, x, x[c0:c0 + w])
+            out[p] = np.sum(Wm * dK)
+        dsum = float(np.sum(s[c0:c0 + w] ** 2 * Y[c0 + np.arange(w), np.arange(w)]))
+        return out, dsum
+
     def _lik_args(self, tr_t, off_t):
         return dict(trials=None if tr_t is None else tr_t.numpy(), offset=None if off_t is None else off_t.numpy())
 
@@ -127,8 +174,12 @@ def _worker(rank, world, port, q):
         from gplite_b200.dist import dist_fit_laplace
         gpb, Xb, yb = _bernoulli_case()
         resb = dist_fit_laplace(gpb, Xb, yb, nb=128, ops=TorchOps(gpb), dist=dist, device="cpu")
+        # energy gradient: distributed inverse (two more panel sweeps) + block trace
+        from gplite_b200.dist import dist_energy_grad
+        gpg = g.gp_init(cfs=[g.cf_matern52(lscale=1.1), g.cf_lin(magn=0.3)], lik=g.lik_gaussian(sigma=0.4))
+        e, gr = dist_energy_grad(gpg, X, y, nb=128, ops=TorchOps(gpg), dist=dist, device="cpu")
         q.put((rank, res["log_evidence"], res["alpha"].numpy().copy(), resb["log_evidence"],
-               resb["fmean"].numpy().copy(), resb["iters"]))
+               resb["fmean"].numpy().copy(), resb["iters"], e, gr))
     finally:
         dist.destroy_process_group()
 
@@ -155,7 +206,11 @@ def test_distributed_driver_world2_matches_oracle():
     o.gp_fit(gpo, X, y)
     gpb, Xb, yb = _bernoulli_case()
     o.gp_fit(gpb, Xb, yb)
-    for rank, le, alpha, leb, fb, itb in out:
+    gpg = g.gp_init(cfs=[g.cf_matern52(lscale=1.1), g.cf_lin(magn=0.3)], lik=g.lik_gaussian(sigma=0.4))
+    eo, go = o.energy_grad_gaussian_full(gpg, X, y)
+    for rank, le, alpha, leb, fb, itb, e, gr in out:
+        assert abs(e - eo) < 1e-9 * abs(eo)
+        assert np.max(np.abs(gr - go)) < 1e-6 * max(1.0, np.max(np.abs(go))), (gr, go)
         assert abs(le - gpo.fit["log_evidence"]) < 1e-9 * abs(gpo.fit["log_evidence"])
         assert np.max(np.abs(alpha - gpo.fit["alpha"])) < 1e-7 * np.max(np.abs(gpo.fit["alpha"]))
         assert itb == gpb.fit["iters"] and itb > 2

@@ -87,6 +87,24 @@ def test_laplace_driver_single_rank_matches_oracle(lik):
     assert np.max(np.abs(fm - gpo.fit["fmean"])) < 1e-8 * np.max(np.abs(gpo.fit["fmean"]))
 
 
+@pytest.mark.parametrize("n,nb", [(768, 128), (1100, 256), (2048, 1024)])
+def test_energy_grad_driver_single_rank_matches_oracle(n, nb):
+    """SURVEY 8e "C^-1 + trace term": block-cyclic trtri / lauum sweeps + gpl_grad_trace_block_dev."""
+    from gplite_b200.dist import dist_energy_grad
+    rng = np.random.default_rng(n + 1)
+    X = rng.normal(size=(n, 3))
+    y = np.sin(X[:, 0]) + 0.4 * X[:, 1] + 0.3 * rng.normal(size=n)
+    gp = g.gp_init(cfs=[g.cf_matern32(lscale=1.1), g.cf_sexp(lscale=0.7, magn=0.5) * g.cf_lin(prior_magn=g.prior_fixed())],
+                   lik=g.lik_gaussian(sigma=0.4))
+    gpo = copy.deepcopy(gp)
+    e, gr = dist_energy_grad(gp, X, y, nb=nb, dist=OneRank)
+    eo, go = o.energy_grad_gaussian_full(gpo, X, y)
+    assert abs(e - eo) < 1e-8 * abs(eo)
+    assert np.max(np.abs(gr - go)) < 1e-7 * max(1.0, np.max(np.abs(go))), (gr, go)
+    e1, g1 = g.gp_energy_grad(copy.deepcopy(gpo), X, y)
+    assert np.max(np.abs(gr - g1)) < 1e-9 * max(1.0, np.max(np.abs(g1)))
+
+
 def test_fitc_driver_single_rank_matches_oracle():
     from gplite_b200.dist import dist_fit_fitc_gaussian
     rng = np.random.default_rng(8)

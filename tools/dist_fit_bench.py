@@ -39,6 +39,8 @@ def main():
     ap.add_argument("--check", action="store_true")
     ap.add_argument("--fitc", action="store_true", help="config 4: row-sharded FITC instead of the full GP")
     ap.add_argument("--inducing", type=int, default=4096)
+    ap.add_argument("--grad", action="store_true",
+                    help="energy + analytic gradient (distributed inverse: two more panel sweeps + block trace)")
     ap.add_argument("--bernoulli", action="store_true",
                     help="config 3 style: lik_bernoulli + cf_sexp*cf_lin, Laplace Newton loop over the sharded factor")
     args = ap.parse_args()
@@ -49,7 +51,7 @@ def main():
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     mk = {"matern32": g.cf_matern32, "matern52": g.cf_matern52, "sexp": g.cf_sexp}[args.kind]
 
-    if args.check:
+    if args.check and not args.grad:
         X, y = data(6000, args.d, 5)
         gp = g.gp_init(cfs=mk(lscale=1.3), lik=g.lik_gaussian(sigma=0.5))
         res = dist_fit_gaussian(gp, X, y, nb=256)
@@ -124,6 +126,35 @@ def main():
 
     X, y = data(args.n, args.d, 5)
     gp = g.gp_init(cfs=mk(lscale=1.3), lik=g.lik_gaussian(sigma=0.5))
+    if args.grad:
+        from gplite_b200.dist import dist_energy_grad
+        tm = {}
+        torch.cuda.synchronize()
+        dist.barrier()
+        t0 = time.perf_counter()
+        e, gr = dist_energy_grad(gp, X, y, nb=args.nb, timings=tm)
+        torch.cuda.synchronize()
+        vals = torch.tensor([tm["kbuild"], tm["factor"], tm["solve"], tm["trtri"], tm["lauum"], tm["trace"],
+                             time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+        dist.all_reduce(vals, op=dist.ReduceOp.MAX)
+        single = {}
+        if args.check and rank == 0 and args.n <= 40000:      # same evaluation on one GPU
+            e1, g1 = g.gp_energy_grad(g.gp_init(cfs=mk(lscale=1.3), lik=g.lik_gaussian(sigma=0.5)), X, y)
+            single = {"single_gpu_energy": e1, "energy_rel_diff": abs(e - e1) / abs(e1),
+                      "grad_max_rel_diff": float(np.max(np.abs(gr - g1)) / np.max(np.abs(g1)))}
+        if rank == 0:
+            kb, fa, so, ti, la, tr, tot = [float(v) for v in vals]
+            n = args.n
+            print(json.dumps({"workload": f"cfg5-style energy+gradient: full GP n={n}, d={args.d}, cf_{args.kind} + "
+                                          f"lik_gaussian, 1-D block-cyclic (nb={args.nb}) over {world} GPU(s)",
+                              "n_gpus": world, "kbuild_s": kb, "factor_s": fa, "solve_s": so, "trtri_s": ti,
+                              "lauum_s": la, "trace_s": tr, "total_s": tot,
+                              "evals_per_s": 1.0 / tot, "tflops_aggregate_of_n3": n ** 3 / tot / 1e12,
+                              "energy": e, "grad": [float(v) for v in gr],
+                              "matrix_gb_per_gpu": 2 * 8.0 * n * n / world / 1e9, **single}), flush=True)
+        dist.barrier()
+        dist.destroy_process_group()
+        return
     tm = {}
     torch.cuda.synchronize()
     dist.barrier()
