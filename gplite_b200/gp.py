@@ -211,12 +211,10 @@ def gp_fit(gp, x, y, trials=None, offset=None, jitter=None, ctx=None):
         else:
             _lib.check(status)                                # non-PD aborts (R/gp_fit.R:95-97)
     else:
-        zind = gp.method.inducing
-        if zind is None:
-            raise NotImplementedError(
-                "method_fitc needs explicit inducing points here (inducing=...): the reference's "
-                "k-means selection uses R's RNG (R/gp_fit.R:192-234) and is outside the hot path")
-        zind = _as_matrix(zind)
+        if gp.method.inducing is None:
+            gp.method.inducing = get_inducing(gp, x, ctx=ctx)      # kept for later fits (R/gp_fit.R:112)
+            gp.method.num_inducing = gp.method.inducing.shape[0]
+        zind = _as_matrix(gp.method.inducing)
         m = zind.shape[0]
         status = ctx.lib.gpl_fit_fitc(ctx.h, pm.ref(), C.byref(lik), C.byref(ap), _lib._ptr(x), n, d,
                                       _lib._ptr(zind), m, _lib._ptr(y), _lib._ptr(tr),
@@ -248,6 +246,61 @@ def gp_fit(gp, x, y, trials=None, offset=None, jitter=None, ctx=None):
     gp.fit["type"] = "analytic"
     gp.fitted = True
     return gp
+
+
+def kmeans_centers(x, m, rng, ctx=None, maxiter=10):
+    """stats::kmeans(x, m)$centers as used by get_inducing: Lloyd iterations on the device
+    (gpl_kmeans) from m distinct rows drawn with `rng`; x is used as given (already standardised)."""
+    ctx = ctx or _lib.default_context()
+    x = _as_matrix(x)
+    n, d = x.shape
+    if m > n:
+        raise ValueError("more cluster centers than distinct data points.")      # stats::kmeans' message
+    idx = np.ascontiguousarray(np.sort(rng.choice(n, size=m, replace=False)), dtype=np.int64)
+    cen = np.empty((m, d), dtype=np.float64, order="F")
+    iters = C.c_int32()
+    _lib.check(ctx.lib.gpl_kmeans(ctx.h, _lib._ptr(x), n, d, _lib._ptr(idx), m, int(maxiter), _lib._ptr(cen),
+                                  None, C.byref(iters)))
+    return cen, idx
+
+
+def _scale(x):
+    """R's scale(): centre, divide by the (n - 1) standard deviation."""
+    mu = x.mean(axis=0)
+    sd = x.std(axis=0, ddof=1)
+    return (x - mu) / sd, mu, sd
+
+
+def get_inducing(gp, x, ctx=None):
+    """R/gp_fit.R:190-234: k-means centres of the standardised inputs, optionally per bin along one
+    variable.  The reference seeds R's RNG with method$seed; here numpy's default_rng(seed) picks the
+    initial centres, so the points agree with the reference in distribution, not draw by draw."""
+    if gp.method.inducing is not None:
+        return gp.method.inducing
+    x = _as_matrix(x)
+    rng = np.random.default_rng(gp.method.seed)
+    m = int(gp.method.num_inducing)
+    if gp.method.bin_along is None:
+        xs, mu, sd = _scale(x)
+        zs, _ = kmeans_centers(xs, m, rng, ctx)
+        return np.asfortranarray(zs * sd + mu)
+    var = int(gp.method.bin_along) - 1                                 # R is 1-based
+    nb = int(gp.method.bin_count)
+    eps2 = 2 * np.finfo(np.float64).eps
+    cut = np.linspace(x[:, var].min() - eps2, x[:, var].max() + eps2, nb + 1)
+    bins = [x[(x[:, var] > cut[i]) & (x[:, var] < cut[i + 1])] for i in range(nb)]
+    bins.sort(key=lambda b: -b.shape[0])                               # order(bin_sizes, decreasing = TRUE)
+    per_bin = [m // nb] * nb
+    for i in range(m - sum(per_bin)):
+        per_bin[i] += 1
+    out = []
+    for xb, k in zip(bins, per_bin):
+        if k == 0:
+            continue
+        xs, mu, sd = _scale(xb)
+        zs, _ = kmeans_centers(xs, k, rng, ctx)
+        out.append(zs * sd + mu)
+    return np.asfortranarray(np.vstack(out))
 
 
 def fit_member(gp, what):

@@ -155,6 +155,17 @@ int gpl_dev_free(gpl_ctx* ctx, void* dptr);
 int gpl_memcpy_h2d(gpl_ctx* ctx, void* dst, const void* src, uint64_t bytes);
 int gpl_memcpy_d2h(gpl_ctx* ctx, void* dst, const void* src, uint64_t bytes);
 
+/* ---- inducing-point selection ---------------------------------------------- */
+
+/* k-means (Lloyd) on x (n x d host, column-major), as used by get_inducing (R/gp_fit.R:190-234;
+ * the reference calls stats::kmeans on the standardised inputs -- standardising is the caller's
+ * job).  init_idx: m distinct rows of x used as initial centres (the reference draws them with R's
+ * RNG, which cannot be reproduced outside R).  Stops when no assignment changes or after maxiter
+ * (stats::kmeans: 10).  centers: m x d column-major; labels (may be NULL): n; iters (may be NULL).
+ * Empty clusters keep their centre; ties go to the lowest centre index. */
+int gpl_kmeans(gpl_ctx* ctx, const double* x, int64_t n, int32_t d, const int64_t* init_idx, int64_t m,
+               int32_t maxiter, double* centers, int32_t* labels, int32_t* iters);
+
 /* ---- covariance matrices -------------------------------------------- */
 
 /* K = eval_cf(cfs, x1, x2, cfind)  [+ jitter on the diagonal when `same` != 0].

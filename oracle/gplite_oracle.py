@@ -561,6 +561,29 @@ def laplace_full(gp, K, y, maxiter=100, tol=1e-4, trials=None, offset=None):
     return fit
 
 
+def kmeans_lloyd(x, init_idx, maxiter=10):
+    """Deterministic restatement of what gpl_kmeans computes (the reference calls stats::kmeans,
+    R/gp_fit.R:221,228, whose Hartigan-Wong variant and RNG stream are R-only): Lloyd iterations
+    from the given initial rows, ties to the lowest centre index, empty clusters keep their centre,
+    stop when no assignment changes."""
+    x = _as_matrix(x)
+    cen = x[np.asarray(init_idx)].copy()
+    lab = np.full(len(x), -1)
+    it = 0
+    for it in range(1, maxiter + 1):
+        d2 = ((x[:, None, :] - cen[None, :, :]) ** 2).sum(axis=2)
+        new = np.argmin(d2, axis=1)
+        changed = np.any(new != lab)
+        lab = new
+        if not changed:
+            break
+        for c in range(len(cen)):
+            sel = lab == c
+            if sel.any():
+                cen[c] = x[sel].mean(axis=0)
+    return cen, lab, it
+
+
 def fitc_prepare(gp, x, z_ind, jitter):
     """R/gp_fit.R:105-110 (identical in :167-172)."""
     m = z_ind.shape[0]

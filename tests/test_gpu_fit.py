@@ -434,3 +434,46 @@ def test_non_log_concave_sites(ctx, approx, seed, phi):
     assert scaled_err(p["var"], po["var"]) < TOL
     with pytest.raises(g.GplError):
         g.fit_member(gp, "C_chol")
+
+
+@pytest.mark.parametrize("n,m,d", [(3000, 64, 3), (5000, 300, 6), (777, 5, 1), (2000, 130, 11)])
+def test_kmeans_inducing_vs_oracle(ctx, n, m, d):
+    """gpl_kmeans (device Lloyd) against the numpy restatement from the same initial rows."""
+    from gplite_b200.gp import kmeans_centers
+    rng = np.random.default_rng(n + m)
+    X = np.concatenate([rng.normal(size=(n // 2, d)), rng.normal(size=(n - n // 2, d)) * 0.5 + 2.0])
+    cen, idx = kmeans_centers(X, m, np.random.default_rng(5), ctx=ctx)
+    ceno, labo, ito = o.kmeans_lloyd(X, idx, maxiter=10)
+    assert scaled_err(cen, ceno) < 1e-10
+    # every centre is the mean of a non-empty cluster after at least one update
+    assert ito >= 2 and np.all(np.isfinite(cen))
+
+
+def test_method_fitc_default_inducing(ctx):
+    """method_fitc() without explicit inducing points: k-means selection (R/gp_fit.R:190-234), kept on
+    the model for later fits (R/gp_fit.R:112), also per bin along one input."""
+    rng = np.random.default_rng(3)
+    n = 1500
+    X = rng.uniform(-3, 3, size=(n, 2))
+    y = np.sin(X[:, 0]) * np.cos(0.5 * X[:, 1]) + 0.2 * rng.normal(size=n)
+    gp = g.gp_init(cfs=g.cf_sexp(lscale=1.0), lik=g.lik_gaussian(sigma=0.3), method=g.method_fitc(num_inducing=40))
+    g.gp_fit(gp, X, y, ctx=ctx)
+    z1 = gp.method.inducing.copy()
+    assert z1.shape == (40, 2) and np.isfinite(gp.fit["log_evidence"])
+    assert np.all(z1.min(axis=0) >= X.min(axis=0)) and np.all(z1.max(axis=0) <= X.max(axis=0))
+    # the oracle, given the same inducing points, agrees on the fit
+    gpo = g.gp_init(cfs=g.cf_sexp(lscale=1.0), lik=g.lik_gaussian(sigma=0.3), method=g.method_fitc(inducing=z1))
+    o.gp_fit(gpo, X, y)
+    assert abs(gp.fit["log_evidence"] - gpo.fit["log_evidence"]) < TOL * abs(gpo.fit["log_evidence"])
+    g.gp_fit(gp, X, y + 0.1, ctx=ctx)
+    assert np.array_equal(gp.method.inducing, z1)                 # chosen once
+    p = g.gp_pred(gp, X[:50], var=True)
+    assert np.sqrt(np.mean((p["mean"] - 0.1 - np.sin(X[:50, 0]) * np.cos(0.5 * X[:50, 1])) ** 2)) < 0.2
+    gpb = g.gp_init(cfs=g.cf_sexp(lscale=1.0), lik=g.lik_gaussian(sigma=0.3),
+                    method=g.method_fitc(num_inducing=23, bin_along=1, bin_count=5))
+    g.gp_fit(gpb, X, y, ctx=ctx)
+    zb = gpb.method.inducing
+    assert zb.shape == (23, 2) and np.isfinite(gpb.fit["log_evidence"])
+    cut = np.linspace(X[:, 0].min(), X[:, 0].max(), 6)
+    per_bin = np.histogram(zb[:, 0], bins=cut)[0]
+    assert sorted(per_bin.tolist()) == [4, 4, 5, 5, 5]

@@ -188,3 +188,13 @@ def test_bad_site_branch_block_elimination_equals_lu(approx):
     r = Kt[:, bad] - at @ W.T
     var = np.diag(o.eval_cf(gp.cfs, Xt, Xt)) - np.sum(at * at, axis=1) - np.sum(r * np.linalg.solve(S, r.T).T, axis=1)
     assert scaled_err(var, po["var"]) < 1e-10
+
+
+def test_kmeans_restatement_fixed_point():
+    rng = np.random.default_rng(2)
+    X = np.concatenate([rng.normal(size=(200, 2)) + c for c in ((0, 0), (4, 0), (0, 5))])
+    cen, lab, it = o.kmeans_lloyd(X, [0, 250, 450], maxiter=50)
+    assert it < 50
+    for c in range(3):
+        assert np.allclose(cen[c], X[lab == c].mean(axis=0))
+    assert np.all(np.abs(np.bincount(lab) - 200) <= 10)
