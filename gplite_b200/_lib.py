@@ -103,6 +103,8 @@ SIGNATURES = {
     "gpl_lik_pseudodata_la_dev": (C.c_int, [_P, C.POINTER(Lik), _I64, _P, _P, _P, _P, _P, _P]),
     "gpl_grad_trace_block_dev": (C.c_int, [_P, C.POINTER(CfModel), _P, _I64, _I32, _I64, _I64, _P, _I64, _P, _P,
                                            _I32, _P, _P, _P, C.POINTER(_D)]),
+    "gpl_pred_full_cov": (C.c_int, [_P, _P, C.POINTER(CfModel), _P, _I64, _U64, _D, _P, _P]),
+    "gpl_draw_full": (C.c_int, [_P, _P, C.POINTER(CfModel), _P, _I64, _I32, _U64, _D, _P, _I64, _P]),
     "gpl_kmeans": (C.c_int, [_P, _P, _I64, _I32, _P, _I64, _I32, _P, _P, C.POINTER(_I32)]),
     "gpl_lik_loglik_dev": (C.c_int, [_P, C.POINTER(Lik), _I64, _P, _P, _P, _P, C.POINTER(_D)]),
     "gpl_fit_full": (C.c_int, [_P, C.POINTER(CfModel), C.POINTER(Lik), C.POINTER(Approx), _P, _I64,

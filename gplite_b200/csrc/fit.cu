@@ -936,6 +936,124 @@ int pred_full_impl(Ctx* ctx, const Fit* fit, const gpl_cf_model* cf, const doubl
   return GPL_OK;
 }
 
+// ---- joint prediction / draws (gp_draw, R/gp_draw.R; gp_pred_post(cov = TRUE),
+// R/gp_pred.R:202-232).  d_mean: nt, d_cov: nt x nt (ld ldc) on the device, cov includes jitter.
+int pred_full_cov_dev(Ctx* ctx, const Fit* fit, const gpl_cf_model* cf, const double* xt, int64_t nt,
+                      uint64_t term_mask, double jitter, double* d_mean, double* d_cov, int64_t ldc) {
+  const int64_t n = fit->n, ng = fit->ng, nb = fit->nb;
+  const int d = fit->d;
+  if ((double)nt * (double)n * 8.0 > 48e9) {
+    set_error("joint prediction of %lld points against n = %lld needs a %0.f GB cross-covariance; "
+              "predict fewer points at a time", (long long)nt, (long long)n, 8e-9 * nt * n);
+    return GPL_ERR_NOMEM;
+  }
+  HostPlan hp;
+  GPL_TRY(make_plan(cf, d, term_mask, &hp));
+  const int F = hp.plan.nfeat > 0 ? hp.plan.nfeat : 1;
+  const double* xtrain = nb > 0 ? fit->xp.d() : fit->x.d();
+  const double* alpha = nb > 0 ? fit->alpha_p.d() : fit->alpha.d();
+  DevBuf dxt, Zx, Zt, Kt, sinv;
+  const int64_t ldk = round_up(nt, 16);
+  GPL_TRY(upload(ctx, dxt, xt, (size_t)nt * d));
+  GPL_TRY(Zx.alloc(ctx, sizeof(double) * n * F));
+  GPL_TRY(Zt.alloc(ctx, sizeof(double) * nt * F));
+  GPL_TRY(prep_features(ctx, hp, xtrain, n, n, Zx.d(), n));
+  GPL_TRY(prep_features(ctx, hp, dxt.d(), nt, nt, Zt.d(), nt));
+  GPL_TRY(Kt.alloc(ctx, sizeof(double) * ldk * n));
+  GPL_TRY(sinv.alloc(ctx, sizeof(double) * n));
+  GPL_TRY(cf_pairwise(ctx, hp.plan, Zt.d(), nt, nt, Zx.d(), n, n, false, 0.0, Kt.d(), ldk));
+  GPL_TRY(gemv_n(ctx, nt, n, Kt.d(), ldk, alpha, d_mean));
+  GPL_TRY(cf_pairwise(ctx, hp.plan, Zt.d(), nt, nt, nullptr, nt, nt, true, jitter, d_cov, ldc));
+  GPL_TRY(vec_op(ctx, VOP_INV, ng, fit->sqrtV.d(), nullptr, sinv.d()));
+  GPL_TRY(scale_cols(ctx, nt, ng, Kt.d(), ldk, sinv.d()));
+  GPL_TRY(dtrsm_right_with(ctx, fit->dinv.d(), true, nt, ng, fit->Lb.d(), fit->ld, Kt.d(), ldk));
+  GPL_TRY(dgemm(ctx, false, true, nt, nt, ng, -1.0, Kt.d(), ldk, Kt.d(), ldk, 1.0, d_cov, ldc, false));
+  if (nb > 0) {
+    // cov -= r S^-1 r^T = (r V_b^-1) r^T - H H^T,  H = (r V_b^-1) Lk A_chol^-T   (cf. bad_quad)
+    double* R = Kt.d() + ng * ldk;
+    GPL_TRY(dgemm(ctx, false, true, nt, nb, ng, -1.0, Kt.d(), ldk, fit->W.d(), fit->ldw, 1.0, R, ldk,
+                  false));
+    DevBuf G, H;
+    GPL_TRY(G.alloc(ctx, sizeof(double) * ldk * nb));
+    GPL_TRY(H.alloc(ctx, sizeof(double) * ldk * nb));
+    GPL_TRY(copy_block(ctx, nt, nb, R, ldk, G.d(), ldk));
+    GPL_TRY(scale_cols(ctx, nt, nb, G.d(), ldk, fit->invVb.d()));
+    GPL_TRY(dgemm(ctx, false, false, nt, nb, nb, 1.0, G.d(), ldk, fit->Lk.d(), fit->ldp, 0.0, H.d(),
+                  ldk, false));
+    GPL_TRY(dtrsm_right_with(ctx, fit->Ac_dinv.d(), true, nt, nb, fit->Ac.d(), fit->ldp, H.d(), ldk));
+    GPL_TRY(dgemm(ctx, false, true, nt, nt, nb, -1.0, G.d(), ldk, R, ldk, 1.0, d_cov, ldc, false));
+    GPL_TRY(dgemm(ctx, false, true, nt, nt, nb, 1.0, H.d(), ldk, H.d(), ldk, 1.0, d_cov, ldc, false));
+  }
+  return GPL_OK;
+}
+
+int pred_full_cov_impl(Ctx* ctx, const Fit* fit, const gpl_cf_model* cf, const double* xt, int64_t nt,
+                       uint64_t term_mask, double jitter, double* mean, double* cov) {
+  if (!fit || fit->method != 0 || nt <= 0 || !xt || !mean || !cov) {
+    set_error("gpl_pred_full_cov: bad arguments");
+    return GPL_ERR_BAD_ARG;
+  }
+  DevBuf dm, dc;
+  const int64_t ldc = round_up(nt, 16);
+  GPL_TRY(dm.alloc(ctx, sizeof(double) * nt));
+  GPL_TRY(dc.alloc(ctx, sizeof(double) * ldc * nt));
+  GPL_TRY(pred_full_cov_dev(ctx, fit, cf, xt, nt, term_mask, jitter, dm.d(), dc.d(), ldc));
+  GPL_TRY(download(ctx, mean, dm.d(), nt));
+  GPL_CUDA(cudaMemcpy2DAsync(cov, sizeof(double) * nt, dc.d(), sizeof(double) * ldc,
+                             sizeof(double) * nt, nt, cudaMemcpyDeviceToHost, ctx->stream));
+  GPL_CUDA(cudaStreamSynchronize(ctx->stream));
+  return GPL_OK;
+}
+
+// out (nt x draws) = mean + chol(cov) normals.  fit == NULL: draws from the prior at xt (nt x d),
+// mean 0, cov = K(xt, xt) + jitter I (gp_draw_prior.method_full, R/gp_draw.R:66-78).
+int draw_full_impl(Ctx* ctx, const Fit* fit, const gpl_cf_model* cf, const double* xt, int64_t nt,
+                   int d_prior, uint64_t term_mask, double jitter, const double* normals,
+                   int64_t draws, double* out) {
+  if ((fit && fit->method != 0) || nt <= 0 || draws <= 0 || !xt || !normals || !out ||
+      (!fit && d_prior <= 0)) {
+    set_error("gpl_draw_full: bad arguments");
+    return GPL_ERR_BAD_ARG;
+  }
+  DevBuf dm, dc, dcd, Lc, dn, dout;
+  const int64_t ldc = round_up(nt, 16);
+  GPL_TRY(dm.alloc(ctx, sizeof(double) * nt));
+  GPL_TRY(dc.alloc(ctx, sizeof(double) * ldc * nt));
+  GPL_TRY(Lc.alloc(ctx, sizeof(double) * ldc * nt));
+  GPL_TRY(dcd.alloc(ctx, sizeof(double) * ((nt + NB - 1) / NB) * NB * NB));
+  if (fit) {
+    GPL_TRY(pred_full_cov_dev(ctx, fit, cf, xt, nt, term_mask, jitter, dm.d(), dc.d(), ldc));
+  } else {
+    HostPlan hp;
+    GPL_TRY(make_plan(cf, d_prior, term_mask, &hp));
+    const int F = hp.plan.nfeat > 0 ? hp.plan.nfeat : 1;
+    DevBuf dxt, Zt;
+    GPL_TRY(upload(ctx, dxt, xt, (size_t)nt * d_prior));
+    GPL_TRY(Zt.alloc(ctx, sizeof(double) * nt * F));
+    GPL_TRY(prep_features(ctx, hp, dxt.d(), nt, nt, Zt.d(), nt));
+    GPL_TRY(cf_pairwise(ctx, hp.plan, Zt.d(), nt, nt, nullptr, nt, nt, true, jitter, dc.d(), ldc));
+    GPL_TRY(vec_op(ctx, VOP_FILL, nt, nullptr, nullptr, dm.d(), 0.0));
+    GPL_CUDA(cudaStreamSynchronize(ctx->stream));     // dxt, Zt are released at scope exit
+  }
+  int32_t info = 0;
+  GPL_TRY(dpotrf_with(ctx, dcd.d(), nt, dc.d(), ldc, &info, nullptr));       // t(chol(pred$cov))
+  GPL_TRY(tril_scale(ctx, nt, dc.d(), ldc, nullptr, Lc.d(), ldc));
+  const int64_t ldn = round_up(nt, 16);
+  GPL_TRY(dn.alloc(ctx, sizeof(double) * ldn * draws));
+  GPL_TRY(dout.alloc(ctx, sizeof(double) * ldn * draws));
+  GPL_CUDA(cudaMemcpy2DAsync(dn.d(), sizeof(double) * ldn, normals, sizeof(double) * nt,
+                             sizeof(double) * nt, draws, cudaMemcpyHostToDevice, ctx->stream));
+  GPL_TRY(dgemm(ctx, false, false, nt, draws, nt, 1.0, Lc.d(), ldc, dn.d(), ldn, 0.0, dout.d(), ldn,
+                false));
+  // + mean on every column: rows scaled by 1 and shifted -- reuse scale_block's machinery via axpy
+  for (int64_t j = 0; j < draws; ++j)
+    GPL_TRY(vec_op(ctx, VOP_ADD, nt, dout.d() + j * ldn, dm.d(), dout.d() + j * ldn));
+  GPL_CUDA(cudaMemcpy2DAsync(out, sizeof(double) * nt, dout.d(), sizeof(double) * ldn,
+                             sizeof(double) * nt, draws, cudaMemcpyDeviceToHost, ctx->stream));
+  GPL_CUDA(cudaStreamSynchronize(ctx->stream));
+  return GPL_OK;
+}
+
 int fit_get_impl(Ctx* ctx, const Fit* fit, const char* what, double* out) {
   if (!fit || !what || !out) return GPL_ERR_BAD_ARG;
   const int64_t n = fit->n;
@@ -1019,6 +1137,19 @@ int gpl_grad_trace_block_dev(gpl_ctx* h, const gpl_cf_model* cf, const double* x
   return gpl::grad_trace_block_impl(reinterpret_cast<gpl::Ctx*>(h), cf, x, n, d, col0, ncols,
                                     Cinv_blk, ld, s, alpha, nparam, param_factor, param_slot, out,
                                     diag_sum);
+}
+
+int gpl_pred_full_cov(gpl_ctx* h, const gpl_fit* fit, const gpl_cf_model* cf, const double* xt,
+                      int64_t nt, uint64_t term_mask, double jitter, double* mean, double* cov) {
+  return gpl::pred_full_cov_impl(reinterpret_cast<gpl::Ctx*>(h), reinterpret_cast<const gpl::Fit*>(fit),
+                                 cf, xt, nt, term_mask, jitter, mean, cov);
+}
+
+int gpl_draw_full(gpl_ctx* h, const gpl_fit* fit, const gpl_cf_model* cf, const double* xt, int64_t nt,
+                  int32_t d, uint64_t term_mask, double jitter, const double* normals, int64_t draws,
+                  double* out) {
+  return gpl::draw_full_impl(reinterpret_cast<gpl::Ctx*>(h), reinterpret_cast<const gpl::Fit*>(fit), cf,
+                             xt, nt, d, term_mask, jitter, normals, draws, out);
 }
 
 int gpl_pred_full(gpl_ctx* h, const gpl_fit* fit, const gpl_cf_model* cf, const double* xt,

@@ -500,6 +500,82 @@ def gp_pred(gp, xnew, var=False, quantiles=None, transform=False, cfind=None, ji
     return pred
 
 
+# ------------------------------------------------------------------------------- gp_draw
+def gp_pred_cov(gp, xnew, cfind=None, jitter=None, ctx=None):
+    """gp_pred_post / gp_pred_prior with cov = TRUE (R/gp_pred.R:142-156, 202-232), method_full:
+    dict(mean, cov) of the latent, jitter on the diagonal of cov."""
+    xnew = _as_matrix(xnew)
+    nt = xnew.shape[0]
+    jit = 1e-6 if jitter is None else float(jitter)
+    if not is_fitted(gp, "analytic"):
+        K = eval_cf(gp.cfs, xnew, xnew, cfind=cfind, ctx=ctx)
+        return dict(mean=np.zeros(nt), cov=K + jit * np.eye(nt))
+    if gp.method.name != "full":
+        raise NotImplementedError("joint predictive covariance is implemented for method_full")
+    c = gp._ctx
+    factors, _ = M.flatten_cfs(gp.cfs)
+    pm = _lib.PackedModel(factors)
+    mean = np.empty(nt)
+    cov = np.empty((nt, nt), order="F")
+    _lib.check(c.lib.gpl_pred_full_cov(c.h, gp._handle, pm.ref(), _lib._ptr(xnew), nt, _term_mask(gp, cfind),
+                                       jit, _lib._ptr(mean), _lib._ptr(cov)))
+    return dict(mean=mean, cov=cov)
+
+
+def generate_target(lik, f, rng, trials=None):
+    """R/lik.R:502-537: sample observations given latent values (one column per draw)."""
+    mu = _get_response(lik, f)
+    if lik.name == "lik_gaussian":
+        return rng.standard_normal(f.shape) * lik.sigma + f
+    if lik.name == "lik_poisson":
+        return rng.poisson(mu).astype(float)
+    t = np.ones(f.shape[0]) if lik.name == "lik_bernoulli" else np.asarray(trials, dtype=np.float64)
+    t = np.broadcast_to(t.reshape(-1, *([1] * (f.ndim - 1))), f.shape).astype(np.int64)
+    if lik.name == "lik_betabinom":
+        mu = rng.beta(mu / lik.phi, (1 - mu) / lik.phi)
+    return rng.binomial(t, mu).astype(float)
+
+
+def gp_draw(gp, xnew, draws=1, transform=True, target=False, marginal=False, cfind=None, jitter=None,
+            seed=None, offset=None, trials=None, normals=None, ctx=None):
+    """R/gp_draw.R:8-123: draws from the posterior (fitted model) or prior of the latent function at
+    xnew, nt x draws.  The joint draw mean + t(chol(cov)) z runs on the device (gpl_draw_full);
+    z comes from numpy's default_rng(seed) -- or `normals` -- instead of R's rnorm stream."""
+    xnew = _as_matrix(xnew)
+    nt = xnew.shape[0]
+    draws = int(draws or 1)
+    rng = np.random.default_rng(seed)
+    if normals is None:
+        normals = rng.standard_normal((nt, draws))
+    normals = np.asfortranarray(np.asarray(normals, dtype=np.float64).reshape(nt, draws))
+    jit = 1e-6 if jitter is None else float(jitter)
+    fitted = is_fitted(gp, "analytic")
+    if fitted and "alpha" not in gp.fit:
+        raise RuntimeError("the fit failed (log_evidence = -Inf); cannot draw")
+    if fitted and marginal:                                      # R/gp_draw.R:107-110,127-130
+        pred = gp_pred(gp, xnew, var=True, cfind=cfind, jitter=jitter, ctx=ctx)
+        sample = pred["mean"][:, None] + np.sqrt(pred["var"])[:, None] * normals
+    else:
+        if gp.method.name != "full":
+            raise NotImplementedError("joint draws are implemented for method_full (use marginal=True for FITC)")
+        c = gp._ctx if fitted else (ctx or _lib.default_context())
+        factors, _ = M.flatten_cfs(gp.cfs)
+        pm = _lib.PackedModel(factors)
+        if fitted and xnew.shape[1] != gp.x.shape[1]:
+            raise ValueError("xnew has a different number of columns than the training inputs")
+        sample = np.empty((nt, draws), order="F")
+        _lib.check(c.lib.gpl_draw_full(c.h, gp._handle if fitted else None, pm.ref(), _lib._ptr(xnew), nt,
+                                       xnew.shape[1], _term_mask(gp, cfind), jit, _lib._ptr(normals), draws,
+                                       _lib._ptr(sample)))
+    if offset is not None:
+        sample = sample + np.asarray(offset, dtype=np.float64).reshape(-1, 1)
+    if target:
+        sample = generate_target(gp.lik, sample, rng, trials=trials)
+    elif transform:
+        sample = _get_response(gp.lik, sample)
+    return sample
+
+
 # ------------------------------------------------------------------------------- gp_loo (SURVEY 8f rank 1)
 def _get_loglik_grid(lik, fgrid, y, trials=None, offset=None):
     """get_loglik(..., sum = FALSE) on an n x q grid (R/lik.R:297-366).  Host side: n*q values."""

@@ -902,6 +902,23 @@ def gp_pred_post_full(gp, xt, var=False, cov=False, cfind=None, jitter=None):
     return dict(mean=mean)
 
 
+def gp_draw_latent(gp, xt, normals, marginal=False, cfind=None, jitter=None):
+    """Latent part of gp_draw (R/gp_draw.R:66-78,105-123; mvnrnd :183-207) for method_full with
+    the standard normal variates supplied: mean + t(chol(cov)) %*% normals, or the marginal form
+    mean + sqrt(var) * normals; prior (mean 0, K(xt, xt) + jitter I) when the model is not fitted."""
+    xt = _as_matrix(xt)
+    nt = len(xt)
+    jit = 1e-6 if jitter is None else jitter
+    if not getattr(gp, "fitted", False):
+        cov = eval_cf(gp.cfs, xt, xt, cfind) + jit * np.eye(nt)          # R/gp_pred.R:142-156
+        return _chol_lower(cov) @ normals
+    if marginal:
+        pred = gp_pred_post_full(gp, xt, var=True, cfind=cfind, jitter=jitter)
+        return pred["mean"][:, None] + np.sqrt(pred["var"])[:, None] * normals
+    pred = gp_pred_post_full(gp, xt, cov=True, cfind=cfind, jitter=jitter)
+    return pred["mean"][:, None] + _chol_lower(pred["cov"]) @ normals
+
+
 def gp_pred_post_fitc(gp, xt, var=False, cfind=None, jitter=None, train=False):
     """R/gp_pred.R:234-296 (mean and var; cov=TRUE not restated)."""
     z_ind = _as_matrix(gp.method.inducing)

@@ -477,3 +477,53 @@ def test_method_fitc_default_inducing(ctx):
     cut = np.linspace(X[:, 0].min(), X[:, 0].max(), 6)
     per_bin = np.histogram(zb[:, 0], bins=cut)[0]
     assert sorted(per_bin.tolist()) == [4, 4, 5, 5, 5]
+
+
+def test_gp_draw_and_joint_covariance(ctx):
+    """gp_draw (prior, posterior joint and marginal) and gp_pred_post(cov = TRUE) for
+    method_full against the oracle with the same standard normal variates; also on a fit with
+    non-log-concave sites (the reference's C_lu prediction branch)."""
+    rng = np.random.default_rng(12)
+    n, nt, draws = 300, 57, 4
+    X = rng.normal(size=(n, 2))
+    y = np.sin(X[:, 0]) + 0.3 * X[:, 1] + 0.2 * rng.normal(size=n)
+    Xt = rng.normal(size=(nt, 2))
+    Zn = rng.standard_normal((nt, draws))
+    cfs = [g.cf_matern52(lscale=0.9), g.cf_lin(magn=0.4)]
+    gp = g.gp_init(cfs=cfs, lik=g.lik_gaussian(sigma=0.3))
+    gpo = copy.deepcopy(gp)
+    # prior draw (unfitted model)
+    s0 = g.gp_draw(gp, Xt, draws=draws, normals=Zn, transform=False, ctx=ctx)
+    assert scaled_err(s0, o.gp_draw_latent(gpo, Xt, Zn)) < 1e-7         # chol of a jitter-regularised matrix
+    g.gp_fit(gp, X, y, ctx=ctx)
+    o.gp_fit(gpo, X, y)
+    pc = g.gp_pred_cov(gp, Xt)
+    pco = o.gp_pred_post_full(gpo, Xt, cov=True)
+    assert scaled_err(pc["mean"], pco["mean"]) < TOL and scaled_err(pc["cov"], pco["cov"]) < TOL
+    s1 = g.gp_draw(gp, Xt, draws=draws, normals=Zn, transform=False)
+    assert scaled_err(s1, o.gp_draw_latent(gpo, Xt, Zn)) < 1e-6
+    s2 = g.gp_draw(gp, Xt, draws=draws, normals=Zn, marginal=True, cfind=[0])
+    assert scaled_err(s2, o.gp_draw_latent(gpo, Xt, Zn, marginal=True, cfind=[0])) < TOL
+    # seeded draws are reproducible, targets have the likelihood's noise
+    a = g.gp_draw(gp, Xt, draws=3, seed=5)
+    b = g.gp_draw(gp, Xt, draws=3, seed=5)
+    assert np.array_equal(a, b) and a.shape == (nt, 3)
+    t = g.gp_draw(gp, Xt, draws=200, seed=6, target=True)
+    f = g.gp_draw(gp, Xt, draws=200, seed=6)
+    assert abs(np.std(t - f) - 0.3) < 0.03
+    # classification + bad sites
+    Xc, yc, trials = outlier_counts(44)
+    gpc = g.gp_init(cfs=g.cf_sexp(lscale=1.0), lik=g.lik_betabinom(phi=0.3))
+    gpco = copy.deepcopy(gpc)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        g.gp_fit(gpc, Xc, yc, trials=trials, ctx=ctx)
+        o.gp_fit(gpco, Xc, yc, trials=trials)
+    assert gpc.fit["n_bad"] > 0
+    pc = g.gp_pred_cov(gpc, Xt)
+    pco = o.gp_pred_post_full(gpco, Xt, cov=True)
+    assert scaled_err(pc["cov"], pco["cov"]) < TOL
+    pr = g.gp_draw(gpc, Xt, draws=2, seed=1)
+    assert np.all((pr > 0) & (pr < 1))
+    tr = g.gp_draw(gpc, Xt, draws=2, seed=1, target=True, trials=np.full(nt, 7.0))
+    assert np.all((tr >= 0) & (tr <= 7) & (tr == np.round(tr)))
