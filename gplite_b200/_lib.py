@@ -54,6 +54,11 @@ class Approx(C.Structure):
                 ("quad_w", C.POINTER(C.c_double))]
 
 
+class RfSpec(C.Structure):
+    _fields_ = [("nterms", C.c_int32), ("num_basis", C.POINTER(C.c_int32)),
+                ("weights", C.POINTER(C.c_double)), ("nweights", C.c_int64)]
+
+
 class FitOut(C.Structure):
     _fields_ = [("log_evidence", C.c_double), ("iters", C.c_int32), ("converged", C.c_int32),
                 ("quad_ok", C.c_int32), ("n_bad", C.c_int32)]
@@ -105,6 +110,9 @@ SIGNATURES = {
                                            _I32, _P, _P, _P, C.POINTER(_D)]),
     "gpl_pred_full_cov": (C.c_int, [_P, _P, C.POINTER(CfModel), _P, _I64, _U64, _D, _P, _P]),
     "gpl_draw_full": (C.c_int, [_P, _P, C.POINTER(CfModel), _P, _I64, _I32, _U64, _D, _P, _I64, _P]),
+    "gpl_fit_rf": (C.c_int, [_P, C.POINTER(CfModel), C.POINTER(Lik), C.POINTER(Approx), C.POINTER(RfSpec), _P,
+                             _I64, _I32, _P, _P, _P, C.POINTER(FitOut), _P, _P, _P, _P, C.POINTER(_P)]),
+    "gpl_pred_rf": (C.c_int, [_P, _P, C.POINTER(CfModel), _P, _I64, _U64, _P, _P]),
     "gpl_kmeans": (C.c_int, [_P, _P, _I64, _I32, _P, _I64, _I32, _P, _P, C.POINTER(_I32)]),
     "gpl_lik_loglik_dev": (C.c_int, [_P, C.POINTER(Lik), _I64, _P, _P, _P, _P, C.POINTER(_D)]),
     "gpl_fit_full": (C.c_int, [_P, C.POINTER(CfModel), C.POINTER(Lik), C.POINTER(Approx), _P, _I64,

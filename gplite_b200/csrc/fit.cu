@@ -1057,7 +1057,7 @@ int draw_full_impl(Ctx* ctx, const Fit* fit, const gpl_cf_model* cf, const doubl
 int fit_get_impl(Ctx* ctx, const Fit* fit, const char* what, double* out) {
   if (!fit || !what || !out) return GPL_ERR_BAD_ARG;
   const int64_t n = fit->n;
-  if (!strcmp(what, "alpha")) {
+  if (!strcmp(what, "alpha") && fit->method != 2) {
     GPL_TRY(download(ctx, out, fit->alpha.d(), n));
     GPL_CUDA(cudaStreamSynchronize(ctx->stream));
     return GPL_OK;
@@ -1089,6 +1089,17 @@ int fit_get_impl(Ctx* ctx, const Fit* fit, const char* what, double* out) {
       for (int64_t j = 1; j < cols; ++j)
         for (int64_t i = 0; i < j; ++i) out[j * rows + i] = 0.0;
     }
+    return GPL_OK;
+  }
+  if (fit->method == 2 && (!strcmp(what, "wcov") || !strcmp(what, "wmean"))) {
+    const int64_t M = fit->m;
+    if (!strcmp(what, "wmean")) {
+      GPL_TRY(download(ctx, out, fit->alpha.d(), M));
+    } else {
+      GPL_CUDA(cudaMemcpy2DAsync(out, sizeof(double) * M, fit->Lm.d(), sizeof(double) * fit->ldm,
+                                 sizeof(double) * M, M, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    GPL_CUDA(cudaStreamSynchronize(ctx->stream));
     return GPL_OK;
   }
   set_error("gpl_fit_get: unknown member '%s'", what);

@@ -3,6 +3,8 @@
 
 #include "cf.cuh"
 
+#include <vector>
+
 namespace gpl {
 
 // chol.cu (explicit block-inverse buffer variants)
@@ -61,6 +63,10 @@ int tril_scale(Ctx* ctx, int64_t n, const double* L, int64_t ldl, const double* 
 // out_i = sum_j A_ij^2 w_j
 int rowsumsq_w(Ctx* ctx, int64_t m, int64_t n, const double* A, int64_t lda, const double* w,
                double* out);
+
+// out_i = sum_j A_ij B_ij
+int rowdot(Ctx* ctx, int64_t m, int64_t n, const double* A, int64_t lda, const double* B, int64_t ldb,
+           double* out);
 
 enum VecOp {
   VOP_DIV = 0,        // out = a / b
@@ -140,7 +146,8 @@ int grad_trace(Ctx* ctx, const CfPlan& plan, const double* z, int64_t ldz, const
 
 // ---- fit object --------------------------------------------------------------------------------
 struct Fit {
-  int method = 0;        // 0 full, 1 fitc
+  int method = 0;        // 0 full, 1 fitc, 2 rf (m = basis functions, Lm = wcov, alpha = wmean,
+                         //                        zind = random weights)
   int64_t n = 0, m = 0;
   int d = 0;
   int64_t ld = 0;        // leading dimension of Lb
@@ -172,6 +179,9 @@ struct Fit {
   DevBuf Ac, Ac_dinv;    // nb x nb factor of A
   int64_t ldp = 0;
   DevBuf invVb;          // nb: 1 / V_bad
+  // method_rf
+  std::vector<int32_t> rf_num_basis;
+  int64_t rf_nweights = 0;
 };
 
 }  // namespace gpl

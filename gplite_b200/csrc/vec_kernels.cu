@@ -532,6 +532,16 @@ __global__ void rowsumsq_w_kernel(int64_t m, int64_t n, const double* __restrict
   out[i] = s;
 }
 
+// out_i = sum_j A_ij B_ij
+__global__ void rowdot_kernel(int64_t m, int64_t n, const double* __restrict__ A, int64_t lda,
+                              const double* __restrict__ B, int64_t ldb, double* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= m) return;
+  double s = 0.0;
+  for (int64_t j = 0; j < n; ++j) s = fma(A[j * lda + i], B[j * ldb + i], s);
+  out[i] = s;
+}
+
 // bad-site EP evidence terms (R/ep.R:112-114): sum logZ + 0.5 sum log((vc+V)/V) + 0.5 sum (mc-z)^2/(vc+V)
 __global__ void ep_evidence_bad_kernel(int64_t n, const double* __restrict__ logZ,
                                        const double* __restrict__ vc, const double* __restrict__ mc,
@@ -783,6 +793,14 @@ int rowsumsq_w(Ctx* ctx, int64_t m, int64_t n, const double* A, int64_t lda, con
                double* out) {
   if (m <= 0) return GPL_OK;
   rowsumsq_w_kernel<<<(unsigned)((m + 255) / 256), 256, 0, ctx->stream>>>(m, n, A, lda, w, out);
+  GPL_LAUNCH_CHECK(ctx);
+  return GPL_OK;
+}
+
+int rowdot(Ctx* ctx, int64_t m, int64_t n, const double* A, int64_t lda, const double* B, int64_t ldb,
+           double* out) {
+  if (m <= 0) return GPL_OK;
+  rowdot_kernel<<<(unsigned)((m + 255) / 256), 256, 0, ctx->stream>>>(m, n, A, lda, B, ldb, out);
   GPL_LAUNCH_CHECK(ctx);
   return GPL_OK;
 }

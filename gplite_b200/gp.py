@@ -190,7 +190,7 @@ def gp_fit(gp, x, y, trials=None, offset=None, jitter=None, ctx=None):
     pm = _lib.PackedModel(factors)
     lik = _pack_lik(gp.lik)
     meth = gp.method.name
-    if meth not in ("full", "fitc"):
+    if meth not in ("full", "fitc", "rf"):
         raise NotImplementedError(f"method_{meth} is outside the GPU hot path (SURVEY section 2)")
     ap, keep = _pack_approx(gp, fitc=(meth == "fitc"))
     tr = _vec(trials, n)
@@ -203,7 +203,22 @@ def gp_fit(gp, x, y, trials=None, offset=None, jitter=None, ctx=None):
     args_tail = [jit, C.byref(out)] + [_lib._ptr(vec[k]) for k in
                                        ("fmean", "z", "V", "alpha", "fvar", "cavity_mean", "cavity_var")] \
         + [C.byref(handle)]
-    if meth == "full":
+    if meth == "rf":
+        if gp.approx.name != "laplace":
+            raise NotImplementedError("No EP implementation for method_rf yet.")      # R/gp_fit.R:146-148
+        nbasis = M.check_num_basis(gp.cfs, gp.method.num_basis, d)
+        gp.method.num_basis = nbasis                                                   # R/gp_fit.R:128
+        w = np.ascontiguousarray(M.rf_weights(gp.cfs, nbasis, d, gp.method.seed))
+        nb_arr = np.ascontiguousarray(nbasis, dtype=np.int32)
+        spec = _lib.RfSpec(len(nbasis), nb_arr.ctypes.data_as(C.POINTER(C.c_int32)),
+                           w.ctypes.data_as(C.POINTER(C.c_double)), len(w))
+        wmean = np.empty(int(sum(nbasis)))
+        _lib.check(ctx.lib.gpl_fit_rf(ctx.h, pm.ref(), C.byref(lik), C.byref(ap), C.byref(spec), _lib._ptr(x),
+                                      n, d, _lib._ptr(y), _lib._ptr(tr), _lib._ptr(off), C.byref(out),
+                                      _lib._ptr(vec["fmean"]), _lib._ptr(vec["z"]), _lib._ptr(vec["V"]),
+                                      _lib._ptr(wmean), C.byref(handle)))
+        status = _lib.GPL_OK
+    elif meth == "full":
         status = ctx.lib.gpl_fit_full(ctx.h, pm.ref(), C.byref(lik), C.byref(ap), _lib._ptr(x), n, d,
                                       _lib._ptr(y), _lib._ptr(tr), _lib._ptr(off), *args_tail)
         if status == _lib.GPL_ERR_NONFINITE:
@@ -232,6 +247,9 @@ def gp_fit(gp, x, y, trials=None, offset=None, jitter=None, ctx=None):
         if out.n_bad > 500:                                   # R/laplace.R:48-50, R/ep.R:59-61
             warnings.warn("More than 500 data points with pseudo-variance < 0 (outliers), computation "
                           "getting slow. Check that the model and hyperparameter values are sensible.")
+        if meth == "rf":
+            fit.pop("alpha")
+            fit["wmean"] = wmean
         if gp.approx.name == "ep":
             fit.update(fvar=vec["fvar"], cavity_mean=vec["cavity_mean"], cavity_var=vec["cavity_var"],
                        P=1.0 / vec["V"], quad_ok=bool(out.quad_ok))
@@ -307,7 +325,9 @@ def fit_member(gp, what):
     """Materialise a device-resident member of gp$fit on demand ("C_chol", "alpha")."""
     n = gp.x.shape[0]
     m = gp.method.inducing.shape[0] if gp.method.name == "fitc" else 0
-    shape = {"C_chol": (n, n), "alpha": (n,), "Kxz": (n, m), "Kz_chol": (m, m)}[what]
+    M_rf = int(sum(gp.method.num_basis)) if gp.method.name == "rf" else 0
+    shape = {"C_chol": (n, n), "alpha": (n,), "Kxz": (n, m), "Kz_chol": (m, m), "wmean": (M_rf,),
+             "wcov": (M_rf, M_rf)}[what]
     out = np.empty(shape, dtype=np.float64, order="F")
     _lib.check(gp._ctx.lib.gpl_fit_get(gp._ctx.h, gp._handle, what.encode(), _lib._ptr(out)))
     return out
@@ -470,14 +490,14 @@ def gp_pred(gp, xnew, var=False, quantiles=None, transform=False, cfind=None, ji
         if var:
             pred["var"] = eval_cf(gp.cfs, xnew, xnew, cfind=cfind, diag_only=True, ctx=ctx)
     else:
-        if "alpha" not in gp.fit:
+        if "alpha" not in gp.fit and "wmean" not in gp.fit:
             raise RuntimeError("the fit failed (log_evidence = -Inf); cannot predict")
         c = gp._ctx
         factors, _ = M.flatten_cfs(gp.cfs)
         pm = _lib.PackedModel(factors)
         mean = np.empty(nt)
         v = np.empty(nt) if var else None
-        fn = c.lib.gpl_pred_full if gp.method.name == "full" else c.lib.gpl_pred_fitc
+        fn = {"full": c.lib.gpl_pred_full, "fitc": c.lib.gpl_pred_fitc, "rf": c.lib.gpl_pred_rf}[gp.method.name]
         if xnew.shape[1] != gp.x.shape[1]:
             raise ValueError("xnew has a different number of columns than the training inputs")
         _lib.check(fn(c.h, gp._handle, pm.ref(), _lib._ptr(xnew), nt, _term_mask(gp, cfind),

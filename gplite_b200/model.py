@@ -243,7 +243,51 @@ def method_fitc(inducing=None, num_inducing=100, bin_along=None, bin_count=10, s
 
 
 def method_rf(num_basis=400, seed=12345):
+    """R/method.R:129-133: random features (linearised GP).  num_basis: one number or one per cf."""
     return Method("rf", seed=seed, num_basis=num_basis)
+
+
+def check_num_basis(cfs, num_basis, num_inputs):
+    """R/gp.R:205-228."""
+    nb = [int(num_basis)] * len(cfs) if np.isscalar(num_basis) else [int(v) for v in num_basis]
+    if len(nb) != len(cfs):
+        raise ValueError("The length of num_basis must match to the number of covariance functions.")
+    for k, cf in enumerate(cfs):
+        if cf.name == "cf_const":
+            nb[k] = 1
+        elif cf.name == "cf_lin":
+            nb[k] = len(cf.vars) if cf.vars is not None else num_inputs
+    return nb
+
+
+def rf_weights(cfs, num_basis, num_inputs, seed):
+    """The random draws of rf_featmap.* (R/cf.R:571-657), one block per factor in flatten_cfs order,
+    laid out as gpl_rf_spec.weights expects.  Every covariance function re-seeds with the same seed
+    in the reference (set.seed(seed) inside each rf_featmap), so every factor restarts the stream;
+    numpy's default_rng replaces R's generator."""
+    out = []
+    for k, cf in enumerate(cfs):
+        members = cf.cfs if cf.name == "cf_prod" else [cf]
+        for m in members:
+            base = m.base if m.name == "cf_periodic" else m
+            nsel = len(m.vars) if m.vars is not None else num_inputs
+            nf = 2 * nsel if m.name == "cf_periodic" else nsel
+            rng = np.random.default_rng(seed)
+            if base.name == "cf_sexp":
+                if num_basis[k] % 2:
+                    raise ValueError("number of features must be an even number.")
+                mw = num_basis[k] // 2
+                w = rng.standard_normal(mw * nf).reshape(mw, nf).T / base.lscale     # nf x mw
+                out.append(np.asfortranarray(w).ravel(order="F"))
+            elif base.name == "cf_nn":
+                mw = num_basis[k]
+                w = rng.standard_normal(mw * nf).reshape(mw, nf).T                   # nf x mw, * sigma via the inputs
+                w0 = rng.standard_normal(mw) * base.sigma0 * base.sigma
+                out.append(np.asfortranarray(w).ravel(order="F"))
+                out.append(w0)
+            elif base.name in ("cf_matern32", "cf_matern52"):
+                raise NotImplementedError("Random Fourier features for Matern kernels not implemented yet.")
+    return np.concatenate(out) if out else np.zeros(0)
 
 
 class ApproxObj:

@@ -296,6 +296,33 @@ int gpl_energy_grad(gpl_ctx* ctx, const gpl_cf_model* cf, const gpl_lik* lik, co
                     int32_t nparam, const int32_t* param_factor, const int32_t* param_slot,
                     double* energy, double* grad, gpl_fit** fit /* may be NULL */);
 
+/* ---- method_rf: random-feature (linearised) GP, SURVEY 8f-3 --------------------------------- */
+
+/* Basis sizes and the random draws of rf_featmap (R/cf.R:532-690).  num_basis: one entry per
+ * summand after check_num_basis (R/gp.R:205-228: cf_const 1, cf_lin one per input column; even for
+ * cf_sexp).  weights: for each factor in model order that has random features --
+ *   cf_sexp (also as the base of cf_periodic): W, nf x num_basis/2 column-major, = N(0,1) / lscale,
+ *     nf = selected inputs (twice that for a periodic factor);
+ *   cf_nn: W, nf x num_basis column-major, = N(0,1) (the prepared inputs already carry sigma),
+ *     followed by w0, num_basis values = N(0,1) * sigma0 * sigma;
+ * nothing for cf_lin / cf_const.  cf_matern32/52 are rejected as in the reference. */
+typedef struct gpl_rf_spec {
+  int32_t nterms;
+  const int32_t* num_basis;
+  const double* weights;
+  int64_t nweights;
+} gpl_rf_spec;
+
+/* fit_laplace.method_rf (R/gp_fit.R:125-132; laplace_iter.method_rf R/laplace.R:241-262,327-350).
+ * Returns fmean, z, V (n) and wmean (sum num_basis); wcov stays behind *fit ("wcov" of gpl_fit_get). */
+int gpl_fit_rf(gpl_ctx* ctx, const gpl_cf_model* cf, const gpl_lik* lik, const gpl_approx* approx,
+               const gpl_rf_spec* rf, const double* x, int64_t n, int32_t d, const double* y,
+               const double* trials, const double* offset, gpl_fit_out* out, double* fmean, double* z,
+               double* V, double* wmean, gpl_fit** fit);
+/* gp_pred_post.method_rf (R/gp_pred.R:298-315); term_mask = cfind. */
+int gpl_pred_rf(gpl_ctx* ctx, const gpl_fit* fit, const gpl_cf_model* cf, const double* xt, int64_t nt,
+                uint64_t term_mask, double* mean, double* var);
+
 /* ---- prediction ---------------------------------------------------- */
 
 /* mean[nt] (and var[nt] if var != NULL) of the latent at xt (nt x d host). */
@@ -318,7 +345,8 @@ int gpl_draw_full(gpl_ctx* ctx, const gpl_fit* fit, const gpl_cf_model* cf, cons
                   double* out);
 
 /* Materialise members of gp$fit on demand: what = "C_chol" (n x n), "Kxz" (n x m),
- * "Kz_chol" (m x m), "alpha" (n).  out must hold rows*cols doubles. */
+ * "Kz_chol" (m x m), "alpha" (n); method_rf: "wmean" (M), "wcov" (M x M).  out must hold
+ * rows*cols doubles. */
 int gpl_fit_get(gpl_ctx* ctx, const gpl_fit* fit, const char* what, double* out);
 int gpl_fit_free(gpl_ctx* ctx, gpl_fit* fit);
 

@@ -779,6 +779,136 @@ def ep_fitc(gp, Kz, Kz_chol, Kxz, K_diag, D, y, damping=0.9, damping_min=0.1, ma
 # fit dispatch  (R/gp_fit.R)
 # --------------------------------------------------------------------------------------
 
+# --------------------------------------------------------------------------------------
+# method_rf  (R/cf.R:532-690, R/gp.R:205-262, R/laplace.R:241-262,327-350, R/gp_pred.R:298-315)
+# --------------------------------------------------------------------------------------
+def _erf(t):
+    from scipy.special import erf
+    return erf(t)                      # == pnorm(t, sd = sqrt(.5)) - pnorm(-t, sd = sqrt(.5)), R/cf.R:646
+
+
+def rf_featmap_one(cf, num_feat, num_inputs, normals):
+    """rf_featmap.<class> for one covariance function; `normals(count)` replaces stats::rnorm after
+    set.seed(seed) (every call restarts the same stream, as every rf_featmap re-seeds)."""
+    if cf.name == "cf_const":
+        return lambda x: cf.magn * np.ones((len(_as_matrix(x)), 1))              # R/cf.R:553-559
+    if cf.name == "cf_lin":
+        return lambda x: cf.magn * prepare_inputmat(cf, x)                       # :561-569
+    if cf.name == "cf_sexp":
+        nin = len(cf.vars) if cf.vars is not None else num_inputs
+        if num_feat % 2:
+            raise ValueError("number of features must be an even number.")
+        m = num_feat // 2
+        w = normals(m * nin).reshape(m, nin).T * (1 / cf.lscale)                 # :598-600 (column-major fill)
+
+        def fm(x):
+            h = prepare_inputmat(cf, x) @ w
+            return cf.magn * np.sqrt(1 / m) * np.hstack([np.cos(h), np.sin(h)])  # :602-606
+        return fm
+    if cf.name == "cf_nn":
+        nin = len(cf.vars) if cf.vars is not None else num_inputs
+        m = num_feat
+        stream = normals(m * nin + m)
+        w = stream[:m * nin].reshape(m, nin).T * cf.sigma                        # :643
+        w0 = stream[m * nin:][None, :] * cf.sigma0 * cf.sigma                    # :644
+        w_aug = np.vstack([w0, w])
+
+        def fm(x):
+            xp = prepare_inputmat(cf, x)
+            return cf.magn / np.sqrt(m) * _erf(np.hstack([np.ones((len(xp), 1)), xp]) @ w_aug)
+        return fm
+    if cf.name == "cf_periodic":
+        nin = len(cf.vars) if cf.vars is not None else num_inputs
+        base = rf_featmap_one(cf.base, num_feat, 2 * nin, normals)               # :667
+
+        def fm(x):
+            xp = prepare_inputmat(cf, x)
+            return base(np.hstack([np.sin(2 * np.pi / cf.period * xp), np.cos(2 * np.pi / cf.period * xp)]))
+        return fm
+    if cf.name == "cf_prod":
+        if any(m.name in ("cf_lin", "cf_const") for m in cf.cfs):
+            raise ValueError("Random features for product kernel containing constant or linear kernel "
+                             "not implemented yet.")
+        maps = [rf_featmap_one(m, num_feat, num_inputs, normals) for m in cf.cfs]
+
+        def fm(x):
+            z = 1.0
+            for f in maps:
+                z = z * f(x)
+            return z
+        return fm
+    raise NotImplementedError("Random Fourier features for Matern kernels not implemented yet.")
+
+
+def rf_check_num_basis(cfs, num_basis, num_inputs):
+    """R/gp.R:205-228."""
+    nb = [int(num_basis)] * len(cfs) if np.isscalar(num_basis) else [int(v) for v in num_basis]
+    for k, cf in enumerate(cfs):
+        if cf.name == "cf_const":
+            nb[k] = 1
+        elif cf.name == "cf_lin":
+            nb[k] = len(cf.vars) if cf.vars is not None else num_inputs
+    return nb
+
+
+def rf_featuremap(gp, num_inputs):
+    nb = rf_check_num_basis(gp.cfs, gp.method.num_basis, num_inputs)
+    normals = lambda count: np.random.default_rng(gp.method.seed).standard_normal(count)
+    maps = [rf_featmap_one(cf, nb[k], num_inputs, normals) for k, cf in enumerate(gp.cfs)]
+
+    def featuremap(x, cfind=None):                                               # R/cf.R:534-551
+        idx = range(len(maps)) if cfind is None else cfind
+        return np.hstack([maps[k](x) for k in idx])
+    return featuremap, nb
+
+
+def laplace_iter_rf(gp, Z, y, fhat_old, trials=None, offset=None):
+    """R/laplace.R:241-262."""
+    z, V = get_pseudodata_la(gp.lik, fhat_old, y, trials=trials, offset=offset)
+    n, d = Z.shape
+    H = Z.T @ (Z / V[:, None])
+    L = _chol_lower(H + np.eye(d))
+    what = _bsolve_t(L, _fsolve(L, Z.T @ (z / V)))
+    wcov = _bsolve_t(L, _fsolve(L, np.eye(d)))
+    wcov_logdet = -2 * np.sum(np.log(np.diag(L)))
+    fhat_new = Z @ what
+    log_prior = -0.5 * d * np.log(2 * np.pi) - 0.5 * np.sum(what ** 2)
+    log_lik = get_loglik(gp.lik, fhat_new, y, trials=trials, offset=offset)
+    log_evidence = 0.5 * n * np.log(2 * np.pi) + 0.5 * wcov_logdet + log_prior + log_lik
+    return dict(fmean=fhat_new, wmean=what, wcov=wcov, z=z, V=V, log_evidence=float(log_evidence))
+
+
+def laplace_rf(gp, Z, y, maxiter=100, tol=1e-4, trials=None, offset=None):
+    """R/laplace.R:327-350."""
+    fhat = np.zeros(len(y))
+    if gp.lik.name == "lik_gaussian":
+        maxiter = 1
+    it = 0
+    for it in range(1, maxiter + 1):
+        fit = laplace_iter_rf(gp, Z, y, fhat, trials=trials, offset=offset)
+        fnew = Z @ fit["wmean"]
+        diff = np.max(np.abs(fhat - fnew))
+        fhat = fnew
+        if diff < tol:
+            break
+    fit["iters"] = it
+    return fit
+
+
+def gp_pred_post_rf(gp, xt, var=False, cfind=None):
+    """R/gp_pred.R:298-315 with get_w_mean / get_w_cov (R/gp.R:230-262)."""
+    xt = _as_matrix(xt)
+    featuremap, nb = rf_featuremap(gp, xt.shape[1])
+    zt = featuremap(xt, cfind)
+    ends = np.concatenate([[0], np.cumsum(nb)])
+    idx = range(len(nb)) if cfind is None else cfind
+    inds = np.concatenate([np.arange(ends[k], ends[k + 1]) for k in idx])
+    mean = zt @ gp.fit["wmean"][inds]
+    if var:
+        return dict(mean=mean, var=np.diag(zt @ (gp.fit["wcov"][np.ix_(inds, inds)] @ zt.T)).copy())
+    return dict(mean=mean)
+
+
 def gp_fit(gp, x, y, trials=None, offset=None, jitter=None):
     """R/gp_fit.R:54-60 -> learn_scales -> fit_model -> fit_{laplace,ep}.method_{full,fitc}.
     Mutates and returns `gp` (sets gp.x, gp.fit, gp.fitted)."""
@@ -810,6 +940,10 @@ def gp_fit(gp, x, y, trials=None, offset=None, jitter=None):
                               maxiter=gp.approx.maxiter, trials=trials, offset=offset)
         except (np.linalg.LinAlgError, sla.LinAlgError):
             fit = dict(log_evidence=-np.inf)                      # R/gp_fit.R:113-121
+    elif meth == "rf":
+        featuremap, nb = rf_featuremap(gp, x.shape[1])                 # R/gp_fit.R:125-132
+        fit = laplace_rf(gp, featuremap(x), y, maxiter=gp.approx.maxiter, tol=gp.approx.tol,
+                         trials=trials, offset=offset)
     else:
         raise ValueError(meth)
     gp.x = x
@@ -966,6 +1100,8 @@ def gp_pred(gp, xnew, var=False, cfind=None, jitter=None, offset=None, transform
             pred["var"] = np.diag(eval_cf(gp.cfs, xnew, xnew, cfind)).copy()
     elif gp.method.name == "full":
         pred = gp_pred_post_full(gp, xnew, var=var, cfind=cfind, jitter=jitter)
+    elif gp.method.name == "rf":
+        pred = gp_pred_post_rf(gp, xnew, var=var, cfind=cfind)
     else:
         pred = gp_pred_post_fitc(gp, xnew, var=var, cfind=cfind, jitter=jitter)
     pred["mean"] = _offset(pred["mean"], offset)

@@ -527,3 +527,60 @@ def test_gp_draw_and_joint_covariance(ctx):
     assert np.all((pr > 0) & (pr < 1))
     tr = g.gp_draw(gpc, Xt, draws=2, seed=1, target=True, trials=np.full(nt, 7.0))
     assert np.all((tr >= 0) & (tr <= 7) & (tr == np.round(tr)))
+
+
+def _rf_models():
+    return [
+        ("sexp", lambda: [g.cf_sexp(lscale=0.8, magn=1.2)], 60),
+        ("sexp+lin+const", lambda: [g.cf_sexp(lscale=1.1, vars=[0, 2]), g.cf_lin(magn=0.5), g.cf_const(magn=0.7)], 40),
+        ("nn", lambda: [g.cf_nn(sigma0=0.8, sigma=1.5, magn=1.1)], 50),
+        ("periodic+sexp*nn", lambda: [g.cf_periodic(period=2.0, cf_base=g.cf_sexp(lscale=0.9), vars=[1]),
+                                      g.cf_sexp(lscale=1.4) * g.cf_nn(sigma=1.0, prior_magn=g.prior_fixed())], [30, 44]),
+    ]
+
+
+@pytest.mark.parametrize("name", [m[0] for m in _rf_models()])
+@pytest.mark.parametrize("lik", ["gaussian", "bernoulli"])
+def test_method_rf(ctx, name, lik):
+    """method_rf (random-feature GP): feature maps, weight-space Laplace, prediction with
+    cfind, against the oracle with the same random draws (numpy's generator in place of R's)."""
+    _, mk, nb = next(m for m in _rf_models() if m[0] == name)
+    rng = np.random.default_rng(17)
+    n, nt = 700, 45
+    X = rng.normal(size=(n, 3))
+    f = np.sin(X[:, 0]) + 0.5 * X[:, 1] - 0.3 * X[:, 2]
+    Xt = rng.normal(size=(nt, 3))
+    if lik == "gaussian":
+        y, L = f + 0.2 * rng.normal(size=n), g.lik_gaussian(sigma=0.3)
+    else:
+        y, L = (rng.uniform(size=n) < 1 / (1 + np.exp(-2 * f))).astype(float), g.lik_bernoulli()
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        gp = g.gp_init(cfs=mk(), lik=L, method=g.method_rf(num_basis=nb, seed=7))
+    gpo = copy.deepcopy(gp)
+    g.gp_fit(gp, X, y, ctx=ctx)
+    o.gp_fit(gpo, X, y)
+    assert gp.fit["iters"] == gpo.fit["iters"]
+    assert abs(gp.fit["log_evidence"] - gpo.fit["log_evidence"]) < TOL * abs(gpo.fit["log_evidence"])
+    assert scaled_err(gp.fit["wmean"], gpo.fit["wmean"]) < 1e-7
+    assert scaled_err(gp.fit["fmean"], gpo.fit["fmean"]) < TOL
+    assert scaled_err(g.fit_member(gp, "wcov"), gpo.fit["wcov"]) < 1e-7
+    assert abs(g.gp_energy(gp) - o.gp_energy(gpo)) < TOL * abs(o.gp_energy(gpo))
+    for cfind in (None, [0]) if len(gp.cfs) > 1 else (None,):
+        p = g.gp_pred(gp, Xt, var=True, cfind=cfind)
+        po = o.gp_pred(gpo, Xt, var=True, cfind=cfind)
+        assert scaled_err(p["mean"], po["mean"]) < 1e-7, cfind
+        assert scaled_err(p["var"], po["var"]) < 1e-7, cfind
+
+
+def test_method_rf_rejections(ctx):
+    X = np.random.default_rng(0).normal(size=(50, 2))
+    y = X[:, 0]
+    with pytest.raises(NotImplementedError):
+        g.gp_fit(g.gp_init(cfs=g.cf_matern32(), method=g.method_rf(num_basis=10)), X, y, ctx=ctx)
+    with pytest.raises(ValueError):
+        g.gp_fit(g.gp_init(cfs=g.cf_sexp(), method=g.method_rf(num_basis=11)), X, y, ctx=ctx)
+    with pytest.raises(g.GplError):
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            g.gp_fit(g.gp_init(cfs=g.cf_sexp() * g.cf_lin(), method=g.method_rf(num_basis=10)), X, y, ctx=ctx)
