@@ -91,9 +91,17 @@ def test_flatten_descriptor():
 
 
 def test_unfitted_and_unsupported_paths_need_no_gpu():
-    gp = g.gp_init(method=g.method_rf())
-    with pytest.raises(NotImplementedError):
+    gp = g.gp_init(method=g.method_rf(), lik=g.lik_bernoulli(), approx=g.approx_ep())
+    with pytest.raises(NotImplementedError):            # "No EP implementation for method_rf yet."
         g.gp_fit(gp, np.zeros((3, 1)), np.zeros(3), ctx=object())
+    gp = g.gp_init(cfs=g.cf_matern52(), method=g.method_rf())
+    with pytest.raises(NotImplementedError):            # no random features for Matern kernels
+        g.gp_fit(gp, np.zeros((3, 1)), np.zeros(3), ctx=object())
+    assert g.model.check_num_basis([g.cf_sexp(), g.cf_lin(), g.cf_const(), g.cf_lin(vars=[1, 2])], 50, 4) == [50, 4, 1, 2]
+    w = g.model.rf_weights([g.cf_sexp(lscale=0.5), g.cf_nn(sigma0=2.0, sigma=3.0)], [6, 4], 2, seed=1)
+    assert w.shape == (3 * 2 + 4 * 2 + 4,)
+    nrm = np.random.default_rng(1).standard_normal(12)
+    assert np.allclose(w[:6], nrm[:6] / 0.5) and np.allclose(w[6:14], nrm[:8]) and np.allclose(w[14:], nrm[8:12] * 6.0)
     gp = g.gp_init()
     with pytest.raises(RuntimeError):
         g.gp_energy(gp)
