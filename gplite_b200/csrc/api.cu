@@ -371,4 +371,42 @@ int gpl_lik_loglik_dev(gpl_ctx* h, const gpl_lik* lik, int64_t n, const double* 
   return fetch_scalars(c, 1, loglik_host);
 }
 
+int gpl_lik_ep_sites_dev(gpl_ctx* h, const gpl_lik* lik, int64_t n, const double* fmean,
+                         const double* fvar, const double* z_old, const double* P_old, const double* y,
+                         const double* trials, const double* offset, double damping, int32_t quad_order,
+                         const double* quad_x, const double* quad_w, double* z_new, double* V_new,
+                         double* P_new, double* cavity_mean, double* cavity_var, double* logZ,
+                         int32_t* flags) {
+  if (!lik || n < 0 || !fmean || !fvar || !z_old || !P_old || !y || !quad_x || !quad_w || !z_new ||
+      !V_new || !P_new || !cavity_mean || !cavity_var || !logZ || !flags) {
+    set_error("gpl_lik_ep_sites_dev: bad arguments");
+    return GPL_ERR_BAD_ARG;
+  }
+  Ctx* c = reinterpret_cast<Ctx*>(h);
+  LikDev ld{lik->kind, lik->link, lik->param, trials, offset};
+  EpSiteArgs ea;
+  ea.fmean = fmean; ea.fvar = fvar; ea.z_old = z_old; ea.P_old = P_old; ea.y = y;
+  ea.z_new = z_new; ea.V_new = V_new; ea.P_new = P_new;
+  ea.cav_mean = cavity_mean; ea.cav_var = cavity_var; ea.logZ = logZ;
+  ea.damping = damping;
+  ea.quad_order = quad_order;
+  ea.quad_x = quad_x; ea.quad_w = quad_w;
+  DevBuf fl;
+  GPL_TRY(fl.alloc(c, sizeof(int) * 4));
+  GPL_TRY(lik_ep_sites(c, ld, n, ea, static_cast<int*>(fl.p)));
+  int hf = 0;
+  GPL_CUDA(cudaMemcpyAsync(&hf, fl.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  GPL_CUDA(cudaStreamSynchronize(c->stream));
+  *flags = hf;
+  return GPL_OK;
+}
+
+int gpl_colsumsq_dev(gpl_ctx* h, int64_t m, int64_t n, const double* A, int64_t lda, double* out) {
+  if (m < 0 || n < 0 || !A || !out) {
+    set_error("gpl_colsumsq_dev: bad arguments");
+    return GPL_ERR_BAD_ARG;
+  }
+  return colsumsq(reinterpret_cast<Ctx*>(h), m, n, A, lda, out);
+}
+
 }  // extern "C"

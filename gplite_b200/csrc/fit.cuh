@@ -64,6 +64,8 @@ int tril_scale(Ctx* ctx, int64_t n, const double* L, int64_t ldl, const double* 
 int rowsumsq_w(Ctx* ctx, int64_t m, int64_t n, const double* A, int64_t lda, const double* w,
                double* out);
 
+// out_j = sum_i A_ij^2
+int colsumsq(Ctx* ctx, int64_t m, int64_t n, const double* A, int64_t lda, double* out);
 // out_i = sum_j A_ij B_ij
 int rowdot(Ctx* ctx, int64_t m, int64_t n, const double* A, int64_t lda, const double* B, int64_t ldb,
            double* out);

@@ -532,6 +532,17 @@ __global__ void rowsumsq_w_kernel(int64_t m, int64_t n, const double* __restrict
   out[i] = s;
 }
 
+// out_j = sum_i A_ij^2, one CTA per column
+__global__ void colsumsq_kernel(int64_t m, const double* __restrict__ A, int64_t lda,
+                                double* __restrict__ out) {
+  __shared__ double red[32];
+  const double* col = A + (int64_t)blockIdx.x * lda;
+  double s = 0.0;
+  for (int64_t i = threadIdx.x; i < m; i += blockDim.x) s = fma(col[i], col[i], s);
+  const double t = block_sum(s, red);
+  if (threadIdx.x == 0) out[blockIdx.x] = t;
+}
+
 // out_i = sum_j A_ij B_ij
 __global__ void rowdot_kernel(int64_t m, int64_t n, const double* __restrict__ A, int64_t lda,
                               const double* __restrict__ B, int64_t ldb, double* __restrict__ out) {
@@ -793,6 +804,13 @@ int rowsumsq_w(Ctx* ctx, int64_t m, int64_t n, const double* A, int64_t lda, con
                double* out) {
   if (m <= 0) return GPL_OK;
   rowsumsq_w_kernel<<<(unsigned)((m + 255) / 256), 256, 0, ctx->stream>>>(m, n, A, lda, w, out);
+  GPL_LAUNCH_CHECK(ctx);
+  return GPL_OK;
+}
+
+int colsumsq(Ctx* ctx, int64_t m, int64_t n, const double* A, int64_t lda, double* out) {
+  if (n <= 0) return GPL_OK;
+  colsumsq_kernel<<<(unsigned)n, 256, 0, ctx->stream>>>(m, A, lda, out);
   GPL_LAUNCH_CHECK(ctx);
   return GPL_OK;
 }

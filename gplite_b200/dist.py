@@ -110,6 +110,29 @@ class GpuOps:
             self._p(alpha_t), len(pf), _lib._ptr(pf), _lib._ptr(ps), _lib._ptr(out), C.byref(dsum)))
         return out, dsum.value
 
+    def colsumsq(self, A_t, lc0, r0, rows, ncols, out_t, out_off):
+        """out[out_off + j] = sum_i A[r0 + i, lc0 + j]^2"""
+        ld = A_t.shape[1]
+        _lib.check(self.lib.gpl_colsumsq_dev(self.ctx.h, rows, ncols, self._p(A_t, lc0 * ld + r0), ld,
+                                             self._p(out_t, out_off)))
+
+    def kdiag(self, pm, X_t, n, d, jitter, out_t):
+        """diag(K) + jitter"""
+        _lib.check(self.lib.gpl_cf_eval_dev(self.ctx.h, pm.ref(), self._p(X_t), n, self._p(X_t), n, d, 1, 0, 1,
+                                            float(jitter), self._p(out_t), n))
+
+    def ep_sites(self, lik, fmean, fvar, z_old, P_old, y_t, tr_t, off_t, damping, xq_t, wq_t,
+                 z_t, V_t, P_t, cm_t, cv_t, logZ_t):
+        """parallel EP site update on replicated device n-vectors; returns the flag word"""
+        flags = C.c_int32()
+        _lib.check(self.lib.gpl_lik_ep_sites_dev(
+            self.ctx.h, C.byref(lik), fmean.numel(), self._p(fmean), self._p(fvar), self._p(z_old), self._p(P_old),
+            self._p(y_t), self._p(tr_t) if tr_t is not None else None,
+            self._p(off_t) if off_t is not None else None, float(damping), xq_t.numel(), self._p(xq_t),
+            self._p(wq_t), self._p(z_t), self._p(V_t), self._p(P_t), self._p(cm_t), self._p(cv_t),
+            self._p(logZ_t), C.byref(flags)))
+        return flags.value
+
     def pseudodata(self, lik, f_t, y_t, tr_t, off_t, z_t, V_t):
         """z, V <- get_pseudodata_la(lik, f, y) on replicated device n-vectors (R/lik.R:188-201)"""
         _lib.check(self.lib.gpl_lik_pseudodata_la_dev(
@@ -162,6 +185,300 @@ class GpuOps:
         self.ctx.sync()
 
 
+class ShardedFactor:
+    """B = I + V^-1/2 (K + jitter I) V^-1/2 built, factorised and (optionally) inverted in the 1-D
+    block-cyclic column layout.  All n x n arithmetic goes through `ops` (the C ABI); `dist` moves
+    panels; replicated n-vectors are torch tensors."""
+
+    def __init__(self, gp, x, nb, ops, dist, device, jitter, timings=None):
+        import torch
+        self.torch = torch
+        self.dist = dist
+        self.rank, self.world = dist.get_rank(), dist.get_world_size()
+        x = np.asarray(x, dtype=np.float64)
+        if x.ndim == 1:
+            x = x[:, None]
+        self.n, self.d = n, d = x.shape
+        if nb % 128 or n % 2:
+            raise ValueError("nb must be a multiple of 128 and n even")
+        for cf in gp.cfs:
+            M.learn_scales(cf, x)
+        self.jit = 1e-6 if jitter is None else float(jitter)
+        factors, _ = M.flatten_cfs(gp.cfs)
+        self.pm = _lib.PackedModel(factors)
+        if ops is None:
+            # same stream as torch: kernels, copies and NCCL collectives are then ordered without
+            # host synchronisation
+            # (torch's default stream has handle 0, which the C ABI reads as "create your own": pass
+            # cudaStreamLegacy = 1 for it)
+            ops = GpuOps(_lib.Context(torch.cuda.current_device(), torch.cuda.current_stream().cuda_stream or 1))
+        self.ops, self.device, self.nb = ops, device, nb
+        self.lay = lay = BlockCyclic(n, nb, self.world, self.rank)
+        self.ld = ld = (n + 15) // 16 * 16
+        self.X_t = torch.from_numpy(np.ascontiguousarray(x.T)).to(device)     # (d, n): column-major n x d
+        self.A_t = torch.empty((max(lay.nloc, 1), ld), dtype=torch.float64, device=device)
+        self.Xi_t = None
+        self.dinv = {b: torch.empty(((lay.width[b] + 127) // 128) * 128 * 128, dtype=torch.float64, device=device)
+                     for b in lay.owned}
+        self.panels = [torch.empty(nb * ld, dtype=torch.float64, device=device) for _ in range(2)]
+        self.tmpb = None
+        self.timings = timings
+        self.t_acc = {}
+        self._t0 = None
+
+    # ---- timing -------------------------------------------------------------------------------
+    def tick(self):
+        if self.timings is not None:
+            import time
+            self.ops.sync()
+            if self.device == "cuda":
+                self.torch.cuda.synchronize()
+            self._t0 = time.perf_counter()
+
+    def tock(self, name):
+        if self.timings is not None:
+            import time
+            self.ops.sync()
+            if self.device == "cuda":
+                self.torch.cuda.synchronize()
+            t = time.perf_counter()
+            self.t_acc[name] = self.t_acc.get(name, 0.0) + t - self._t0
+            self._t0 = t
+
+    def vec(self, v):
+        return None if v is None else self.torch.from_numpy(
+            np.asarray(v, dtype=np.float64).ravel().copy()).to(self.device)
+
+    def panel_view(self, k):
+        w, mp = self.lay.width[k], self.n - self.lay.col0(k)
+        return self.panels[k % 2][: w * mp].view(w, mp)
+
+    def _sweep(self, prep, apply):
+        """panel k+1 is prepared by its owner and broadcast (async) while panel k is applied"""
+        lay, dist = self.lay, self.dist
+        if lay.owner(0) == self.rank:
+            prep(0)
+        work = dist.broadcast(self.panel_view(0), src=lay.owner(0), async_op=True)
+        for k in range(lay.nblk):
+            if work is not None:
+                work.wait()
+            work = None
+            if k + 1 < lay.nblk:
+                if lay.owner(k + 1) == self.rank:
+                    prep(k + 1)
+                work = dist.broadcast(self.panel_view(k + 1), src=lay.owner(k + 1), async_op=True)
+            apply(k)
+
+    # ---- build + factorise --------------------------------------------------------------------
+    def factor(self, s_t):
+        """B(s) = I + S (K + jitter I) S, S = diag(s_t); returns logdet(B).  Right-looking with panel
+        broadcasts and one step of look-ahead: the owner of panel k+1 updates that block column
+        first, factors it and starts its broadcast (async, NCCL stream) while every rank is still
+        applying panel k to its other columns, so the panel factorisation and the NVLink transfer
+        leave the critical path."""
+        torch, lay, ops, n, dist = self.torch, self.lay, self.ops, self.n, self.dist
+        A_t = self.A_t
+        self.tick()
+        # K (owned block columns, rows at and below the diagonal block), scaled in place
+        for b in lay.owned:
+            c0, w, lc0 = lay.col0(b), lay.width[b], lay.local_col0[b]
+            ops.kblock(self.pm, self.X_t, n, self.d, c0, n - c0, c0, w, A_t, lc0)
+            ops.scale_block(A_t, lc0, w, c0, n - c0, 1.0, 0.0, 0, s_t, c0)
+        diag_add = 1.0 + self.jit * s_t * s_t                              # replicated n-vector
+        for b in lay.owned:
+            c0, w, lc0 = lay.col0(b), lay.width[b], lay.local_col0[b]
+            A_t[lc0:lc0 + w, c0:c0 + w].diagonal().add_(diag_add[c0:c0 + w])
+        self.tock("kbuild")
+        state = {"logdet": 0.0, "fail": 0}
+
+        def factor_panel(k):
+            """owner only: potrf of the diagonal block, TRSM of the rows below, pack for broadcast"""
+            k0, w, lc0 = lay.col0(k), lay.width[k], lay.local_col0[k]
+            st, info, ld_k = ops.potrf(A_t, lc0, k0, w)
+            if st != _lib.GPL_OK:
+                state["fail"] = max(state["fail"], k0 + info if st == _lib.GPL_ERR_NOT_PD else 1)
+            else:
+                ops.save_dinv(w, self.dinv[k])
+                state["logdet"] += ld_k
+                if n - k0 - w > 0:
+                    ops.trsm_below(A_t, lc0, k0, w, n - k0 - w)
+            self.panel_view(k).copy_(A_t[lc0:lc0 + w, k0:n])
+
+        def apply_panel(k, j):
+            k0, w = lay.col0(k), lay.width[k]
+            j0, wj = lay.col0(j), lay.width[j]
+            ops.update(self.panel_view(k), n - k0, w, j0 - k0, n - j0, j0 - k0, wj, A_t, lay.local_col0[j], j0)
+
+        if lay.owner(0) == self.rank:
+            factor_panel(0)
+        work = dist.broadcast(self.panel_view(0), src=lay.owner(0), async_op=True)
+        for k in range(lay.nblk):
+            if work is not None:
+                work.wait()
+            nxt = k + 1
+            work = None
+            if nxt < lay.nblk:
+                if lay.owner(nxt) == self.rank:
+                    apply_panel(k, nxt)
+                    factor_panel(nxt)
+                work = dist.broadcast(self.panel_view(nxt), src=lay.owner(nxt), async_op=True)
+            for j in lay.owned:
+                if j > k and not (j == nxt):
+                    apply_panel(k, j)
+        red = torch.tensor([float(state["fail"])], dtype=torch.float64, device=self.device)
+        dist.all_reduce(red, op=dist.ReduceOp.MAX)
+        if red.item() != 0:
+            raise _lib.NotPositiveDefinite(_lib.GPL_ERR_NOT_PD,
+                                           f"the leading minor of order {int(red.item())} is not positive definite")
+        ldt = torch.tensor([state["logdet"]], dtype=torch.float64, device=self.device)
+        dist.all_reduce(ldt)
+        self.tock("factor")
+        return float(ldt.item())
+
+    # ---- triangular solves --------------------------------------------------------------------
+    def solve(self, rhs):
+        """B^-1 rhs (replicated in, replicated out): block forward / backward substitution with an
+        8 KB all-reduce / broadcast per block"""
+        torch, lay, ops, n, dist, A_t, nb = self.torch, self.lay, self.ops, self.n, self.dist, self.A_t, self.nb
+        dev = self.device
+        self.tick()
+        u = torch.zeros(n, dtype=torch.float64, device=dev)       # local partial sums  sum_j L[:, j] w_j
+        wv = torch.zeros(n, dtype=torch.float64, device=dev)      # forward solution (owned blocks)
+        tmp = torch.empty(nb, dtype=torch.float64, device=dev)
+        tmp2 = torch.empty(nb, dtype=torch.float64, device=dev)
+        for k in range(lay.nblk):
+            k0, w = lay.col0(k), lay.width[k]
+            blk = u[k0:k0 + w].clone()
+            dist.all_reduce(blk)
+            if lay.owner(k) == self.rank:
+                lc0 = lay.local_col0[k]
+                tmp[:w] = rhs[k0:k0 + w] - blk
+                ops.trsv(0, w, A_t, lc0, k0, self.dinv[k], tmp, tmp2)
+                wv[k0:k0 + w] = tmp2[:w]
+                if n - k0 - w > 0:
+                    upd = torch.empty(n - k0 - w, dtype=torch.float64, device=dev)
+                    ops.gemv(0, n - k0 - w, w, A_t, lc0, k0 + w, tmp2, 0, upd, 0)
+                    u[k0 + w:] += upd
+        xv = torch.zeros(n, dtype=torch.float64, device=dev)      # backward solution, replicated
+        for k in reversed(range(lay.nblk)):
+            k0, w = lay.col0(k), lay.width[k]
+            blk = torch.zeros(w, dtype=torch.float64, device=dev)
+            if lay.owner(k) == self.rank:
+                lc0 = lay.local_col0[k]
+                tmp[:w] = wv[k0:k0 + w]
+                if n - k0 - w > 0:
+                    dot = torch.empty(w, dtype=torch.float64, device=dev)
+                    ops.gemv(1, n - k0 - w, w, A_t, lc0, k0 + w, xv, k0 + w, dot, 0)
+                    tmp[:w] -= dot
+                ops.trsv(1, w, A_t, lc0, k0, self.dinv[k], tmp, tmp2)
+                blk.copy_(tmp2[:w])
+            dist.broadcast(blk, src=lay.owner(k))
+            xv[k0:k0 + w] = blk
+        self.tock("solve")
+        return xv
+
+    # ---- inverse: B^-1 = X^T X, X = L^-1 (SURVEY 8e "C^-1 + trace term") ----------------------------
+    # Two more sweeps of panel broadcasts, each n^3/3 flops spread like the factorisation:
+    #   X sweep: panel k = [L_kk^-1 ; L[k1:, k]] goes to every rank; for its own columns j < k a rank
+    #            finishes block row k of X (X_kj = L_kk^-1 R_kj) and pushes the update down
+    #            (R[k1:, j] -= L[k1:, k] X_kj); the running right-hand side R lives in X's slab.
+    #   Y sweep: panel i = X[i0:, i]; Y_ij = X[i0:, i]^T X[i0:, j] for own columns j <= i, written
+    #            over the block row of X it no longer needs.
+    # Panels depend only on finished data, so panel k+1 is always in flight during step k.
+    def x_sweep(self):
+        torch, lay, ops, n, A_t, ldn = self.torch, self.lay, self.ops, self.n, self.A_t, self.ld
+        self.tick()
+        if self.Xi_t is None:
+            self.Xi_t = torch.empty((max(lay.nloc, 1), self.ld), dtype=torch.float64, device=self.device)
+            self.tmpb = torch.empty(self.nb * self.nb, dtype=torch.float64, device=self.device)
+        Xi_t, tmpb = self.Xi_t, self.tmpb
+        Xi_t.zero_()
+
+        def prep_L_panel(k):
+            k0, w, lc0 = lay.col0(k), lay.width[k], lay.local_col0[k]
+            pv = self.panel_view(k)                              # (w, n - k0): column-major (n-k0) x w
+            pv.copy_(A_t[lc0:lc0 + w, k0:n])
+            ops.inv_diag(A_t, lc0, k0, w, self.dinv[k], pv, n - k0)   # diagonal block <- L_kk^-1
+            # this rank's own column k of X:  X_kk = L_kk^-1,  R[k1:, k] = -L[k1:, k] L_kk^-1
+            Xi_t[lc0:lc0 + w, k0:k0 + w] = pv[:, :w]
+            if n - k0 - w > 0:
+                ops.gemm(0, 0, n - k0 - w, w, w, -1.0, (pv, w, n - k0), (pv, 0, n - k0), 0.0,
+                         (Xi_t, lc0 * ldn + k0 + w, ldn))
+
+        def apply_L_panel(k):
+            k0, w = lay.col0(k), lay.width[k]
+            pv = self.panel_view(k)
+            for j in lay.owned:
+                if j >= k:
+                    break
+                wj, lcj = lay.width[j], lay.local_col0[j]
+                # X_kj = L_kk^-1 R_kj (into a scratch block, then over R_kj)
+                ops.gemm(0, 0, w, wj, w, 1.0, (pv, 0, n - k0), (Xi_t, lcj * ldn + k0, ldn), 0.0, (tmpb, 0, w))
+                if n - k0 - w > 0:
+                    ops.gemm(0, 0, n - k0 - w, wj, w, -1.0, (pv, w, n - k0), (tmpb, 0, w), 1.0,
+                             (Xi_t, lcj * ldn + k0 + w, ldn))
+                Xi_t[lcj:lcj + wj, k0:k0 + w] = torch.as_strided(tmpb, (wj, w), (w, 1))
+
+        self._sweep(prep_L_panel, apply_L_panel)
+        self.tock("trtri")
+
+    def diag_binv(self):
+        """diag(B^-1)_i = sum_k X_ki^2 after x_sweep: column sums of squares of the owned block
+        columns, assembled with one all-reduce of an n-vector"""
+        torch, lay, n = self.torch, self.lay, self.n
+        out = torch.zeros(n, dtype=torch.float64, device=self.device)
+        for j in lay.owned:
+            j0, w, lcj = lay.col0(j), lay.width[j], lay.local_col0[j]
+            self.ops.colsumsq(self.Xi_t, lcj, j0, n - j0, w, out, j0)
+        self.dist.all_reduce(out)
+        self.tock("diag")
+        return out
+
+    def y_sweep(self):
+        torch, lay, ops, n, ldn = self.torch, self.lay, self.ops, self.n, self.ld
+        Xi_t, tmpb = self.Xi_t, self.tmpb
+        self.tick()
+
+        def prep_X_panel(i):
+            i0, w, lc0 = lay.col0(i), lay.width[i], lay.local_col0[i]
+            self.panel_view(i).copy_(Xi_t[lc0:lc0 + w, i0:n])
+
+        def apply_X_panel(i):
+            i0, w = lay.col0(i), lay.width[i]
+            pv = self.panel_view(i)
+            for j in lay.owned:
+                if j > i:
+                    break
+                wj, lcj = lay.width[j], lay.local_col0[j]
+                ops.gemm(1, 0, w, wj, n - i0, 1.0, (pv, 0, n - i0), (Xi_t, lcj * ldn + i0, ldn), 0.0,
+                         (tmpb, 0, w), 1 if j == i else 0)
+                Xi_t[lcj:lcj + wj, i0:i0 + w] = torch.as_strided(tmpb, (wj, w), (w, 1))
+
+        self._sweep(prep_X_panel, apply_X_panel)
+        self.tock("lauum")
+
+    def grad_trace(self, s_t, alpha, pf, ps):
+        """sum_ij (alpha_i alpha_j - s_i Binv_ij s_j) dK_ij/dlog(theta_p) and sum_j s_j^2 Binv_jj after
+        y_sweep: local block traces + one all-reduce of |theta| + 1 numbers"""
+        torch, lay = self.torch, self.lay
+        g_loc = np.zeros(len(pf), dtype=np.float64)
+        dsum_loc = 0.0
+        for j in lay.owned:
+            gj, dj = self.ops.grad_trace_block(self.pm, self.X_t, self.n, self.d, lay.col0(j), lay.width[j],
+                                               self.Xi_t, lay.local_col0[j], s_t, alpha, pf, ps)
+            g_loc += gj
+            dsum_loc += dj
+        red = torch.from_numpy(np.concatenate([g_loc, [dsum_loc]])).to(self.device)
+        self.dist.all_reduce(red)
+        red = red.cpu().numpy()
+        self.tock("trace")
+        return red[:-1], red[-1]
+
+    def finish_timings(self):
+        if self.timings is not None:
+            self.timings.update(self.t_acc)
+
+
 def dist_fit_gaussian(gp, x, y, jitter=None, nb=1024, ops=None, dist=None, device="cuda", timings=None):
     """lik_gaussian entry point kept for callers of the first version: see dist_fit_laplace."""
     if gp.lik.name != "lik_gaussian":
@@ -181,297 +498,139 @@ def dist_fit_laplace(gp, x, y, trials=None, offset=None, jitter=None, nb=1024, o
 
     grad_params=(param_factor, param_slot) (lik_gaussian only): also return `grad_raw`, the
     derivative of the energy without priors w.r.t. those log-parameters -- see dist_energy_grad."""
+    import time
     import torch
     from .gp import _pack_lik
     if gp.method.name != "full" or gp.approx.name != "laplace":
-        raise NotImplementedError("the multi-GPU path covers method_full + approx_laplace")
+        raise NotImplementedError("dist_fit_laplace covers method_full + approx_laplace (EP: dist_fit_ep)")
     if dist is None:
         import torch.distributed as dist
-    rank, world = dist.get_rank(), dist.get_world_size()
-    x = np.asarray(x, dtype=np.float64)
-    if x.ndim == 1:
-        x = x[:, None]
-    y = np.asarray(y, dtype=np.float64).ravel()
-    n, d = x.shape
-    if nb % 128 or n % 2:
-        raise ValueError("nb must be a multiple of 128 and n even")
-    for cf in gp.cfs:
-        M.learn_scales(cf, x)
-    jit = 1e-6 if jitter is None else float(jitter)
+    t_start = time.perf_counter()
+    sf = ShardedFactor(gp, x, nb, ops, dist, device, jitter, timings)
+    ops, n = sf.ops, sf.n
     gaussian = gp.lik.name == "lik_gaussian"
     lik = _pack_lik(gp.lik)
-    factors, _ = M.flatten_cfs(gp.cfs)
-    pm = _lib.PackedModel(factors)
-    if ops is None:
-        # same stream as torch: kernels, copies and NCCL collectives are then ordered without
-        # host synchronisation
-        # (torch's default stream has handle 0, which the C ABI reads as "create your own": pass
-        # cudaStreamLegacy = 1 for it)
-        ops = GpuOps(_lib.Context(torch.cuda.current_device(), torch.cuda.current_stream().cuda_stream or 1))
-    lay = BlockCyclic(n, nb, world, rank)
-    ld = (n + 15) // 16 * 16
-    t_mark = {}
-    t_acc = {"kbuild": 0.0, "factor": 0.0, "solve": 0.0}
-
-    def mark(name):
-        if timings is not None:
-            ops.sync()
-            if device == "cuda":
-                torch.cuda.synchronize()
-            import time
-            t_mark[name] = time.perf_counter()
-
-    def vec(v):
-        return None if v is None else torch.from_numpy(np.asarray(v, dtype=np.float64).ravel().copy()).to(device)
-
-    X_t = torch.from_numpy(np.ascontiguousarray(x.T)).to(device)          # (d, n): column-major n x d
-    y_t = vec(y)
-    tr_t, off_t = vec(trials), vec(offset)
+    y_t, tr_t, off_t = sf.vec(y), sf.vec(trials), sf.vec(offset)
     if gp.lik.name in ("lik_binomial", "lik_betabinom") and tr_t is None:
         raise ValueError("trials must be provided for the binomial / beta-binomial likelihood")
-    A_t = torch.empty((max(lay.nloc, 1), ld), dtype=torch.float64, device=device)
-    dinv = {b: torch.empty(((lay.width[b] + 127) // 128) * 128 * 128, dtype=torch.float64, device=device)
-            for b in lay.owned}
-    panels = [torch.empty(nb * ld, dtype=torch.float64, device=device) for _ in range(2)]
     f_t = torch.zeros(n, dtype=torch.float64, device=device)               # R/laplace.R:280
     z_t = torch.empty(n, dtype=torch.float64, device=device)
     V_t = torch.empty(n, dtype=torch.float64, device=device)
     maxiter = 1 if gaussian else max(int(gp.approx.maxiter), 1)            # R/laplace.R:281-283
     tol = float(gp.approx.tol)
-    state = {"logdet": 0.0, "fail": 0}
-
-    def panel_view(k):
-        w, mp = lay.width[k], n - lay.col0(k)
-        return panels[k % 2][: w * mp].view(w, mp)
-
-    def factor_panel(k):
-        """owner only: potrf of the diagonal block, TRSM of the rows below, pack for broadcast"""
-        k0, w, lc0 = lay.col0(k), lay.width[k], lay.local_col0[k]
-        st, info, ld_k = ops.potrf(A_t, lc0, k0, w)
-        if st != _lib.GPL_OK:
-            state["fail"] = max(state["fail"], k0 + info if st == _lib.GPL_ERR_NOT_PD else 1)
-        else:
-            ops.save_dinv(w, dinv[k])
-            state["logdet"] += ld_k
-            if n - k0 - w > 0:
-                ops.trsm_below(A_t, lc0, k0, w, n - k0 - w)
-        panel_view(k).copy_(A_t[lc0:lc0 + w, k0:n])
-
-    def apply_panel(k, j):
-        k0, w = lay.col0(k), lay.width[k]
-        j0, wj = lay.col0(j), lay.width[j]
-        ops.update(panel_view(k), n - k0, w, j0 - k0, n - j0, j0 - k0, wj, A_t, lay.local_col0[j], j0)
-
-    def newton_step():
-        """one laplace_iter.method_full (R/laplace.R:13-38) on the sharded matrix"""
+    it = 0
+    for it in range(1, maxiter + 1):                                       # R/laplace.R:285-292
+        # one laplace_iter.method_full (R/laplace.R:13-38) on the sharded matrix
         ops.pseudodata(lik, f_t, y_t, tr_t, off_t, z_t, V_t)
         if not bool((V_t > 0).all().item()):
             raise _lib.GplError(_lib.GPL_ERR_NOT_LOGCONCAVE,
                                 "pseudo-variance <= 0: the non-log-concave branch (R/laplace.R:40-117) "
                                 "is single-GPU only")
         s_t = torch.rsqrt(V_t)
-        mark("iter_start")
-        # ---- K (owned block columns, rows at and below the diagonal block), then
-        # B = I + V^-1/2 K V^-1/2 in place (jitter on K's diagonal)
-        for b in lay.owned:
-            c0, w, lc0 = lay.col0(b), lay.width[b], lay.local_col0[b]
-            ops.kblock(pm, X_t, n, d, c0, n - c0, c0, w, A_t, lc0)
-            ops.scale_block(A_t, lc0, w, c0, n - c0, 1.0, 0.0, 0, s_t, c0)
-        diag_add = 1.0 + jit * s_t * s_t                                   # replicated n-vector
-        for b in lay.owned:
-            c0, w, lc0 = lay.col0(b), lay.width[b], lay.local_col0[b]
-            A_t[lc0:lc0 + w, c0:c0 + w].diagonal().add_(diag_add[c0:c0 + w])
-        mark("kbuild")
-
-        # ---- right-looking factorisation with panel broadcasts and one step of look-ahead:
-        # the owner of panel k+1 updates that block column first, factors it and starts its broadcast
-        # (async, NCCL stream) while every rank is still applying panel k to its other columns, so the
-        # panel factorisation and the NVLink transfer leave the critical path.
-        state["logdet"], state["fail"] = 0.0, 0
-        if lay.owner(0) == rank:
-            factor_panel(0)
-        work = dist.broadcast(panel_view(0), src=lay.owner(0), async_op=True)
-        for k in range(lay.nblk):
-            if work is not None:
-                work.wait()
-            nxt = k + 1
-            work = None
-            if nxt < lay.nblk:
-                if lay.owner(nxt) == rank:
-                    apply_panel(k, nxt)
-                    factor_panel(nxt)
-                work = dist.broadcast(panel_view(nxt), src=lay.owner(nxt), async_op=True)
-            for j in lay.owned:
-                if j > k and not (j == nxt):
-                    apply_panel(k, j)
-        flag = torch.tensor([float(state["fail"])], dtype=torch.float64, device=device)
-        dist.all_reduce(flag, op=dist.ReduceOp.MAX)
-        if flag.item() != 0:
-            raise _lib.NotPositiveDefinite(_lib.GPL_ERR_NOT_PD,
-                                           f"the leading minor of order {int(flag.item())} is not positive definite")
-        mark("factor")
-
-        # ---- alpha = C^-1 z, C = diag(sqrtV) L L^T diag(sqrtV)  (R/laplace.R:29)
-        rhs = z_t * s_t
-        u = torch.zeros(n, dtype=torch.float64, device=device)      # local partial sums  sum_j L[:, j] w_j
-        wv = torch.zeros(n, dtype=torch.float64, device=device)     # forward solution (owned blocks)
-        tmp = torch.empty(nb, dtype=torch.float64, device=device)
-        tmp2 = torch.empty(nb, dtype=torch.float64, device=device)
-        for k in range(lay.nblk):
-            k0, w = lay.col0(k), lay.width[k]
-            blk = u[k0:k0 + w].clone()
-            dist.all_reduce(blk)
-            if lay.owner(k) == rank:
-                lc0 = lay.local_col0[k]
-                tmp[:w] = rhs[k0:k0 + w] - blk
-                ops.trsv(0, w, A_t, lc0, k0, dinv[k], tmp, tmp2)
-                wv[k0:k0 + w] = tmp2[:w]
-                if n - k0 - w > 0:
-                    upd = torch.empty(n - k0 - w, dtype=torch.float64, device=device)
-                    ops.gemv(0, n - k0 - w, w, A_t, lc0, k0 + w, tmp2, 0, upd, 0)
-                    u[k0 + w:] += upd
-        xv = torch.zeros(n, dtype=torch.float64, device=device)     # backward solution, replicated
-        for k in reversed(range(lay.nblk)):
-            k0, w = lay.col0(k), lay.width[k]
-            blk = torch.zeros(w, dtype=torch.float64, device=device)
-            if lay.owner(k) == rank:
-                lc0 = lay.local_col0[k]
-                tmp[:w] = wv[k0:k0 + w]
-                if n - k0 - w > 0:
-                    dot = torch.empty(w, dtype=torch.float64, device=device)
-                    ops.gemv(1, n - k0 - w, w, A_t, lc0, k0 + w, xv, k0 + w, dot, 0)
-                    tmp[:w] -= dot
-                ops.trsv(1, w, A_t, lc0, k0, dinv[k], tmp, tmp2)
-                blk.copy_(tmp2[:w])
-            dist.broadcast(blk, src=lay.owner(k))
-            xv[k0:k0 + w] = blk
-        alpha = xv * s_t
-        mark("solve")
-        if timings is not None:
-            for a, b in (("iter_start", "kbuild"), ("kbuild", "factor"), ("factor", "solve")):
-                t_acc[b] += t_mark[b] - t_mark[a]
-
-        # ---- log evidence (R/laplace.R:33-38); C_logdet - V_logdet = logdet(B)
-        ldt = torch.tensor([state["logdet"]], dtype=torch.float64, device=device)
-        dist.all_reduce(ldt)
-        fnew = z_t - V_t * alpha                                      # == K alpha
+        logdet = sf.factor(s_t)                                            # C_logdet - V_logdet = logdet(B)
+        alpha = sf.solve(z_t * s_t) * s_t                                  # R/laplace.R:29
+        fnew = z_t - V_t * alpha                                           # == K alpha
         log_lik = ops.loglik(lik, fnew, y_t, tr_t, off_t)
-        f_invK_f = float(torch.dot(fnew, alpha).item())
-        return fnew, alpha, log_lik - 0.5 * f_invK_f - 0.5 * float(ldt.item())
-
-    mark("start")
-    it = 0
-    for it in range(1, maxiter + 1):                                   # R/laplace.R:285-292
-        fnew, alpha, log_evidence = newton_step()
+        log_evidence = log_lik - 0.5 * float(torch.dot(fnew, alpha).item()) - 0.5 * logdet   # R/laplace.R:33-38
         diff = float(torch.max(torch.abs(f_t - fnew)).item())
         f_t = fnew
         if diff < tol:
             break
-    mark("done")
     out = dict(log_evidence=log_evidence, alpha=alpha, fmean=f_t, z=z_t, V=V_t, iters=it,
-               converged=not (maxiter > 1 and it == maxiter), layout=lay)
-
+               converged=not (maxiter > 1 and it == maxiter), layout=sf.lay)
     if grad_params is not None:
-        # ---- energy gradient (SURVEY 8e "C^-1 + trace term"): B^-1 = X^T X, X = L^-1, in the same
-        # block-cyclic layout.  Two more sweeps of panel broadcasts, each n^3/3 flops spread like the
-        # factorisation:
-        #   X sweep: panel k = [L_kk^-1 ; L[k1:, k]] goes to every rank; for its own columns j < k a
-        #            rank finishes block row k of X (X_kj = L_kk^-1 R_kj) and pushes the update down
-        #            (R[k1:, j] -= L[k1:, k] X_kj); the running right-hand side R lives in X's slab.
-        #   Y sweep: panel i = X[i0:, i]; Y_ij = X[i0:, i]^T X[i0:, j] for own columns j <= i,
-        #            written over the block row of X it no longer needs.
-        # Panels depend only on finished data, so panel k+1 is always in flight during step k.
         if not gaussian:
             raise NotImplementedError("the analytic gradient is implemented for lik_gaussian")
         pf, ps = (np.ascontiguousarray(v, dtype=np.int32) for v in grad_params)
-        s_t = torch.rsqrt(V_t)
-        Xi_t = torch.zeros((max(lay.nloc, 1), ld), dtype=torch.float64, device=device)
-        tmpb = torch.empty(nb * nb, dtype=torch.float64, device=device)
-        ldn = ld
-
-        def prep_L_panel(k):
-            k0, w, lc0 = lay.col0(k), lay.width[k], lay.local_col0[k]
-            pv = panel_view(k)                                   # (w, n - k0): column-major (n-k0) x w
-            pv.copy_(A_t[lc0:lc0 + w, k0:n])
-            ops.inv_diag(A_t, lc0, k0, w, dinv[k], pv, n - k0)   # diagonal block <- L_kk^-1
-            # this rank's own column k of X:  X_kk = L_kk^-1,  R[k1:, k] = -L[k1:, k] L_kk^-1
-            Xi_t[lc0:lc0 + w, k0:k0 + w] = pv[:, :w]
-            if n - k0 - w > 0:
-                ops.gemm(0, 0, n - k0 - w, w, w, -1.0, (pv, w, n - k0), (pv, 0, n - k0), 0.0,
-                         (Xi_t, lc0 * ldn + k0 + w, ldn))
-
-        def sweep(prep, apply):
-            if lay.owner(0) == rank:
-                prep(0)
-            work = dist.broadcast(panel_view(0), src=lay.owner(0), async_op=True)
-            for k in range(lay.nblk):
-                if work is not None:
-                    work.wait()
-                work = None
-                if k + 1 < lay.nblk:
-                    if lay.owner(k + 1) == rank:
-                        prep(k + 1)
-                    work = dist.broadcast(panel_view(k + 1), src=lay.owner(k + 1), async_op=True)
-                apply(k)
-
-        def apply_L_panel(k):
-            k0, w = lay.col0(k), lay.width[k]
-            pv = panel_view(k)
-            for j in lay.owned:
-                if j >= k:
-                    break
-                wj, lcj = lay.width[j], lay.local_col0[j]
-                # X_kj = L_kk^-1 R_kj (into a scratch block, then over R_kj)
-                ops.gemm(0, 0, w, wj, w, 1.0, (pv, 0, n - k0), (Xi_t, lcj * ldn + k0, ldn), 0.0, (tmpb, 0, w))
-                if n - k0 - w > 0:
-                    ops.gemm(0, 0, n - k0 - w, wj, w, -1.0, (pv, w, n - k0), (tmpb, 0, w), 1.0,
-                             (Xi_t, lcj * ldn + k0 + w, ldn))
-                Xi_t[lcj:lcj + wj, k0:k0 + w] = torch.as_strided(tmpb, (wj, w), (w, 1))
-
-        def prep_X_panel(i):
-            i0, w, lc0 = lay.col0(i), lay.width[i], lay.local_col0[i]
-            panel_view(i).copy_(Xi_t[lc0:lc0 + w, i0:n])
-
-        def apply_X_panel(i):
-            i0, w = lay.col0(i), lay.width[i]
-            pv = panel_view(i)
-            for j in lay.owned:
-                if j > i:
-                    break
-                wj, lcj = lay.width[j], lay.local_col0[j]
-                ops.gemm(1, 0, w, wj, n - i0, 1.0, (pv, 0, n - i0), (Xi_t, lcj * ldn + i0, ldn), 0.0,
-                         (tmpb, 0, w), 1 if j == i else 0)
-                Xi_t[lcj:lcj + wj, i0:i0 + w] = torch.as_strided(tmpb, (wj, w), (w, 1))
-
-        sweep(prep_L_panel, apply_L_panel)
-        mark("trtri")
-        sweep(prep_X_panel, apply_X_panel)
-        mark("lauum")
-        g_loc = np.zeros(len(pf), dtype=np.float64)
-        dsum_loc = 0.0
-        for j in lay.owned:
-            gj, dj = ops.grad_trace_block(pm, X_t, n, d, lay.col0(j), lay.width[j], Xi_t, lay.local_col0[j],
-                                          s_t, alpha, pf, ps)
-            g_loc += gj
-            dsum_loc += dj
-        red = torch.from_numpy(np.concatenate([g_loc, [dsum_loc]])).to(device)
-        dist.all_reduce(red)
-        red = red.cpu().numpy()
+        sf.x_sweep()
+        sf.y_sweep()
+        g_cf, dsum = sf.grad_trace(s_t, alpha, pf, ps)
         sigma2 = gp.lik.sigma ** 2
-        tr_w = float(torch.dot(alpha, alpha).item()) - red[-1]            # tr(alpha alpha^T - C^-1)
-        graw = np.where(pf < 0, -0.5 * 2.0 * sigma2 * tr_w, -0.5 * red[:-1])
-        mark("trace")
-        out["grad_raw"] = graw
-        if timings is not None:
-            timings["trtri"] = t_mark["trtri"] - t_mark["done"]
-            timings["lauum"] = t_mark["lauum"] - t_mark["trtri"]
-            timings["trace"] = t_mark["trace"] - t_mark["lauum"]
-
+        tr_w = float(torch.dot(alpha, alpha).item()) - dsum                # tr(alpha alpha^T - C^-1)
+        out["grad_raw"] = np.where(pf < 0, -0.5 * 2.0 * sigma2 * tr_w, -0.5 * g_cf)
+    sf.finish_timings()
     if timings is not None:
-        timings.update(t_acc)
-        timings["done"] = 0.0
-        timings["total"] = t_mark["done"] - t_mark["start"]
+        for k in ("kbuild", "factor", "solve", "trtri", "lauum", "trace"):
+            timings.setdefault(k, 0.0)
+        ops.sync()
+        timings["total"] = time.perf_counter() - t_start
     return out
+
+
+def dist_fit_ep(gp, x, y, trials=None, offset=None, jitter=None, nb=1024, ops=None, dist=None,
+                device="cuda", timings=None):
+    """Distributed gp_fit for method_full + approx_ep (SURVEY 8e "Laplace/EP site sweeps"): parallel
+    EP (R/ep.R:16-49, 286-330) over the sharded factor.  Per sweep: the site update on replicated
+    n-vectors (gpl_lik_ep_sites_dev), B = I + V^-1/2 K V^-1/2 rebuilt and factorised, alpha, and the
+    marginal variances from diag(B^-1) (the X sweep: fvar = V - V diag(B^-1), the same identity as on
+    one GPU instead of the reference's n x n solve, R/ep.R:42,141)."""
+    import torch
+    from .gp import _pack_lik
+    from .quadrature import gauss_hermite_points
+    if gp.method.name != "full" or gp.approx.name != "ep":
+        raise NotImplementedError("dist_fit_ep covers method_full + approx_ep")
+    if dist is None:
+        import torch.distributed as dist
+    sf = ShardedFactor(gp, x, nb, ops, dist, device, jitter, timings)
+    ops, n = sf.ops, sf.n
+    lik = _pack_lik(gp.lik)
+    y_t, tr_t, off_t = sf.vec(y), sf.vec(trials), sf.vec(offset)
+    if gp.lik.name in ("lik_binomial", "lik_betabinom") and tr_t is None:
+        raise ValueError("trials must be provided for the binomial / beta-binomial likelihood")
+    a = gp.approx
+    xq, wq = gauss_hermite_points(int(a.quad_order))
+    xq_t, wq_t = sf.vec(xq), sf.vec(wq)
+    new = lambda: torch.zeros(n, dtype=torch.float64, device=device)
+    P_old, z_old, fmean_old = new(), new(), new()
+    fvar_old = new()
+    ops.kdiag(sf.pm, sf.X_t, n, sf.d, sf.jit, fvar_old)                    # fvar_old = diag(K), R/ep.R:297
+    z_t, V_t, P_t, cm_t, cv_t, logZ_t = new(), new(), new(), new(), new(), new()
+    maxiter = max(int(a.maxiter), 1)
+    tol, damping, damping_min = 1e-4, float(a.damping), 0.1                # R/ep.R:286-287
+    diff_old, damp = math.inf, damping
+    quad_ok, it = True, 0
+    fit = None
+    for it in range(1, maxiter + 1):
+        flags = ops.ep_sites(lik, fmean_old, fvar_old, z_old, P_old, y_t, tr_t, off_t, damp, xq_t, wq_t,
+                             z_t, V_t, P_t, cm_t, cv_t, logZ_t)
+        quad_ok = not (flags & 1)
+        if flags & 2:                                                      # R/ep.R:30-32
+            return dict(log_evidence=-math.inf, iters=it, converged=False, quad_ok=quad_ok)
+        if flags & 4:
+            raise _lib.GplError(_lib.GPL_ERR_NOT_LOGCONCAVE,
+                                "pseudo-variance <= 0: the non-log-concave branch (R/ep.R:50-138) is single-GPU only")
+        s_t = torch.rsqrt(V_t)
+        logdet_b = sf.factor(s_t)
+        alpha = sf.solve(z_t * s_t) * s_t
+        fmean = z_t - V_t * alpha                                          # == K alpha
+        sf.x_sweep()
+        fvar = V_t - V_t * sf.diag_binv()                                  # diag(V C^-1 K)
+        C_logdet = float(torch.sum(torch.log(V_t)).item()) + logdet_b
+        tot = cv_t + V_t
+        log_evidence = (-0.5 * C_logdet - 0.5 * float(torch.dot(z_t, alpha).item())
+                        + float((torch.sum(logZ_t) + 0.5 * torch.sum(torch.log(tot))
+                                 + 0.5 * torch.sum((cm_t - z_t) ** 2 / tot)).item()))       # R/ep.R:45-49
+        fit = dict(fmean=fmean, fvar=fvar, z=z_t.clone(), V=V_t.clone(), P=P_t.clone(), alpha=alpha,
+                   cavity_mean=cm_t.clone(), cavity_var=cv_t.clone(), log_evidence=log_evidence)
+        diff_new = float(torch.max(torch.abs(fmean_old - fmean)).item())
+        if diff_new > diff_old:                                            # R/ep.R:306-310
+            damp *= damping
+            continue
+        damp = max(damp, damping_min)
+        fmean_old, fvar_old, z_old, P_old = fmean, fvar, fit["z"], fit["P"]
+        diff_old = diff_new
+        if diff_new < tol:
+            break
+    fit["iters"] = it
+    fit["converged"] = not (maxiter > 1 and it == maxiter)
+    fit["quad_ok"] = quad_ok
+    if maxiter > 1 and it == maxiter:                                      # R/ep.R:322-325
+        fit["log_evidence"] = -math.inf
+    if not quad_ok:
+        fit["log_evidence"] = -math.inf
+    fit["layout"] = sf.lay
+    sf.finish_timings()
+    return fit
 
 
 def dist_energy_grad(gp, x, y, jitter=None, include_prior=True, nb=1024, ops=None, dist=None, device="cuda",

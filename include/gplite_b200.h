@@ -246,6 +246,19 @@ int gpl_lik_pseudodata_la_dev(gpl_ctx* ctx, const gpl_lik* lik, int64_t n, const
 /* sum_i log p(y_i | f_i) (get_loglik, R/lik.R:297-366) returned to the host. */
 int gpl_lik_loglik_dev(gpl_ctx* ctx, const gpl_lik* lik, int64_t n, const double* f, const double* y,
                        const double* trials, const double* offset, double* loglik_host);
+/* EP site update on device n-vectors (get_pseudodata_ep + get_tilted_moments, R/lik.R:207-270):
+ * cavity from (fmean, fvar, z_old, P_old), Gauss-Hermite tilted moments with the device arrays
+ * quad_x / quad_w (quad_order entries), damped new sites z_new, V_new = 1 / P_new, P_new, plus the
+ * cavity mean / variance and log Z.  *flags: bit 0 quadrature not ok, bit 1 NaN pseudo-data
+ * (R/ep.R:30-32), bit 2 some V_new <= 0. */
+int gpl_lik_ep_sites_dev(gpl_ctx* ctx, const gpl_lik* lik, int64_t n, const double* fmean,
+                         const double* fvar, const double* z_old, const double* P_old, const double* y,
+                         const double* trials, const double* offset, double damping, int32_t quad_order,
+                         const double* quad_x, const double* quad_w, double* z_new, double* V_new,
+                         double* P_new, double* cavity_mean, double* cavity_var, double* logZ,
+                         int32_t* flags);
+/* out_j = sum_i A_ij^2 for the n columns of A (m x n): diag(B^-1) from X = L^-1. */
+int gpl_colsumsq_dev(gpl_ctx* ctx, int64_t m, int64_t n, const double* A, int64_t lda, double* out);
 /* One block column's share of the gradient trace (multi-GPU energy gradient; the single-GPU path is
  * gpl_energy_grad).  Cinv_blk: columns [col0, col0 + ncols) of the lower triangle of
  * Binv = (I + S K S)^-1, all n rows with leading dimension ld (rows above the block's diagonal are

@@ -124,6 +124,33 @@ class TorchOps:
         dsum = float(np.sum(s[c0:c0 + w] ** 2 * Y[c0 + np.arange(w), np.arange(w)]))
         return out, dsum
 
+    def colsumsq(self, A_t, lc0, r0, rows, ncols, out_t, out_off):
+        blk = A_t[lc0:lc0 + ncols, r0:r0 + rows]
+        out_t[out_off:out_off + ncols] = (blk * blk).sum(dim=1)
+
+    def kdiag(self, pm, X_t, n, d, jitter, out_t):
+        import torch
+        from oracle import gplite_oracle as o
+        x = X_t.numpy().T
+        out_t.copy_(torch.from_numpy(o.eval_cf(self.gp.cfs, x, x, diag_only=True) + jitter))
+
+    def ep_sites(self, lik, fmean, fvar, z_old, P_old, y_t, tr_t, off_t, damping, xq_t, wq_t,
+                 z_t, V_t, P_t, cm_t, cv_t, logZ_t):
+        import torch
+        from oracle import gplite_oracle as o
+        pobs = o.get_pseudodata_ep(self.gp.lik, fmean.numpy(), 1 / fvar.numpy(), z_old.numpy(), P_old.numpy(),
+                                   y_t.numpy(), quad_order=xq_t.numel(), damping=damping,
+                                   **self._lik_args(tr_t, off_t))
+        for t, v in ((z_t, pobs["z"]), (V_t, pobs["var"]), (P_t, 1 / pobs["var"]), (cm_t, pobs["mean_cavity"]),
+                     (cv_t, pobs["var_cavity"]), (logZ_t, pobs["log_normalizing_const"])):
+            t.copy_(torch.from_numpy(np.asarray(v, dtype=np.float64)))
+        fl = 0 if pobs["quad_ok"] else 1
+        if np.any(np.isnan(pobs["var"]) | np.isnan(pobs["z"])):
+            fl |= 2
+        elif not np.all(pobs["var"] > 0):
+            fl |= 4
+        return fl
+
     def _lik_args(self, tr_t, off_t):
         return dict(trials=None if tr_t is None else tr_t.numpy(), offset=None if off_t is None else off_t.numpy())
 
@@ -178,8 +205,14 @@ def _worker(rank, world, port, q):
         from gplite_b200.dist import dist_energy_grad
         gpg = g.gp_init(cfs=[g.cf_matern52(lscale=1.1), g.cf_lin(magn=0.3)], lik=g.lik_gaussian(sigma=0.4))
         e, gr = dist_energy_grad(gpg, X, y, nb=128, ops=TorchOps(gpg), dist=dist, device="cpu")
+        # parallel EP over the sharded factor
+        from gplite_b200.dist import dist_fit_ep
+        gpe, Xe, ye = _bernoulli_case()
+        gpe.approx = g.approx_ep()
+        rese = dist_fit_ep(gpe, Xe[:300], ye[:300], nb=128, ops=TorchOps(gpe), dist=dist, device="cpu")
         q.put((rank, res["log_evidence"], res["alpha"].numpy().copy(), resb["log_evidence"],
-               resb["fmean"].numpy().copy(), resb["iters"], e, gr))
+               resb["fmean"].numpy().copy(), resb["iters"], e, gr, rese["log_evidence"],
+               rese["fvar"].numpy().copy(), rese["iters"]))
     finally:
         dist.destroy_process_group()
 
@@ -208,7 +241,13 @@ def test_distributed_driver_world2_matches_oracle():
     o.gp_fit(gpb, Xb, yb)
     gpg = g.gp_init(cfs=[g.cf_matern52(lscale=1.1), g.cf_lin(magn=0.3)], lik=g.lik_gaussian(sigma=0.4))
     eo, go = o.energy_grad_gaussian_full(gpg, X, y)
-    for rank, le, alpha, leb, fb, itb, e, gr in out:
+    gpe, Xe, ye = _bernoulli_case()
+    gpe.approx = g.approx_ep()
+    o.gp_fit(gpe, Xe[:300], ye[:300])
+    for rank, le, alpha, leb, fb, itb, e, gr, lee, fve, ite in out:
+        assert ite == gpe.fit["iters"]
+        assert abs(lee - gpe.fit["log_evidence"]) < 1e-8 * abs(gpe.fit["log_evidence"])
+        assert np.max(np.abs(fve - gpe.fit["fvar"])) < 1e-8 * np.max(np.abs(gpe.fit["fvar"]))
         assert abs(e - eo) < 1e-9 * abs(eo)
         assert np.max(np.abs(gr - go)) < 1e-6 * max(1.0, np.max(np.abs(go))), (gr, go)
         assert abs(le - gpo.fit["log_evidence"]) < 1e-9 * abs(gpo.fit["log_evidence"])

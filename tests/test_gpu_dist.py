@@ -105,6 +105,30 @@ def test_energy_grad_driver_single_rank_matches_oracle(n, nb):
     assert np.max(np.abs(gr - g1)) < 1e-9 * max(1.0, np.max(np.abs(g1)))
 
 
+@pytest.mark.parametrize("lik", ["bernoulli", "poisson"])
+def test_ep_driver_single_rank_matches_oracle(lik):
+    """SURVEY 8e "EP site sweeps": parallel EP over the block-cyclic factor; marginal variances from
+    the distributed X = L^-1 sweep."""
+    from gplite_b200.dist import dist_fit_ep
+    rng = np.random.default_rng(23)
+    n = 700
+    X = rng.normal(size=(n, 3))
+    f = 1.5 * X[:, 0] - X[:, 1]
+    if lik == "bernoulli":
+        y, L = (rng.uniform(size=n) < 1 / (1 + np.exp(-f))).astype(float), g.lik_bernoulli(link="probit")
+    else:
+        y, L = rng.poisson(np.exp(0.5 * f + 0.3)).astype(float), g.lik_poisson()
+    gp = g.gp_init(cfs=[g.cf_matern32(lscale=1.1), g.cf_const(magn=0.3)], lik=L, approx=g.approx_ep(damping=0.8))
+    gpo = copy.deepcopy(gp)
+    res = dist_fit_ep(gp, X, y, nb=256, dist=OneRank)
+    o.gp_fit(gpo, X, y)
+    assert res["iters"] == gpo.fit["iters"] and res["iters"] > 2
+    assert abs(res["log_evidence"] - gpo.fit["log_evidence"]) < 1e-8 * abs(gpo.fit["log_evidence"])
+    for k in ("fmean", "fvar", "alpha"):
+        a = res[k].cpu().numpy()
+        assert np.max(np.abs(a - gpo.fit[k])) < 1e-6 * np.max(np.abs(gpo.fit[k])), k
+
+
 def test_fitc_driver_single_rank_matches_oracle():
     from gplite_b200.dist import dist_fit_fitc_gaussian
     rng = np.random.default_rng(8)
