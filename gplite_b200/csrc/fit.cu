@@ -15,6 +15,93 @@
 
 namespace gpl {
 
+// ---- nb x nb algebra of the non-log-concave branch, shared by method_full and method_fitc ------
+int bad_small_alloc(Ctx* ctx, BadSmall& sm, int64_t nb, const double* V_b) {
+  sm.nb = nb;
+  sm.ldp = round_up(nb, 16);
+  GPL_TRY(sm.invVb.alloc(ctx, sizeof(double) * nb));
+  for (int i = 0; i < 8; ++i) GPL_TRY(sm.b[i].alloc(ctx, sizeof(double) * nb));
+  GPL_TRY(vec_op(ctx, VOP_INV, nb, V_b, nullptr, sm.invVb.d()));
+  const size_t pp = sizeof(double) * sm.ldp * nb, pd = sizeof(double) * ((nb + NB - 1) / NB) * NB * NB;
+  GPL_TRY(sm.P.alloc(ctx, pp));
+  GPL_TRY(sm.Lk.alloc(ctx, pp));
+  GPL_TRY(sm.T.alloc(ctx, pp));
+  GPL_TRY(sm.A.alloc(ctx, pp));
+  GPL_TRY(sm.Pd.alloc(ctx, pd));
+  GPL_TRY(sm.Ad.alloc(ctx, pd));
+  return GPL_OK;
+}
+
+// P holds pred_cov (lower triangle) on entry.  Lk = chol(pred_cov) -- failure means the posterior
+// of the whole data is improper and is an error (R/laplace.R:69-71); A = I + Lk^T V_b^-1 Lk and its
+// factor -- failure sets a_fail (R/laplace.R:73-80, R/ep.R:90-97).
+int bad_small_factor(Ctx* ctx, BadSmall& sm) {
+  const int64_t nb = sm.nb;
+  int32_t info = 0;
+  GPL_TRY(dpotrf_with(ctx, sm.Pd.d(), nb, sm.P.d(), sm.ldp, &info, nullptr));
+  GPL_TRY(tril_scale(ctx, nb, sm.P.d(), sm.ldp, nullptr, sm.Lk.d(), sm.ldp));
+  GPL_TRY(tril_scale(ctx, nb, sm.P.d(), sm.ldp, sm.invVb.d(), sm.T.d(), sm.ldp));
+  GPL_TRY(dgemm(ctx, true, false, nb, nb, nb, 1.0, sm.Lk.d(), sm.ldp, sm.T.d(), sm.ldp, 0.0, sm.A.d(),
+                sm.ldp, false));
+  GPL_TRY(scale_block(ctx, nb, nb, sm.A.d(), sm.ldp, nullptr, nullptr, 1.0, 1.0, 0));
+  sm.a_fail = false;
+  const int rc = dpotrf_with(ctx, sm.Ad.d(), nb, sm.A.d(), sm.ldp, &info, &sm.logdetA);
+  if (rc == GPL_ERR_NOT_PD || (rc == GPL_OK && !std::isfinite(sm.logdetA))) {
+    sm.a_fail = true;
+    return GPL_OK;
+  }
+  return rc;
+}
+
+// out = A^-1 c  (A = Ac Ac^T); c is destroyed; tmp, out distinct nb-vectors
+static int bad_small_solve_A(Ctx* ctx, BadSmall& sm, double* c, double* tmp, double* out) {
+  GPL_TRY(trsv_lower(ctx, sm.Ad.d(), false, sm.nb, sm.A.d(), sm.ldp, c, tmp));
+  GPL_TRY(trsv_lower(ctx, sm.Ad.d(), true, sm.nb, sm.A.d(), sm.ldp, tmp, out));
+  return GPL_OK;
+}
+
+// out = S^-1 v, S = pred_cov + V_bad (Woodbury through A); v is kept
+int bad_small_solve_S(Ctx* ctx, BadSmall& sm, const double* v, double* out) {
+  const int64_t nb = sm.nb;
+  double *t = sm.b[4].d(), *u = sm.b[5].d(), *u2 = sm.b[6].d(), *w = sm.b[7].d();
+  GPL_TRY(vec_op(ctx, VOP_MUL, nb, v, sm.invVb.d(), t));
+  GPL_TRY(gemv_t(ctx, nb, nb, sm.Lk.d(), sm.ldp, t, u));
+  GPL_TRY(bad_small_solve_A(ctx, sm, u, u2, w));
+  GPL_TRY(gemv_n(ctx, nb, nb, sm.Lk.d(), sm.ldp, w, u));
+  GPL_TRY(vec_op(ctx, VOP_MUL, nb, u, sm.invVb.d(), u2));
+  GPL_TRY(vec_op(ctx, VOP_SUB, nb, t, u2, out));
+  return GPL_OK;
+}
+
+// Laplace terms of the bad sites (R/laplace.R:81-99): f2hat = Lk w, w = A^-1 (Lk^T (z_b / V_b) +
+// Lk^-1 pred_mean); |Lk^-1 (f2hat - pred_mean)|^2 -> slot_df2, loglik(f2hat, y_b) -> slot_ll
+int bad_small_laplace(Ctx* ctx, BadSmall& sm, const double* pm, const double* z_b, const double* y_b,
+                      const LikDev& lik_b, int slot_df2, int slot_ll) {
+  const int64_t nb = sm.nb;
+  double *c1 = sm.b[0].d(), *c2 = sm.b[1].d(), *c = sm.b[2].d(), *w = sm.b[3].d();
+  double *t = sm.b[4].d(), *u = sm.b[5].d();
+  GPL_TRY(vec_op(ctx, VOP_MUL, nb, z_b, sm.invVb.d(), t));
+  GPL_TRY(gemv_t(ctx, nb, nb, sm.Lk.d(), sm.ldp, t, c1));
+  GPL_TRY(vec_op(ctx, VOP_COPY, nb, pm, nullptr, t));
+  GPL_TRY(trsv_lower(ctx, sm.Pd.d(), false, nb, sm.P.d(), sm.ldp, t, c2));
+  GPL_TRY(vec_op(ctx, VOP_ADD, nb, c1, c2, c));
+  GPL_TRY(bad_small_solve_A(ctx, sm, c, u, w));
+  GPL_TRY(gemv_n(ctx, nb, nb, sm.Lk.d(), sm.ldp, w, t));              // f2hat
+  GPL_TRY(vec_op(ctx, VOP_SUB, nb, w, c2, u));                        // Lk^-1 (f2hat - pred_mean)
+  GPL_TRY(reduce(ctx, RED_SUMSQ, nb, u, nullptr, slot_df2));
+  GPL_TRY(lik_loglik_sum(ctx, lik_b, nb, t, y_b, slot_ll));
+  return GPL_OK;
+}
+
+// EP: (pred_mean - z_b)^T S^-1 (pred_mean - z_b) -> slot (R/ep.R:107-110)
+int bad_small_ep(Ctx* ctx, BadSmall& sm, const double* pm, const double* z_b, int slot_df2) {
+  double *dz = sm.b[0].d(), *sdz = sm.b[1].d();
+  GPL_TRY(vec_op(ctx, VOP_SUB, sm.nb, pm, z_b, dz));
+  GPL_TRY(bad_small_solve_S(ctx, sm, dz, sdz));
+  GPL_TRY(reduce(ctx, RED_DOT, sm.nb, dz, sdz, slot_df2));
+  return GPL_OK;
+}
+
 namespace {
 
 // GPL_TIMING=1: per-phase wall times of gpl_energy_grad on stderr (each phase fenced by a stream
@@ -195,17 +282,15 @@ int factor_and_solve(Ctx* ctx, FullState& st) {
 // Same alpha / fmean / fvar / predictions as the LU (block elimination of the same system) at a
 // third of its flops and without a pivoted panel kernel.
 struct BadSite {
-  int64_t n = 0, ng = 0, nb = 0, ldw = 0, ldp = 0;
+  int64_t n = 0, ng = 0, nb = 0, ldw = 0;
   bool active = false;     // the last iteration took this branch
-  bool a_fail = false;     // A not positive definite: improper posterior (log_evidence = -Inf)
-  double logdetA = 0.0;
+  BadSmall sm;             // nb x nb algebra (shared with method_fitc)
   std::vector<int32_t> perm_h;
   DevBuf perm, Zp, xp;
   DevBuf yp, trp, offp, zp, Vp, sp, sqp, alpha_p;
   DevBuf a1, f1, pm, ab;
-  DevBuf W, P, Pd, Lk, T, A, Ad, invVb;
+  DevBuf W;
   DevBuf g[4];             // n-sized scratch
-  DevBuf b[8];             // nb-sized scratch
   LikDev lik_g, lik_b;
 };
 
@@ -240,7 +325,6 @@ int bad_prepare(Ctx* ctx, FullState& st, BadSite& bs) {
   }
   const int64_t nb = bs.nb;
   bs.ldw = round_up(nb, 16);
-  bs.ldp = round_up(nb, 16);
   GPL_TRY(bs.perm.alloc(ctx, sizeof(int32_t) * n));
   GPL_CUDA(cudaMemcpyAsync(bs.perm.p, bs.perm_h.data(), sizeof(int32_t) * n, cudaMemcpyHostToDevice,
                            ctx->stream));
@@ -277,17 +361,8 @@ int bad_prepare(Ctx* ctx, FullState& st, BadSite& bs) {
   GPL_TRY(vec_op(ctx, VOP_SQRT, ng, bs.Vp.d(), nullptr, bs.sqp.d()));
   GPL_TRY(bs.pm.alloc(ctx, sizeof(double) * nb));
   GPL_TRY(bs.ab.alloc(ctx, sizeof(double) * nb));
-  GPL_TRY(bs.invVb.alloc(ctx, sizeof(double) * nb));
-  for (int i = 0; i < 8; ++i) GPL_TRY(bs.b[i].alloc(ctx, sizeof(double) * nb));
-  GPL_TRY(vec_op(ctx, VOP_INV, nb, bs.Vp.d() + ng, nullptr, bs.invVb.d()));
+  GPL_TRY(bad_small_alloc(ctx, bs.sm, nb, bs.Vp.d() + ng));
   GPL_TRY(bs.W.alloc(ctx, sizeof(double) * bs.ldw * ng));
-  const size_t pp = sizeof(double) * bs.ldp * nb, pd = sizeof(double) * ((nb + NB - 1) / NB) * NB * NB;
-  GPL_TRY(bs.P.alloc(ctx, pp));
-  GPL_TRY(bs.Lk.alloc(ctx, pp));
-  GPL_TRY(bs.T.alloc(ctx, pp));
-  GPL_TRY(bs.A.alloc(ctx, pp));
-  GPL_TRY(bs.Pd.alloc(ctx, pd));
-  GPL_TRY(bs.Ad.alloc(ctx, pd));
   return GPL_OK;
 }
 
@@ -308,43 +383,14 @@ int bad_factor(Ctx* ctx, FullState& st, BadSite& bs) {
   GPL_TRY(copy_block(ctx, nb, ng, Kbg, ld, bs.W.d(), bs.ldw));
   GPL_TRY(scale_cols(ctx, nb, ng, bs.W.d(), bs.ldw, bs.sp.d()));
   GPL_TRY(dtrsm_right_with(ctx, st.dinv.d(), true, nb, ng, st.B.d(), ld, bs.W.d(), bs.ldw));
-  GPL_TRY(copy_block(ctx, nb, nb, K + ng + ng * ld, ld, bs.P.d(), bs.ldp));
+  GPL_TRY(copy_block(ctx, nb, nb, K + ng + ng * ld, ld, bs.sm.P.d(), bs.sm.ldp));
   GPL_TRY(dgemm(ctx, false, true, nb, nb, ng, -1.0, bs.W.d(), bs.ldw, bs.W.d(), bs.ldw, 1.0,
-                bs.P.d(), bs.ldp, true));
-  // chol(pred_cov): failure means the posterior of the whole data is improper (R/laplace.R:69-71)
-  GPL_TRY(dpotrf_with(ctx, bs.Pd.d(), nb, bs.P.d(), bs.ldp, &info, nullptr));
-  GPL_TRY(tril_scale(ctx, nb, bs.P.d(), bs.ldp, nullptr, bs.Lk.d(), bs.ldp));
-  GPL_TRY(tril_scale(ctx, nb, bs.P.d(), bs.ldp, bs.invVb.d(), bs.T.d(), bs.ldp));
-  GPL_TRY(dgemm(ctx, true, false, nb, nb, nb, 1.0, bs.Lk.d(), bs.ldp, bs.T.d(), bs.ldp, 0.0,
-                bs.A.d(), bs.ldp, false));
-  GPL_TRY(scale_block(ctx, nb, nb, bs.A.d(), bs.ldp, nullptr, nullptr, 1.0, 1.0, 0));
-  bs.a_fail = false;
-  const int rc = dpotrf_with(ctx, bs.Ad.d(), nb, bs.A.d(), bs.ldp, &info, &bs.logdetA);
-  if (rc == GPL_ERR_NOT_PD || (rc == GPL_OK && !std::isfinite(bs.logdetA))) {
-    bs.a_fail = true;                                  // R/laplace.R:73-80, R/ep.R:90-97
-    return GPL_OK;
-  }
-  return rc;
+                bs.sm.P.d(), bs.sm.ldp, true));
+  return bad_small_factor(ctx, bs.sm);
 }
 
-// out = A^-1 c  (A = Ac Ac^T); c is destroyed; tmp, out distinct nb-vectors
-int bad_solve_A(Ctx* ctx, BadSite& bs, double* c, double* tmp, double* out) {
-  GPL_TRY(trsv_lower(ctx, bs.Ad.d(), false, bs.nb, bs.A.d(), bs.ldp, c, tmp));
-  GPL_TRY(trsv_lower(ctx, bs.Ad.d(), true, bs.nb, bs.A.d(), bs.ldp, tmp, out));
-  return GPL_OK;
-}
-
-// out = S^-1 v, S = pred_cov + V_bad (Woodbury through A); v is kept
 int bad_solve_S(Ctx* ctx, BadSite& bs, const double* v, double* out) {
-  const int64_t nb = bs.nb;
-  double *t = bs.b[4].d(), *u = bs.b[5].d(), *u2 = bs.b[6].d(), *w = bs.b[7].d();
-  GPL_TRY(vec_op(ctx, VOP_MUL, nb, v, bs.invVb.d(), t));
-  GPL_TRY(gemv_t(ctx, nb, nb, bs.Lk.d(), bs.ldp, t, u));
-  GPL_TRY(bad_solve_A(ctx, bs, u, u2, w));
-  GPL_TRY(gemv_n(ctx, nb, nb, bs.Lk.d(), bs.ldp, w, u));
-  GPL_TRY(vec_op(ctx, VOP_MUL, nb, u, bs.invVb.d(), u2));
-  GPL_TRY(vec_op(ctx, VOP_SUB, nb, t, u2, out));
-  return GPL_OK;
+  return bad_small_solve_S(ctx, bs.sm, v, out);
 }
 
 // out_i = r_i S^-1 r_i^T for the rows of R (rows x nb, ld ldr); R is kept
@@ -370,8 +416,8 @@ int bad_quad(Ctx* ctx, const Fit* f, int64_t rows, const double* R, int64_t ldr,
 struct FitView {
   Fit f;
   explicit FitView(BadSite& bs) {
-    f.nb = bs.nb; f.ng = bs.ng; f.ldp = bs.ldp; f.ldw = bs.ldw;
-    f.Lk.p = bs.Lk.p; f.Ac.p = bs.A.p; f.Ac_dinv.p = bs.Ad.p; f.invVb.p = bs.invVb.p;
+    f.nb = bs.nb; f.ng = bs.ng; f.ldp = bs.sm.ldp; f.ldw = bs.ldw;
+    f.Lk.p = bs.sm.Lk.p; f.Ac.p = bs.sm.A.p; f.Ac_dinv.p = bs.sm.Ad.p; f.invVb.p = bs.sm.invVb.p;
   }
   ~FitView() { f.Lk.p = f.Ac.p = f.Ac_dinv.p = f.invVb.p = nullptr; }
 };
@@ -381,7 +427,7 @@ struct FitView {
 int bad_final_solve(Ctx* ctx, FullState& st, BadSite& bs) {
   const int64_t n = st.n, ng = bs.ng, nb = bs.nb;
   const int32_t* perm = static_cast<const int32_t*>(bs.perm.p);
-  double* rhs = bs.b[0].d();
+  double* rhs = bs.sm.b[0].d();
   GPL_TRY(vec_op(ctx, VOP_SUB, nb, bs.zp.d() + ng, bs.pm.d(), rhs));
   GPL_TRY(bad_solve_S(ctx, bs, rhs, bs.ab.d()));
   GPL_TRY(gemv_t(ctx, nb, ng, bs.W.d(), bs.ldw, bs.ab.d(), bs.g[0].d()));
@@ -395,13 +441,13 @@ int bad_final_solve(Ctx* ctx, FullState& st, BadSite& bs) {
   return GPL_OK;
 }
 
-// one Laplace step with bad sites; *log_evidence = -Inf and bs.a_fail when the posterior is improper
+// one Laplace step with bad sites; *log_evidence = -Inf and bs.sm.a_fail when the posterior is improper
 int bad_laplace_iter(Ctx* ctx, FullState& st, BadSite& bs, double* log_evidence) {
   double sc[8];
   GPL_TRY(bad_prepare(ctx, st, bs));
   GPL_TRY(bad_factor(ctx, st, bs));
   bs.active = true;
-  if (bs.a_fail) {
+  if (bs.sm.a_fail) {
     *log_evidence = -INFINITY;
     return GPL_OK;
   }
@@ -411,22 +457,10 @@ int bad_laplace_iter(Ctx* ctx, FullState& st, BadSite& bs, double* log_evidence)
   GPL_TRY(reduce(ctx, RED_SUMLOG, ng, bs.Vp.d(), nullptr, 1));
   GPL_TRY(reduce(ctx, RED_DOT, ng, bs.f1.d(), bs.a1.d(), 2));
   GPL_TRY(lik_loglik_sum(ctx, bs.lik_g, ng, bs.f1.d(), bs.yp.d(), 3));
-  // bad sites (R/laplace.R:81-99): f2hat = Lk w, w = A^-1 (Lk^T (z_b / V_b) + Lk^-1 pred_mean)
-  double *c1 = bs.b[0].d(), *c2 = bs.b[1].d(), *c = bs.b[2].d(), *w = bs.b[3].d();
-  double *t = bs.b[4].d(), *u = bs.b[5].d();
-  GPL_TRY(vec_op(ctx, VOP_MUL, nb, bs.zp.d() + ng, bs.invVb.d(), t));
-  GPL_TRY(gemv_t(ctx, nb, nb, bs.Lk.d(), bs.ldp, t, c1));
-  GPL_TRY(vec_op(ctx, VOP_COPY, nb, bs.pm.d(), nullptr, t));
-  GPL_TRY(trsv_lower(ctx, bs.Pd.d(), false, nb, bs.P.d(), bs.ldp, t, c2));
-  GPL_TRY(vec_op(ctx, VOP_ADD, nb, c1, c2, c));
-  GPL_TRY(bad_solve_A(ctx, bs, c, u, w));
-  GPL_TRY(gemv_n(ctx, nb, nb, bs.Lk.d(), bs.ldp, w, t));              // f2hat
-  GPL_TRY(vec_op(ctx, VOP_SUB, nb, w, c2, u));                        // Lk^-1 (f2hat - pred_mean)
-  GPL_TRY(reduce(ctx, RED_SUMSQ, nb, u, nullptr, 4));
-  GPL_TRY(lik_loglik_sum(ctx, bs.lik_b, nb, t, bs.yp.d() + ng, 5));
+  GPL_TRY(bad_small_laplace(ctx, bs.sm, bs.pm.d(), bs.zp.d() + ng, bs.yp.d() + ng, bs.lik_b, 4, 5));
   GPL_TRY(fetch_scalars(ctx, 6, sc));
   const double le1 = sc[3] - 0.5 * sc[2] - 0.5 * (2.0 * sc[0] - sc[1]);
-  const double le2 = sc[5] - 0.5 * sc[4] + 0.5 * bs.logdetA;          // R/laplace.R:100
+  const double le2 = sc[5] - 0.5 * sc[4] + 0.5 * bs.sm.logdetA;          // R/laplace.R:100
   *log_evidence = le1 + le2;
   return bad_final_solve(ctx, st, bs);
 }
@@ -438,7 +472,7 @@ int bad_ep_iter(Ctx* ctx, FullState& st, BadSite& bs, double* X, double* log_evi
   GPL_TRY(bad_prepare(ctx, st, bs));
   GPL_TRY(bad_factor(ctx, st, bs));
   bs.active = true;
-  if (bs.a_fail) {
+  if (bs.sm.a_fail) {
     *log_evidence = -INFINITY;
     return GPL_OK;
   }
@@ -454,15 +488,12 @@ int bad_ep_iter(Ctx* ctx, FullState& st, BadSite& bs, double* X, double* log_evi
   GPL_TRY(reduce(ctx, RED_SUMLOG_PROD, ng, bs.sqp.d(), st.v[V_DIAG].d(), 0));
   GPL_TRY(reduce(ctx, RED_DOT, ng, bs.zp.d(), bs.a1.d(), 1));
   GPL_TRY(ep_evidence_terms(ctx, ng, logZ.d(), vc.d(), mc.d(), bs.zp.d(), bs.Vp.d(), 2));
-  double *dz = bs.b[0].d(), *sdz = bs.b[1].d();
-  GPL_TRY(vec_op(ctx, VOP_SUB, nb, bs.pm.d(), bs.zp.d() + ng, dz));
-  GPL_TRY(bad_solve_S(ctx, bs, dz, sdz));
-  GPL_TRY(reduce(ctx, RED_DOT, nb, dz, sdz, 3));                        // R/ep.R:107-110
+  GPL_TRY(bad_small_ep(ctx, bs.sm, bs.pm.d(), bs.zp.d() + ng, 3));     // R/ep.R:107-110
   GPL_TRY(ep_evidence_terms_bad(ctx, nb, logZ.d() + ng, vc.d() + ng, mc.d() + ng, bs.zp.d() + ng,
                                 bs.Vp.d() + ng, 4));
   GPL_TRY(fetch_scalars(ctx, 5, sc));
   const double le1 = -0.5 * (2.0 * sc[0]) - 0.5 * sc[1] + sc[2];
-  const double le2 = -0.5 * sc[3] + 0.5 * bs.logdetA + sc[4];           // R/ep.R:112-114
+  const double le2 = -0.5 * sc[3] + 0.5 * bs.sm.logdetA + sc[4];           // R/ep.R:112-114
   *log_evidence = le1 + le2;
   GPL_TRY(bad_final_solve(ctx, st, bs));
   // marginal variances.  diag(C^-1)_good = s^2 colsumsq(L^-1) + rows of U S^-1 U^T with
@@ -486,12 +517,12 @@ int bad_ep_iter(Ctx* ctx, FullState& st, BadSite& bs, double* X, double* log_evi
   GPL_TRY(vec_op(ctx, VOP_MUL, ng, bs.Vp.d(), bs.Vp.d(), bs.g[1].d()));       // V^2
   GPL_TRY(vec_op(ctx, VOP_MUL, ng, bs.g[1].d(), bs.g[0].d(), bs.g[1].d()));   // V^2 q
   GPL_TRY(vec_op(ctx, VOP_SUB, ng, fv, bs.g[1].d(), fv));
-  GPL_CUDA(cudaMemsetAsync(bs.T.d(), 0, sizeof(double) * bs.ldp * nb, ctx->stream));
-  GPL_TRY(scale_block(ctx, nb, nb, bs.T.d(), bs.ldp, nullptr, nullptr, 1.0, 1.0, 0));   // I
-  GPL_TRY(bad_quad(ctx, &view.f, nb, bs.T.d(), bs.ldp, bs.b[0].d(), bs.b[1].d()));
-  GPL_TRY(vec_op(ctx, VOP_MUL, nb, bs.Vp.d() + ng, bs.Vp.d() + ng, bs.b[1].d()));
-  GPL_TRY(vec_op(ctx, VOP_MUL, nb, bs.b[1].d(), bs.b[0].d(), bs.b[1].d()));
-  GPL_TRY(vec_op(ctx, VOP_SUB, nb, bs.Vp.d() + ng, bs.b[1].d(), fv + ng));
+  GPL_CUDA(cudaMemsetAsync(bs.sm.T.d(), 0, sizeof(double) * bs.sm.ldp * nb, ctx->stream));
+  GPL_TRY(scale_block(ctx, nb, nb, bs.sm.T.d(), bs.sm.ldp, nullptr, nullptr, 1.0, 1.0, 0));   // I
+  GPL_TRY(bad_quad(ctx, &view.f, nb, bs.sm.T.d(), bs.sm.ldp, bs.sm.b[0].d(), bs.sm.b[1].d()));
+  GPL_TRY(vec_op(ctx, VOP_MUL, nb, bs.Vp.d() + ng, bs.Vp.d() + ng, bs.sm.b[1].d()));
+  GPL_TRY(vec_op(ctx, VOP_MUL, nb, bs.sm.b[1].d(), bs.sm.b[0].d(), bs.sm.b[1].d()));
+  GPL_TRY(vec_op(ctx, VOP_SUB, nb, bs.Vp.d() + ng, bs.sm.b[1].d(), fv + ng));
   GPL_TRY(scatter_vec(ctx, n, fv, perm, st.v[V_FVAR].d()));
   return GPL_OK;
 }
@@ -517,17 +548,17 @@ int save_fit(Ctx* ctx, FullState& st, Fit** out, BadSite* bs = nullptr) {
     f->ng = bs->ng;
     f->nb = bs->nb;
     f->ldw = bs->ldw;
-    f->ldp = bs->ldp;
+    f->ldp = bs->sm.ldp;
     take(f->sqrtV, bs->sqp);
     take(f->perm, bs->perm);
     take(f->xp, bs->xp);
     take(f->alpha_p, bs->alpha_p);
     take(f->W, bs->W);
-    take(f->Lk, bs->Lk);
-    take(f->Lk_dinv, bs->Pd);
-    take(f->Ac, bs->A);
-    take(f->Ac_dinv, bs->Ad);
-    take(f->invVb, bs->invVb);
+    take(f->Lk, bs->sm.Lk);
+    take(f->Lk_dinv, bs->sm.Pd);
+    take(f->Ac, bs->sm.A);
+    take(f->Ac_dinv, bs->sm.Ad);
+    take(f->invVb, bs->sm.invVb);
   } else {
     take(f->sqrtV, st.v[V_SQRTV]);
   }
@@ -567,7 +598,7 @@ int fit_full_impl(Ctx* ctx, const gpl_cf_model* cf, const gpl_lik* lik, const gp
       GPL_TRY(fetch_scalars(ctx, 1, sc));
       if (!(sc[0] > 0.0)) {                       // non-log-concave sites: R/laplace.R:40-117
         GPL_TRY(bad_laplace_iter(ctx, st, bs, &log_evidence));
-        if (bs.a_fail) {                          // fit = list(fmean = fhat_old, log_evidence = -Inf)
+        if (bs.sm.a_fail) {                          // fit = list(fmean = fhat_old, log_evidence = -Inf)
           out->log_evidence = -INFINITY;
           out->iters = it;
           out->converged = 0;
@@ -658,7 +689,7 @@ int fit_full_impl(Ctx* ctx, const gpl_cf_model* cf, const gpl_lik* lik, const gp
     }
     if (hflags & 4) {                                                      // R/ep.R:50-138
       GPL_TRY(bad_ep_iter(ctx, st, bs, X.d(), &log_evidence));
-      if (bs.a_fail) {
+      if (bs.sm.a_fail) {
         // the reference returns fmean = Inf here and lets its loop run on NaNs; report it instead
         out->log_evidence = -INFINITY;
         out->iters = it;

@@ -146,6 +146,25 @@ int grad_trace(Ctx* ctx, const CfPlan& plan, const double* z, int64_t ldz, const
 // col0 >= 0: block mode -- Binv holds only the block column [col0, col0 + ncols) (all n rows, rows
 // above the block's diagonal are never read); the result is that block column's share of the sum.
 
+// ---- nb x nb algebra of the non-log-concave branch (R/laplace.R:66-100, R/ep.R:81-114), shared by
+// method_full (fit.cu) and method_fitc (fitc.cu) ------------------------------------------------
+struct BadSmall {
+  int64_t nb = 0, ldp = 0;
+  bool a_fail = false;     // A not positive definite: improper posterior (log_evidence = -Inf)
+  double logdetA = 0.0;
+  DevBuf P, Pd;            // pred_cov -> its factor (+ block inverses)
+  DevBuf Lk, T;            // clean lower factor of pred_cov; scratch
+  DevBuf A, Ad;            // factor of A = I + Lk^T V_b^-1 Lk
+  DevBuf invVb;
+  DevBuf b[8];             // nb-sized scratch
+};
+int bad_small_alloc(Ctx* ctx, BadSmall& sm, int64_t nb, const double* V_b);
+int bad_small_factor(Ctx* ctx, BadSmall& sm);
+int bad_small_solve_S(Ctx* ctx, BadSmall& sm, const double* v, double* out);
+int bad_small_laplace(Ctx* ctx, BadSmall& sm, const double* pm, const double* z_b, const double* y_b,
+                      const LikDev& lik_b, int slot_df2, int slot_ll);
+int bad_small_ep(Ctx* ctx, BadSmall& sm, const double* pm, const double* z_b, int slot_df2);
+
 // ---- fit object --------------------------------------------------------------------------------
 struct Fit {
   int method = 0;        // 0 full, 1 fitc, 2 rf (m = basis functions, Lm = wcov, alpha = wmean,

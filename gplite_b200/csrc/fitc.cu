@@ -16,6 +16,8 @@
 #include <math.h>
 #include <string.h>
 
+#include <vector>
+
 namespace gpl {
 
 namespace {
@@ -44,7 +46,22 @@ __global__ void fitc_vec_kernel(int op, int64_t n, const double* __restrict__ a,
       break;
     }
     case 3: out[i] = 1.0 / sqrt(a[i]); break;                   // S^-1/2
+    case 4: out[i] = b[i] > 0.0 ? 1.0 / sqrt(a[i]) : 0.0; break; // S^-1/2 on the good sites (V > 0), else 0
+    case 5: out[i] = b[i] > 0.0 ? 1.0 : 0.0; break;              // good-site mask
+    case 6: out[i] = a[i] * b[i]; break;
   }
+}
+
+__global__ void add_diag_vec_kernel(int64_t n, double* __restrict__ A, int64_t lda,
+                                    const double* __restrict__ v) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) A[i * lda + i] += v[i];
+}
+
+__global__ void mirror_lower_to_upper_kernel(int64_t n, double* __restrict__ A, int64_t lda) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t j = blockIdx.y;
+  if (i < n && i > j) A[i * lda + j] = A[j * lda + i];
 }
 
 int fvec(Ctx* ctx, int op, int64_t n, const double* a, const double* b, const double* c,
@@ -173,6 +190,8 @@ int fitc_setup(Ctx* ctx, FitcState& st, const gpl_cf_model* cf, const gpl_lik* l
   return GPL_OK;
 }
 
+int fitc_alpha_f(Ctx* ctx, FitcState& st, const double* mask);
+
 // inv_lemma_get + alpha + f for the current z (v[F_Z]) and V (v[F_V]);   R/linear_algebra.R:3-43,
 // R/laplace.R:139-141.  Leaves: S, factor in A (+A_dinv), alpha, fnew, and scalars
 //   slot 0: sum log S, slot 1: 2 sum log diag L (via logdetA), slot 2: f . alpha
@@ -192,19 +211,208 @@ int fitc_core(Ctx* ctx, FitcState& st, double* logdetA) {
   }
   int32_t info = 0;
   GPL_TRY(dpotrf_with(ctx, st.A_dinv.d(), m, st.A.d(), st.ldm, &info, logdetA));
+  return fitc_alpha_f(ctx, st, nullptr);
+}
+
+// alpha = C^-1 z by the inversion lemma from the factor in A (any non-zero S), f = Kxz Kz^-1 Kzx alpha
+// + D alpha (R/linear_algebra.R:45-126, R/laplace.R:140-141).  mask (0/1 per site, may be NULL)
+// restricts the system to a subset of the sites: alpha is zero elsewhere.
+int fitc_alpha_f(Ctx* ctx, FitcState& st, const double* mask) {
+  const int64_t n = st.n, m = st.m;
   // alpha = z/S - S^-1 Kxz A^-1 Kzx (z/S)
   GPL_TRY(vec_op(ctx, VOP_DIV, n, st.v[F_Z].d(), st.S.d(), st.v[F_T1].d()));
+  if (mask) GPL_TRY(vec_op(ctx, VOP_MUL, n, st.v[F_T1].d(), mask, st.v[F_T1].d()));
   GPL_TRY(gemv_t(ctx, n, m, st.Kxz.d(), st.ldx, st.v[F_T1].d(), st.mv[0].d()));
   GPL_TRY(trsv_lower(ctx, st.A_dinv.d(), false, m, st.A.d(), st.ldm, st.mv[0].d(), st.mv[1].d()));
   GPL_TRY(trsv_lower(ctx, st.A_dinv.d(), true, m, st.A.d(), st.ldm, st.mv[1].d(), st.mv[0].d()));
   GPL_TRY(gemv_n(ctx, n, m, st.Kxz.d(), st.ldx, st.mv[0].d(), st.v[F_T2].d()));
   GPL_TRY(fvec(ctx, 0, n, st.v[F_T1].d(), st.v[F_T2].d(), st.S.d(), nullptr, st.v[F_ALPHA].d()));
+  if (mask) GPL_TRY(vec_op(ctx, VOP_MUL, n, st.v[F_ALPHA].d(), mask, st.v[F_ALPHA].d()));
   // f = Kxz Kz^-1 Kzx alpha + D alpha ;  beta = Kz^-1 Kzx alpha is kept in mv[2]
   GPL_TRY(gemv_t(ctx, n, m, st.Kxz.d(), st.ldx, st.v[F_ALPHA].d(), st.mv[3].d()));
   GPL_TRY(trsv_lower(ctx, st.Lz_dinv.d(), false, m, st.Lz.d(), st.ldm, st.mv[3].d(), st.mv[4].d()));
   GPL_TRY(trsv_lower(ctx, st.Lz_dinv.d(), true, m, st.Lz.d(), st.ldm, st.mv[4].d(), st.mv[2].d()));
   GPL_TRY(gemv_n(ctx, n, m, st.Kxz.d(), st.ldx, st.mv[2].d(), st.v[F_T2].d()));
   GPL_TRY(fvec(ctx, 1, n, st.v[F_T2].d(), st.Dg.d(), st.v[F_ALPHA].d(), nullptr, st.v[F_FNEW].d()));
+  return GPL_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Non-log-concave sites with FITC (R/laplace.R:153-232, R/ep.R:186-272): p(y) = p(y_good) p(y_bad |
+// y_good), then the fit of all sites by the inversion lemma with S = D + V of mixed sign.
+// Everything n-sized is a masked pass over Kxz; the bad block lives in the m-dimensional space of
+// U = Kxz Lz^-T (K_21 = U_b U_g^T is never formed):
+//   E = sum_good k_i k_i^T / S_i,  A1 = Kz + E = L1 L1^T            (fit of the good sites)
+//   K21 C1^-1 K12 = U_b G U_b^T,   G = T - Y^T Y,  T = Lz^-1 E Lz^-T,  Y = L1^-1 E Lz^-T
+//   pred_cov = U_b (I - G) U_b^T + diag(D_b),  pred_mean = U_b Lz^-1 Kzx alpha1
+//   final factor: A = A1 + K_b^T diag(1 / S_b) K_b                  (rank-nb update, S_b may be < 0)
+struct FitcBad {
+  int64_t ng = 0, nb = 0;
+  BadSmall sm;
+};
+
+int fitc_bad_iter(Ctx* ctx, FitcState& st, bool ep, FitcBad& fb, double* log_evidence,
+                  double* log_post_unnorm) {
+  const int64_t n = st.n, m = st.m, ldm = st.ldm;
+  double sc[8];
+  // ---- permutation good-first (only n-vectors are permuted)
+  std::vector<double> hV(n);
+  GPL_CUDA(cudaMemcpyAsync(hV.data(), st.v[F_V].d(), sizeof(double) * n, cudaMemcpyDeviceToHost,
+                           ctx->stream));
+  GPL_CUDA(cudaStreamSynchronize(ctx->stream));
+  std::vector<int32_t> perm(n);
+  int64_t ng = 0;
+  for (int64_t i = 0; i < n; ++i)
+    if (hV[i] > 0.0) perm[ng++] = (int32_t)i;
+  int64_t k = ng;
+  for (int64_t i = 0; i < n; ++i)
+    if (!(hV[i] > 0.0)) perm[k++] = (int32_t)i;
+  const int64_t nb = n - ng;
+  fb.ng = ng;
+  fb.nb = nb;
+  if (ng == 0) {
+    set_error("all pseudo-variances are <= 0: the posterior is not proper");
+    return GPL_ERR_NOT_PD;
+  }
+  DevBuf dperm, mask, yp, trp, offp, zp, Vp, Sp, f1p, Dp, lz, cvp, cmp;
+  GPL_TRY(dperm.alloc(ctx, sizeof(int32_t) * n));
+  GPL_CUDA(cudaMemcpyAsync(dperm.p, perm.data(), sizeof(int32_t) * n, cudaMemcpyHostToDevice, ctx->stream));
+  const int32_t* pp = static_cast<const int32_t*>(dperm.p);
+  for (DevBuf* b : {&mask, &yp, &zp, &Vp, &Sp, &f1p, &Dp}) GPL_TRY(b->alloc(ctx, sizeof(double) * n));
+  GPL_TRY(vec_op(ctx, VOP_ADD, n, st.Dg.d(), st.v[F_V].d(), st.S.d()));
+  GPL_TRY(fvec(ctx, 5, n, nullptr, st.v[F_V].d(), nullptr, nullptr, mask.d()));
+  GPL_TRY(fvec(ctx, 4, n, st.S.d(), st.v[F_V].d(), nullptr, nullptr, st.rs.d()));
+  // ---- fit of the good sites: E, A1 = Kz + E, alpha1, f1
+  DevBuf E;
+  GPL_TRY(E.alloc(ctx, sizeof(double) * ldm * m));
+  for (int64_t r0 = 0; r0 < n; r0 += st.chunk) {
+    const int64_t c = (n - r0) < st.chunk ? (n - r0) : st.chunk;
+    GPL_TRY(scaled_copy_rows(ctx, c, m, st.Kxz.d() + r0, st.ldx, st.rs.d() + r0, st.W.d(), st.ldw));
+    GPL_TRY(dgemm(ctx, true, false, m, m, c, 1.0, st.W.d(), st.ldw, st.W.d(), st.ldw, r0 == 0 ? 0.0 : 1.0,
+                  E.d(), ldm, true));
+  }
+  dim3 g2((unsigned)((m + 255) / 256), (unsigned)m);
+  mirror_lower_to_upper_kernel<<<g2, 256, 0, ctx->stream>>>(m, E.d(), ldm);
+  GPL_LAUNCH_CHECK(ctx);
+  copy_lower_add_kernel<<<g2, 256, 0, ctx->stream>>>(m, st.Kz.d(), ldm, st.A.d(), ldm);
+  GPL_LAUNCH_CHECK(ctx);
+  // A1 = Kz + E (lower): E is full, adding everywhere is harmless (the factorisation reads the lower part)
+  GPL_TRY(vec_op(ctx, VOP_ADD, ldm * m, st.A.d(), E.d(), st.A.d()));
+  int32_t info = 0;
+  double logdetA1 = 0.0;
+  GPL_TRY(dpotrf_with(ctx, st.A_dinv.d(), m, st.A.d(), ldm, &info, &logdetA1));
+  GPL_TRY(fitc_alpha_f(ctx, st, mask.d()));                 // alpha1 (zero on bad sites), f1
+  // ---- evidence of the good sites
+  GPL_TRY(gather_vec(ctx, n, st.y.d(), pp, yp.d()));
+  GPL_TRY(gather_vec(ctx, n, st.v[F_Z].d(), pp, zp.d()));
+  GPL_TRY(gather_vec(ctx, n, st.v[F_V].d(), pp, Vp.d()));
+  GPL_TRY(gather_vec(ctx, n, st.S.d(), pp, Sp.d()));
+  GPL_TRY(gather_vec(ctx, n, st.Dg.d(), pp, Dp.d()));
+  GPL_TRY(gather_vec(ctx, n, st.v[F_FNEW].d(), pp, f1p.d()));
+  LikDev lik_g = st.lik, lik_b = st.lik;
+  if (st.lik.trials) {
+    GPL_TRY(trp.alloc(ctx, sizeof(double) * n));
+    GPL_TRY(gather_vec(ctx, n, st.lik.trials, pp, trp.d()));
+    lik_g.trials = trp.d();
+    lik_b.trials = trp.d() + ng;
+  }
+  if (st.lik.offset) {
+    GPL_TRY(offp.alloc(ctx, sizeof(double) * n));
+    GPL_TRY(gather_vec(ctx, n, st.lik.offset, pp, offp.d()));
+    lik_g.offset = offp.d();
+    lik_b.offset = offp.d() + ng;
+  }
+  GPL_TRY(reduce(ctx, RED_SUMLOG, ng, Sp.d(), nullptr, 0));
+  GPL_TRY(reduce(ctx, RED_SUMLOG, ng, Vp.d(), nullptr, 1));
+  double le1 = 0.0, lpu1 = 0.0;
+  if (!ep) {
+    GPL_TRY(reduce(ctx, RED_DOT, n, st.v[F_FNEW].d(), st.v[F_ALPHA].d(), 2));      // alpha1 = 0 on bad sites
+    GPL_TRY(lik_loglik_sum(ctx, lik_g, ng, f1p.d(), yp.d(), 3));
+    GPL_TRY(fetch_scalars(ctx, 4, sc));
+    const double C_logdet = sc[0] - st.logdet_z + logdetA1;
+    le1 = sc[3] - 0.5 * sc[2] + 0.5 * (sc[1] - C_logdet);
+    lpu1 = sc[3] - 0.5 * sc[2];
+  } else {
+    GPL_TRY(lz.alloc(ctx, sizeof(double) * n));
+    GPL_TRY(cvp.alloc(ctx, sizeof(double) * n));
+    GPL_TRY(cmp.alloc(ctx, sizeof(double) * n));
+    GPL_TRY(gather_vec(ctx, n, st.v[F_LOGZ].d(), pp, lz.d()));
+    GPL_TRY(gather_vec(ctx, n, st.v[F_CV].d(), pp, cvp.d()));
+    GPL_TRY(gather_vec(ctx, n, st.v[F_CM].d(), pp, cmp.d()));
+    GPL_TRY(reduce(ctx, RED_DOT, n, st.v[F_Z].d(), st.v[F_ALPHA].d(), 2));
+    GPL_TRY(ep_evidence_terms(ctx, ng, lz.d(), cvp.d(), cmp.d(), zp.d(), Vp.d(), 3));
+    GPL_TRY(fetch_scalars(ctx, 4, sc));
+    const double C_logdet = sc[0] - st.logdet_z + logdetA1;
+    le1 = -0.5 * C_logdet - 0.5 * sc[2] + sc[3];
+  }
+  // ---- the bad block in U-space
+  const int64_t ldb = round_up(nb, 16);
+  DevBuf Kb, Ub, R, Rt, Tm, Yt, H, pm, pvec;
+  GPL_TRY(Kb.alloc(ctx, sizeof(double) * ldb * m));
+  GPL_TRY(Ub.alloc(ctx, sizeof(double) * ldb * m));
+  GPL_TRY(H.alloc(ctx, sizeof(double) * ldb * m));
+  for (DevBuf* b : {&R, &Rt, &Tm, &Yt}) GPL_TRY(b->alloc(ctx, sizeof(double) * ldm * m));
+  GPL_TRY(pm.alloc(ctx, sizeof(double) * nb));
+  GPL_TRY(pvec.alloc(ctx, sizeof(double) * m));
+  GPL_TRY(gather_rows(ctx, nb, m, st.Kxz.d(), st.ldx, pp + ng, Kb.d(), ldb));
+  GPL_CUDA(cudaMemcpyAsync(Ub.d(), Kb.d(), sizeof(double) * ldb * m, cudaMemcpyDeviceToDevice, ctx->stream));
+  GPL_TRY(dtrsm_right_with(ctx, st.Lz_dinv.d(), true, nb, m, st.Lz.d(), ldm, Ub.d(), ldb));
+  // pred_mean = U_b Lz^-1 (Kzx alpha1)
+  GPL_TRY(gemv_t(ctx, n, m, st.Kxz.d(), st.ldx, st.v[F_ALPHA].d(), st.mv[3].d()));
+  GPL_TRY(trsv_lower(ctx, st.Lz_dinv.d(), false, m, st.Lz.d(), ldm, st.mv[3].d(), pvec.d()));
+  GPL_TRY(gemv_n(ctx, nb, m, Ub.d(), ldb, pvec.d(), pm.d()));
+  // R = E Lz^-T, T = Lz^-1 E Lz^-T = R^T Lz^-T, Y^T = R^T L1^-T
+  GPL_CUDA(cudaMemcpyAsync(R.d(), E.d(), sizeof(double) * ldm * m, cudaMemcpyDeviceToDevice, ctx->stream));
+  GPL_TRY(dtrsm_right_with(ctx, st.Lz_dinv.d(), true, m, m, st.Lz.d(), ldm, R.d(), ldm));
+  GPL_TRY(transpose(ctx, m, m, R.d(), ldm, Rt.d(), ldm));
+  GPL_CUDA(cudaMemcpyAsync(Tm.d(), Rt.d(), sizeof(double) * ldm * m, cudaMemcpyDeviceToDevice, ctx->stream));
+  GPL_TRY(dtrsm_right_with(ctx, st.Lz_dinv.d(), true, m, m, st.Lz.d(), ldm, Tm.d(), ldm));
+  GPL_CUDA(cudaMemcpyAsync(Yt.d(), Rt.d(), sizeof(double) * ldm * m, cudaMemcpyDeviceToDevice, ctx->stream));
+  GPL_TRY(dtrsm_right_with(ctx, st.A_dinv.d(), true, m, m, st.A.d(), ldm, Yt.d(), ldm));
+  // Tm <- I - T + Y^T Y
+  GPL_TRY(scale_block(ctx, m, m, Tm.d(), ldm, nullptr, nullptr, -1.0, 1.0, 0));
+  GPL_TRY(dgemm(ctx, false, true, m, m, m, 1.0, Yt.d(), ldm, Yt.d(), ldm, 1.0, Tm.d(), ldm, false));
+  // pred_cov = U_b (I - G) U_b^T + diag(D_b)
+  GPL_TRY(bad_small_alloc(ctx, fb.sm, nb, Vp.d() + ng));
+  GPL_TRY(dgemm(ctx, false, false, nb, m, m, 1.0, Ub.d(), ldb, Tm.d(), ldm, 0.0, H.d(), ldb, false));
+  GPL_TRY(dgemm(ctx, false, true, nb, nb, m, 1.0, H.d(), ldb, Ub.d(), ldb, 0.0, fb.sm.P.d(), fb.sm.ldp, false));
+  add_diag_vec_kernel<<<(unsigned)((nb + 255) / 256), 256, 0, ctx->stream>>>(nb, fb.sm.P.d(), fb.sm.ldp,
+                                                                             Dp.d() + ng);
+  GPL_LAUNCH_CHECK(ctx);
+  GPL_TRY(bad_small_factor(ctx, fb.sm));
+  if (fb.sm.a_fail) {
+    *log_evidence = -INFINITY;
+    *log_post_unnorm = -INFINITY;
+    return GPL_OK;
+  }
+  if (!ep) {
+    GPL_TRY(bad_small_laplace(ctx, fb.sm, pm.d(), zp.d() + ng, yp.d() + ng, lik_b, 0, 1));
+    GPL_TRY(fetch_scalars(ctx, 2, sc));
+    const double lpu2 = sc[1] - 0.5 * sc[0];
+    *log_post_unnorm = lpu1 + lpu2;
+    *log_evidence = le1 + lpu2 + 0.5 * fb.sm.logdetA;                        // R/laplace.R:216-221
+  } else {
+    GPL_TRY(bad_small_ep(ctx, fb.sm, pm.d(), zp.d() + ng, 0));
+    GPL_TRY(ep_evidence_terms_bad(ctx, nb, lz.d() + ng, cvp.d() + ng, cmp.d() + ng, zp.d() + ng,
+                                  Vp.d() + ng, 1));
+    GPL_TRY(fetch_scalars(ctx, 2, sc));
+    *log_evidence = le1 - 0.5 * sc[0] + 0.5 * fb.sm.logdetA + sc[1];         // R/ep.R:249-254
+    *log_post_unnorm = 0.0;
+  }
+  // ---- fit of all sites: A = Kz + E + K_b^T diag(1/S_b) K_b, then alpha, f by the inversion lemma
+  copy_lower_add_kernel<<<g2, 256, 0, ctx->stream>>>(m, st.Kz.d(), ldm, st.A.d(), ldm);
+  GPL_LAUNCH_CHECK(ctx);
+  GPL_TRY(vec_op(ctx, VOP_ADD, ldm * m, st.A.d(), E.d(), st.A.d()));
+  DevBuf iSb;
+  GPL_TRY(iSb.alloc(ctx, sizeof(double) * nb));
+  GPL_TRY(vec_op(ctx, VOP_INV, nb, Sp.d() + ng, nullptr, iSb.d()));
+  GPL_CUDA(cudaMemcpyAsync(H.d(), Kb.d(), sizeof(double) * ldb * m, cudaMemcpyDeviceToDevice, ctx->stream));
+  GPL_TRY(scale_rows(ctx, nb, m, H.d(), ldb, iSb.d()));
+  GPL_TRY(dgemm(ctx, true, false, m, m, nb, 1.0, H.d(), ldb, Kb.d(), ldb, 1.0, st.A.d(), ldm, true));
+  double logdetA = 0.0;
+  GPL_TRY(dpotrf_with(ctx, st.A_dinv.d(), m, st.A.d(), ldm, &info, &logdetA));
+  GPL_TRY(fitc_alpha_f(ctx, st, nullptr));
+  GPL_CUDA(cudaStreamSynchronize(ctx->stream));            // local buffers are released at scope exit
   return GPL_OK;
 }
 
@@ -257,16 +465,29 @@ int fit_fitc_impl(Ctx* ctx, const gpl_cf_model* cf, const gpl_lik* lik, const gp
     if (maxiter < 1) maxiter = 1;
     GPL_TRY(vec_op(ctx, VOP_FILL, n, nullptr, nullptr, st.v[F_F].d(), 0.0));
     double log_post_old = -INFINITY, log_evidence = 0.0;
-    int it = 0;
+    int it = 0, n_bad = 0;
     for (it = 1; it <= maxiter; ++it) {
       GPL_TRY(lik_pseudodata_la(ctx, st.lik, n, st.v[F_F].d(), st.y.d(), st.v[F_Z].d(), st.v[F_V].d()));
       GPL_TRY(reduce(ctx, RED_MIN, n, st.v[F_V].d(), nullptr, 0));
       GPL_TRY(fetch_scalars(ctx, 1, sc));
-      if (!(sc[0] > 0.0)) {
-        set_error("Laplace (FITC): pseudo-variance <= 0; the reference's bad-site branch "
-                  "(R/laplace.R:153-232) is not implemented");
-        return GPL_ERR_NOT_LOGCONCAVE;
+      if (!(sc[0] > 0.0)) {                                   // R/laplace.R:153-232
+        FitcBad fb;
+        double log_post = 0.0;
+        GPL_TRY(fitc_bad_iter(ctx, st, false, fb, &log_evidence, &log_post));
+        n_bad = (int)fb.nb;
+        if (fb.sm.a_fail) {                                   // list(fmean = fhat_old, log_evidence = -Inf)
+          out->log_evidence = -INFINITY;
+          out->iters = it;
+          set_error("Laplace (FITC): the posterior with non-log-concave sites is not proper");
+          return GPL_ERR_NONFINITE;
+        }
+        std::swap(st.v[F_F].p, st.v[F_FNEW].p);
+        const double diff = log_post - log_post_old;
+        log_post_old = log_post;
+        if (fabs(diff) < approx->tol) break;
+        continue;
       }
+      n_bad = 0;
       double logdetA = 0.0;
       GPL_TRY(fitc_core(ctx, st, &logdetA));
       GPL_TRY(reduce(ctx, RED_SUMLOG, n, st.S.d(), nullptr, 0));
@@ -286,6 +507,7 @@ int fit_fitc_impl(Ctx* ctx, const gpl_cf_model* cf, const gpl_lik* lik, const gp
     out->log_evidence = log_evidence;
     out->iters = it;
     out->converged = !(maxiter > 1 && it == maxiter);
+    out->n_bad = n_bad;
     GPL_TRY(dl(h_fmean, st.v[F_F].d()));
     GPL_TRY(dl(h_z, st.v[F_Z].d()));
     GPL_TRY(dl(h_V, st.v[F_V].d()));
@@ -317,7 +539,7 @@ int fit_fitc_impl(Ctx* ctx, const gpl_cf_model* cf, const gpl_lik* lik, const gp
   GPL_TRY(vec_op(ctx, VOP_COPY, n, st.Kdiag.d(), nullptr, fvar_old.d()));
   double diff_old = INFINITY, damp = approx->damping, log_evidence = 0.0, diff_new = 0.0;
   const int maxiter = approx->maxiter < 1 ? 1 : approx->maxiter;
-  int it = 0, quad_ok = 1;
+  int it = 0, quad_ok = 1, n_bad = 0;
   for (it = 1; it <= maxiter; ++it) {
     EpSiteArgs ea;
     ea.fmean = fmean_old.d(); ea.fvar = fvar_old.d(); ea.z_old = z_old.d(); ea.P_old = P_old.d();
@@ -339,25 +561,40 @@ int fit_fitc_impl(Ctx* ctx, const gpl_cf_model* cf, const gpl_lik* lik, const gp
       set_error("EP (FITC): NaN pseudo-data");
       return GPL_ERR_NONFINITE;
     }
-    if (hflags & 4) {
-      set_error("EP (FITC): pseudo-variance <= 0; the reference's bad-site branch "
-                "(R/ep.R:186-272) is not implemented");
-      return GPL_ERR_NOT_LOGCONCAVE;
+    if (hflags & 4) {                                                        // R/ep.R:186-272
+      FitcBad fb;
+      double unused = 0.0;
+      GPL_TRY(fitc_bad_iter(ctx, st, true, fb, &log_evidence, &unused));
+      n_bad = (int)fb.nb;
+      if (fb.sm.a_fail) {
+        out->log_evidence = -INFINITY;
+        out->iters = it;
+        out->quad_ok = quad_ok;
+        set_error("EP (FITC): the posterior with non-log-concave sites is not proper");
+        return GPL_ERR_NONFINITE;
+      }
+      GPL_TRY(row_norms_via(ctx, st, st.A.d(), st.A_dinv.d(), st.v[F_W].d()));
+      GPL_TRY(fvec(ctx, 2, n, st.v[F_V].d(), st.Dg.d(), st.S.d(), st.v[F_W].d(), st.v[F_FVAR].d()));
+      GPL_TRY(reduce(ctx, RED_MAXABSDIFF, n, fmean_old.d(), st.v[F_FNEW].d(), 0));
+      GPL_TRY(fetch_scalars(ctx, 1, sc));
+      diff_new = sc[0];
+    } else {
+      n_bad = 0;
+      double logdetA = 0.0;
+      GPL_TRY(fitc_core(ctx, st, &logdetA));
+      // fvar = V D / S + (V / S)^2 |L^-1 k_zi|^2
+      GPL_TRY(row_norms_via(ctx, st, st.A.d(), st.A_dinv.d(), st.v[F_W].d()));
+      GPL_TRY(fvec(ctx, 2, n, st.v[F_V].d(), st.Dg.d(), st.S.d(), st.v[F_W].d(), st.v[F_FVAR].d()));
+      GPL_TRY(reduce(ctx, RED_SUMLOG, n, st.S.d(), nullptr, 0));
+      GPL_TRY(reduce(ctx, RED_DOT, n, st.v[F_Z].d(), st.v[F_ALPHA].d(), 1));
+      GPL_TRY(ep_evidence_terms(ctx, n, st.v[F_LOGZ].d(), st.v[F_CV].d(), st.v[F_CM].d(), st.v[F_Z].d(),
+                                st.v[F_V].d(), 2));
+      GPL_TRY(reduce(ctx, RED_MAXABSDIFF, n, fmean_old.d(), st.v[F_FNEW].d(), 3));
+      GPL_TRY(fetch_scalars(ctx, 4, sc));
+      const double C_logdet = sc[0] - st.logdet_z + logdetA;
+      log_evidence = -0.5 * C_logdet - 0.5 * sc[1] + sc[2];                  // R/ep.R:182-184
+      diff_new = sc[3];
     }
-    double logdetA = 0.0;
-    GPL_TRY(fitc_core(ctx, st, &logdetA));
-    // fvar = V D / S + (V / S)^2 |L^-1 k_zi|^2
-    GPL_TRY(row_norms_via(ctx, st, st.A.d(), st.A_dinv.d(), st.v[F_W].d()));
-    GPL_TRY(fvec(ctx, 2, n, st.v[F_V].d(), st.Dg.d(), st.S.d(), st.v[F_W].d(), st.v[F_FVAR].d()));
-    GPL_TRY(reduce(ctx, RED_SUMLOG, n, st.S.d(), nullptr, 0));
-    GPL_TRY(reduce(ctx, RED_DOT, n, st.v[F_Z].d(), st.v[F_ALPHA].d(), 1));
-    GPL_TRY(ep_evidence_terms(ctx, n, st.v[F_LOGZ].d(), st.v[F_CV].d(), st.v[F_CM].d(), st.v[F_Z].d(),
-                              st.v[F_V].d(), 2));
-    GPL_TRY(reduce(ctx, RED_MAXABSDIFF, n, fmean_old.d(), st.v[F_FNEW].d(), 3));
-    GPL_TRY(fetch_scalars(ctx, 4, sc));
-    const double C_logdet = sc[0] - st.logdet_z + logdetA;
-    log_evidence = -0.5 * C_logdet - 0.5 * sc[1] + sc[2];                  // R/ep.R:182-184
-    diff_new = sc[3];
     if (diff_new > diff_old) {
       damp *= approx->damping;
       continue;
@@ -377,6 +614,7 @@ int fit_fitc_impl(Ctx* ctx, const gpl_cf_model* cf, const gpl_lik* lik, const gp
   if (maxiter > 1 && it == maxiter) log_evidence = -INFINITY;
   if (!quad_ok) log_evidence = -INFINITY;
   out->log_evidence = log_evidence;
+  out->n_bad = n_bad;
   GPL_TRY(dl(h_fmean, st.v[F_FNEW].d()));
   GPL_TRY(dl(h_fvar, st.v[F_FVAR].d()));
   GPL_TRY(dl(h_z, st.v[F_Z].d()));

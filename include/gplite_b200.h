@@ -52,9 +52,9 @@ typedef enum gpl_status {
   GPL_ERR_CUDA = 4,
   GPL_ERR_NCCL = 5,
   GPL_ERR_NOMEM = 6,
-  GPL_ERR_NOT_LOGCONCAVE = 7 /* FITC only: some pseudo-variance V <= 0 and the reference's FITC
-                                bad-site branch (R/laplace.R:153-232, R/ep.R:186-272) is not
-                                implemented; method_full handles V <= 0 (gpl_fit_out.n_bad) */
+  GPL_ERR_NOT_LOGCONCAVE = 7 /* some pseudo-variance V <= 0 on a path without the non-log-concave
+                                branch (the multi-GPU drivers); gpl_fit_full / gpl_fit_fitc handle
+                                V <= 0 themselves and report gpl_fit_out.n_bad */
 } gpl_status;
 
 /* ---- model descriptors ---------------------------------------------------------------- */

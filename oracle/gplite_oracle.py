@@ -599,7 +599,57 @@ def laplace_iter_fitc(gp, Kz, Kz_chol, Kxz, D, y, fhat_old, trials=None, offset=
     """R/laplace.R:122-152,234-237."""
     z, V = get_pseudodata_la(gp.lik, fhat_old, y, trials=trials, offset=offset)
     if not np.all(V > 0):
-        raise NonLogConcave("V <= 0 branch (R/laplace.R:153-232) is out of scope")
+        return _laplace_iter_fitc_bad(gp, Kz, Kz_chol, Kxz, D, y, fhat_old, z, V, trials, offset)
+    return _laplace_iter_fitc_good(gp, Kz, Kz_chol, Kxz, D, y, z, V, trials, offset)
+
+
+def _fitc_bad_common(Kz_chol, Kxz, D, z, V, good, bad, fit1):
+    """R/laplace.R:183-203 == R/ep.R:226-246."""
+    Lb = _fsolve(Kz_chol, Kxz[bad].T)
+    Lg = _fsolve(Kz_chol, Kxz[good].T)
+    K21 = Lb.T @ Lg
+    prior_cov = Lb.T @ Lb + np.diag(D[bad])
+    pred_mean = K21 @ fit1["alpha"]
+    pred_cov = prior_cov - K21 @ inv_lemma_solve(fit1["C_inv"], K21.T)
+    Lk = _chol_lower(pred_cov)
+    A = np.eye(len(bad)) + Lk.T @ ((1 / V[bad])[:, None] * Lk)
+    try:
+        A_chol = _chol_lower(A)
+        if not np.all(np.isfinite(A_chol)):
+            A_chol = None
+    except (np.linalg.LinAlgError, sla.LinAlgError):
+        A_chol = None
+    return pred_mean, pred_cov, Lk, A_chol
+
+
+def _laplace_iter_fitc_bad(gp, Kz, Kz_chol, Kxz, D, y, fhat_old, z, V, trials, offset):
+    """R/laplace.R:153-232."""
+    good = np.where(V > 0)[0]
+    bad = np.where(~(V > 0))[0]
+    fit1 = _laplace_iter_fitc_good(gp, Kz, Kz_chol, Kxz[good], D[good], y[good], z[good], V[good],
+                                   _sub(trials, good), _sub(offset, good))
+    pred_mean, pred_cov, Lk, A_chol = _fitc_bad_common(Kz_chol, Kxz, D, z, V, good, bad, fit1)
+    if A_chol is None:
+        return dict(fmean=fhat_old, log_evidence=-np.inf, log_post_unnorm=-np.inf)
+    Q = lambda v: _bsolve_t(Lk, _bsolve_t(A_chol, _fsolve(A_chol, Lk.T @ v)))
+    alpha2 = Q(z[bad] / V[bad])
+    aux = Q(_bsolve_t(Lk, _fsolve(Lk, pred_mean)))
+    f2hat = pred_cov @ (alpha2 + aux)
+    invC2_V2_logdet = 2 * np.sum(np.log(np.diag(A_chol)))
+    df2 = np.sum(_fsolve(Lk, f2hat - pred_mean) ** 2)
+    log_lik2 = get_loglik(gp.lik, f2hat, y[bad], trials=_sub(trials, bad), offset=_sub(offset, bad))
+    lpu = fit1["log_post_unnorm"] + float(log_lik2 - 0.5 * df2)
+    le = fit1["log_evidence"] + float(log_lik2 - 0.5 * df2 + 0.5 * invC2_V2_logdet)
+    S = D + V
+    C_inv = inv_lemma_get(Kz, Kxz, S, logdet=False)                             # :225
+    alpha = inv_lemma_solve(C_inv, z)
+    fhat_new = Kxz @ _bsolve_t(Kz_chol, _fsolve(Kz_chol, Kxz.T @ alpha)) + D * alpha
+    return dict(fmean=fhat_new, z=z, V=V, Kz=Kz, Kxz=Kxz, Kz_chol=Kz_chol, C_inv=C_inv, diag=D,
+                alpha=alpha, log_evidence=le, log_post_unnorm=lpu, n_bad=len(bad))
+
+
+def _laplace_iter_fitc_good(gp, Kz, Kz_chol, Kxz, D, y, z, V, trials, offset):
+    """R/laplace.R:134-152 (all pseudo-variances positive)."""
     S = D + V
     C_inv = inv_lemma_get(Kz, Kxz, S)
     alpha = inv_lemma_solve(C_inv, z)
@@ -747,7 +797,44 @@ def ep_iter_fitc(gp, Kz, Kz_chol, Kxz, D, y, fmean_old, fvar_old, z_old, P_old, 
     if np.any(np.isnan(V) | np.isnan(z)):
         return dict(fmean=None, log_evidence=-np.inf)
     if not np.all(V > 0):
-        raise NonLogConcave("V <= 0 branch (R/ep.R:186-272) is out of scope")
+        return _ep_iter_fitc_bad(gp, Kz, Kz_chol, Kxz, D, pobs)
+    return _ep_iter_fitc_good(Kz, Kz_chol, Kxz, D, pobs)
+
+
+def _ep_iter_fitc_bad(gp, Kz, Kz_chol, Kxz, D, pobs):
+    """R/ep.R:186-272."""
+    z, V = pobs["z"], pobs["var"]
+    good = np.where(V > 0)[0]
+    bad = np.where(~(V > 0))[0]
+    sub = {k: (v[good] if isinstance(v, np.ndarray) else v) for k, v in pobs.items()}
+    fit1 = _ep_iter_fitc_good(Kz, Kz_chol, Kxz[good], D[good], sub)
+    pred_mean, pred_cov, Lk, A_chol = _fitc_bad_common(Kz_chol, Kxz, D, z, V, good, bad, fit1)
+    if A_chol is None:
+        return dict(fmean=None, log_evidence=-np.inf)
+    Q = lambda v: _bsolve_t(Lk, _bsolve_t(A_chol, _fsolve(A_chol, Lk.T @ v)))
+    invC2_V2_logdet = 2 * np.sum(np.log(np.diag(A_chol)))
+    dz = pred_mean - z[bad]
+    df2 = dz @ Q(dz / V[bad])
+    mc, vc, logZ = pobs["mean_cavity"], pobs["var_cavity"], pobs["log_normalizing_const"]
+    le2 = -0.5 * df2 + 0.5 * invC2_V2_logdet + np.sum(logZ[bad]) \
+        + 0.5 * np.sum(np.log((vc[bad] + V[bad]) / V[bad])) \
+        + 0.5 * np.sum((mc[bad] - z[bad]) ** 2 / (vc[bad] + V[bad]))
+    S = D + V
+    C_inv = inv_lemma_get(Kz, Kxz, S, logdet=False)                             # :259
+    alpha = inv_lemma_solve(C_inv, z)
+    inv_Kz_Kzx = _bsolve_t(Kz_chol, _fsolve(Kz_chol, Kxz.T))
+    aux = inv_lemma_solve(C_inv, V, inv_Kz_Kzx, rhs_diag=True)
+    diag1 = np.sum(Kxz.T * aux, axis=0)
+    diag2 = inv_lemma_solve(C_inv, V, D, rhs_diag=True, lhs_diag=True, diag_only=True)
+    fmean_new = Kxz @ _bsolve_t(Kz_chol, _fsolve(Kz_chol, Kxz.T @ alpha)) + D * alpha
+    return dict(fmean=fmean_new, fvar=diag1 + diag2, cavity_mean=mc, cavity_var=vc, z=z, P=1 / V,
+                Kz=Kz, Kxz=Kxz, Kz_chol=Kz_chol, C_inv=C_inv, diag=D, alpha=alpha,
+                log_evidence=float(fit1["log_evidence"] + le2), quad_ok=pobs["quad_ok"], n_bad=len(bad))
+
+
+def _ep_iter_fitc_good(Kz, Kz_chol, Kxz, D, pobs):
+    """R/ep.R:169-185 (all pseudo-variances positive)."""
+    z, V = pobs["z"], pobs["var"]
     S = D + V
     C_inv = inv_lemma_get(Kz, Kxz, S)
     alpha = inv_lemma_solve(C_inv, z)

@@ -584,3 +584,34 @@ def test_method_rf_rejections(ctx):
         with warnings.catch_warnings():
             warnings.simplefilter("ignore")
             g.gp_fit(g.gp_init(cfs=g.cf_sexp() * g.cf_lin(), method=g.method_rf(num_basis=10)), X, y, ctx=ctx)
+
+
+@pytest.mark.parametrize("seed", [44, 41, 42])
+@pytest.mark.parametrize("approx", ["laplace", "ep"])
+def test_non_log_concave_sites_fitc(ctx, approx, seed):
+    """SURVEY 8f-2, FITC variants (R/laplace.R:153-232, R/ep.R:186-272): evidence split over good /
+    bad sites in the m-dimensional space of Kxz Lz^-T, final fit by the inversion lemma with S of
+    mixed sign."""
+    X, y, trials = outlier_counts(seed)
+    Zi = X[np.random.default_rng(seed).permutation(len(X))[:30]].copy()
+    mk = g.approx_laplace if approx == "laplace" else g.approx_ep
+    gp = g.gp_init(cfs=g.cf_sexp(lscale=1.0), lik=g.lik_betabinom(phi=0.3), approx=mk(),
+                   method=g.method_fitc(inducing=Zi))
+    gpo = copy.deepcopy(gp)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        o.gp_fit(gpo, X, y, trials=trials)
+        g.gp_fit(gp, X, y, trials=trials, ctx=ctx)
+    assert gpo.fit.get("n_bad", 0) >= 1, "scenario no longer exercises the bad-site branch"
+    assert gp.fit["n_bad"] == gpo.fit["n_bad"]
+    assert gp.fit["iters"] == gpo.fit["iters"]
+    assert abs(gp.fit["log_evidence"] - gpo.fit["log_evidence"]) < 1e-7 * abs(gpo.fit["log_evidence"])
+    assert scaled_err(gp.fit["alpha"], gpo.fit["alpha"]) < 1e-6
+    assert scaled_err(gp.fit["fmean"], gpo.fit["fmean"]) < 1e-7
+    if approx == "ep":
+        assert scaled_err(gp.fit["fvar"], gpo.fit["fvar"]) < 1e-7
+    Xt = np.random.default_rng(seed + 1).normal(size=(37, 2))
+    p = g.gp_pred(gp, Xt, var=True)
+    po = o.gp_pred(gpo, Xt, var=True)
+    assert scaled_err(p["mean"], po["mean"]) < 1e-7
+    assert scaled_err(p["var"], po["var"]) < 1e-7
