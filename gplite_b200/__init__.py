@@ -10,7 +10,7 @@ from .model import (cf_const, cf_lin, cf_sexp, cf_matern32, cf_matern52, cf_nn, 
                     method_full, method_fitc, method_rf, approx_laplace, approx_ep)
 from .gp import (gp_init, gp_fit, gp_energy, gp_energy_grad, gp_optim, gp_pred, get_param,
                  get_param_vector, set_param, eval_cf, fit_member, lpdf_prior, is_fitted, GP,
-                 gp_loo, gp_compare, gp_draw, gp_pred_cov, get_inducing)
+                 gp_loo, gp_compare, gp_draw, gp_pred_cov, get_inducing, gp_save, gp_load)
 from .quadrature import gauss_hermite_points
 from ._lib import Context, default_context, GplError, NotPositiveDefinite, load as load_library
 

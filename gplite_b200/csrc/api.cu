@@ -88,6 +88,10 @@ int gpl_ctx_create(int device, uint64_t stream, gpl_ctx** out) {
     GPL_CUDA(cudaStreamCreateWithPriority(&c->panel_stream, cudaStreamNonBlocking, hi));
     GPL_CUDA(cudaEventCreateWithFlags(&c->ev_col, cudaEventDisableTiming));
     GPL_CUDA(cudaEventCreateWithFlags(&c->ev_diag, cudaEventDisableTiming));
+    for (int i = 0; i < Ctx::NAUX; ++i) {
+      GPL_CUDA(cudaStreamCreateWithFlags(&c->aux[i], cudaStreamNonBlocking));
+      GPL_CUDA(cudaEventCreateWithFlags(&c->aux_ev[i], cudaEventDisableTiming));
+    }
   }
   cudaDeviceProp prop;
   GPL_CUDA(cudaGetDeviceProperties(&prop, device));
@@ -118,6 +122,10 @@ int gpl_ctx_destroy(gpl_ctx* h) {
   if (c->panel_stream) cudaStreamDestroy(c->panel_stream);
   if (c->ev_col) cudaEventDestroy(c->ev_col);
   if (c->ev_diag) cudaEventDestroy(c->ev_diag);
+  for (int i = 0; i < Ctx::NAUX; ++i) {
+    if (c->aux[i]) cudaStreamDestroy(c->aux[i]);
+    if (c->aux_ev[i]) cudaEventDestroy(c->aux_ev[i]);
+  }
   if (c->own_stream) cudaStreamDestroy(c->stream);
   delete c;
   return GPL_OK;

@@ -398,10 +398,30 @@ int lauum_rec(const Fac& f, double* X, int64_t ldx, int64_t n) {
 constexpr int64_t LL_NB = 1024;
 
 int trtri_ll(const Fac& f, double* L, int64_t ldl, int64_t n, double* T, int64_t ldt) {
-  for (int64_t i0 = 0; i0 < n; i0 += LL_NB) {
-    const int64_t w = (n - i0) < LL_NB ? (n - i0) : LL_NB;
-    GPL_TRY(trtri_rec(f, L + i0 * ldl + i0, ldl, w, i0 / NB));
+  // The diagonal-block inversions are independent chains of small, latency-bound kernels (~60
+  // launches of ~10 us per block, a few SMs each): spread them over the side streams.
+  Ctx* ctx = f.ctx;
+  static const int no_aux = getenv("GPL_NO_AUX_STREAMS") ? 1 : 0;
+  const bool fork = !no_aux && !ctx->profile && ctx->aux[0] != nullptr && n > 2 * LL_NB;
+  cudaStream_t main = ctx->stream;
+  if (fork) {
+    GPL_CUDA(cudaEventRecord(ctx->ev_col, main));
+    for (int i = 0; i < Ctx::NAUX; ++i) GPL_CUDA(cudaStreamWaitEvent(ctx->aux[i], ctx->ev_col, 0));
   }
+  int rc = GPL_OK, b = 0;
+  for (int64_t i0 = 0; i0 < n && rc == GPL_OK; i0 += LL_NB, ++b) {
+    const int64_t w = (n - i0) < LL_NB ? (n - i0) : LL_NB;
+    if (fork) ctx->stream = ctx->aux[b % Ctx::NAUX];
+    rc = trtri_rec(f, L + i0 * ldl + i0, ldl, w, i0 / NB);
+  }
+  ctx->stream = main;
+  if (fork) {
+    for (int i = 0; i < Ctx::NAUX; ++i) {
+      GPL_CUDA(cudaEventRecord(ctx->aux_ev[i], ctx->aux[i]));
+      GPL_CUDA(cudaStreamWaitEvent(main, ctx->aux_ev[i], 0));
+    }
+  }
+  GPL_TRY(rc);
   for (int64_t i0 = LL_NB; i0 < n; i0 += LL_NB) {
     const int64_t w = (n - i0) < LL_NB ? (n - i0) : LL_NB;
     GPL_TRY(dgemm(f.ctx, false, false, w, i0, i0, 1.0, L + i0, ldl, L, ldl, 0.0, T, ldt, false, 0, 2));

@@ -23,6 +23,10 @@ struct Ctx {
   // of step k+1 overlaps the trailing update of step k)
   cudaStream_t panel_stream = nullptr;
   cudaEvent_t ev_col = nullptr, ev_diag = nullptr;
+  // side streams for independent latency-bound chains (the diagonal-block inversions of trtri)
+  static constexpr int NAUX = 4;
+  cudaStream_t aux[NAUX] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t aux_ev[NAUX] = {nullptr, nullptr, nullptr, nullptr};
   int sm_count = 148;
   int64_t launches = 0;
   // scratch: diagonal-block inverses of the most recent factorisation living in this ctx

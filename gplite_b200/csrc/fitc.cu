@@ -52,6 +52,22 @@ __global__ void fitc_vec_kernel(int op, int64_t n, const double* __restrict__ a,
   }
 }
 
+// gp_pred_post.method_fitc(train = TRUE)$var at the training sites as the reference computes it
+// (R/gp_pred.R:245-246,253-256,280-286): its Dt carries no jitter while the fit's D does, so with
+// the exact marginal variance v = V D / S + (V / S)^2 w and c = (C^-1)_ii = 1 / S - w / S^2 the
+// reference's value is v + jitter - (2 jitter V + jitter^2) c.
+__global__ void fitc_train_var_kernel(int64_t n, const double* __restrict__ V,
+                                      const double* __restrict__ D, const double* __restrict__ S,
+                                      const double* __restrict__ w, double jitter,
+                                      double* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double r = V[i] / S[i];
+  const double v = r * D[i] + r * r * w[i];
+  const double c = 1.0 / S[i] - w[i] / (S[i] * S[i]);
+  out[i] = v + jitter - (2.0 * jitter * V[i] + jitter * jitter) * c;
+}
+
 __global__ void add_diag_vec_kernel(int64_t n, double* __restrict__ A, int64_t lda,
                                     const double* __restrict__ v) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -508,6 +524,15 @@ int fit_fitc_impl(Ctx* ctx, const gpl_cf_model* cf, const gpl_lik* lik, const gp
     out->iters = it;
     out->converged = !(maxiter > 1 && it == maxiter);
     out->n_bad = n_bad;
+    if (h_fvar) {
+      // variances at the training sites as gp_loo needs them (gp_pred_post(train = TRUE),
+      // R/gp_loo.R:123)
+      GPL_TRY(row_norms_via(ctx, st, st.A.d(), st.A_dinv.d(), st.v[F_W].d()));
+      fitc_train_var_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(
+          n, st.v[F_V].d(), st.Dg.d(), st.S.d(), st.v[F_W].d(), jitter, st.v[F_FVAR].d());
+      GPL_LAUNCH_CHECK(ctx);
+      GPL_TRY(dl(h_fvar, st.v[F_FVAR].d()));
+    }
     GPL_TRY(dl(h_fmean, st.v[F_F].d()));
     GPL_TRY(dl(h_z, st.v[F_Z].d()));
     GPL_TRY(dl(h_V, st.v[F_V].d()));

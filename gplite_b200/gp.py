@@ -27,6 +27,13 @@ class GP:
         self.x = None
         self._handle = None      # device-resident gp$fit members (C_chol, Kxz ...)
         self._ctx = None
+        self._train = None       # (y, trials, offset, jitter) of the last gp_fit, for gp_save / gp_load
+
+    def __getstate__(self):      # device handles do not travel (gp_save)
+        st = dict(self.__dict__)
+        st["_handle"] = None
+        st["_ctx"] = None
+        return st
 
     def __repr__(self):
         return f"GP(cfs={self.cfs}, lik={self.lik}, {self.method}, {self.approx})"
@@ -250,6 +257,8 @@ def gp_fit(gp, x, y, trials=None, offset=None, jitter=None, ctx=None):
         if meth == "rf":
             fit.pop("alpha")
             fit["wmean"] = wmean
+        if meth == "fitc" and gp.approx.name == "laplace":
+            fit["var_train"] = vec["fvar"]     # gp_pred_post(train = TRUE)$var at the training sites (gp_loo)
         if gp.approx.name == "ep":
             fit.update(fvar=vec["fvar"], cavity_mean=vec["cavity_mean"], cavity_var=vec["cavity_var"],
                        P=1.0 / vec["V"], quad_ok=bool(out.quad_ok))
@@ -263,6 +272,29 @@ def gp_fit(gp, x, y, trials=None, offset=None, jitter=None, ctx=None):
     gp.x = x
     gp.fit["type"] = "analytic"
     gp.fitted = True
+    gp._train = (y, None if trials is None else np.asarray(trials, dtype=np.float64),
+                 None if offset is None else np.asarray(offset, dtype=np.float64), jitter)
+    return gp
+
+
+def gp_save(gp, filename):
+    """R/saveload.R:32-34.  The model, its hyperparameters, the host-side members of gp$fit and the
+    training data are pickled; the device-resident factor is not (see gp_load)."""
+    import pickle
+    with open(filename, "wb") as f:
+        pickle.dump(gp, f)
+
+
+def gp_load(filename, ctx=None):
+    """R/saveload.R:38-41.  A model saved after gp_fit is refitted on load from the stored training
+    data (deterministic: same hyperparameters, same inducing points / random features), which
+    rebuilds the device-resident factor that prediction needs."""
+    import pickle
+    with open(filename, "rb") as f:
+        gp = pickle.load(f)
+    if gp.fitted and gp.fit is not None and gp._train is not None and gp.x is not None:
+        y, trials, offset, jitter = gp._train
+        gp_fit(gp, gp.x, y, trials=trials, offset=offset, jitter=jitter, ctx=ctx)
     return gp
 
 
@@ -621,12 +653,12 @@ def _get_loglik_grid(lik, fgrid, y, trials=None, offset=None):
 
 def gp_loo(gp, x, y, quad_order=11, trials=None, offset=None):
     """Leave-one-out predictive densities, R/gp_loo.R:73-133 (quadrature = TRUE branch), for
-    method_full.  The O(n^3) part -- the posterior variances at the training points for the
-    Laplace approximation -- runs on the GPU through gp_pred; the n x q quadrature is host side."""
+    every method.  The expensive part -- the posterior variances at the training points for the
+    Laplace approximation (gp_pred_post with train = TRUE, R/gp_loo.R:123) -- runs on the GPU: through
+    gp_pred for method_full / method_rf, and as the fit's own marginal variances for method_fitc; the
+    n x q quadrature is host side."""
     if not is_fitted(gp, "analytic"):
         raise RuntimeError("The provied GP model is not fitted. Please call gp_fit (or gp_optim) first.")
-    if gp.method.name != "full":
-        raise NotImplementedError("gp_loo is implemented for method_full")
     y = np.asarray(y, dtype=np.float64).ravel()
     n = len(y)
     if gp.approx.name == "ep":                                     # R/gp_loo.R:131-133
@@ -634,7 +666,7 @@ def gp_loo(gp, x, y, quad_order=11, trials=None, offset=None):
     else:                                                          # R/gp_loo.R:119-129
         fhat, z, V = gp.fit["fmean"], gp.fit["z"], gp.fit["V"]
         grad = (z - fhat) / V
-        post_var = gp_pred(gp, x, var=True)["var"]
+        post_var = gp.fit["var_train"] if gp.method.name == "fitc" else gp_pred(gp, x, var=True)["var"]
         loo_var = 1.0 / (1.0 / post_var - 1.0 / V)
         loo_mean = fhat - loo_var * grad
     xq, wq = gauss_hermite_points(quad_order)

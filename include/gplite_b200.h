@@ -292,7 +292,9 @@ int gpl_fit_full(gpl_ctx* ctx, const gpl_cf_model* cf, const gpl_lik* lik, const
                  double* V, double* alpha, double* fvar, double* cavity_mean, double* cavity_var,
                  gpl_fit** fit);
 
-/* method_fitc with explicit inducing points zind (m x d). */
+/* method_fitc with explicit inducing points zind (m x d).  With approx_laplace, fvar (if not NULL)
+ * receives gp_pred_post.method_fitc(train = TRUE)$var at the training sites, which gp_loo needs
+ * (R/gp_loo.R:123; R/gp_pred.R:245-256,280-286, including that code's jitter-free Dt). */
 int gpl_fit_fitc(gpl_ctx* ctx, const gpl_cf_model* cf, const gpl_lik* lik, const gpl_approx* approx,
                  const double* x, int64_t n, int32_t d, const double* zind, int64_t m,
                  const double* y, const double* trials, const double* offset, double jitter,

@@ -1207,14 +1207,20 @@ def gp_pred(gp, xnew, var=False, cfind=None, jitter=None, offset=None, transform
 
 
 def gp_loo(gp, x, y, quad_order=11, trials=None, offset=None):
-    """R/gp_loo.R:73-133, quadrature = TRUE branch, method_full."""
+    """R/gp_loo.R:73-133, quadrature = TRUE branch (any method: the Laplace branch predicts at the
+    training points with train = TRUE, R/gp_loo.R:123)."""
     y = np.asarray(y, dtype=np.float64)
     if gp.approx.name == "ep":
         loo_mean, loo_var = gp.fit["cavity_mean"], gp.fit["cavity_var"]
     else:
         fhat, z, V = gp.fit["fmean"], gp.fit["z"], gp.fit["V"]
         grad = (z - fhat) / V
-        post_var = gp_pred_post_full(gp, _as_matrix(x), var=True)["var"]
+        if gp.method.name == "full":
+            post_var = gp_pred_post_full(gp, _as_matrix(x), var=True)["var"]
+        elif gp.method.name == "fitc":
+            post_var = gp_pred_post_fitc(gp, _as_matrix(x), var=True, train=True)["var"]
+        else:
+            post_var = gp_pred_post_rf(gp, _as_matrix(x), var=True)["var"]
         loo_var = 1 / (1 / post_var - 1 / V)
         loo_mean = fhat - loo_var * grad
     xq, wq = gauss_hermite_points(quad_order)

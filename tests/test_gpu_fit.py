@@ -615,3 +615,42 @@ def test_non_log_concave_sites_fitc(ctx, approx, seed):
     po = o.gp_pred(gpo, Xt, var=True)
     assert scaled_err(p["mean"], po["mean"]) < 1e-7
     assert scaled_err(p["var"], po["var"]) < 1e-7
+
+
+@pytest.mark.parametrize("method", ["fitc", "rf"])
+def test_gp_loo_other_methods(ctx, method):
+    """gp_loo dispatches on the approximation only (R/gp_loo.R:111-133): the Laplace branch predicts at
+    the training points with train = TRUE, which for FITC carries the diagonal correction
+    (R/gp_pred.R:253-256,280-286) -- here the fit's own marginal variances."""
+    X, y = _classification(300, 2, 10)
+    Zi = X[np.random.default_rng(1).permutation(300)[:25]].copy()
+    meth = g.method_fitc(inducing=Zi) if method == "fitc" else g.method_rf(num_basis=40, seed=2)
+    for approx in ((g.approx_laplace(), g.approx_ep()) if method == "fitc" else (g.approx_laplace(),)):
+        gp = g.gp_init(cfs=g.cf_sexp(lscale=1.0), lik=g.lik_bernoulli(), approx=approx, method=meth)
+        gpo = copy.deepcopy(gp)
+        g.gp_fit(gp, X, y, ctx=ctx)
+        o.gp_fit(gpo, X, y)
+        l = g.gp_loo(gp, X, y)
+        lo = o.gp_loo(gpo, X, y)
+        assert abs(l["loo"] - lo["loo"]) < 1e-7 * abs(lo["loo"]), (method, approx)
+        assert scaled_err(l["loos"], lo["loos"]) < 1e-6, (method, approx)
+
+
+def test_gp_save_load_roundtrip(ctx, tmp_path):
+    """R/saveload.R: a fitted model survives gp_save / gp_load and predicts the same."""
+    rng = np.random.default_rng(4)
+    X = rng.normal(size=(200, 2))
+    y = np.sin(X[:, 0]) + 0.1 * rng.normal(size=200)
+    gp = g.gp_init(cfs=g.cf_matern32(lscale=0.8), lik=g.lik_gaussian(sigma=0.2), method=g.method_fitc(num_inducing=20))
+    g.gp_fit(gp, X, y, ctx=ctx)
+    p0 = g.gp_pred(gp, X[:30], var=True)
+    fn = str(tmp_path / "model.pkl")
+    g.gp_save(gp, fn)
+    gp2 = g.gp_load(fn, ctx=ctx)
+    assert gp2.fitted and np.array_equal(gp2.method.inducing, gp.method.inducing)
+    assert abs(gp2.fit["log_evidence"] - gp.fit["log_evidence"]) < 1e-9 * abs(gp.fit["log_evidence"])
+    p1 = g.gp_pred(gp2, X[:30], var=True)
+    assert scaled_err(p1["mean"], p0["mean"]) < 1e-10 and scaled_err(p1["var"], p0["var"]) < 1e-10
+    fn2 = str(tmp_path / "unfitted.pkl")
+    g.gp_save(g.gp_init(cfs=g.cf_sexp()), fn2)
+    assert not g.gp_load(fn2).fitted
