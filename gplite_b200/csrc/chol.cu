@@ -454,9 +454,16 @@ int potrf_ll(const Fac& f, double* A, int64_t lda, int64_t n) {
 // factored (the recursive routine: a latency-bound chain of small kernels) on a high-priority side
 // stream while the main stream applies panel k to the rest of the trailing matrix -- so the
 // small-kernel chain leaves the critical path.
-constexpr int64_t LA_NB = 2048;
+// Panel width: measured (tools/potrf_variants.sh) 1024 wins up to n = 16384 (53.7 vs 56.9 ms), 2048
+// at n = 32768 (372.3 vs 374.6 ms; plain recursion 383.9 ms).  GPL_LA_NB overrides (multiple of 128).
+static int64_t la_nb_for(int64_t n) {
+  static const int64_t forced = getenv("GPL_LA_NB") ? atoll(getenv("GPL_LA_NB")) : 0;
+  if (forced > 0) return forced;
+  return n >= 24576 ? 2048 : 1024;
+}
 
 int potrf_lookahead(const Fac& f, double* A, int64_t lda, int64_t n) {
+  const int64_t LA_NB = la_nb_for(n);
   Ctx* ctx = f.ctx;
   cudaStream_t main = ctx->stream, side = ctx->panel_stream;
   const int64_t nblk = (n + LA_NB - 1) / LA_NB;
@@ -530,16 +537,17 @@ int dpotrf_with(Ctx* ctx, double* dinv, int64_t n, double* A, int64_t lda, int32
   const int32_t big = 0x7fffffff;
   GPL_CUDA(cudaMemcpyAsync(ctx->d_info, &big, sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
   Fac f{ctx, dinv};
-  // Measured on B200 (profiles/r01_probe_v8_lookahead.jsonl): 409 ms vs 403 ms for the plain
-  // recursion at n = 32768 -- the K = 2048 blocked updates lose what the overlap gains -- so the
-  // look-ahead path is opt-in (GPL_LOOKAHEAD=1) until the side-stream chain is shortened.
-  static const int lookahead_on = getenv("GPL_LOOKAHEAD") ? atoi(getenv("GPL_LOOKAHEAD")) : 0;
+  // Look-ahead (diagonal-block chain of step k+1 on a high-priority side stream) is the default:
+  // 372 ms vs 384 ms for the plain recursion at n = 32768 once the GEMM epilogue stopped penalising
+  // the K = 1024..2048 blocked updates (it had measured 409 vs 403 ms before); GPL_LOOKAHEAD=0
+  // disables it.
+  static const int lookahead_on = getenv("GPL_LOOKAHEAD") ? atoi(getenv("GPL_LOOKAHEAD")) : 1;
   static const int ll_off = getenv("GPL_NO_LEFTLOOKING") ? 1 : 0;
   // Left-looking potrf measured 436 ms vs 403 ms for the recursion at n = 32768 (its panel TRSMs and
   // 1024-block factorisations are exposed), so it is opt-in; left-looking trtri is a win (370 vs 411 ms)
   // and is the default.
   static const int potrf_ll_on = getenv("GPL_POTRF_LL") ? atoi(getenv("GPL_POTRF_LL")) : 0;
-  if (n >= 4 * LA_NB && ctx->panel_stream && lookahead_on && !ctx->profile) {
+  if (n >= 4 * la_nb_for(n) && ctx->panel_stream && lookahead_on && !ctx->profile) {
     GPL_TRY(potrf_lookahead(f, A, lda, n));
   } else if (n >= 4 * LL_NB && !ll_off && potrf_ll_on) {
     GPL_TRY(potrf_ll(f, A, lda, n));
