@@ -266,7 +266,7 @@ def run_ours(args, rank, world, local_rank):
         del a, b
         traffic = None
         try:      # DRAM bytes of all GEMM launches of one step, from the committed ncu capture
-            tj = json.load(open(os.path.join(ROOT, "profiles", "r01_gemm_traffic_egrad32768_v16.json")))
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r01_gemm_traffic_egrad32768_v19.json")))
             if n == N_FULL:
                 traffic = tj["dram_bytes_total"]
         except Exception:
@@ -274,7 +274,7 @@ def run_ours(args, rank, world, local_rank):
         line["roofline"] = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                             "frac": achieved / peak, "traffic": traffic,
                             "traffic_note": "bytes per step over all launches of the kernel (ncu dram__bytes_read+write, "
-                                            "profiles/r01_gemm_traffic_egrad32768_v16.json, launch list profiles/r01_launches_egrad32768_v16.csv); achieved is per step likewise",
+                                            "profiles/r01_gemm_traffic_egrad32768_v19.json, launch list profiles/r01_launches_egrad32768_v19.csv); achieved is per step likewise",
                             "kernel": "gemm_f64_kernel (DMMA.8x8x4 FP64 tensor path)",
                             "peak_source": "cuBLAS DGEMM 8192^3 burst measured in this run (no fp64 entry in "
                                            "MEASURED_PEAKS.json); nominal B200 FP64 tensor 37-40 TFLOP/s",

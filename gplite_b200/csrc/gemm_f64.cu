@@ -157,13 +157,13 @@ __global__ void __launch_bounds__(CF::THREADS) gemm_f64_kernel(const GemmArgs p)
   const int g = lane >> 2, t = lane & 3;
   const int wm = warp % CF::WARPS_M, wn = warp / CF::WARPS_M;
 
-  // Grouped rasterisation: consecutive CTAs walk GROUP_M row-tiles x all column-tiles, so the ~148
-  // tiles resident at any time share ~8 + 18 operand panels instead of 1 + 148 (DRAM traffic of the
+  // Grouped rasterisation: consecutive CTAs walk GROUP_M row-tiles (1024 rows) x all column-tiles, so
+  // the ~148 tiles resident at any time share ~8 + 18 operand panels instead of 1 + 148 (DRAM traffic of the
   // plain column-major order was 811 GB per energy+gradient evaluation at n = 32768).  In lower
   // mode the same order runs over the full square of tiles and CTAs above the diagonal exit.
   int bm, bn;
   {
-    constexpr int GROUP_M = 8;
+    constexpr int GROUP_M = 1024 / BM;     // 1024 rows per group for every tile size
     const int L = blockIdx.x;
     const int per_group = GROUP_M * p.tiles_n;
     const int group = L / per_group;
