@@ -114,10 +114,27 @@ def test_dpotrf_reports_non_pd(ctx):
     assert b"201" in ctx.lib.gpl_last_error()
 
 
+def test_dpotrf_reports_non_pd_on_the_lookahead_path(ctx):
+    """n >= 4 panels: the factorisation runs on two streams (look-ahead); the first failing pivot must
+    still be reported exactly."""
+    n, bad = 4608, 3333
+    gen = torch.Generator(device="cuda").manual_seed(1)
+    Q = torch.randn(n, 64, dtype=torch.float64, device="cuda", generator=gen)
+    A = Q @ Q.T / 64 + 0.5 * torch.eye(n, dtype=torch.float64, device="cuda")
+    A[bad, bad] = -1.0
+    ld = (n + 15) // 16 * 16
+    dA = torch.zeros(n, ld, dtype=torch.float64, device="cuda")
+    dA[:, :n] = A
+    info = C.c_int32(0)
+    torch.cuda.synchronize()
+    st = ctx.lib.gpl_dpotrf_dev(ctx.h, n, ptr(dA), ld, C.byref(info), None)
+    sync(ctx)
+    assert st == _lib.GPL_ERR_NOT_PD and info.value == bad + 1
+
+
 @pytest.mark.parametrize("n", [8192, 8500])
 def test_dpotrf_large(ctx, n):
-    """Large n (all three GEMM tile configurations, deep recursion; with GPL_LOOKAHEAD=1 also the
-    blocked look-ahead path): check against cuSOLVER through torch on the device, plus the inverse
+    """Large n (all three GEMM tile configurations, deep recursion, the blocked look-ahead path): check against cuSOLVER through torch on the device, plus the inverse
     built on the same factor."""
     gen = torch.Generator(device="cuda").manual_seed(n)
     Q = torch.randn(n, 96, dtype=torch.float64, device="cuda", generator=gen)
