@@ -1020,15 +1020,18 @@ int pred_full_cov_dev(Ctx* ctx, const Fit* fit, const gpl_cf_model* cf, const do
 
 int pred_full_cov_impl(Ctx* ctx, const Fit* fit, const gpl_cf_model* cf, const double* xt, int64_t nt,
                        uint64_t term_mask, double jitter, double* mean, double* cov) {
-  if (!fit || fit->method != 0 || nt <= 0 || !xt || !mean || !cov) {
-    set_error("gpl_pred_full_cov: bad arguments");
+  if (!fit || fit->method > 1 || nt <= 0 || !xt || !mean || !cov) {
+    set_error("gpl_pred_full_cov: bad arguments (method_full and method_fitc fits)");
     return GPL_ERR_BAD_ARG;
   }
   DevBuf dm, dc;
   const int64_t ldc = round_up(nt, 16);
   GPL_TRY(dm.alloc(ctx, sizeof(double) * nt));
   GPL_TRY(dc.alloc(ctx, sizeof(double) * ldc * nt));
-  GPL_TRY(pred_full_cov_dev(ctx, fit, cf, xt, nt, term_mask, jitter, dm.d(), dc.d(), ldc));
+  if (fit->method == 0)
+    GPL_TRY(pred_full_cov_dev(ctx, fit, cf, xt, nt, term_mask, jitter, dm.d(), dc.d(), ldc));
+  else
+    GPL_TRY(pred_fitc_cov_dev(ctx, fit, cf, xt, nt, term_mask, jitter, dm.d(), dc.d(), ldc));
   GPL_TRY(download(ctx, mean, dm.d(), nt));
   GPL_CUDA(cudaMemcpy2DAsync(cov, sizeof(double) * nt, dc.d(), sizeof(double) * ldc,
                              sizeof(double) * nt, nt, cudaMemcpyDeviceToHost, ctx->stream));
@@ -1041,7 +1044,7 @@ int pred_full_cov_impl(Ctx* ctx, const Fit* fit, const gpl_cf_model* cf, const d
 int draw_full_impl(Ctx* ctx, const Fit* fit, const gpl_cf_model* cf, const double* xt, int64_t nt,
                    int d_prior, uint64_t term_mask, double jitter, const double* normals,
                    int64_t draws, double* out) {
-  if ((fit && fit->method != 0) || nt <= 0 || draws <= 0 || !xt || !normals || !out ||
+  if ((fit && fit->method > 1) || nt <= 0 || draws <= 0 || !xt || !normals || !out ||
       (!fit && d_prior <= 0)) {
     set_error("gpl_draw_full: bad arguments");
     return GPL_ERR_BAD_ARG;
@@ -1052,7 +1055,9 @@ int draw_full_impl(Ctx* ctx, const Fit* fit, const gpl_cf_model* cf, const doubl
   GPL_TRY(dc.alloc(ctx, sizeof(double) * ldc * nt));
   GPL_TRY(Lc.alloc(ctx, sizeof(double) * ldc * nt));
   GPL_TRY(dcd.alloc(ctx, sizeof(double) * ((nt + NB - 1) / NB) * NB * NB));
-  if (fit) {
+  if (fit && fit->method == 1) {
+    GPL_TRY(pred_fitc_cov_dev(ctx, fit, cf, xt, nt, term_mask, jitter, dm.d(), dc.d(), ldc));
+  } else if (fit) {
     GPL_TRY(pred_full_cov_dev(ctx, fit, cf, xt, nt, term_mask, jitter, dm.d(), dc.d(), ldc));
   } else {
     HostPlan hp;

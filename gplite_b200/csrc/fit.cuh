@@ -205,4 +205,10 @@ struct Fit {
   int64_t rf_nweights = 0;
 };
 
+// joint predictions on the device (mean nt, cov nt x nt with jitter on the diagonal)
+int pred_full_cov_dev(Ctx* ctx, const Fit* fit, const gpl_cf_model* cf, const double* xt, int64_t nt,
+                      uint64_t term_mask, double jitter, double* d_mean, double* d_cov, int64_t ldc);
+int pred_fitc_cov_dev(Ctx* ctx, const Fit* fit, const gpl_cf_model* cf, const double* xt, int64_t nt,
+                      uint64_t term_mask, double jitter, double* d_mean, double* d_cov, int64_t ldc);
+
 }  // namespace gpl

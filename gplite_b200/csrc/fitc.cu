@@ -706,6 +706,51 @@ int pred_fitc_impl(Ctx* ctx, const Fit* fit, const gpl_cf_model* cf, const doubl
   return GPL_OK;
 }
 
+// Joint prediction for method_fitc (gp_pred_post.method_fitc with cov = TRUE, R/gp_pred.R:262-273):
+// substituting the inversion lemma, prior_cov - Kt_aux2^T (Kt_aux1 C^-1 Kt_aux1^T) Kt_aux2 collapses to
+//   cov = diag(k_tt - |Lz^-1 k_zt|^2) + (Ktz L^-T)(Ktz L^-T)^T + jitter I,   L L^T = Kz + Kzx S^-1 Kxz
+// (the same identity as the variances above).  d_mean: nt, d_cov: nt x nt (ld ldc), on the device.
+int pred_fitc_cov_dev(Ctx* ctx, const Fit* fit, const gpl_cf_model* cf, const double* xt, int64_t nt,
+                      uint64_t term_mask, double jitter, double* d_mean, double* d_cov, int64_t ldc) {
+  const int64_t m = fit->m;
+  const int d = fit->d;
+  if ((double)nt * (double)m * 8.0 > 48e9) {
+    set_error("joint prediction of %lld points with m = %lld is too large; predict fewer points at a time",
+              (long long)nt, (long long)m);
+    return GPL_ERR_NOMEM;
+  }
+  HostPlan hp;
+  GPL_TRY(make_plan(cf, d, term_mask, &hp));
+  const int F = hp.plan.nfeat > 0 ? hp.plan.nfeat : 1;
+  DevBuf dxt, Zz, Zt, Ktz, W, dt, t1;
+  const int64_t ldk = round_up(nt, 16);
+  GPL_TRY(dxt.alloc(ctx, sizeof(double) * nt * d));
+  GPL_CUDA(cudaMemcpyAsync(dxt.p, xt, sizeof(double) * nt * d, cudaMemcpyHostToDevice, ctx->stream));
+  GPL_TRY(Zz.alloc(ctx, sizeof(double) * m * F));
+  GPL_TRY(Zt.alloc(ctx, sizeof(double) * nt * F));
+  GPL_TRY(prep_features(ctx, hp, fit->zind.d(), m, m, Zz.d(), m));
+  GPL_TRY(prep_features(ctx, hp, dxt.d(), nt, nt, Zt.d(), nt));
+  GPL_TRY(Ktz.alloc(ctx, sizeof(double) * ldk * m));
+  GPL_TRY(W.alloc(ctx, sizeof(double) * ldk * m));
+  GPL_TRY(dt.alloc(ctx, sizeof(double) * nt));
+  GPL_TRY(t1.alloc(ctx, sizeof(double) * nt));
+  GPL_TRY(cf_pairwise(ctx, hp.plan, Zt.d(), nt, nt, Zz.d(), m, m, false, 0.0, Ktz.d(), ldk));
+  GPL_TRY(gemv_n(ctx, nt, m, Ktz.d(), ldk, fit->sqrtV.d(), d_mean));          // beta rides in sqrtV
+  GPL_TRY(cf_diag(ctx, hp.plan, Zt.d(), nt, Zt.d(), nt, nt, 0.0, dt.d()));
+  GPL_TRY(scaled_copy_rows(ctx, nt, m, Ktz.d(), ldk, nullptr, W.d(), ldk));
+  GPL_TRY(dtrsm_right_with(ctx, fit->Kz_dinv.d(), true, nt, m, fit->Kz_chol.d(), fit->ldm, W.d(), ldk));
+  GPL_TRY(rowsumsq(ctx, nt, m, W.d(), ldk, t1.d()));
+  GPL_TRY(vec_op(ctx, VOP_SUB, nt, dt.d(), t1.d(), dt.d()));                   // Dt
+  GPL_TRY(dtrsm_right_with(ctx, fit->Lm_dinv.d(), true, nt, m, fit->Lm.d(), fit->ldm, Ktz.d(), ldk));
+  GPL_TRY(dgemm(ctx, false, true, nt, nt, m, 1.0, Ktz.d(), ldk, Ktz.d(), ldk, 0.0, d_cov, ldc, false));
+  GPL_TRY(vec_op(ctx, VOP_FILL, nt, nullptr, nullptr, t1.d(), jitter));
+  GPL_TRY(vec_op(ctx, VOP_ADD, nt, dt.d(), t1.d(), dt.d()));
+  add_diag_vec_kernel<<<(unsigned)((nt + 255) / 256), 256, 0, ctx->stream>>>(nt, d_cov, ldc, dt.d());
+  GPL_LAUNCH_CHECK(ctx);
+  GPL_CUDA(cudaStreamSynchronize(ctx->stream));     // local buffers are released at scope exit
+  return GPL_OK;
+}
+
 }  // namespace gpl
 
 using namespace gpl;

@@ -554,7 +554,7 @@ def gp_pred(gp, xnew, var=False, quantiles=None, transform=False, cfind=None, ji
 
 # ------------------------------------------------------------------------------- gp_draw
 def gp_pred_cov(gp, xnew, cfind=None, jitter=None, ctx=None):
-    """gp_pred_post / gp_pred_prior with cov = TRUE (R/gp_pred.R:142-156, 202-232), method_full:
+    """gp_pred_post / gp_pred_prior with cov = TRUE (R/gp_pred.R:142-156, 202-232, 262-273):
     dict(mean, cov) of the latent, jitter on the diagonal of cov."""
     xnew = _as_matrix(xnew)
     nt = xnew.shape[0]
@@ -562,8 +562,8 @@ def gp_pred_cov(gp, xnew, cfind=None, jitter=None, ctx=None):
     if not is_fitted(gp, "analytic"):
         K = eval_cf(gp.cfs, xnew, xnew, cfind=cfind, ctx=ctx)
         return dict(mean=np.zeros(nt), cov=K + jit * np.eye(nt))
-    if gp.method.name != "full":
-        raise NotImplementedError("joint predictive covariance is implemented for method_full")
+    if gp.method.name not in ("full", "fitc"):
+        raise NotImplementedError("joint predictive covariance is implemented for method_full and method_fitc")
     c = gp._ctx
     factors, _ = M.flatten_cfs(gp.cfs)
     pm = _lib.PackedModel(factors)
@@ -608,8 +608,9 @@ def gp_draw(gp, xnew, draws=1, transform=True, target=False, marginal=False, cfi
         pred = gp_pred(gp, xnew, var=True, cfind=cfind, jitter=jitter, ctx=ctx)
         sample = pred["mean"][:, None] + np.sqrt(pred["var"])[:, None] * normals
     else:
-        if gp.method.name != "full":
-            raise NotImplementedError("joint draws are implemented for method_full (use marginal=True for FITC)")
+        if gp.method.name not in ("full", "fitc") or (gp.method.name == "fitc" and not fitted):
+            raise NotImplementedError("joint draws are implemented for method_full (prior and posterior) "
+                                      "and fitted method_fitc models; use marginal=True otherwise")
         c = gp._ctx if fitted else (ctx or _lib.default_context())
         factors, _ = M.flatten_cfs(gp.cfs)
         pm = _lib.PackedModel(factors)

@@ -346,14 +346,16 @@ int gpl_pred_full(gpl_ctx* ctx, const gpl_fit* fit, const gpl_cf_model* cf, cons
 int gpl_pred_fitc(gpl_ctx* ctx, const gpl_fit* fit, const gpl_cf_model* cf, const double* xt,
                   int64_t nt, uint64_t term_mask, double* mean, double* var);
 
-/* Joint prediction, method_full: mean[nt] and cov[nt x nt] (column-major) of the latent at xt,
- * jitter on the diagonal of cov (gp_pred_post.method_full with cov = TRUE, R/gp_pred.R:202-232). */
+/* Joint prediction for method_full and method_fitc fits: mean[nt] and cov[nt x nt] (column-major)
+ * of the latent at xt, jitter on the diagonal of cov (gp_pred_post.method_full / .method_fitc with
+ * cov = TRUE, R/gp_pred.R:202-232, 262-273). */
 int gpl_pred_full_cov(gpl_ctx* ctx, const gpl_fit* fit, const gpl_cf_model* cf, const double* xt,
                       int64_t nt, uint64_t term_mask, double jitter, double* mean, double* cov);
 /* gp_draw (R/gp_draw.R:66-78,105-123, mvnrnd :183-207): out (nt x draws, column-major) =
  * mean + t(chol(cov)) %*% normals, normals nt x draws standard normal variates supplied by the
  * caller (R's stats::rnorm stream is not reproducible outside R).  fit != NULL: posterior of a
- * method_full fit (d ignored); fit == NULL: prior, mean 0, cov = K(xt, xt) + jitter I, xt nt x d.
+ * method_full or method_fitc fit (d ignored); fit == NULL: method_full prior, mean 0,
+ * cov = K(xt, xt) + jitter I, xt nt x d.
  * Offsets, the response transform and generate_target stay with the caller. */
 int gpl_draw_full(gpl_ctx* ctx, const gpl_fit* fit, const gpl_cf_model* cf, const double* xt, int64_t nt,
                   int32_t d, uint64_t term_mask, double jitter, const double* normals, int64_t draws,

@@ -1133,22 +1133,23 @@ def gp_draw_latent(gp, xt, normals, marginal=False, cfind=None, jitter=None):
     if not getattr(gp, "fitted", False):
         cov = eval_cf(gp.cfs, xt, xt, cfind) + jit * np.eye(nt)          # R/gp_pred.R:142-156
         return _chol_lower(cov) @ normals
+    post = gp_pred_post_full if gp.method.name == "full" else gp_pred_post_fitc
     if marginal:
-        pred = gp_pred_post_full(gp, xt, var=True, cfind=cfind, jitter=jitter)
+        pred = post(gp, xt, var=True, cfind=cfind, jitter=jitter)
         return pred["mean"][:, None] + np.sqrt(pred["var"])[:, None] * normals
-    pred = gp_pred_post_full(gp, xt, cov=True, cfind=cfind, jitter=jitter)
+    pred = post(gp, xt, cov=True, cfind=cfind, jitter=jitter)
     return pred["mean"][:, None] + _chol_lower(pred["cov"]) @ normals
 
 
-def gp_pred_post_fitc(gp, xt, var=False, cfind=None, jitter=None, train=False):
-    """R/gp_pred.R:234-296 (mean and var; cov=TRUE not restated)."""
+def gp_pred_post_fitc(gp, xt, var=False, cfind=None, jitter=None, train=False, cov=False):
+    """R/gp_pred.R:234-296."""
     z_ind = _as_matrix(gp.method.inducing)
     alpha = gp.fit["alpha"]
     Ktz = eval_cf(gp.cfs, xt, z_ind, cfind)
     Kxz = gp.fit["Kxz"]
     Kz_chol = gp.fit["Kz_chol"]
     Dt = None
-    if var or train:
+    if var or train or cov:
         Dt = eval_cf(gp.cfs, xt, xt, cfind, diag_only=True)
         Dt = Dt - np.sum(_fsolve(Kz_chol, Ktz.T) ** 2, axis=0)
     Kt_aux1 = _fsolve(Kz_chol, Kxz.T)
@@ -1156,9 +1157,15 @@ def gp_pred_post_fitc(gp, xt, var=False, cfind=None, jitter=None, train=False):
     mean = Kt_aux2.T @ (Kt_aux1 @ alpha)
     if train:
         mean = mean + Dt * alpha
-    if not var:
+    if not (var or cov):
         return dict(mean=mean)
     C_inv = gp.fit["C_inv"]
+    if cov:                                                       # :262-273 (train = FALSE branch)
+        jit = 1e-6 if jitter is None else jitter
+        Linv_Ktz = _fsolve(Kz_chol, Ktz.T)
+        prior_cov = Linv_Ktz.T @ Linv_Ktz + np.diag(Dt)
+        pred_cov = prior_cov - Kt_aux2.T @ (Kt_aux1 @ inv_lemma_solve(C_inv, Kt_aux1.T)) @ Kt_aux2
+        return dict(mean=mean, cov=pred_cov + jit * np.eye(len(mean)))
     Kz_inv_Ktz = _bsolve_t(Kz_chol, _fsolve(Kz_chol, Ktz.T))
     prior_var = np.sum(Ktz * Kz_inv_Ktz.T, axis=1) + Dt
     if train:

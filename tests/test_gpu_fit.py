@@ -654,3 +654,22 @@ def test_gp_save_load_roundtrip(ctx, tmp_path):
     fn2 = str(tmp_path / "unfitted.pkl")
     g.gp_save(g.gp_init(cfs=g.cf_sexp()), fn2)
     assert not g.gp_load(fn2).fitted
+
+
+def test_fitc_joint_covariance_and_draws(ctx):
+    """gp_pred_post.method_fitc(cov = TRUE) (R/gp_pred.R:262-273) and joint gp_draw for FITC: the device
+    uses the collapsed form diag(Dt) + (Ktz L^-T)(Ktz L^-T)^T, the oracle the reference's expression."""
+    X, y = _classification(400, 2, 12)
+    Zi = X[np.random.default_rng(3).permutation(400)[:35]].copy()
+    Xt = np.random.default_rng(4).normal(size=(41, 2))
+    Zn = np.random.default_rng(5).standard_normal((41, 3))
+    for lik, yy in ((g.lik_gaussian(sigma=0.4), X[:, 0] + 0.3 * y), (g.lik_bernoulli(), y)):
+        gp = g.gp_init(cfs=[g.cf_sexp(lscale=1.0), g.cf_lin(magn=0.3)], lik=lik, method=g.method_fitc(inducing=Zi))
+        gpo = copy.deepcopy(gp)
+        g.gp_fit(gp, X, yy, ctx=ctx)
+        o.gp_fit(gpo, X, yy)
+        pc = g.gp_pred_cov(gp, Xt)
+        pco = o.gp_pred_post_fitc(gpo, Xt, cov=True)
+        assert scaled_err(pc["mean"], pco["mean"]) < 1e-7 and scaled_err(pc["cov"], pco["cov"]) < 1e-7
+        s1 = g.gp_draw(gp, Xt, draws=3, normals=Zn, transform=False)
+        assert scaled_err(s1, o.gp_draw_latent(gpo, Xt, Zn)) < 1e-5
