@@ -1127,6 +1127,7 @@ int fit_get_impl(Ctx* ctx, const Fit* fit, const char* what, double* out) {
     }
     return GPL_OK;
   }
+  if (fit->method == 1 && !strcmp(what, "var_train")) return fitc_var_train(ctx, fit, out);
   if (fit->method == 2 && (!strcmp(what, "wcov") || !strcmp(what, "wmean"))) {
     const int64_t M = fit->m;
     if (!strcmp(what, "wmean")) {

@@ -200,11 +200,13 @@ struct Fit {
   DevBuf Ac, Ac_dinv;    // nb x nb factor of A
   int64_t ldp = 0;
   DevBuf invVb;          // nb: 1 / V_bad
+  double jitter = 0.0;   // FITC: the jitter of the fit (fitc_var_train)
   // method_rf
   std::vector<int32_t> rf_num_basis;
   int64_t rf_nweights = 0;
 };
 
+int fitc_var_train(Ctx* ctx, const Fit* fit, double* out);
 // joint predictions on the device (mean nt, cov nt x nt with jitter on the diagonal)
 int pred_full_cov_dev(Ctx* ctx, const Fit* fit, const gpl_cf_model* cf, const double* xt, int64_t nt,
                       uint64_t term_mask, double jitter, double* d_mean, double* d_cov, int64_t ldc);

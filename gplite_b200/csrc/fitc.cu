@@ -119,6 +119,7 @@ struct FitcState {
   HostPlan hp;
   LikDev lik;
   double logdet_z = 0.0;
+  double jitter = 0.0;
 };
 
 enum { F_F = 0, F_Z, F_V, F_ALPHA, F_FNEW, F_T1, F_T2, F_FVAR, F_P, F_CM, F_CV, F_LOGZ, F_W, F_T3 };
@@ -138,6 +139,7 @@ int fitc_setup(Ctx* ctx, FitcState& st, const gpl_cf_model* cf, const gpl_lik* l
                int64_t n, int d, const double* zind, int64_t m, const double* y,
                const double* trials, const double* offset, double jitter) {
   st.n = n; st.m = m; st.d = d;
+  st.jitter = jitter;
   st.ldx = round_up(n, 16);
   st.ldm = round_up(m, 16);
   GPL_TRY(st.x.alloc(ctx, sizeof(double) * n * d));
@@ -450,6 +452,7 @@ int save_fitc(Ctx* ctx, FitcState& st, Fit** out) {
   take(f->Dg, st.Dg);
   take(f->S, st.S);
   take(f->sqrtV, st.mv[2]);      // beta = Kz^-1 Kzx alpha (m-vector) rides in the sqrtV slot
+  f->jitter = st.jitter;
   *out = f;
   return GPL_OK;
 }
@@ -524,15 +527,6 @@ int fit_fitc_impl(Ctx* ctx, const gpl_cf_model* cf, const gpl_lik* lik, const gp
     out->iters = it;
     out->converged = !(maxiter > 1 && it == maxiter);
     out->n_bad = n_bad;
-    if (h_fvar) {
-      // variances at the training sites as gp_loo needs them (gp_pred_post(train = TRUE),
-      // R/gp_loo.R:123)
-      GPL_TRY(row_norms_via(ctx, st, st.A.d(), st.A_dinv.d(), st.v[F_W].d()));
-      fitc_train_var_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(
-          n, st.v[F_V].d(), st.Dg.d(), st.S.d(), st.v[F_W].d(), jitter, st.v[F_FVAR].d());
-      GPL_LAUNCH_CHECK(ctx);
-      GPL_TRY(dl(h_fvar, st.v[F_FVAR].d()));
-    }
     GPL_TRY(dl(h_fmean, st.v[F_F].d()));
     GPL_TRY(dl(h_z, st.v[F_Z].d()));
     GPL_TRY(dl(h_V, st.v[F_V].d()));
@@ -702,6 +696,36 @@ int pred_fitc_impl(Ctx* ctx, const Fit* fit, const gpl_cf_model* cf, const doubl
     GPL_TRY(vec_op(ctx, VOP_ADD, nt, dvar.d(), t2.d(), dvar.d()));
     GPL_CUDA(cudaMemcpyAsync(var, dvar.p, sizeof(double) * nt, cudaMemcpyDeviceToHost, ctx->stream));
   }
+  GPL_CUDA(cudaStreamSynchronize(ctx->stream));
+  return GPL_OK;
+}
+
+// gp_pred_post.method_fitc(train = TRUE)$var at the training sites, on demand (gp_loo with the
+// Laplace approximation, R/gp_loo.R:123): one more streamed pass over Kxz (n m^2 flops), so it is
+// not part of the fit.  out: n doubles on the host.
+int fitc_var_train(Ctx* ctx, const Fit* fit, double* out) {
+  const int64_t n = fit->n, m = fit->m;
+  int64_t chunk = (int64_t)(2.0e9 / (8.0 * (double)m));
+  chunk = chunk / 128 * 128;
+  if (chunk < 1024) chunk = 1024;
+  if (chunk > n) chunk = n;
+  const int64_t ldw = round_up(chunk, 16);
+  DevBuf W, w, V, res;
+  GPL_TRY(W.alloc(ctx, sizeof(double) * ldw * m));
+  GPL_TRY(w.alloc(ctx, sizeof(double) * n));
+  GPL_TRY(V.alloc(ctx, sizeof(double) * n));
+  GPL_TRY(res.alloc(ctx, sizeof(double) * n));
+  for (int64_t r0 = 0; r0 < n; r0 += chunk) {
+    const int64_t c = (n - r0) < chunk ? (n - r0) : chunk;
+    GPL_TRY(scaled_copy_rows(ctx, c, m, fit->Kxz.d() + r0, fit->ldkxz, nullptr, W.d(), ldw));
+    GPL_TRY(dtrsm_right_with(ctx, fit->Lm_dinv.d(), true, c, m, fit->Lm.d(), fit->ldm, W.d(), ldw));
+    GPL_TRY(rowsumsq(ctx, c, m, W.d(), ldw, w.d() + r0));
+  }
+  GPL_TRY(vec_op(ctx, VOP_SUB, n, fit->S.d(), fit->Dg.d(), V.d()));          // V = S - D
+  fitc_train_var_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(
+      n, V.d(), fit->Dg.d(), fit->S.d(), w.d(), fit->jitter, res.d());
+  GPL_LAUNCH_CHECK(ctx);
+  GPL_CUDA(cudaMemcpyAsync(out, res.d(), sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->stream));
   GPL_CUDA(cudaStreamSynchronize(ctx->stream));
   return GPL_OK;
 }

@@ -257,8 +257,6 @@ def gp_fit(gp, x, y, trials=None, offset=None, jitter=None, ctx=None):
         if meth == "rf":
             fit.pop("alpha")
             fit["wmean"] = wmean
-        if meth == "fitc" and gp.approx.name == "laplace":
-            fit["var_train"] = vec["fvar"]     # gp_pred_post(train = TRUE)$var at the training sites (gp_loo)
         if gp.approx.name == "ep":
             fit.update(fvar=vec["fvar"], cavity_mean=vec["cavity_mean"], cavity_var=vec["cavity_var"],
                        P=1.0 / vec["V"], quad_ok=bool(out.quad_ok))
@@ -358,7 +356,7 @@ def fit_member(gp, what):
     n = gp.x.shape[0]
     m = gp.method.inducing.shape[0] if gp.method.name == "fitc" else 0
     M_rf = int(sum(gp.method.num_basis)) if gp.method.name == "rf" else 0
-    shape = {"C_chol": (n, n), "alpha": (n,), "Kxz": (n, m), "Kz_chol": (m, m), "wmean": (M_rf,),
+    shape = {"C_chol": (n, n), "alpha": (n,), "Kxz": (n, m), "Kz_chol": (m, m), "var_train": (n,), "wmean": (M_rf,),
              "wcov": (M_rf, M_rf)}[what]
     out = np.empty(shape, dtype=np.float64, order="F")
     _lib.check(gp._ctx.lib.gpl_fit_get(gp._ctx.h, gp._handle, what.encode(), _lib._ptr(out)))
@@ -667,7 +665,7 @@ def gp_loo(gp, x, y, quad_order=11, trials=None, offset=None):
     else:                                                          # R/gp_loo.R:119-129
         fhat, z, V = gp.fit["fmean"], gp.fit["z"], gp.fit["V"]
         grad = (z - fhat) / V
-        post_var = gp.fit["var_train"] if gp.method.name == "fitc" else gp_pred(gp, x, var=True)["var"]
+        post_var = fit_member(gp, "var_train") if gp.method.name == "fitc" else gp_pred(gp, x, var=True)["var"]
         loo_var = 1.0 / (1.0 / post_var - 1.0 / V)
         loo_mean = fhat - loo_var * grad
     xq, wq = gauss_hermite_points(quad_order)

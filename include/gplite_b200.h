@@ -292,9 +292,7 @@ int gpl_fit_full(gpl_ctx* ctx, const gpl_cf_model* cf, const gpl_lik* lik, const
                  double* V, double* alpha, double* fvar, double* cavity_mean, double* cavity_var,
                  gpl_fit** fit);
 
-/* method_fitc with explicit inducing points zind (m x d).  With approx_laplace, fvar (if not NULL)
- * receives gp_pred_post.method_fitc(train = TRUE)$var at the training sites, which gp_loo needs
- * (R/gp_loo.R:123; R/gp_pred.R:245-256,280-286, including that code's jitter-free Dt). */
+/* method_fitc with explicit inducing points zind (m x d). */
 int gpl_fit_fitc(gpl_ctx* ctx, const gpl_cf_model* cf, const gpl_lik* lik, const gpl_approx* approx,
                  const double* x, int64_t n, int32_t d, const double* zind, int64_t m,
                  const double* y, const double* trials, const double* offset, double jitter,
@@ -362,8 +360,10 @@ int gpl_draw_full(gpl_ctx* ctx, const gpl_fit* fit, const gpl_cf_model* cf, cons
                   double* out);
 
 /* Materialise members of gp$fit on demand: what = "C_chol" (n x n), "Kxz" (n x m),
- * "Kz_chol" (m x m), "alpha" (n); method_rf: "wmean" (M), "wcov" (M x M).  out must hold
- * rows*cols doubles. */
+ * "Kz_chol" (m x m), "alpha" (n); method_fitc also "var_train" (n):
+ * gp_pred_post.method_fitc(train = TRUE)$var at the training sites as gp_loo needs it (R/gp_loo.R:123;
+ * R/gp_pred.R:245-256,280-286 including that code's jitter-free Dt), computed on demand by one more
+ * pass over Kxz; method_rf: "wmean" (M), "wcov" (M x M).  out must hold rows*cols doubles. */
 int gpl_fit_get(gpl_ctx* ctx, const gpl_fit* fit, const char* what, double* out);
 int gpl_fit_free(gpl_ctx* ctx, gpl_fit* fit);
 
