@@ -51,3 +51,25 @@ def test_product_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 txt = open(os.path.join(dirpath, f)).read()
                 assert "oracle" not in txt.replace("no oracle", ""), f"{f} references the oracle"
+
+
+def test_header_is_plain_c_and_links(tmp_path):
+    """The boundary is a C ABI: the header must compile as C (not only as C++), and a C translation
+    unit that takes the address of every declared function must link against the library."""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("gcc not available")
+    syms = declared_symbols()
+    src = tmp_path / "abi_check.c"
+    src.write_text('#include "gplite_b200.h"\n#include <stddef.h>\n'
+                   'typedef void (*fn)(void);\n'
+                   'fn table[] = {' + ", ".join(f"(fn){s}" for s in syms) + '};\n'
+                   'int main(void) { return table[0] == NULL; }\n')
+    exe = tmp_path / "abi_check"
+    inc = os.path.join(ROOT, "include")
+    libdir = os.path.dirname(_lib.LIB_PATH)
+    cmd = ["gcc", "-std=c99", "-Wall", "-Werror", "-pedantic", f"-I{inc}", str(src), "-o", str(exe),
+           f"-L{libdir}", "-lgplite_b200", f"-Wl,-rpath,{libdir}"]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr
