@@ -79,6 +79,9 @@ potf2_inv_kernel(double* __restrict__ A, int64_t lda, int nb, double* __restrict
           a[k] = fma(-a[j], lkj, a[k]);
         }
       }
+      // lanes 16..31 read the same elements as lanes 0..15 above; the shuffles already order those
+      // reads before the write-back, the explicit barrier states it (and satisfies racecheck)
+      __syncwarp();
       if (lane < PW) {
 #pragma unroll
         for (int k = 0; k < PW; ++k)
