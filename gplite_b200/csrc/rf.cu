@@ -335,6 +335,34 @@ int pred_rf_impl(Ctx* ctx, const Fit* fit, const gpl_cf_model* cf, const double*
   return GPL_OK;
 }
 
+// Phi_t (nt x M, column-major, host) for a fitted method_rf model: the featuremap(xt, cfind) of
+// gp_draw_analytic.method_rf (R/gp_draw.R:145-163); unselected summands give zero columns.
+int rf_features_impl(Ctx* ctx, const Fit* fit, const gpl_cf_model* cf, const double* xt, int64_t nt,
+                     uint64_t term_mask, double* phi_out) {
+  if (!fit || fit->method != 2 || nt <= 0 || !xt || !phi_out) {
+    set_error("gpl_rf_features: bad arguments");
+    return GPL_ERR_BAD_ARG;
+  }
+  HostPlan hp;
+  GPL_TRY(make_plan(cf, fit->d, 0, &hp));
+  gpl_rf_spec rf;
+  rf.nterms = (int32_t)fit->rf_num_basis.size();
+  rf.num_basis = fit->rf_num_basis.data();
+  rf.weights = fit->zind.d();
+  rf.nweights = fit->rf_nweights;
+  RfPlan rp;
+  GPL_TRY(make_rf_plan(cf, hp, &rf, &rp));
+  DevBuf dxt, Phi;
+  const int64_t ldp = round_up(nt, 16);
+  GPL_TRY(up(ctx, dxt, xt, (size_t)nt * fit->d));
+  GPL_TRY(Phi.alloc(ctx, sizeof(double) * ldp * rp.M));
+  GPL_TRY(rf_features(ctx, rp, hp, dxt.d(), nt, fit->zind.d(), term_mask, Phi.d(), ldp));
+  GPL_CUDA(cudaMemcpy2DAsync(phi_out, sizeof(double) * nt, Phi.d(), sizeof(double) * ldp,
+                             sizeof(double) * nt, rp.M, cudaMemcpyDeviceToHost, ctx->stream));
+  GPL_CUDA(cudaStreamSynchronize(ctx->stream));
+  return GPL_OK;
+}
+
 }  // namespace gpl
 
 extern "C" {
@@ -352,6 +380,12 @@ int gpl_fit_rf(gpl_ctx* h, const gpl_cf_model* cf, const gpl_lik* lik, const gpl
   if (fit) *fit = reinterpret_cast<gpl_fit*>(f);
   if (rc != GPL_OK) cudaStreamSynchronize(reinterpret_cast<Ctx*>(h)->stream);
   return rc;
+}
+
+int gpl_rf_features(gpl_ctx* h, const gpl_fit* fit, const gpl_cf_model* cf, const double* xt, int64_t nt,
+                    uint64_t term_mask, double* phi) {
+  return rf_features_impl(reinterpret_cast<Ctx*>(h), reinterpret_cast<const Fit*>(fit), cf, xt, nt,
+                          term_mask, phi);
 }
 
 int gpl_pred_rf(gpl_ctx* h, const gpl_fit* fit, const gpl_cf_model* cf, const double* xt, int64_t nt,

@@ -595,14 +595,35 @@ def gp_draw(gp, xnew, draws=1, transform=True, target=False, marginal=False, cfi
     nt = xnew.shape[0]
     draws = int(draws or 1)
     rng = np.random.default_rng(seed)
-    if normals is None:
-        normals = rng.standard_normal((nt, draws))
-    normals = np.asfortranarray(np.asarray(normals, dtype=np.float64).reshape(nt, draws))
     jit = 1e-6 if jitter is None else float(jitter)
     fitted = is_fitted(gp, "analytic")
-    if fitted and "alpha" not in gp.fit:
+    rf = fitted and gp.method.name == "rf"         # draws live in weight space: normals is M_selected x draws
+    if not rf:
+        if normals is None:
+            normals = rng.standard_normal((nt, draws))
+        normals = np.asfortranarray(np.asarray(normals, dtype=np.float64).reshape(nt, draws))
+    if fitted and "alpha" not in gp.fit and "wmean" not in gp.fit:
         raise RuntimeError("the fit failed (log_evidence = -Inf); cannot draw")
-    if fitted and marginal:                                      # R/gp_draw.R:107-110,127-130
+    if rf:                                                       # R/gp_draw.R:145-163
+        # w ~ N(wmean, wcov) restricted to the selected summands, sample = featuremap(xt, cfind) w; the
+        # M x M factor and the M-vector draws are host-sized, the features come from the device
+        c = gp._ctx
+        factors, _ = M.flatten_cfs(gp.cfs)
+        pm = _lib.PackedModel(factors)
+        nb = list(gp.method.num_basis)
+        ends = np.concatenate([[0], np.cumsum(nb)])
+        idx = range(len(nb)) if cfind is None else list(cfind)
+        inds = np.concatenate([np.arange(ends[k], ends[k + 1]) for k in idx])
+        Mtot = int(ends[-1])
+        phi = np.empty((nt, Mtot), order="F")
+        _lib.check(c.lib.gpl_rf_features(c.h, gp._handle, pm.ref(), _lib._ptr(xnew), nt, _term_mask(gp, cfind),
+                                         _lib._ptr(phi)))
+        wcov = fit_member(gp, "wcov")[np.ix_(inds, inds)]
+        zw = rng.standard_normal((len(inds), draws)) if normals is None \
+            else np.asarray(normals, dtype=np.float64).reshape(len(inds), draws)
+        w = gp.fit["wmean"][inds][:, None] + np.linalg.cholesky(wcov) @ zw
+        sample = phi[:, inds] @ w
+    elif fitted and marginal:                                    # R/gp_draw.R:107-110,127-130
         pred = gp_pred(gp, xnew, var=True, cfind=cfind, jitter=jitter, ctx=ctx)
         sample = pred["mean"][:, None] + np.sqrt(pred["var"])[:, None] * normals
     else:

@@ -332,6 +332,11 @@ int gpl_fit_rf(gpl_ctx* ctx, const gpl_cf_model* cf, const gpl_lik* lik, const g
                const gpl_rf_spec* rf, const double* x, int64_t n, int32_t d, const double* y,
                const double* trials, const double* offset, gpl_fit_out* out, double* fmean, double* z,
                double* V, double* wmean, gpl_fit** fit);
+/* featuremap(xt, cfind) of a fitted method_rf model: phi is nt x sum(num_basis), column-major, host;
+ * columns of unselected summands are zero (gp_draw_analytic.method_rf, R/gp_draw.R:145-163, draws the
+ * weights on the host and needs the features of the test points). */
+int gpl_rf_features(gpl_ctx* ctx, const gpl_fit* fit, const gpl_cf_model* cf, const double* xt, int64_t nt,
+                    uint64_t term_mask, double* phi);
 /* gp_pred_post.method_rf (R/gp_pred.R:298-315); term_mask = cfind. */
 int gpl_pred_rf(gpl_ctx* ctx, const gpl_fit* fit, const gpl_cf_model* cf, const double* xt, int64_t nt,
                 uint64_t term_mask, double* mean, double* var);

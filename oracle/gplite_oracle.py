@@ -1133,6 +1133,13 @@ def gp_draw_latent(gp, xt, normals, marginal=False, cfind=None, jitter=None):
     if not getattr(gp, "fitted", False):
         cov = eval_cf(gp.cfs, xt, xt, cfind) + jit * np.eye(nt)          # R/gp_pred.R:142-156
         return _chol_lower(cov) @ normals
+    if gp.method.name == "rf":                                    # R/gp_draw.R:145-163; normals: M_sel x draws
+        featuremap, nb = rf_featuremap(gp, xt.shape[1])
+        ends = np.concatenate([[0], np.cumsum(nb)])
+        idx = range(len(nb)) if cfind is None else cfind
+        inds = np.concatenate([np.arange(ends[k], ends[k + 1]) for k in idx])
+        w = gp.fit["wmean"][inds][:, None] + _chol_lower(gp.fit["wcov"][np.ix_(inds, inds)]) @ normals
+        return featuremap(xt, cfind) @ w
     post = gp_pred_post_full if gp.method.name == "full" else gp_pred_post_fitc
     if marginal:
         pred = post(gp, xt, var=True, cfind=cfind, jitter=jitter)

@@ -673,3 +673,23 @@ def test_fitc_joint_covariance_and_draws(ctx):
         assert scaled_err(pc["mean"], pco["mean"]) < 1e-7 and scaled_err(pc["cov"], pco["cov"]) < 1e-7
         s1 = g.gp_draw(gp, Xt, draws=3, normals=Zn, transform=False)
         assert scaled_err(s1, o.gp_draw_latent(gpo, Xt, Zn)) < 1e-5
+
+
+def test_gp_draw_method_rf(ctx):
+    """gp_draw_analytic.method_rf (R/gp_draw.R:145-163): weights drawn from N(wmean, wcov), pushed
+    through the test-point features (gpl_rf_features)."""
+    rng = np.random.default_rng(21)
+    X = rng.normal(size=(400, 2))
+    y = np.sin(X[:, 0]) + 0.3 * X[:, 1] + 0.1 * rng.normal(size=400)
+    Xt = rng.normal(size=(33, 2))
+    gp = g.gp_init(cfs=[g.cf_sexp(lscale=0.9), g.cf_lin(magn=0.4)], lik=g.lik_gaussian(sigma=0.2),
+                   method=g.method_rf(num_basis=30, seed=3))
+    gpo = copy.deepcopy(gp)
+    g.gp_fit(gp, X, y, ctx=ctx)
+    o.gp_fit(gpo, X, y)
+    for cfind, msel in ((None, 32), ([0], 30)):
+        Zn = rng.standard_normal((msel, 4))
+        s1 = g.gp_draw(gp, Xt, draws=4, normals=Zn, transform=False, cfind=cfind)
+        s0 = o.gp_draw_latent(gpo, Xt, Zn, cfind=cfind)
+        assert s1.shape == (33, 4) and scaled_err(s1, s0) < 1e-6, cfind
+    assert g.gp_draw(gp, Xt, draws=2, seed=1).shape == (33, 2)
