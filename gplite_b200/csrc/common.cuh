@@ -15,6 +15,9 @@ constexpr int NB = 128;   // base block of the recursive factorisation / solves
 
 void set_error(const char* fmt, ...);
 
+// gridDim.y is limited to 65535: kernels that map columns to blockIdx.y stride over them
+inline unsigned grid_y_cap(int64_t n) { return (unsigned)(n < 65535 ? (n > 0 ? n : 1) : 65535); }
+
 struct Ctx {
   int device = 0;
   cudaStream_t stream = nullptr;

@@ -150,9 +150,9 @@ __global__ void copy_lower_kernel(int64_t n, const double* __restrict__ A, int64
 __global__ void cchol_kernel(int64_t n, const double* __restrict__ L, int64_t ldl,
                              const double* __restrict__ sqrtV, double* __restrict__ out) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int64_t j = blockIdx.y;
   if (i >= n) return;
-  out[j * n + i] = (i >= j) ? sqrtV[i] * L[j * ldl + i] : 0.0;
+  for (int64_t j = blockIdx.y; j < n; j += gridDim.y)
+    out[j * n + i] = (i >= j) ? sqrtV[i] * L[j * ldl + i] : 0.0;
 }
 
 int diag_extract(Ctx* ctx, int64_t n, const double* A, int64_t lda, double* out) {
@@ -1106,7 +1106,7 @@ int fit_get_impl(Ctx* ctx, const Fit* fit, const char* what, double* out) {
   if (!strcmp(what, "C_chol") && fit->method == 0) {
     DevBuf tmp;
     GPL_TRY(tmp.alloc(ctx, sizeof(double) * n * n));
-    dim3 grid((unsigned)((n + 255) / 256), (unsigned)n);
+    dim3 grid((unsigned)((n + 255) / 256), grid_y_cap(n));
     cchol_kernel<<<grid, 256, 0, ctx->stream>>>(n, fit->Lb.d(), fit->ld, fit->sqrtV.d(), tmp.d());
     GPL_LAUNCH_CHECK(ctx);
     GPL_TRY(download(ctx, out, tmp.d(), (size_t)n * n));

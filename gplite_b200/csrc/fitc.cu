@@ -468,6 +468,10 @@ int fit_fitc_impl(Ctx* ctx, const gpl_cf_model* cf, const gpl_lik* lik, const gp
     set_error("gpl_fit_fitc: bad arguments");
     return GPL_ERR_BAD_ARG;
   }
+  if (m > 65535) {          // the m-indexed helper kernels map inducing points to gridDim.y
+    set_error("gpl_fit_fitc: at most 65535 inducing points (got %lld)", (long long)m);
+    return GPL_ERR_BAD_ARG;
+  }
   FitcState st;
   GPL_TRY(fitc_setup(ctx, st, cf, lik, x, n, d, zind, m, y, trials, offset, jitter));
   memset(out, 0, sizeof(*out));

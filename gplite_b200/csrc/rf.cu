@@ -107,6 +107,10 @@ int make_rf_plan(const gpl_cf_model* cf, const HostPlan& hp, const gpl_rf_spec* 
     col += p.ncols[t];
   }
   p.M = col;
+  if (p.M > 65535) {        // basis functions map to gridDim.y in the feature kernel
+    set_error("method_rf: at most 65535 basis functions in total (got %d)", p.M);
+    return GPL_ERR_BAD_ARG;
+  }
   int64_t woff = 0;
   for (int q = 0; q < p.nfactors; ++q) {
     const FactorDev& fd = hp.plan.f[q];

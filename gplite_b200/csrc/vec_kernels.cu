@@ -179,23 +179,23 @@ __global__ void lower_colsumsq_kernel(int64_t n, const double* __restrict__ X, i
 __global__ void scale_kernel(int64_t m, int64_t n, double* __restrict__ A, int64_t lda,
                              const double* __restrict__ s, int by_col) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int64_t j = blockIdx.y;
-  if (i >= m || j >= n) return;
-  A[j * lda + i] *= by_col ? s[j] : s[i];
+  if (i >= m) return;
+  for (int64_t j = blockIdx.y; j < n; j += gridDim.y) A[j * lda + i] *= by_col ? s[j] : s[i];
 }
 
 __global__ void scale_block_kernel(int64_t m, int64_t n, double* __restrict__ A, int64_t lda,
                                    const double* __restrict__ r, const double* __restrict__ c,
                                    double alpha, double diag_add, int64_t diag_offset) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int64_t j = blockIdx.y;
-  if (i >= m || j >= n) return;
-  double v = A[j * lda + i];
-  if (c) v *= c[j];
-  if (r) v *= r[i];
-  v *= alpha;
-  if (i == j + diag_offset) v += diag_add;
-  A[j * lda + i] = v;
+  if (i >= m) return;
+  for (int64_t j = blockIdx.y; j < n; j += gridDim.y) {
+    double v = A[j * lda + i];
+    if (c) v *= c[j];
+    if (r) v *= r[i];
+    v *= alpha;
+    if (i == j + diag_offset) v += diag_add;
+    A[j * lda + i] = v;
+  }
 }
 
 __global__ void vec_op_kernel(int op, int64_t n, const double* __restrict__ a,
@@ -485,12 +485,13 @@ __global__ void scatter_vec_kernel(int64_t n, const double* __restrict__ src,
   if (i < n) dst[perm[i]] = src[i];
 }
 
-__global__ void gather_rows_kernel(int64_t n, const double* __restrict__ src, int64_t lds,
-                                   const int32_t* __restrict__ perm, double* __restrict__ dst,
-                                   int64_t ldd) {
+__global__ void gather_rows_kernel(int64_t n, int64_t ncols, const double* __restrict__ src,
+                                   int64_t lds, const int32_t* __restrict__ perm,
+                                   double* __restrict__ dst, int64_t ldd) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int64_t j = blockIdx.y;
-  if (i < n) dst[j * ldd + i] = src[j * lds + perm[i]];
+  if (i >= n) return;
+  const int64_t pi = perm[i];
+  for (int64_t j = blockIdx.y; j < ncols; j += gridDim.y) dst[j * ldd + i] = src[j * lds + pi];
 }
 
 // B (n x m) = A^T, A m x n; 32 x 32 tiles through shared memory
@@ -514,9 +515,9 @@ __global__ void tril_scale_kernel(int64_t n, const double* __restrict__ L, int64
                                   const double* __restrict__ r, double* __restrict__ out,
                                   int64_t ldo) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int64_t j = blockIdx.y;
   if (i >= n) return;
-  out[j * ldo + i] = (i >= j) ? (r ? r[i] : 1.0) * L[j * ldl + i] : 0.0;
+  for (int64_t j = blockIdx.y; j < n; j += gridDim.y)
+    out[j * ldo + i] = (i >= j) ? (r ? r[i] : 1.0) * L[j * ldl + i] : 0.0;
 }
 
 // out_i = sum_j A_ij^2 w_j   (one warp per row; A m x n with small n)
@@ -675,7 +676,7 @@ int lower_colsumsq(Ctx* ctx, int64_t n, const double* X, int64_t ldx, double* ou
 
 int scale_cols(Ctx* ctx, int64_t m, int64_t n, double* A, int64_t lda, const double* s) {
   if (m <= 0 || n <= 0) return GPL_OK;
-  dim3 grid((unsigned)((m + 255) / 256), (unsigned)n);
+  dim3 grid((unsigned)((m + 255) / 256), grid_y_cap(n));
   scale_kernel<<<grid, 256, 0, ctx->stream>>>(m, n, A, lda, s, 1);
   GPL_LAUNCH_CHECK(ctx);
   return GPL_OK;
@@ -683,7 +684,7 @@ int scale_cols(Ctx* ctx, int64_t m, int64_t n, double* A, int64_t lda, const dou
 
 int scale_rows(Ctx* ctx, int64_t m, int64_t n, double* A, int64_t lda, const double* s) {
   if (m <= 0 || n <= 0) return GPL_OK;
-  dim3 grid((unsigned)((m + 255) / 256), (unsigned)n);
+  dim3 grid((unsigned)((m + 255) / 256), grid_y_cap(n));
   scale_kernel<<<grid, 256, 0, ctx->stream>>>(m, n, A, lda, s, 0);
   GPL_LAUNCH_CHECK(ctx);
   return GPL_OK;
@@ -692,7 +693,7 @@ int scale_rows(Ctx* ctx, int64_t m, int64_t n, double* A, int64_t lda, const dou
 int scale_block(Ctx* ctx, int64_t m, int64_t n, double* A, int64_t lda, const double* r,
                 const double* c, double alpha, double diag_add, int64_t diag_offset) {
   if (m <= 0 || n <= 0) return GPL_OK;
-  dim3 grid((unsigned)((m + 255) / 256), (unsigned)n);
+  dim3 grid((unsigned)((m + 255) / 256), grid_y_cap(n));
   scale_block_kernel<<<grid, 256, 0, ctx->stream>>>(m, n, A, lda, r, c, alpha, diag_add, diag_offset);
   GPL_LAUNCH_CHECK(ctx);
   return GPL_OK;
@@ -777,8 +778,8 @@ int scatter_vec(Ctx* ctx, int64_t n, const double* src, const int32_t* perm, dou
 int gather_rows(Ctx* ctx, int64_t n, int64_t ncols, const double* src, int64_t lds,
                 const int32_t* perm, double* dst, int64_t ldd) {
   if (n <= 0 || ncols <= 0) return GPL_OK;
-  dim3 grid((unsigned)((n + 255) / 256), (unsigned)ncols);
-  gather_rows_kernel<<<grid, 256, 0, ctx->stream>>>(n, src, lds, perm, dst, ldd);
+  dim3 grid((unsigned)((n + 255) / 256), grid_y_cap(ncols));
+  gather_rows_kernel<<<grid, 256, 0, ctx->stream>>>(n, ncols, src, lds, perm, dst, ldd);
   GPL_LAUNCH_CHECK(ctx);
   return GPL_OK;
 }
@@ -794,7 +795,7 @@ int transpose(Ctx* ctx, int64_t m, int64_t n, const double* A, int64_t lda, doub
 int tril_scale(Ctx* ctx, int64_t n, const double* L, int64_t ldl, const double* r, double* out,
                int64_t ldo) {
   if (n <= 0) return GPL_OK;
-  dim3 grid((unsigned)((n + 255) / 256), (unsigned)n);
+  dim3 grid((unsigned)((n + 255) / 256), grid_y_cap(n));
   tril_scale_kernel<<<grid, 256, 0, ctx->stream>>>(n, L, ldl, r, out, ldo);
   GPL_LAUNCH_CHECK(ctx);
   return GPL_OK;

@@ -158,3 +158,19 @@ def test_dpotrf_large(ctx, n):
     Ainv = torch.tril(dA[:, :n].T)
     want = torch.tril(torch.cholesky_inverse(Lw))
     assert float((Ainv - want).abs().max()) < 1e-8 * float(want.abs().max())
+
+
+def test_column_indexed_helpers_beyond_65535_columns(ctx):
+    """gridDim.y is limited to 65535: the helpers that map columns to blockIdx.y (used on nt x n
+    cross-covariances when predicting from more than 65535 training points) must stride."""
+    m, n = 8, 70001
+    ld = 16
+    gen = torch.Generator(device="cuda").manual_seed(3)
+    A = torch.randn(n, ld, dtype=torch.float64, device="cuda", generator=gen)     # column-major m x n
+    r = torch.rand(m, dtype=torch.float64, device="cuda", generator=gen) + 0.5
+    c = torch.rand(n, dtype=torch.float64, device="cuda", generator=gen) + 0.5
+    want = 1.5 * A[:, :m] * r[None, :] * c[:, None]
+    torch.cuda.synchronize()
+    _lib.check(ctx.lib.gpl_scale_block_dev(ctx.h, m, n, ptr(A), ld, ptr(r), ptr(c), 1.5, 0.0, 0))
+    sync(ctx)
+    assert float((A[:, :m] - want).abs().max()) < 1e-14
