@@ -114,6 +114,8 @@ SIGNATURES = {
                              _I64, _I32, _P, _P, _P, C.POINTER(FitOut), _P, _P, _P, _P, C.POINTER(_P)]),
     "gpl_rf_features": (C.c_int, [_P, _P, C.POINTER(CfModel), _P, _I64, _U64, _P]),
     "gpl_pred_rf": (C.c_int, [_P, _P, C.POINTER(CfModel), _P, _I64, _U64, _P, _P]),
+    "gpl_energy_grad_laplace": (C.c_int, [_P, C.POINTER(CfModel), C.POINTER(Lik), C.POINTER(Approx), _P, _I64, _I32,
+                                          _P, _P, _P, _D, _I32, _P, _P, C.POINTER(_D), _P, C.POINTER(FitOut)]),
     "gpl_kmeans": (C.c_int, [_P, _P, _I64, _I32, _P, _I64, _I32, _P, _P, C.POINTER(_I32)]),
     "gpl_lik_ep_sites_dev": (C.c_int, [_P, C.POINTER(Lik), _I64, _P, _P, _P, _P, _P, _P, _P, _D, _I32, _P, _P,
                                        _P, _P, _P, _P, _P, _P, C.POINTER(_I32)]),

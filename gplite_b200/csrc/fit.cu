@@ -566,6 +566,67 @@ int save_fit(Ctx* ctx, FullState& st, Fit** out, BadSite* bs = nullptr) {
   return GPL_OK;
 }
 
+// Newton iterations of laplace.method_full (R/laplace.R:274-297) on a set-up state.  Leaves f in
+// v[V_F], the pseudo-data z, V of the last step, alpha, the factor of B in st.B (or the block factor
+// in bs when the last step had non-log-concave sites).
+int laplace_loop(Ctx* ctx, FullState& st, BadSite& bs, const gpl_lik* lik, const gpl_approx* approx,
+               gpl_fit_out* out) {
+  const int64_t n = st.n;
+  double sc[8];
+  int maxiter = approx->maxiter;
+  if (lik->kind == GPL_LIK_GAUSSIAN) maxiter = 1;                        // R/laplace.R:281-283
+  if (maxiter < 1) maxiter = 1;
+  GPL_TRY(vec_op(ctx, VOP_FILL, n, nullptr, nullptr, st.v[V_F].d(), 0.0));
+  int it = 0;
+  double diff = 0.0, log_evidence = 0.0;
+  for (it = 1; it <= maxiter; ++it) {
+    GPL_TRY(lik_pseudodata_la(ctx, st.lik, n, st.v[V_F].d(), st.y.d(), st.v[V_Z].d(),
+                              st.v[V_V].d()));
+    GPL_TRY(reduce(ctx, RED_MIN, n, st.v[V_V].d(), nullptr, 0));
+    GPL_TRY(fetch_scalars(ctx, 1, sc));
+    if (!(sc[0] > 0.0)) {                       // non-log-concave sites: R/laplace.R:40-117
+      GPL_TRY(bad_laplace_iter(ctx, st, bs, &log_evidence));
+      if (bs.sm.a_fail) {                          // fit = list(fmean = fhat_old, log_evidence = -Inf)
+        out->log_evidence = -INFINITY;
+        out->iters = it;
+        out->converged = 0;
+        set_error("Laplace: the posterior with non-log-concave sites is not proper");
+        return GPL_ERR_NONFINITE;
+      }
+      GPL_TRY(reduce(ctx, RED_MAXABSDIFF, n, st.v[V_F].d(), st.v[V_FNEW].d(), 0));
+      GPL_TRY(fetch_scalars(ctx, 1, sc));
+      diff = sc[0];
+      std::swap(st.v[V_F].p, st.v[V_FNEW].p);
+      if (diff < approx->tol) break;
+      continue;
+    }
+    bs.active = false;
+    if (st.K_permuted) {                        // a previous step left K in bad-site order
+      GPL_TRY(cf_pairwise(ctx, st.hp.plan, st.Z.d(), n, n, nullptr, n, n, true, st.jitter,
+                          st.K.d(), st.ld));
+      st.K_permuted = false;
+    }
+    GPL_TRY(factor_and_solve(ctx, st));
+    GPL_TRY(reduce(ctx, RED_SUMLOG_PROD, n, st.v[V_SQRTV].d(), st.v[V_DIAG].d(), 0));
+    GPL_TRY(reduce(ctx, RED_SUMLOG, n, st.v[V_V].d(), nullptr, 1));
+    GPL_TRY(reduce(ctx, RED_DOT, n, st.v[V_FNEW].d(), st.v[V_ALPHA].d(), 2));
+    GPL_TRY(lik_loglik_sum(ctx, st.lik, n, st.v[V_FNEW].d(), st.y.d(), 3));
+    GPL_TRY(reduce(ctx, RED_MAXABSDIFF, n, st.v[V_F].d(), st.v[V_FNEW].d(), 4));
+    GPL_TRY(fetch_scalars(ctx, 5, sc));
+    const double C_logdet = 2.0 * sc[0], V_logdet = sc[1];
+    log_evidence = sc[3] - 0.5 * sc[2] - 0.5 * (C_logdet - V_logdet);   // R/laplace.R:37
+    diff = sc[4];
+    std::swap(st.v[V_F].p, st.v[V_FNEW].p);
+    if (diff < approx->tol) break;
+  }
+  if (it > maxiter) it = maxiter;
+  out->log_evidence = log_evidence;
+  out->iters = it;
+  out->converged = !(maxiter > 1 && it == maxiter);
+  out->n_bad = bs.active ? (int32_t)bs.nb : 0;
+  return GPL_OK;
+}
+
 }  // namespace
 
 int fit_full_impl(Ctx* ctx, const gpl_cf_model* cf, const gpl_lik* lik, const gpl_approx* approx,
@@ -585,62 +646,12 @@ int fit_full_impl(Ctx* ctx, const gpl_cf_model* cf, const gpl_lik* lik, const gp
   BadSite bs;
 
   if (approx->kind == GPL_APPROX_LAPLACE) {
-    int maxiter = approx->maxiter;
-    if (lik->kind == GPL_LIK_GAUSSIAN) maxiter = 1;                        // R/laplace.R:281-283
-    if (maxiter < 1) maxiter = 1;
-    GPL_TRY(vec_op(ctx, VOP_FILL, n, nullptr, nullptr, st.v[V_F].d(), 0.0));
-    int it = 0;
-    double diff = 0.0, log_evidence = 0.0;
-    for (it = 1; it <= maxiter; ++it) {
-      GPL_TRY(lik_pseudodata_la(ctx, st.lik, n, st.v[V_F].d(), st.y.d(), st.v[V_Z].d(),
-                                st.v[V_V].d()));
-      GPL_TRY(reduce(ctx, RED_MIN, n, st.v[V_V].d(), nullptr, 0));
-      GPL_TRY(fetch_scalars(ctx, 1, sc));
-      if (!(sc[0] > 0.0)) {                       // non-log-concave sites: R/laplace.R:40-117
-        GPL_TRY(bad_laplace_iter(ctx, st, bs, &log_evidence));
-        if (bs.sm.a_fail) {                          // fit = list(fmean = fhat_old, log_evidence = -Inf)
-          out->log_evidence = -INFINITY;
-          out->iters = it;
-          out->converged = 0;
-          set_error("Laplace: the posterior with non-log-concave sites is not proper");
-          return GPL_ERR_NONFINITE;
-        }
-        GPL_TRY(reduce(ctx, RED_MAXABSDIFF, n, st.v[V_F].d(), st.v[V_FNEW].d(), 0));
-        GPL_TRY(fetch_scalars(ctx, 1, sc));
-        diff = sc[0];
-        std::swap(st.v[V_F].p, st.v[V_FNEW].p);
-        if (diff < approx->tol) break;
-        continue;
-      }
-      bs.active = false;
-      if (st.K_permuted) {                        // a previous step left K in bad-site order
-        GPL_TRY(cf_pairwise(ctx, st.hp.plan, st.Z.d(), n, n, nullptr, n, n, true, st.jitter,
-                            st.K.d(), st.ld));
-        st.K_permuted = false;
-      }
-      GPL_TRY(factor_and_solve(ctx, st));
-      GPL_TRY(reduce(ctx, RED_SUMLOG_PROD, n, st.v[V_SQRTV].d(), st.v[V_DIAG].d(), 0));
-      GPL_TRY(reduce(ctx, RED_SUMLOG, n, st.v[V_V].d(), nullptr, 1));
-      GPL_TRY(reduce(ctx, RED_DOT, n, st.v[V_FNEW].d(), st.v[V_ALPHA].d(), 2));
-      GPL_TRY(lik_loglik_sum(ctx, st.lik, n, st.v[V_FNEW].d(), st.y.d(), 3));
-      GPL_TRY(reduce(ctx, RED_MAXABSDIFF, n, st.v[V_F].d(), st.v[V_FNEW].d(), 4));
-      GPL_TRY(fetch_scalars(ctx, 5, sc));
-      const double C_logdet = 2.0 * sc[0], V_logdet = sc[1];
-      log_evidence = sc[3] - 0.5 * sc[2] - 0.5 * (C_logdet - V_logdet);   // R/laplace.R:37
-      diff = sc[4];
-      std::swap(st.v[V_F].p, st.v[V_FNEW].p);
-      if (diff < approx->tol) break;
-    }
-    if (it > maxiter) it = maxiter;
-    out->log_evidence = log_evidence;
-    out->iters = it;
-    out->converged = !(maxiter > 1 && it == maxiter);
+    GPL_TRY(laplace_loop(ctx, st, bs, lik, approx, out));
     GPL_TRY(download(ctx, h_fmean, st.v[V_F].d(), n));
     GPL_TRY(download(ctx, h_z, st.v[V_Z].d(), n));
     GPL_TRY(download(ctx, h_V, st.v[V_V].d(), n));
     GPL_TRY(download(ctx, h_alpha, st.v[V_ALPHA].d(), n));
     GPL_CUDA(cudaStreamSynchronize(ctx->stream));
-    out->n_bad = bs.active ? (int32_t)bs.nb : 0;
     return save_fit(ctx, st, fit, &bs);
   }
 
@@ -845,6 +856,101 @@ int energy_grad_impl(Ctx* ctx, const gpl_cf_model* cf, const gpl_lik* lik, const
   *energy = -log_evidence;
   GPL_CUDA(cudaStreamSynchronize(ctx->stream));
   if (fit) return save_fit(ctx, st, fit);
+  return GPL_OK;
+}
+
+// Energy and its gradient for approx_laplace with a non-Gaussian likelihood, method_full (new
+// capability, as gpl_energy_grad is for lik_gaussian; Rasmussen & Williams Alg. 5.1 on the reference's
+// objective).  At the mode, with a = alpha, R = (K + W^-1)^-1 = S B^-1 S, the posterior variances
+// pv = V (1 - diag(B^-1)) and d3 = d/df of the second derivative of log p(y|f),
+//   s2 = pv d3 / 2,  u = (I - R K) s2,
+//   dE/dlog(theta_j) = -1/2 sum_ik [(a+u)_i (a+u)_k - u_i u_k - R_ik] dK_ik/dlog(theta_j)
+// (the u terms carry the dependence of the mode on theta).  d3 is a central difference of the
+// reference's own finite-difference curvature (get_loglik_d2, R/lik.R:449-454), so no likelihood
+// needs new derivative code.  Only covariance-function parameters; the Newton loop should be run
+// to a tight tolerance (the implicit-function argument assumes the mode).
+int energy_grad_laplace_impl(Ctx* ctx, const gpl_cf_model* cf, const gpl_lik* lik,
+                             const gpl_approx* approx, const double* x, int64_t n, int d,
+                             const double* y, const double* trials, const double* offset,
+                             double jitter, int nparam, const int32_t* param_factor,
+                             const int32_t* param_slot, double* energy, double* grad,
+                             gpl_fit_out* out) {
+  if (n <= 0 || d <= 0 || !x || !y || !energy || !out || !approx || nparam < 0 ||
+      nparam > MAX_GRAD_PARAMS || (nparam > 0 && !grad)) {
+    set_error("gpl_energy_grad_laplace: bad arguments");
+    return GPL_ERR_BAD_ARG;
+  }
+  if (approx->kind != GPL_APPROX_LAPLACE) {
+    set_error("gpl_energy_grad_laplace: approx_laplace only");
+    return GPL_ERR_BAD_ARG;
+  }
+  bool want_aux = false;
+  for (int j = 0; j < nparam; ++j) {
+    if (param_factor[j] < 0) {
+      set_error("gpl_energy_grad_laplace: only covariance-function parameters have a gradient here "
+                "(fix the likelihood's parameters)");
+      return GPL_ERR_BAD_ARG;
+    }
+    if (param_slot[j] == 3) want_aux = true;
+  }
+  FullState st;
+  GPL_TRY(full_setup(ctx, st, cf, lik, x, n, d, y, trials, offset, false, jitter, want_aux));
+  memset(out, 0, sizeof(*out));
+  out->quad_ok = 1;
+  BadSite bs;
+  GPL_TRY(laplace_loop(ctx, st, bs, lik, approx, out));
+  *energy = -out->log_evidence;
+  if (bs.active) {
+    set_error("gpl_energy_grad_laplace: non-log-concave sites at the mode; no gradient");
+    return GPL_ERR_NOT_LOGCONCAVE;
+  }
+  if (nparam == 0) return GPL_OK;
+  GradParam gp[MAX_GRAD_PARAMS];
+  for (int j = 0; j < nparam; ++j) {
+    if (param_factor[j] >= st.hp.plan.nfactors) {
+      set_error("gpl_energy_grad_laplace: parameter %d refers to factor %d of %d", j, param_factor[j],
+                st.hp.plan.nfactors);
+      return GPL_ERR_BAD_ARG;
+    }
+    gp[j].factor = param_factor[j];
+    gp[j].slot = param_slot[j];
+  }
+  // X = L^-1 in a third buffer (the factor is still needed for R t), diag(B^-1), pv
+  DevBuf X, Vp, Vm, s2, u, p, gout;
+  GPL_TRY(X.alloc(ctx, sizeof(double) * st.ld * n));
+  for (DevBuf* b : {&Vp, &Vm, &s2, &u, &p}) GPL_TRY(b->alloc(ctx, sizeof(double) * n));
+  GPL_TRY(copy_lower(ctx, n, st.B.d(), st.ld, X.d(), st.ld));
+  GPL_TRY(dtrtri_with(ctx, st.dinv.d(), n, X.d(), st.ld));
+  GPL_TRY(lower_colsumsq(ctx, n, X.d(), st.ld, st.v[V_T1].d()));                   // diag(B^-1)
+  GPL_TRY(vec_op(ctx, VOP_MUL, n, st.v[V_V].d(), st.v[V_T1].d(), st.v[V_T2].d()));
+  GPL_TRY(vec_op(ctx, VOP_SUB, n, st.v[V_V].d(), st.v[V_T2].d(), st.v[V_FVAR].d()));   // pv
+  // d3 = (g2(f + h) - g2(f - h)) / 2h with g2 = -1 / V(f)
+  const double h = 1e-4;
+  GPL_TRY(vec_op(ctx, VOP_FILL, n, nullptr, nullptr, st.v[V_T1].d(), h));
+  GPL_TRY(vec_op(ctx, VOP_ADD, n, st.v[V_F].d(), st.v[V_T1].d(), st.v[V_T2].d()));
+  GPL_TRY(lik_pseudodata_la(ctx, st.lik, n, st.v[V_T2].d(), st.y.d(), st.v[V_ZOLD].d(), Vp.d()));
+  GPL_TRY(vec_op(ctx, VOP_SUB, n, st.v[V_F].d(), st.v[V_T1].d(), st.v[V_T2].d()));
+  GPL_TRY(lik_pseudodata_la(ctx, st.lik, n, st.v[V_T2].d(), st.y.d(), st.v[V_ZOLD].d(), Vm.d()));
+  GPL_TRY(vec_op(ctx, VOP_INV, n, Vp.d(), nullptr, Vp.d()));
+  GPL_TRY(vec_op(ctx, VOP_INV, n, Vm.d(), nullptr, Vm.d()));
+  GPL_TRY(vec_op(ctx, VOP_SUB, n, Vm.d(), Vp.d(), st.v[V_T1].d()));                // g2+ - g2- = 1/V- - 1/V+
+  GPL_TRY(vec_op(ctx, VOP_MUL, n, st.v[V_T1].d(), st.v[V_FVAR].d(), st.v[V_T2].d()));
+  GPL_TRY(vec_op(ctx, VOP_AXPBY, n, st.v[V_T2].d(), st.v[V_T2].d(), s2.d(), 0.25 / h, 0.0));   // pv d3 / 2
+  // u = s2 - R (K s2),  R t = C^-1 t by the factor;  p = alpha + u
+  GPL_TRY(gemv_t(ctx, n, n, st.K.d(), st.ld, s2.d(), st.v[V_P].d()));
+  GPL_TRY(solve_alpha(ctx, n, st.B.d(), st.ld, st.dinv.d(), st.v[V_SQRTV].d(), st.v[V_P].d(),
+                      st.v[V_CM].d(), st.v[V_T1].d(), st.v[V_T2].d()));
+  GPL_TRY(vec_op(ctx, VOP_SUB, n, s2.d(), st.v[V_CM].d(), u.d()));
+  GPL_TRY(vec_op(ctx, VOP_ADD, n, st.v[V_ALPHA].d(), u.d(), p.d()));
+  // B^-1 = X^T X into the K buffer (K is dead from here on), then the fused trace
+  GPL_TRY(lauum_oop(ctx, n, X.d(), st.ld, st.K.d(), st.ld));
+  GPL_TRY(gout.alloc(ctx, sizeof(double) * (MAX_GRAD_PARAMS + 8)));
+  GPL_TRY(grad_trace(ctx, st.hp.plan, st.Z.d(), n, st.Zaux.d(), n, st.K.d(), st.ld, st.v[V_S].d(),
+                     p.d(), nparam, gp, gout.d(), -1, 0, u.d()));
+  double hg[MAX_GRAD_PARAMS];
+  GPL_CUDA(cudaMemcpyAsync(hg, gout.p, sizeof(double) * nparam, cudaMemcpyDeviceToHost, ctx->stream));
+  GPL_CUDA(cudaStreamSynchronize(ctx->stream));
+  for (int j = 0; j < nparam; ++j) grad[j] = -0.5 * hg[j];
   return GPL_OK;
 }
 
@@ -1174,6 +1280,18 @@ int gpl_energy_grad(gpl_ctx* h, const gpl_cf_model* cf, const gpl_lik* lik, cons
                             nparam, param_factor, param_slot, energy, grad, fit ? &f : nullptr);
   if (fit) *fit = reinterpret_cast<gpl_fit*>(f);
   if (rc != GPL_OK) cudaStreamSynchronize(reinterpret_cast<Ctx*>(h)->stream);
+  return rc;
+}
+
+int gpl_energy_grad_laplace(gpl_ctx* h, const gpl_cf_model* cf, const gpl_lik* lik,
+                            const gpl_approx* approx, const double* x, int64_t n, int32_t d,
+                            const double* y, const double* trials, const double* offset, double jitter,
+                            int32_t nparam, const int32_t* param_factor, const int32_t* param_slot,
+                            double* energy, double* grad, gpl_fit_out* out) {
+  int rc = gpl::energy_grad_laplace_impl(reinterpret_cast<gpl::Ctx*>(h), cf, lik, approx, x, n, d, y,
+                                         trials, offset, jitter, nparam, param_factor, param_slot,
+                                         energy, grad, out);
+  if (rc != GPL_OK) cudaStreamSynchronize(reinterpret_cast<gpl::Ctx*>(h)->stream);
   return rc;
 }
 

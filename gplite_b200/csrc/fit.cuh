@@ -142,7 +142,9 @@ constexpr int MAX_GRAD_PARAMS = 24;
 int grad_trace(Ctx* ctx, const CfPlan& plan, const double* z, int64_t ldz, const double* zaux,
                int64_t n, const double* Binv, int64_t ldb, const double* s, const double* alpha,
                int nparam, const GradParam* params, double* d_out /* device, nparam doubles */,
-               int64_t col0 = -1, int64_t ncols = 0);
+               int64_t col0 = -1, int64_t ncols = 0, const double* u = nullptr);
+// u != NULL adds - u_i u_k to the weight (the implicit term of the Laplace gradient, where alpha
+// holds a + u: (a+u)(a+u)^T - u u^T = a a^T + a u^T + u a^T).
 // col0 >= 0: block mode -- Binv holds only the block column [col0, col0 + ncols) (all n rows, rows
 // above the block's diagonal are never read); the result is that block column's share of the sum.
 

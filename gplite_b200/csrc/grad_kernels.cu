@@ -24,6 +24,7 @@ struct GradArgs {
   const double* Binv;
   const double* s;
   const double* alpha;
+  const double* u;     // optional: W = alpha alpha^T - u u^T - S Binv S (Laplace implicit term), or null
   double* partial;     // [grid][GP]
   int64_t ldz, ldaux, ldb;
   int n;
@@ -96,6 +97,8 @@ grad_trace_kernel(const __grid_constant__ CfPlan plan, const GradArgs a) {
   double* al1 = sv1 + GT;
   double* sv2 = al1 + GT;
   double* al2 = sv2 + GT;
+  double* uu1 = al2 + GT;
+  double* uu2 = uu1 + GT;
   __shared__ double red[GTHREADS / 32][GP];
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -132,6 +135,8 @@ grad_trace_kernel(const __grid_constant__ CfPlan plan, const GradArgs a) {
     al1[tid] = (i0 + tid < a.n) ? a.alpha[i0 + tid] : 0.0;
     sv2[tid] = (j0 + tid < a.n) ? a.s[j0 + tid] : 0.0;
     al2[tid] = (j0 + tid < a.n) ? a.alpha[j0 + tid] : 0.0;
+    uu1[tid] = (a.u && i0 + tid < a.n) ? a.u[i0 + tid] : 0.0;
+    uu2[tid] = (a.u && j0 + tid < a.n) ? a.u[j0 + tid] : 0.0;
   }
   __syncthreads();
 
@@ -150,7 +155,7 @@ grad_trace_kernel(const __grid_constant__ CfPlan plan, const GradArgs a) {
       const int gi = i0 + il;
       if (gi >= a.n || gi < gj) continue;          // lower triangle only
       const double wgt = (gi == gj) ? 1.0 : 2.0;   // mirror entry
-      const double W = wgt * (al1[il] * al2[jl] -
+      const double W = wgt * (al1[il] * al2[jl] - uu1[il] * uu2[jl] -
                               sv1[il] * a.Binv[((int64_t)gj - bcol0) * a.ldb + gi] * sv2[jl]);
       // walk the terms
       int fi = 0;
@@ -250,7 +255,8 @@ __global__ void sum_grad_partials_kernel(const double* __restrict__ partial, int
 
 int grad_trace(Ctx* ctx, const CfPlan& plan, const double* z, int64_t ldz, const double* zaux,
                int64_t n, const double* Binv, int64_t ldb, const double* s, const double* alpha,
-               int nparam, const GradParam* params, double* d_out, int64_t col0, int64_t ncols) {
+               int nparam, const GradParam* params, double* d_out, int64_t col0, int64_t ncols,
+               const double* u) {
   if (nparam <= 0 || n <= 0) return GPL_OK;
   const int tiles = (int)((n + GT - 1) / GT);
   const bool block_mode = col0 >= 0;
@@ -260,7 +266,7 @@ int grad_trace(Ctx* ctx, const CfPlan& plan, const double* z, int64_t ldz, const
   }
   const int ctiles = block_mode ? (int)((ncols + GT - 1) / GT) : 0;
   const int grid = block_mode ? tiles * ctiles : tiles * (tiles + 1) / 2;
-  const int smem = (2 * (plan.nfeat + plan.naux) * GT + 4 * GT) * (int)sizeof(double);
+  const int smem = (2 * (plan.nfeat + plan.naux) * GT + 6 * GT) * (int)sizeof(double);
   if (smem > 227 * 1024) {
     set_error("grad_trace: too many feature columns (%d) for shared memory", plan.nfeat);
     return GPL_ERR_BAD_ARG;
@@ -271,7 +277,7 @@ int grad_trace(Ctx* ctx, const CfPlan& plan, const double* z, int64_t ldz, const
   GPL_TRY(part.alloc(ctx, sizeof(double) * (size_t)grid * GP));
   for (int p0 = 0; p0 < nparam; p0 += GP) {
     GradArgs a;
-    a.z = z; a.zaux = zaux; a.Binv = Binv; a.s = s; a.alpha = alpha; a.partial = part.d();
+    a.z = z; a.zaux = zaux; a.Binv = Binv; a.s = s; a.alpha = alpha; a.u = u; a.partial = part.d();
     a.ldz = ldz; a.ldaux = ldz; a.ldb = ldb;
     // block mode: columns beyond the block belong to other calls
     a.n = (int)n;

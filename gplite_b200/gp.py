@@ -374,12 +374,19 @@ def gp_energy(gp, include_prior=True):
     return e
 
 
-def gp_energy_grad(gp, x, y, jitter=None, include_prior=True, ctx=None, device_ptrs=None):
+def gp_energy_grad(gp, x, y, jitter=None, include_prior=True, ctx=None, device_ptrs=None, trials=None,
+                   offset=None):
     """Energy and its gradient w.r.t. get_param(gp) -- the new capability (the reference's
-    gp_optim is derivative-free).  lik_gaussian + method_full.
+    gp_optim is derivative-free).  method_full with lik_gaussian, or with any other likelihood under
+    approx_laplace (implicit-function gradient at the Newton mode: use a tight approx_laplace(tol=);
+    the likelihood's own parameters must be fixed).
 
     device_ptrs=(x_ptr, y_ptr, n, d): use data already resident in HBM (bench.py's `value`)."""
     ctx = ctx or _lib.default_context()
+    if gp.method.name != "full":
+        raise NotImplementedError("the analytic gradient is implemented for method_full")
+    if gp.lik.name != "lik_gaussian":
+        return _energy_grad_laplace(gp, x, y, jitter, include_prior, ctx, trials, offset)
     items = M.get_param_objs(gp.cfs, gp.lik)
     if device_ptrs is None:
         x = _as_matrix(x)
@@ -416,12 +423,49 @@ def gp_energy_grad(gp, x, y, jitter=None, include_prior=True, ctx=None, device_p
     return e, grad
 
 
+def _energy_grad_laplace(gp, x, y, jitter, include_prior, ctx, trials, offset):
+    if gp.approx.name != "laplace":
+        raise NotImplementedError("the analytic gradient needs approx_laplace for non-Gaussian likelihoods")
+    items = M.get_param_objs(gp.cfs, gp.lik)
+    if any(owner is gp.lik for _, owner, _ in items):
+        raise NotImplementedError("fix the likelihood's parameters (prior_fixed) to use the analytic gradient")
+    x = _as_matrix(x)
+    y = np.ascontiguousarray(np.asarray(y, dtype=np.float64).ravel())
+    n, d = x.shape
+    for cf in gp.cfs:
+        M.learn_scales(cf, x)
+    factors, where = M.flatten_cfs(gp.cfs)
+    pm = _lib.PackedModel(factors)
+    lik = _pack_lik(gp.lik)
+    ap, keep = _pack_approx(gp)
+    pf = np.empty(len(items), dtype=np.int32)
+    ps = np.empty(len(items), dtype=np.int32)
+    for j, (_, owner, attr) in enumerate(items):
+        pf[j], ps[j] = where[(id(owner), attr)]
+    energy = C.c_double()
+    grad = np.zeros(max(len(items), 1), dtype=np.float64)
+    out = _lib.FitOut()
+    jit = 1e-6 if jitter is None else float(jitter)
+    tr, off = _vec(trials, n), _vec(offset, n)
+    _lib.check(ctx.lib.gpl_energy_grad_laplace(ctx.h, pm.ref(), C.byref(lik), C.byref(ap), _lib._ptr(x), n, d,
+                                               _lib._ptr(y), _lib._ptr(tr), _lib._ptr(off), jit, len(items),
+                                               _lib._ptr(pf), _lib._ptr(ps), C.byref(energy), _lib._ptr(grad),
+                                               C.byref(out)))
+    e, grad = energy.value, grad[:len(items)]
+    if include_prior:
+        for j, (_, owner, attr) in enumerate(items):
+            lp = math.log(getattr(owner, attr))
+            e -= M.lpdf_prior_one(owner.priors[attr], lp)
+            grad[j] -= M.dlpdf_prior_one(owner.priors[attr], lp)
+    return e, grad
+
+
 # ------------------------------------------------------------------------------- gp_optim
 def gp_optim(gp, x, y, tol=1e-4, tol_param=1e-1, maxiter=500, restarts=1, verbose=True,
              warn=True, method="Nelder-Mead", **fit_args):
     """R/gp_optim.R:63-125.  method="Nelder-Mead" reproduces the reference's derivative-free
     search (scipy's simplex in place of stats::optim, fnscale = n); method="L-BFGS-B" uses the
-    analytic gradient (lik_gaussian + method_full only)."""
+    analytic gradient (method_full: lik_gaussian, or any likelihood with approx_laplace)."""
     from scipy.optimize import minimize
     names = list(get_param(gp).keys())
     n = len(np.asarray(y).ravel())

@@ -341,6 +341,18 @@ int gpl_rf_features(gpl_ctx* ctx, const gpl_fit* fit, const gpl_cf_model* cf, co
 int gpl_pred_rf(gpl_ctx* ctx, const gpl_fit* fit, const gpl_cf_model* cf, const double* xt, int64_t nt,
                 uint64_t term_mask, double* mean, double* var);
 
+/* Energy (without priors) and its gradient for approx_laplace with a non-Gaussian likelihood,
+ * method_full: runs the Newton loop of gpl_fit_full, then the implicit-function gradient (mode
+ * dependence included).  Covariance-function parameters only (param_factor >= 0); use a tight
+ * approx->tol.  Not in the reference (its gp_optim is derivative-free, R/gp_optim.R:94).  out (iters,
+ * converged, log_evidence) must not be NULL.  GPL_ERR_NOT_LOGCONCAVE when the mode has sites with
+ * pseudo-variance <= 0 (energy is still returned). */
+int gpl_energy_grad_laplace(gpl_ctx* ctx, const gpl_cf_model* cf, const gpl_lik* lik,
+                            const gpl_approx* approx, const double* x, int64_t n, int32_t d,
+                            const double* y, const double* trials, const double* offset, double jitter,
+                            int32_t nparam, const int32_t* param_factor, const int32_t* param_slot,
+                            double* energy, double* grad, gpl_fit_out* out);
+
 /* ---- prediction ---------------------------------------------------- */
 
 /* mean[nt] (and var[nt] if var != NULL) of the latent at xt (nt x d host). */

@@ -1362,3 +1362,41 @@ def energy_grad_gaussian_full(gp, x, y, jitter=None, include_prior=True):
             lp = math.log(getattr(owner, nm))
             g[j] -= (lpdf_prior_one(pr, lp + h) - lpdf_prior_one(pr, lp - h)) / (2 * h)
     return gp_energy(gp, include_prior), g
+
+
+def energy_grad_laplace_full(gp, x, y, trials=None, offset=None, jitter=None, include_prior=True, h=1e-4):
+    """Energy and gradient w.r.t. the covariance-function log-parameters for approx_laplace with a
+    non-Gaussian likelihood, method_full (NOT in the reference; Rasmussen & Williams Alg. 5.1 applied
+    to the reference's objective).  With a = alpha, R = (K + V)^-1, pv = diag((K^-1 + V^-1)^-1),
+    d3 = d/df of get_loglik_d2 (central difference of the reference's own finite-difference
+    curvature): s2 = pv d3 / 2, u = (I - R K) s2,
+    dE/dphi_j = -1/2 sum [(a+u)(a+u)^T - u u^T - R] o dK/dphi_j  - dlogprior/dphi_j."""
+    x = _as_matrix(x)
+    gp_fit(gp, x, y, trials=trials, offset=offset, jitter=jitter)
+    fit = gp.fit
+    n = len(y)
+    jit = 1e-6 if jitter is None else jitter
+    K = eval_cf(gp.cfs, x, x) + jit * np.eye(n)
+    f, a, V = fit["fmean"], fit["alpha"], fit["V"]
+    s = 1 / np.sqrt(V)
+    L = _chol_lower(np.eye(n) + s[:, None] * K * s[None, :])
+    Binv = sla.cho_solve((L, True), np.eye(n), check_finite=False)
+    R = s[:, None] * Binv * s[None, :]
+    pv = V * (1 - np.diag(Binv))
+    _, Vp = get_pseudodata_la(gp.lik, f + h, y, trials=trials, offset=offset)
+    _, Vm = get_pseudodata_la(gp.lik, f - h, y, trials=trials, offset=offset)
+    d3 = (1 / Vm - 1 / Vp) / (2 * h)
+    s2 = 0.5 * pv * d3
+    u = s2 - R @ (K @ s2)
+    p = a + u
+    W = np.outer(p, p) - np.outer(u, u) - R
+    params = free_params(list(gp.cfs))
+    g = np.zeros(len(params))
+    for j, (owner, nm) in enumerate(params):
+        g[j] = -0.5 * np.sum(W * _dK_dlogparam(gp.cfs, owner, nm, x, x))
+        if include_prior:
+            hh = 1e-6
+            lp = math.log(getattr(owner, nm))
+            pr = owner.priors[nm]
+            g[j] -= (lpdf_prior_one(pr, lp + hh) - lpdf_prior_one(pr, lp - hh)) / (2 * hh)
+    return gp_energy(gp, include_prior), g

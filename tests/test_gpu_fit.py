@@ -693,3 +693,35 @@ def test_gp_draw_method_rf(ctx):
         s0 = o.gp_draw_latent(gpo, Xt, Zn, cfind=cfind)
         assert s1.shape == (33, 4) and scaled_err(s1, s0) < 1e-6, cfind
     assert g.gp_draw(gp, Xt, draws=2, seed=1).shape == (33, 2)
+
+
+@pytest.mark.parametrize("lik", ["bernoulli", "poisson", "binomial"])
+def test_laplace_energy_gradient(ctx, lik):
+    """New capability: analytic energy gradient for approx_laplace with non-Gaussian likelihoods
+    (gpl_energy_grad_laplace) against the oracle formula, and L-BFGS gp_optim on top of it."""
+    rng = np.random.default_rng(5)
+    n = 500
+    X = rng.normal(size=(n, 3))
+    f0 = 1.5 * X[:, 0] - X[:, 1]
+    kw = {}
+    if lik == "bernoulli":
+        y, L = (rng.uniform(size=n) < 1 / (1 + np.exp(-f0))).astype(float), g.lik_bernoulli()
+    elif lik == "poisson":
+        y, L = rng.poisson(np.exp(0.5 * f0)).astype(float), g.lik_poisson()
+    else:
+        kw["trials"] = rng.integers(3, 9, size=n).astype(float)
+        y, L = rng.binomial(kw["trials"].astype(int), 1 / (1 + np.exp(-f0))).astype(float), g.lik_binomial()
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        mk = lambda: g.gp_init(cfs=[g.cf_matern52(lscale=1.1, magn=1.2), g.cf_sexp(lscale=0.7, vars=[0]) *
+                                    g.cf_lin(prior_magn=g.prior_fixed())], lik=L,
+                               approx=g.approx_laplace(maxiter=100, tol=1e-11))
+        e, gr = g.gp_energy_grad(mk(), X, y, ctx=ctx, **kw)
+        eo, go = o.energy_grad_laplace_full(mk(), X, y, **kw)
+    assert abs(e - eo) < TOL * abs(eo)
+    assert np.max(np.abs(gr - go)) < 1e-6 * max(1.0, np.max(np.abs(go))), (gr, go)
+    if lik == "bernoulli":
+        gp = g.gp_init(cfs=g.cf_sexp(lscale=0.4, magn=0.8), lik=L, approx=g.approx_laplace(maxiter=100, tol=1e-10))
+        e0 = g.gp_energy_grad(copy.deepcopy(gp), X, y, ctx=ctx)[0]
+        gp = g.gp_optim(gp, X, y, method="L-BFGS-B", verbose=False, warn=False, maxiter=30)
+        assert g.gp_energy(gp) < e0 - 1.0

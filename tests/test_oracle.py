@@ -198,3 +198,36 @@ def test_kmeans_restatement_fixed_point():
     for c in range(3):
         assert np.allclose(cen[c], X[lab == c].mean(axis=0))
     assert np.all(np.abs(np.bincount(lab) - 200) <= 10)
+
+
+@pytest.mark.parametrize("lik", ["bernoulli", "poisson", "binomial"])
+def test_laplace_gradient_oracle_vs_central_differences(lik):
+    """The Laplace (non-Gaussian) energy gradient is new; its oracle formula is checked against
+    central differences of the restated energy."""
+    rng = np.random.default_rng(3)
+    n = 90
+    X = rng.normal(size=(n, 2))
+    f0 = 1.5 * X[:, 0] - X[:, 1]
+    kw = {}
+    if lik == "bernoulli":
+        y, L = (rng.uniform(size=n) < 1 / (1 + np.exp(-f0))).astype(float), g.lik_bernoulli()
+    elif lik == "poisson":
+        y, L = rng.poisson(np.exp(0.5 * f0)).astype(float), g.lik_poisson()
+    else:
+        kw["trials"] = rng.integers(3, 9, size=n).astype(float)
+        y, L = rng.binomial(kw["trials"].astype(int), 1 / (1 + np.exp(-f0))).astype(float), g.lik_binomial(link="probit")
+    mk = lambda: g.gp_init(cfs=[g.cf_sexp(lscale=0.9, magn=1.3), g.cf_lin(magn=0.5)], lik=L,
+                           approx=g.approx_laplace(maxiter=100, tol=1e-11))
+    e, grad = o.energy_grad_laplace_full(mk(), X, y, **kw)
+    p0 = g.get_param_vector(mk())
+    for k in range(len(p0)):
+        es = []
+        for sgn in (1, -1):
+            gp2 = mk()
+            p = p0.copy()
+            p[k] += sgn * 1e-5
+            g.set_param(gp2, p)
+            o.gp_fit(gp2, X, y, **kw)
+            es.append(o.gp_energy(gp2))
+        fd = (es[0] - es[1]) / 2e-5
+        assert abs(grad[k] - fd) < 2e-5 * max(1.0, abs(fd)), (lik, k, grad[k], fd)
