@@ -1,7 +1,7 @@
 """BASELINE.json configs 3 and 4 at full size on one B200 (run under gpurun): wall time, iterations
 and achieved rates through the public API.  One JSON object per line.
 
-    python tools/config_runs.py cfg3_laplace | cfg3_ep | cfg4_fitc [scale]
+    python tools/config_runs.py cfg3_laplace | cfg3_ep | cfg3_grad | cfg4_fitc [scale]
 
 scale < 1 shrinks n (e.g. 0.5) for quick checks.
 """
@@ -34,6 +34,17 @@ if what.startswith("cfg3"):
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")
         cf = g.cf_sexp(lscale=1.0) * g.cf_lin(prior_magn=g.prior_fixed())
+    if what == "cfg3_grad":          # energy + analytic gradient at the Newton mode (new capability)
+        gp = g.gp_init(cfs=cf, lik=g.lik_bernoulli(), approx=g.approx_laplace(maxiter=100, tol=1e-9))
+        l0 = ctx.launch_count()
+        t0 = time.perf_counter()
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            e, gr = g.gp_energy_grad(gp, X, y, ctx=ctx)
+        t = time.perf_counter() - t0
+        emit(config="3: energy + analytic gradient, cf_sexp*cf_lin + lik_bernoulli, laplace (tol 1e-9)", n=n, d=d,
+             seconds=t, energy=e, grad=[float(v) for v in gr], launches=ctx.launch_count() - l0)
+        sys.exit(0)
     approx = g.approx_laplace() if what == "cfg3_laplace" else g.approx_ep(damping=0.9, quad_order=11, maxiter=100)
     gp = g.gp_init(cfs=cf, lik=g.lik_bernoulli(), approx=approx)
     l0 = ctx.launch_count()
