@@ -725,3 +725,36 @@ def test_laplace_energy_gradient(ctx, lik):
         e0 = g.gp_energy_grad(copy.deepcopy(gp), X, y, ctx=ctx)[0]
         gp = g.gp_optim(gp, X, y, method="L-BFGS-B", verbose=False, warn=False, maxiter=30)
         assert g.gp_energy(gp) < e0 - 1.0
+
+
+def test_analytic_prediction_matches_sampling(ctx):
+    """tests/testthat/test_pred.R:125-142 and test_sparse.R:153-170: the analytic latent prediction
+    agrees with the moments of gp_draw (the reference uses 2e5 draws and tol 1e-2) -- for method_full,
+    method_fitc and method_rf, and the staleness guard of test_pred.R:85-118 on gp_draw."""
+    rng = np.random.default_rng(1)
+    n, nt, draws = 25, 30, 100000
+    x = rng.normal(size=(n, 1))
+    xt = np.linspace(-3, 3, nt)[:, None]
+    f = 2 * x[:, 0] - 4
+    trials = np.full(n, 6.0)
+    cases = [(g.lik_gaussian(), f + 0.3 * rng.normal(size=n), {}),
+             (g.lik_bernoulli(), (rng.uniform(size=n) < 0.5).astype(float), {}),
+             (g.lik_binomial(link="probit"), rng.binomial(6, 0.4, size=n).astype(float), dict(trials=trials)),
+             (g.lik_poisson(), rng.poisson(2.0, size=n).astype(float), {})]
+    methods = [g.method_full(), g.method_fitc(inducing=x[:10].copy()), g.method_rf(num_basis=20, seed=4)]
+    for lik, y, kw in cases:
+        for meth in methods:
+            gp = g.gp_init(cfs=g.cf_sexp(lscale=0.8), lik=lik, method=copy.deepcopy(meth))
+            g.gp_fit(gp, x, y, ctx=ctx, **kw)
+            pred = g.gp_pred(gp, xt, var=True)
+            s = g.gp_draw(gp, xt, draws=draws, transform=False, seed=4321)
+            scale = max(1.0, np.max(np.abs(pred["mean"])))
+            assert np.max(np.abs(s.mean(axis=1) - pred["mean"])) < 2e-2 * scale, (lik, meth)
+            assert np.max(np.abs(s.std(axis=1) - np.sqrt(pred["var"]))) < 2e-2 * max(1.0, np.sqrt(pred["var"]).max()), (lik, meth)
+    p = g.get_param_vector(gp)
+    p[0] = 0.0
+    g.set_param(gp, p)
+    with pytest.raises(RuntimeError):
+        g.gp_draw(gp, xt, draws=1)
+    with pytest.raises(RuntimeError):
+        g.gp_pred(gp, xt, var=True)
