@@ -231,3 +231,40 @@ def test_laplace_gradient_oracle_vs_central_differences(lik):
             es.append(o.gp_energy(gp2))
         fd = (es[0] - es[1]) / 2e-5
         assert abs(grad[k] - fd) < 2e-5 * max(1.0, abs(fd)), (lik, k, grad[k], fd)
+
+
+def test_fitc_bad_site_inducing_space_identities():
+    """The CUDA FITC bad-site branch never forms K21 or gathers the good rows of Kxz; it works in the
+    space of U = Kxz Lz^-T.  Check its identities against the literal restatement on the CPU:
+    K21 C1^-1 K12 = U_b (T - Y^T Y) U_b^T, pred_mean = U_b Lz^-1 Kzx alpha1, and the rank-nb update of
+    the final inversion-lemma factor."""
+    X, y, trials = outlier_counts(44)
+    Zi = X[np.random.default_rng(44).permutation(len(X))[:30]].copy()
+    gp = g.gp_init(cfs=g.cf_sexp(lscale=1.0), lik=g.lik_betabinom(phi=0.3), method=g.method_fitc(inducing=Zi))
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        o.gp_fit(gp, X, y, trials=trials)
+    fit = gp.fit
+    assert fit["n_bad"] >= 3
+    z, V, D, Kxz, Lz, Kz = fit["z"], fit["V"], fit["diag"], fit["Kxz"], fit["Kz_chol"], fit["Kz"]
+    good, bad = np.where(V > 0)[0], np.where(~(V > 0))[0]
+    S = D + V
+    fit1 = o._laplace_iter_fitc_good(gp, Kz, Lz, Kxz[good], D[good], y[good], z[good], V[good],
+                                     trials[good], None)
+    pm, pc, Lk, A_chol = o._fitc_bad_common(Lz, Kxz, D, z, V, good, bad, fit1)
+    E = Kxz[good].T @ (Kxz[good] / S[good][:, None])
+    L1 = np.linalg.cholesky(Kz + E)
+    Ub = sla.solve_triangular(Lz, Kxz[bad].T, lower=True).T
+    R = sla.solve_triangular(Lz, E.T, lower=True).T                # E Lz^-T
+    T = sla.solve_triangular(Lz, R, lower=True)                    # Lz^-1 E Lz^-T
+    Y = sla.solve_triangular(L1, R, lower=True)
+    pc2 = Ub @ (np.eye(len(Lz)) - T + Y.T @ Y) @ Ub.T + np.diag(D[bad])
+    a1 = np.zeros(len(y))
+    a1[good] = fit1["alpha"]
+    pm2 = Ub @ sla.solve_triangular(Lz, Kxz.T @ a1, lower=True)
+    assert scaled_err(pc2, pc) < 1e-8 and scaled_err(pm2, pm) < 1e-9
+    A_full = Kz + Kxz.T @ (Kxz / S[:, None])
+    A_upd = Kz + E + Kxz[bad].T @ (Kxz[bad] / S[bad][:, None])
+    assert scaled_err(A_upd, A_full) < 1e-12
+    # the posterior is proper iff -(pred_cov + V_bad) is positive definite (== A positive definite)
+    assert np.all(np.linalg.eigvalsh(-(pc + np.diag(V[bad]))) > 0) and A_chol is not None
