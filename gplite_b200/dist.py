@@ -710,6 +710,9 @@ class FitcOps:
         _lib.check(self.lib.gpl_dgemv_dev(self.ctx.h, trans, rows, m, self._p(K_t), K_t.shape[1], self._p(x_t),
                                           self._p(y_t)))
 
+    pseudodata = GpuOps.pseudodata
+    loglik = GpuOps.loglik
+
     def trsv(self, trans, m, L_t, dinv_t, b_t, x_t):
         _lib.check(self.lib.gpl_dtrsv_dev(self.ctx.h, trans, m, self._p(L_t), L_t.shape[1], self._p(dinv_t),
                                           self._p(b_t), self._p(x_t)))
@@ -719,13 +722,23 @@ class FitcOps:
 
 
 def dist_fit_fitc_gaussian(gp, x, y, jitter=None, ops=None, dist=None, device="cuda", chunk_rows=None):
-    """Row-sharded FITC fit for lik_gaussian (R/gp_fit.R:101-123 + R/laplace.R:122-152 +
-    R/linear_algebra.R:3-43): rank r owns rows [r n/P, (r+1) n/P) of x; Kz and the m x m
-    factorisations are replicated; the only data-path collectives are one all-reduce of the m x m
-    matrix Kzx S^-1 Kxz and a few m-vectors / scalars.  Every rank passes the full x, y."""
+    """lik_gaussian entry point kept for callers of the first version: see dist_fit_fitc."""
+    if gp.lik.name != "lik_gaussian":
+        raise NotImplementedError("dist_fit_fitc_gaussian is for lik_gaussian; use dist_fit_fitc")
+    return dist_fit_fitc(gp, x, y, jitter=jitter, ops=ops, dist=dist, device=device, chunk_rows=chunk_rows)
+
+
+def dist_fit_fitc(gp, x, y, trials=None, offset=None, jitter=None, ops=None, dist=None, device="cuda",
+                  chunk_rows=None):
+    """Row-sharded FITC fit with approx_laplace for any likelihood with log-concave sites
+    (R/gp_fit.R:101-123 + R/laplace.R:122-152,299-325 + R/linear_algebra.R:3-43): rank r owns rows
+    [r n/P, (r+1) n/P) of x and the site vectors of those rows; Kz and the m x m factorisations are
+    replicated; per Newton step the only data-path collectives are one all-reduce of the m x m matrix
+    Kzx S^-1 Kxz and a few m-vectors / scalars.  Every rank passes the full x, y."""
     import torch
-    if gp.lik.name != "lik_gaussian" or gp.method.name != "fitc":
-        raise NotImplementedError("dist_fit_fitc_gaussian covers lik_gaussian + method_fitc")
+    from .gp import _pack_lik
+    if gp.method.name != "fitc" or gp.approx.name != "laplace":
+        raise NotImplementedError("dist_fit_fitc covers method_fitc + approx_laplace")
     if dist is None:
         import torch.distributed as dist
     rank, world = dist.get_rank(), dist.get_world_size()
@@ -741,7 +754,8 @@ def dist_fit_fitc_gaussian(gp, x, y, jitter=None, ops=None, dist=None, device="c
     for cf in gp.cfs:
         M.learn_scales(cf, x)                       # training means / scales use ALL rows
     jit = 1e-6 if jitter is None else float(jitter)
-    sigma2 = gp.lik.sigma ** 2
+    gaussian = gp.lik.name == "lik_gaussian"
+    lik = _pack_lik(gp.lik)
     factors, _ = M.flatten_cfs(gp.cfs)
     pm = _lib.PackedModel(factors)
     if ops is None:
@@ -752,9 +766,13 @@ def dist_fit_fitc_gaussian(gp, x, y, jitter=None, ops=None, dist=None, device="c
     f64 = dict(dtype=torch.float64, device=device)
     ldr = (max(nr, 1) + 15) // 16 * 16
     ldm = (m + 15) // 16 * 16
+    loc = lambda v: None if v is None else torch.from_numpy(
+        np.asarray(v, dtype=np.float64).ravel()[lo:hi].copy()).to(device)
     X_t = torch.from_numpy(np.ascontiguousarray(x[lo:hi].T)).to(device)          # (d, nr)
     Z_t = torch.from_numpy(np.ascontiguousarray(zind.T)).to(device)              # (d, m)
-    y_t = torch.from_numpy(y[lo:hi].copy()).to(device)
+    y_t, tr_t, off_t = loc(y), loc(trials), loc(offset)
+    if gp.lik.name in ("lik_binomial", "lik_betabinom") and tr_t is None:
+        raise ValueError("trials must be provided for the binomial / beta-binomial likelihood")
     nblk = (m + 127) // 128
     Kz = torch.zeros((m, ldm), **f64)
     Lz = torch.zeros((m, ldm), **f64)
@@ -782,52 +800,75 @@ def dist_fit_fitc_gaussian(gp, x, y, jitter=None, ops=None, dist=None, device="c
         W[:, :c].copy_(Kxz[:, r0:r0 + c])
         ops.rownorms_after_solve(W, c, m, Lz, dinv_z, q, r0)
     D = Kdiag[:nr] - q[:nr]
-    S = D + sigma2
-    rs = torch.rsqrt(S).contiguous()
-    # A = Kz + sum over ranks of Kzx S^-1 Kxz  (lower triangle)
-    part = torch.zeros((m, ldm), **f64)
-    for r0 in range(0, nr, chunk_rows):
-        c = min(chunk_rows, nr - r0)
-        W[:, :c].copy_(Kxz[:, r0:r0 + c])
-        ops.scale_rows(W, c, m, rs, r0)
-        ops.syrk_acc(W, c, m, part)
-    dist.all_reduce(part)
-    A.copy_(Kz + part)
-    st, info, logdet_a = ops.potrf(A, m, dinv_a)
-    if st != _lib.GPL_OK:
-        raise _lib.NotPositiveDefinite(st, "Kz + Kzx S^-1 Kxz is not positive definite")
-    # alpha = z/S - S^-1 Kxz A^-1 Kzx (z/S)
-    t = (y_t / S).contiguous()
-    u = torch.zeros(m, **f64)
-    if nr > 0:
-        ops.gemv(1, nr, m, Kxz, t, u)
-    dist.all_reduce(u)
+    f_loc = torch.zeros(nr, **f64)                                     # R/laplace.R:305
+    z_loc = torch.empty(nr, **f64)
+    V_loc = torch.empty(nr, **f64)
     w1 = torch.empty(m, **f64)
-    v = torch.empty(m, **f64)
-    ops.trsv(0, m, A, dinv_a, u.clone(), w1)
-    ops.trsv(1, m, A, dinv_a, w1.clone(), v)
-    kv = torch.zeros(max(nr, 1), **f64)
-    if nr > 0:
-        ops.gemv(0, nr, m, Kxz, v, kv)
-    alpha = t - kv[:nr] / S
-    # f = Kxz Kz^-1 Kzx alpha + D alpha
-    u2 = torch.zeros(m, **f64)
-    if nr > 0:
-        ops.gemv(1, nr, m, Kxz, alpha.contiguous(), u2)
-    dist.all_reduce(u2)
-    beta = torch.empty(m, **f64)
-    ops.trsv(0, m, Lz, dinv_z, u2.clone(), w1)
-    ops.trsv(1, m, Lz, dinv_z, w1.clone(), beta)
-    kb = torch.zeros(max(nr, 1), **f64)
-    if nr > 0:
-        ops.gemv(0, nr, m, Kxz, beta, kb)
-    fmean = kb[:nr] + D * alpha
-    resid = y_t - fmean
-    sc = torch.stack([torch.log(S).sum(), torch.dot(fmean, alpha), (resid * resid).sum()])
-    dist.all_reduce(sc)
-    sum_log_S, f_invK_f, rss = [float(vv) for vv in sc]
-    log_lik = -0.5 * n * math.log(2 * math.pi * sigma2) - 0.5 * rss / sigma2
-    C_logdet = sum_log_S - logdet_z + logdet_a                                # R/linear_algebra.R:32
-    V_logdet = n * math.log(sigma2)
-    log_evidence = log_lik - 0.5 * f_invK_f + 0.5 * (V_logdet - C_logdet)     # R/laplace.R:143-150
-    return dict(log_evidence=log_evidence, alpha_local=alpha, fmean_local=fmean, rows=(lo, hi), beta=beta)
+    maxiter = 1 if gaussian else max(int(gp.approx.maxiter), 1)        # R/laplace.R:306-308
+    tol = float(gp.approx.tol)
+    log_post_old = -math.inf
+    it = 0
+    for it in range(1, maxiter + 1):
+        # laplace_iter.method_fitc, R/laplace.R:122-152, on the local rows
+        if nr > 0:
+            ops.pseudodata(lik, f_loc, y_t, tr_t, off_t, z_loc, V_loc)
+        vmin = torch.tensor([float(V_loc.min().item()) if nr > 0 else math.inf], **f64)
+        dist.all_reduce(vmin, op=dist.ReduceOp.MIN)
+        if not vmin.item() > 0:
+            raise _lib.GplError(_lib.GPL_ERR_NOT_LOGCONCAVE,
+                                "pseudo-variance <= 0: the non-log-concave branch (R/laplace.R:153-232) "
+                                "is single-GPU only")
+        S = D + V_loc
+        rs = torch.rsqrt(S).contiguous()
+        # A = Kz + sum over ranks of Kzx S^-1 Kxz  (lower triangle)
+        part = torch.zeros((m, ldm), **f64)
+        for r0 in range(0, nr, chunk_rows):
+            c = min(chunk_rows, nr - r0)
+            W[:, :c].copy_(Kxz[:, r0:r0 + c])
+            ops.scale_rows(W, c, m, rs, r0)
+            ops.syrk_acc(W, c, m, part)
+        dist.all_reduce(part)
+        A.copy_(Kz + part)
+        st, info, logdet_a = ops.potrf(A, m, dinv_a)
+        if st != _lib.GPL_OK:
+            raise _lib.NotPositiveDefinite(st, "Kz + Kzx S^-1 Kxz is not positive definite")
+        # alpha = z/S - S^-1 Kxz A^-1 Kzx (z/S)
+        t = (z_loc / S).contiguous()
+        u = torch.zeros(m, **f64)
+        if nr > 0:
+            ops.gemv(1, nr, m, Kxz, t, u)
+        dist.all_reduce(u)
+        v = torch.empty(m, **f64)
+        ops.trsv(0, m, A, dinv_a, u.clone(), w1)
+        ops.trsv(1, m, A, dinv_a, w1.clone(), v)
+        kv = torch.zeros(max(nr, 1), **f64)
+        if nr > 0:
+            ops.gemv(0, nr, m, Kxz, v, kv)
+        alpha = t - kv[:nr] / S
+        # f = Kxz Kz^-1 Kzx alpha + D alpha
+        u2 = torch.zeros(m, **f64)
+        if nr > 0:
+            ops.gemv(1, nr, m, Kxz, alpha.contiguous(), u2)
+        dist.all_reduce(u2)
+        beta = torch.empty(m, **f64)
+        ops.trsv(0, m, Lz, dinv_z, u2.clone(), w1)
+        ops.trsv(1, m, Lz, dinv_z, w1.clone(), beta)
+        kb = torch.zeros(max(nr, 1), **f64)
+        if nr > 0:
+            ops.gemv(0, nr, m, Kxz, beta, kb)
+        fmean = (kb[:nr] + D * alpha).contiguous()
+        ll = ops.loglik(lik, fmean, y_t, tr_t, off_t) if nr > 0 else 0.0
+        sc = torch.stack([torch.log(S).sum(), torch.dot(fmean, alpha), torch.log(V_loc).sum(),
+                          torch.tensor(ll, **f64)])
+        dist.all_reduce(sc)
+        sum_log_S, f_invK_f, V_logdet, log_lik = [float(vv) for vv in sc]
+        C_logdet = sum_log_S - logdet_z + logdet_a                                # R/linear_algebra.R:32
+        log_evidence = log_lik - 0.5 * f_invK_f + 0.5 * (V_logdet - C_logdet)     # R/laplace.R:143-150
+        log_post = log_lik - 0.5 * f_invK_f
+        f_loc = fmean
+        diff = log_post - log_post_old
+        log_post_old = log_post
+        if abs(diff) < tol:                                                       # R/laplace.R:314-318
+            break
+    return dict(log_evidence=log_evidence, alpha_local=alpha, fmean_local=f_loc, z_local=z_loc, V_local=V_loc,
+                rows=(lo, hi), beta=beta, iters=it, converged=not (maxiter > 1 and it == maxiter))

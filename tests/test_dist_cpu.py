@@ -321,6 +321,11 @@ class TorchFitcOps:
         pass
 
 
+TorchFitcOps._lik_args = TorchOps._lik_args
+TorchFitcOps.pseudodata = TorchOps.pseudodata
+TorchFitcOps.loglik = TorchOps.loglik
+
+
 def _fitc_problem():
     rng = np.random.default_rng(8)
     n, m = 501, 40
@@ -343,8 +348,14 @@ def _fitc_worker(rank, world, port, q):
         gp = g.gp_init(cfs=[g.cf_sexp(lscale=1.1), g.cf_const(magn=0.2)], lik=g.lik_gaussian(sigma=0.4),
                        method=g.method_fitc(inducing=Zi))
         res = dist_fit_fitc_gaussian(gp, X, y, ops=TorchFitcOps(gp), dist=dist, device="cpu", chunk_rows=100)
+        # Newton loop over the row shards (Poisson counts)
+        from gplite_b200.dist import dist_fit_fitc
+        yc = np.random.default_rng(5).poisson(np.exp(0.4 * y)).astype(float)
+        gpc = g.gp_init(cfs=g.cf_sexp(lscale=1.1), lik=g.lik_poisson(), method=g.method_fitc(inducing=Zi))
+        resc = dist_fit_fitc(gpc, X, yc, ops=TorchFitcOps(gpc), dist=dist, device="cpu", chunk_rows=100)
         q.put((rank, res["log_evidence"], res["rows"], res["alpha_local"].numpy().copy(),
-               res["fmean_local"].numpy().copy()))
+               res["fmean_local"].numpy().copy(), resc["log_evidence"], resc["fmean_local"].numpy().copy(),
+               resc["iters"]))
     finally:
         dist.destroy_process_group()
 
@@ -367,7 +378,13 @@ def test_distributed_fitc_world2_matches_oracle():
     gpo = g.gp_init(cfs=[g.cf_sexp(lscale=1.1), g.cf_const(magn=0.2)], lik=g.lik_gaussian(sigma=0.4),
                     method=g.method_fitc(inducing=Zi))
     o.gp_fit(gpo, X, y)
-    for rank, le, (lo, hi), alpha, fmean in out:
+    yc = np.random.default_rng(5).poisson(np.exp(0.4 * y)).astype(float)
+    gpc = g.gp_init(cfs=g.cf_sexp(lscale=1.1), lik=g.lik_poisson(), method=g.method_fitc(inducing=Zi))
+    o.gp_fit(gpc, X, yc)
+    for rank, le, (lo, hi), alpha, fmean, lec, fc, itc in out:
+        assert itc == gpc.fit["iters"] and itc > 2
+        assert abs(lec - gpc.fit["log_evidence"]) < 1e-9 * abs(gpc.fit["log_evidence"])
+        assert np.max(np.abs(fc - gpc.fit["fmean"][lo:hi])) < 1e-8 * np.max(np.abs(gpc.fit["fmean"]))
         assert abs(le - gpo.fit["log_evidence"]) < 1e-9 * abs(gpo.fit["log_evidence"])
         assert np.max(np.abs(alpha - gpo.fit["alpha"][lo:hi])) < 1e-7 * np.max(np.abs(gpo.fit["alpha"]))
         assert np.max(np.abs(fmean - gpo.fit["fmean"][lo:hi])) < 1e-8 * np.max(np.abs(gpo.fit["fmean"]))
