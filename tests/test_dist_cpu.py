@@ -388,3 +388,56 @@ def test_distributed_fitc_world2_matches_oracle():
         assert abs(le - gpo.fit["log_evidence"]) < 1e-9 * abs(gpo.fit["log_evidence"])
         assert np.max(np.abs(alpha - gpo.fit["alpha"][lo:hi])) < 1e-7 * np.max(np.abs(gpo.fit["alpha"]))
         assert np.max(np.abs(fmean - gpo.fit["fmean"][lo:hi])) < 1e-8 * np.max(np.abs(gpo.fit["fmean"]))
+
+
+# ------------------------------------------------------ uneven ownership (a rank without blocks)
+def _uneven_worker(rank, world, port, q, n):
+    sys.path.insert(0, ROOT)
+    import torch.distributed as dist
+    import gplite_b200 as g
+    from gplite_b200.dist import dist_energy_grad, dist_fit_ep
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        rng = np.random.default_rng(n)
+        X = rng.normal(size=(n, 2))
+        y = np.sin(X[:, 0]) + 0.3 * X[:, 1] + 0.2 * rng.normal(size=n)
+        gp = g.gp_init(cfs=g.cf_matern32(lscale=0.9), lik=g.lik_gaussian(sigma=0.3))
+        e, gr = dist_energy_grad(gp, X, y, nb=128, ops=TorchOps(gp), dist=dist, device="cpu")
+        yb = (y > 0).astype(float)
+        gpe = g.gp_init(cfs=g.cf_matern32(lscale=0.9), lik=g.lik_bernoulli(), approx=g.approx_ep())
+        rese = dist_fit_ep(gpe, X, yb, nb=128, ops=TorchOps(gpe), dist=dist, device="cpu")
+        q.put((rank, e, gr, rese["log_evidence"], rese["iters"]))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,n", [(3, 600), (4, 300)])
+def test_distributed_driver_uneven_ownership(world, n):
+    """5 blocks on 3 ranks, and 3 blocks on 4 ranks (one rank owns nothing but still takes part in
+    every broadcast / all-reduce): energy gradient and EP must still equal the oracle."""
+    import torch.multiprocessing as mp
+    import gplite_b200 as g
+    from oracle import gplite_oracle as o
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_uneven_worker, args=(r, world, port, q, n)) for r in range(world)]
+    for p in procs:
+        p.start()
+    out = [q.get(timeout=240) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    rng = np.random.default_rng(n)
+    X = rng.normal(size=(n, 2))
+    y = np.sin(X[:, 0]) + 0.3 * X[:, 1] + 0.2 * rng.normal(size=n)
+    eo, go = o.energy_grad_gaussian_full(g.gp_init(cfs=g.cf_matern32(lscale=0.9), lik=g.lik_gaussian(sigma=0.3)), X, y)
+    gpe = g.gp_init(cfs=g.cf_matern32(lscale=0.9), lik=g.lik_bernoulli(), approx=g.approx_ep())
+    o.gp_fit(gpe, X, (y > 0).astype(float))
+    for rank, e, gr, lee, ite in out:
+        assert abs(e - eo) < 1e-9 * abs(eo)
+        assert np.max(np.abs(gr - go)) < 1e-6 * max(1.0, np.max(np.abs(go)))
+        assert ite == gpe.fit["iters"]
+        assert abs(lee - gpe.fit["log_evidence"]) < 1e-8 * abs(gpe.fit["log_evidence"])
