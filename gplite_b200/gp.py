@@ -35,6 +35,11 @@ class GP:
         st["_ctx"] = None
         return st
 
+    def __setstate__(self, st):  # copy.deepcopy / unpickling: the device-resident factor is gone
+        self.__dict__.update(st)
+        self._handle = None
+        self._ctx = None
+
     def __repr__(self):
         return f"GP(cfs={self.cfs}, lik={self.lik}, {self.method}, {self.approx})"
 
@@ -61,7 +66,10 @@ def gp_init(cfs=None, lik=None, method=None, approx=None):
                          "it gives exact results")
     if not isinstance(cfs, (list, tuple)):
         cfs = [cfs]
-    return GP(list(cfs), lik, method, approx)
+    # R value semantics: the model owns copies, so a cf / lik / method object reused in another model
+    # (or twice in this one) is never aliased by set_param / gp_optim / gp_fit
+    import copy
+    return GP([copy.deepcopy(c) for c in cfs], copy.deepcopy(lik), copy.deepcopy(method), copy.deepcopy(approx))
 
 
 # ------------------------------------------------------------------------------- parameters
@@ -144,13 +152,30 @@ def _vec(v, n):
     return v
 
 
-def _term_mask(gp, cfind):
+def _mask_of(cfind, nterms):
+    """cfind (0-based indices into gp$cfs) -> the ABI's 64-bit term mask (0 means "all terms")."""
     if cfind is None:
         return 0
+    idx = [int(k) for k in np.atleast_1d(cfind)]
+    if not idx:
+        raise ValueError("cfind must select at least one covariance function")
+    lim = min(nterms, 64)
     mask = 0
-    for k in np.atleast_1d(cfind):
-        mask |= 1 << int(k)
+    for k in idx:
+        if k < 0 or k >= lim:
+            raise ValueError(f"cfind entry {k} out of range (0 .. {lim - 1})")
+        mask |= 1 << k
     return mask
+
+
+def _term_mask(gp, cfind):
+    return _mask_of(cfind, len(gp.cfs))
+
+
+def _need_handle(gp):
+    if gp._handle is None or gp._ctx is None:
+        raise RuntimeError("the device-resident fit of this GP object is gone (the object was copied or "
+                           "unpickled outside gp_load): call gp_fit again")
 
 
 # ------------------------------------------------------------------------------- eval_cf
@@ -166,10 +191,7 @@ def eval_cf(cfs, x1, x2=None, cfind=None, diag_only=False, jitter=0.0, ctx=None)
         raise ValueError("x1 and x2 must have the same number of columns")
     factors, _ = M.flatten_cfs(cfs)
     pm = _lib.PackedModel(factors)
-    mask = 0
-    if cfind is not None:
-        for k in np.atleast_1d(cfind):
-            mask |= 1 << int(k)
+    mask = _mask_of(cfind, len(cfs))
     n1, n2 = x1.shape[0], x2m.shape[0]
     if diag_only:
         out = np.empty(min(n1, n2), dtype=np.float64)
@@ -332,7 +354,7 @@ def get_inducing(gp, x, ctx=None):
         xs, mu, sd = _scale(x)
         zs, _ = kmeans_centers(xs, m, rng, ctx)
         return np.asfortranarray(zs * sd + mu)
-    var = int(gp.method.bin_along) - 1                                 # R is 1-based
+    var = int(gp.method.bin_along)             # 0-based column index, like `vars` (R: 1-based)
     nb = int(gp.method.bin_count)
     eps2 = 2 * np.finfo(np.float64).eps
     cut = np.linspace(x[:, var].min() - eps2, x[:, var].max() + eps2, nb + 1)
@@ -359,6 +381,7 @@ def fit_member(gp, what):
     shape = {"C_chol": (n, n), "alpha": (n,), "Kxz": (n, m), "Kz_chol": (m, m), "var_train": (n,), "wmean": (M_rf,),
              "wcov": (M_rf, M_rf)}[what]
     out = np.empty(shape, dtype=np.float64, order="F")
+    _need_handle(gp)
     _lib.check(gp._ctx.lib.gpl_fit_get(gp._ctx.h, gp._handle, what.encode(), _lib._ptr(out)))
     return out
 
@@ -387,6 +410,11 @@ def gp_energy_grad(gp, x, y, jitter=None, include_prior=True, ctx=None, device_p
         raise NotImplementedError("the analytic gradient is implemented for method_full")
     if gp.lik.name != "lik_gaussian":
         return _energy_grad_laplace(gp, x, y, jitter, include_prior, ctx, trials, offset)
+    if offset is not None and np.any(np.asarray(offset) != 0):
+        # gp_fit / gp_energy put the offset into the Gaussian log-likelihood (R/lik.R:301-303) while the
+        # pseudo-data ignore it (R/lik.R:188-192); the analytic gradient does not cover that extra term
+        raise NotImplementedError("gp_energy_grad: offset is not supported for lik_gaussian "
+                                  "(use method='Nelder-Mead' in gp_optim)")
     items = M.get_param_objs(gp.cfs, gp.lik)
     if device_ptrs is None:
         x = _as_matrix(x)
@@ -508,6 +536,7 @@ def gp_optim(gp, x, y, tol=1e-4, tol_param=1e-1, maxiter=500, restarts=1, verbos
             if restarts > 0:
                 if verbose:
                     print("Parameters not yet converged, restarting...\n")
+                set_param(gp, res.x)          # R/gp_optim.R:104-113 restarts from param_opt
                 return gp_optim(gp, x, y, tol=tol, tol_param=tol_param, maxiter=maxiter,
                                 restarts=restarts - 1, verbose=verbose, warn=warn, method=method,
                                 **fit_args)
@@ -566,6 +595,7 @@ def gp_pred(gp, xnew, var=False, quantiles=None, transform=False, cfind=None, ji
     else:
         if "alpha" not in gp.fit and "wmean" not in gp.fit:
             raise RuntimeError("the fit failed (log_evidence = -Inf); cannot predict")
+        _need_handle(gp)
         c = gp._ctx
         factors, _ = M.flatten_cfs(gp.cfs)
         pm = _lib.PackedModel(factors)
@@ -606,6 +636,7 @@ def gp_pred_cov(gp, xnew, cfind=None, jitter=None, ctx=None):
         return dict(mean=np.zeros(nt), cov=K + jit * np.eye(nt))
     if gp.method.name not in ("full", "fitc"):
         raise NotImplementedError("joint predictive covariance is implemented for method_full and method_fitc")
+    _need_handle(gp)
     c = gp._ctx
     factors, _ = M.flatten_cfs(gp.cfs)
     pm = _lib.PackedModel(factors)
@@ -648,6 +679,8 @@ def gp_draw(gp, xnew, draws=1, transform=True, target=False, marginal=False, cfi
         normals = np.asfortranarray(np.asarray(normals, dtype=np.float64).reshape(nt, draws))
     if fitted and "alpha" not in gp.fit and "wmean" not in gp.fit:
         raise RuntimeError("the fit failed (log_evidence = -Inf); cannot draw")
+    if fitted:
+        _need_handle(gp)
     if rf:                                                       # R/gp_draw.R:145-163
         # w ~ N(wmean, wcov) restricted to the selected summands, sample = featuremap(xt, cfind) w; the
         # M x M factor and the M-vector draws are host-sized, the features come from the device

@@ -91,8 +91,10 @@ class CF:
 
     def __mul__(self, other):                               # "*.cf", R/cf.R:196-213
         if self.name == "cf_prod":
+            # R value semantics: the product owns copies of its members
             out = copy.copy(self)
-            out.cfs = list(self.cfs) + (list(other.cfs) if other.name == "cf_prod" else [other])
+            out.cfs = [copy.deepcopy(c) for c in self.cfs] + \
+                [copy.deepcopy(c) for c in (other.cfs if other.name == "cf_prod" else [other])]
             check_if_overparametrized_magnitude(out)
             return out
         if other.name == "cf_prod":
@@ -157,7 +159,8 @@ def cf_periodic(vars=None, period=1.0, cf_base=None, prior_period=None):
 
 
 def cf_prod(*cfs):
-    out = CF("cf_prod", cfs=list(cfs))
+    # members are copied (R lists have value semantics: reusing a cf object elsewhere must not alias)
+    out = CF("cf_prod", cfs=[copy.deepcopy(c) for c in cfs])
     check_if_overparametrized_magnitude(out)
     return out
 
@@ -233,6 +236,7 @@ def method_full():
 
 
 def method_fitc(inducing=None, num_inducing=100, bin_along=None, bin_count=10, seed=12345):
+    """R/method.R:105-127.  bin_along is a 0-based input column, like `vars` (1-based in R)."""
     if inducing is not None:
         inducing = np.asarray(inducing, dtype=np.float64)
         if inducing.ndim == 1:

@@ -470,7 +470,7 @@ def test_method_fitc_default_inducing(ctx):
     p = g.gp_pred(gp, X[:50], var=True)
     assert np.sqrt(np.mean((p["mean"] - 0.1 - np.sin(X[:50, 0]) * np.cos(0.5 * X[:50, 1])) ** 2)) < 0.2
     gpb = g.gp_init(cfs=g.cf_sexp(lscale=1.0), lik=g.lik_gaussian(sigma=0.3),
-                    method=g.method_fitc(num_inducing=23, bin_along=1, bin_count=5))
+                    method=g.method_fitc(num_inducing=23, bin_along=0, bin_count=5))
     g.gp_fit(gpb, X, y, ctx=ctx)
     zb = gpb.method.inducing
     assert zb.shape == (23, 2) and np.isfinite(gpb.fit["log_evidence"])
