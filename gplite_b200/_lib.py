@@ -61,7 +61,8 @@ class RfSpec(C.Structure):
 
 class FitOut(C.Structure):
     _fields_ = [("log_evidence", C.c_double), ("iters", C.c_int32), ("converged", C.c_int32),
-                ("quad_ok", C.c_int32), ("n_bad", C.c_int32)]
+                ("quad_ok", C.c_int32), ("n_bad", C.c_int32), ("accepted", C.c_int32),
+                ("reserved", C.c_int32), ("damping_final", C.c_double)]
 
 
 _P = C.c_void_p

@@ -622,6 +622,7 @@ int laplace_loop(Ctx* ctx, FullState& st, BadSite& bs, const gpl_lik* lik, const
   if (it > maxiter) it = maxiter;
   out->log_evidence = log_evidence;
   out->iters = it;
+  out->accepted = it;
   out->converged = !(maxiter > 1 && it == maxiter);
   out->n_bad = bs.active ? (int32_t)bs.nb : 0;
   return GPL_OK;
@@ -675,7 +676,7 @@ int fit_full_impl(Ctx* ctx, const gpl_cf_model* cf, const gpl_lik* lik, const gp
   GPL_TRY(diag_extract(ctx, n, st.K.d(), st.ld, fvar_old.d()));
   double diff_old = INFINITY, damp = approx->damping, log_evidence = 0.0, diff_new = 0.0;
   const int maxiter = approx->maxiter < 1 ? 1 : approx->maxiter;
-  int it = 0, quad_ok = 1;
+  int it = 0, quad_ok = 1, accepted = 0;
   for (it = 1; it <= maxiter; ++it) {
     EpSiteArgs ea;
     ea.fmean = fmean_old.d(); ea.fvar = fvar_old.d(); ea.z_old = z_old.d(); ea.P_old = P_old.d();
@@ -745,9 +746,12 @@ int fit_full_impl(Ctx* ctx, const gpl_cf_model* cf, const gpl_lik* lik, const gp
     GPL_TRY(vec_op(ctx, VOP_COPY, n, st.v[V_Z].d(), nullptr, z_old.d()));
     GPL_TRY(vec_op(ctx, VOP_COPY, n, st.v[V_P].d(), nullptr, P_old.d()));
     diff_old = diff_new;
+    ++accepted;
     if (diff_new < approx->tol) break;
   }
   if (it > maxiter) it = maxiter;
+  out->accepted = accepted;
+  out->damping_final = damp;
   out->iters = it;
   out->converged = !(maxiter > 1 && it == maxiter);
   out->quad_ok = quad_ok;

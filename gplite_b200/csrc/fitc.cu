@@ -529,6 +529,7 @@ int fit_fitc_impl(Ctx* ctx, const gpl_cf_model* cf, const gpl_lik* lik, const gp
     if (it > maxiter) it = maxiter;
     out->log_evidence = log_evidence;
     out->iters = it;
+    out->accepted = it;
     out->converged = !(maxiter > 1 && it == maxiter);
     out->n_bad = n_bad;
     GPL_TRY(dl(h_fmean, st.v[F_F].d()));
@@ -562,7 +563,7 @@ int fit_fitc_impl(Ctx* ctx, const gpl_cf_model* cf, const gpl_lik* lik, const gp
   GPL_TRY(vec_op(ctx, VOP_COPY, n, st.Kdiag.d(), nullptr, fvar_old.d()));
   double diff_old = INFINITY, damp = approx->damping, log_evidence = 0.0, diff_new = 0.0;
   const int maxiter = approx->maxiter < 1 ? 1 : approx->maxiter;
-  int it = 0, quad_ok = 1, n_bad = 0;
+  int it = 0, quad_ok = 1, n_bad = 0, accepted = 0;
   for (it = 1; it <= maxiter; ++it) {
     EpSiteArgs ea;
     ea.fmean = fmean_old.d(); ea.fvar = fvar_old.d(); ea.z_old = z_old.d(); ea.P_old = P_old.d();
@@ -628,9 +629,12 @@ int fit_fitc_impl(Ctx* ctx, const gpl_cf_model* cf, const gpl_lik* lik, const gp
     GPL_TRY(vec_op(ctx, VOP_COPY, n, st.v[F_Z].d(), nullptr, z_old.d()));
     GPL_TRY(vec_op(ctx, VOP_COPY, n, st.v[F_P].d(), nullptr, P_old.d()));
     diff_old = diff_new;
+    ++accepted;
     if (diff_new < approx->tol) break;
   }
   if (it > maxiter) it = maxiter;
+  out->accepted = accepted;
+  out->damping_final = damp;
   out->iters = it;
   out->converged = !(maxiter > 1 && it == maxiter);
   out->quad_ok = quad_ok;

@@ -267,6 +267,7 @@ int fit_rf_impl(Ctx* ctx, const gpl_cf_model* cf, const gpl_lik* lik, const gpl_
   if (it > maxiter) it = maxiter;
   out->log_evidence = log_evidence;
   out->iters = it;
+  out->accepted = it;
   out->converged = !(maxiter > 1 && it == maxiter);
   GPL_TRY(down(ctx, h_fmean, f.d(), n));
   GPL_TRY(down(ctx, h_z, z.d(), n));

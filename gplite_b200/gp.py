@@ -281,7 +281,8 @@ def gp_fit(gp, x, y, trials=None, offset=None, jitter=None, ctx=None):
             fit["wmean"] = wmean
         if gp.approx.name == "ep":
             fit.update(fvar=vec["fvar"], cavity_mean=vec["cavity_mean"], cavity_var=vec["cavity_var"],
-                       P=1.0 / vec["V"], quad_ok=bool(out.quad_ok))
+                       P=1.0 / vec["V"], quad_ok=bool(out.quad_ok), accepted=int(out.accepted),
+                       damp=float(out.damping_final))
         if gp.approx.name == "laplace" and gp.approx.maxiter > 1 and not out.converged \
                 and gp.lik.name != "lik_gaussian":
             warnings.warn("Maximum number of iterations in Laplace reached")

@@ -42,7 +42,7 @@
 extern "C" {
 #endif
 
-#define GPL_ABI_VERSION 1
+#define GPL_ABI_VERSION 2   /* 2: gpl_fit_out grew accepted / damping_final; gpl_dist_* entries */
 
 typedef enum gpl_status {
   GPL_OK = 0,
@@ -281,6 +281,10 @@ typedef struct gpl_fit_out {
   int32_t quad_ok;
   int32_t n_bad;          /* sites with pseudo-variance <= 0 in the returned fit (0: C_chol; > 0: the
                            * reference's C_lu case, R/laplace.R:40-117, R/ep.R:50-138) */
+  int32_t accepted;       /* EP: sweeps that were accepted (iters - accepted were discarded because
+                           * max|delta fmean| grew, R/ep.R:306-310); Laplace: = iters */
+  int32_t reserved;
+  double damping_final;   /* EP: damp_value after the last sweep (R/ep.R:308,311); Laplace: 0 */
 } gpl_fit_out;
 
 /* method_full.  x: n x d host, y: n, trials/offset: n or NULL.  n-vectors are returned eagerly

@@ -756,12 +756,14 @@ def _ep_outer(step, n, fvar0, maxiter, tol, damping, damping_min):
     damp = damping
     it = 0
     accepted = 0
+    history = []          # (diff_new, diff_old) per sweep: lets the tests see how decisive each accept / reject was
     for it in range(1, maxiter + 1):
         fit = step(fmean_old, fvar_old, z_old, P_old, damp)
         if fit["fmean"] is None:
             fit["iters"] = it
             return fit
         diff_new = np.max(np.abs(fmean_old - fit["fmean"]))
+        history.append((float(diff_new), float(diff_old)))
         if diff_new > diff_old:
             damp = damp * damping
             continue
@@ -777,6 +779,8 @@ def _ep_outer(step, n, fvar0, maxiter, tol, damping, damping_min):
         fit["log_evidence"] = -np.inf
     fit["iters"] = it
     fit["accepted"] = accepted
+    fit["damp"] = damp
+    fit["history"] = history
     return fit
 
 

@@ -30,7 +30,7 @@ def test_every_declared_symbol_is_exported_and_bound():
 
 def test_abi_version_and_error_string():
     lib = g.load_library()
-    assert lib.gpl_abi_version() == 1
+    assert lib.gpl_abi_version() == 2
     assert isinstance(lib.gpl_last_error(), bytes)
 
 
