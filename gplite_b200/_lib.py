@@ -65,6 +65,11 @@ class FitOut(C.Structure):
                 ("reserved", C.c_int32), ("damping_final", C.c_double)]
 
 
+class DistTimings(C.Structure):
+    _fields_ = [(k, C.c_double) for k in ("kbuild_s", "factor_s", "solve_s", "trtri_s", "lauum_s", "trace_s",
+                                         "total_s", "nccl_bytes")]
+
+
 _P = C.c_void_p
 _D = C.c_double
 _I64 = C.c_int64
@@ -134,6 +139,18 @@ SIGNATURES = {
     "gpl_pred_fitc": (C.c_int, [_P, _P, C.POINTER(CfModel), _P, _I64, _U64, _P, _P]),
     "gpl_fit_get": (C.c_int, [_P, _P, C.c_char_p, _P]),
     "gpl_fit_free": (C.c_int, [_P, _P]),
+    "gpl_ctx_release_cache": (C.c_int, [_P]),
+    "gpl_dist_unique_id": (C.c_int, [_P]),
+    "gpl_dist_init": (C.c_int, [_P, _P, _I32, _I32, C.POINTER(_P)]),
+    "gpl_dist_destroy": (C.c_int, [_P]),
+    "gpl_dist_release": (C.c_int, [_P]),
+    "gpl_dist_rank": (C.c_int, [_P]),
+    "gpl_dist_world": (C.c_int, [_P]),
+    "gpl_dist_fit_full": (C.c_int, [_P, C.POINTER(CfModel), C.POINTER(Lik), C.POINTER(Approx), _P, _I64, _I32, _P,
+                                    _P, _P, _D, _I64, C.POINTER(FitOut), _P, _P, _P, _P, _P, _P, _P,
+                                    C.POINTER(DistTimings)]),
+    "gpl_dist_energy_grad": (C.c_int, [_P, C.POINTER(CfModel), C.POINTER(Lik), _P, _I64, _I32, _P, _D, _I64, _I32,
+                                       _P, _P, C.POINTER(_D), _P, _P, C.POINTER(DistTimings)]),
 }
 
 _lib = None
@@ -196,6 +213,9 @@ class Context:
 
     def sync(self):
         check(self.lib.gpl_ctx_sync(self.h))
+
+    def release_cache(self):
+        check(self.lib.gpl_ctx_release_cache(self.h))
 
     def launch_count(self):
         return int(self.lib.gpl_ctx_launch_count(self.h))

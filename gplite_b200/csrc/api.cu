@@ -137,6 +137,18 @@ int gpl_ctx_sync(gpl_ctx* h) {
   return GPL_OK;
 }
 
+int gpl_ctx_release_cache(gpl_ctx* h) {
+  Ctx* c = reinterpret_cast<Ctx*>(h);
+  GPL_CUDA(cudaSetDevice(c->device));
+  GPL_CUDA(cudaStreamSynchronize(c->stream));
+  if (c->dinv) GPL_CUDA(cudaFree(c->dinv));
+  c->dinv = nullptr;
+  c->dinv_blocks = 0;
+  cudaMemPool_t pool;
+  if (cudaDeviceGetDefaultMemPool(&pool, c->device) == cudaSuccess) GPL_CUDA(cudaMemPoolTrimTo(pool, 0));
+  return GPL_OK;
+}
+
 int64_t gpl_ctx_launch_count(gpl_ctx* h) { return reinterpret_cast<Ctx*>(h)->launches; }
 
 int gpl_ctx_profile(gpl_ctx* h, int32_t enable) {

@@ -263,6 +263,12 @@ __global__ void copy_block_kernel(const double* __restrict__ src, int64_t lds, d
   }
 }
 
+__global__ void zero_upper_kernel(double* __restrict__ A, int64_t lda, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t j = blockIdx.y;
+  if (i < j && i < n) A[j * lda + i] = 0.0;
+}
+
 inline int64_t split(int64_t n) {
   const int64_t nblk = (n + NB - 1) / NB;
   return (nblk / 2) * NB;
@@ -270,7 +276,9 @@ inline int64_t split(int64_t n) {
 
 struct Fac {
   Ctx* ctx;
-  double* dinv;   // block inverses of the factor being built / used
+  double* dinv;        // block inverses of the factor being built / used
+  int* info = nullptr; // device int receiving the smallest failing pivot (default: ctx->d_info)
+  int pivot0 = 0;      // added to the reported pivot (a diagonal block of a larger matrix)
 };
 
 int potf2(const Fac& f, double* A, int64_t lda, int64_t n, int64_t blk0) {
@@ -281,7 +289,8 @@ int potf2(const Fac& f, double* A, int64_t lda, int64_t n, int64_t blk0) {
     configured[f.ctx->device & 63] = true;
   }
   potf2_inv_kernel<<<1, POTF2_THREADS, POTF2_SMEM, f.ctx->stream>>>(
-      A, lda, (int)n, f.dinv + blk0 * NB * NB, f.ctx->d_info, (int)(blk0 * NB));
+      A, lda, (int)n, f.dinv + blk0 * NB * NB, f.info ? f.info : f.ctx->d_info,
+      f.pivot0 + (int)(blk0 * NB));
   GPL_LAUNCH_CHECK(f.ctx);
   return GPL_OK;
 }
@@ -571,6 +580,33 @@ int dpotrf_with(Ctx* ctx, double* dinv, int64_t n, double* A, int64_t lda, int32
     set_error("the leading minor of order %d is not positive definite", info);
     return GPL_ERR_NOT_PD;
   }
+  return GPL_OK;
+}
+
+// Factor an n x n diagonal block on ctx->stream WITHOUT any host synchronisation: a failing pivot is
+// reported as pivot0 + (1-based index inside the block) by atomicMin into the device int `info`
+// (which the caller initialises to INT_MAX and reads when it chooses to).  Used by the multi-GPU
+// panel step, which must not stall the host between panels.
+int dpotrf_nosync(Ctx* ctx, double* dinv, int64_t n, double* A, int64_t lda, int* d_info, int pivot0) {
+  if (n <= 0) return GPL_OK;
+  if ((lda & 1) || ((uintptr_t)A & 15)) {
+    set_error("dpotrf: A must be 16-byte aligned with an even leading dimension");
+    return GPL_ERR_BAD_ARG;
+  }
+  Fac f{ctx, dinv, d_info, pivot0};
+  return potrf_rec(f, A, lda, n, 0);
+}
+
+// out (n x n, ld ldo) <- L^-1 for a factored diagonal block (exact zeros above the diagonal), from its
+// 128-block inverses: the recursive triangular inverse on a copy
+int dtrtri_block(Ctx* ctx, double* dinv, int64_t n, const double* L, int64_t ldl, double* out, int64_t ldo) {
+  if (n <= 0) return GPL_OK;
+  GPL_CUDA(cudaMemcpy2DAsync(out, sizeof(double) * ldo, L, sizeof(double) * ldl, sizeof(double) * n, n,
+                             cudaMemcpyDeviceToDevice, ctx->stream));
+  Fac f{ctx, dinv};
+  GPL_TRY(trtri_rec(f, out, ldo, n, 0));
+  zero_upper_kernel<<<dim3((unsigned)((n + 255) / 256), (unsigned)n), 256, 0, ctx->stream>>>(out, ldo, n);
+  GPL_LAUNCH_CHECK(ctx);
   return GPL_OK;
 }
 

@@ -81,9 +81,13 @@ struct Ctx {
 inline int64_t round_up(int64_t a, int64_t b) { return (a + b - 1) / b * b; }
 
 // ---- gemm_f64.cu ----
+// Staircase products of the block-cyclic multi-GPU layout: C's columns come in blocks of `nb`
+// (a multiple of 128); column block c is only touched from row first + c * step on, and its rows of
+// the B operand start at c * (nb + bskip) instead of c * nb.
+struct GemmStair { int64_t nb, first, step, bskip; };
 int dgemm(Ctx* ctx, bool ta, bool tb, int64_t m, int64_t n, int64_t k, double alpha,
           const double* A, int64_t lda, const double* B, int64_t ldb, double beta, double* C,
-          int64_t ldc, bool lower, int alias = 0, int kskip = 0);
+          int64_t ldc, bool lower, int alias = 0, int kskip = 0, const GemmStair* stair = nullptr);
 // alias: 0 = C distinct from A and B; 1 = C is A (needs n <= 128); 2 = C is B (needs m <= 128);
 // 3 = both (single tile)
 // kskip: 1 = skip the k-tiles above each output tile's first ROW (op(A) = A^T with A lower
@@ -96,6 +100,8 @@ int dpotrf(Ctx* ctx, int64_t n, double* A, int64_t lda, int32_t* info_host, doub
 int dtrsm_right(Ctx* ctx, bool trans, int64_t m, int64_t n, const double* L, int64_t ldl,
                 double* B, int64_t ldb, int64_t blk0);
 int dpotri(Ctx* ctx, int64_t n, double* A, int64_t lda);
+int dpotrf_nosync(Ctx* ctx, double* dinv, int64_t n, double* A, int64_t lda, int* d_info, int pivot0);
+int dtrtri_block(Ctx* ctx, double* dinv, int64_t n, const double* L, int64_t ldl, double* out, int64_t ldo);
 // Y (lower) <- X^T X for lower-triangular X with clean (zero) upper parts in its diagonal blocks:
 // one triangular-aware SYRK launch, out of place (Y must not alias X)
 int lauum_oop(Ctx* ctx, int64_t n, const double* X, int64_t ldx, double* Y, int64_t ldy);

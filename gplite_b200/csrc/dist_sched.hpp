@@ -1,0 +1,350 @@
+// Schedule of the multi-GPU dense factorisation (BASELINE config 5): B = I + S K S built,
+// factorised, solved against and inverted across the ranks of one box, one process per GPU.
+//
+// This header is pure C++ (no CUDA, no NCCL): it decides WHO does WHAT on WHICH stream and in which
+// order collectives are issued; every device operation, stream/event primitive and collective goes
+// through the `Ops` policy class.  libgplite_b200.so instantiates it with the CUDA + NCCL back end
+// (dist.cu); tests/sim/dist_sim.cpp instantiates it with a host back end whose collectives are
+// callbacks into torch.distributed (gloo), so that the index arithmetic and the collective order are
+// exercised on CPUs with world sizes 2 and 3.  The sim back end is test infrastructure, not a
+// product path.
+//
+// Layout: 1-D block-cyclic by block COLUMNS of width nb (block b lives on rank b % P, stored as a
+// column-major slab of full height).  On NVSwitch every peer is equally far, so the 2-D layout's only
+// advantage (less panel traffic per link) buys nothing on 8 GPUs: panel traffic is n^2/2 * 8 bytes per
+// rank in total (160 GB at n = 200k) against n^3/(3P) flops, a few per cent of the step time and
+// hidden behind the look-ahead.  What the 1-D layout gives in exchange: the panel step (potrf of the
+// diagonal block + TRSM of the rows below) is local to one rank, and the whole trailing update of a
+// rank is ONE staircase GEMM per panel (all its remaining block columns at once, the panel rows of
+// every P-th block read in place), instead of one launch per block column.
+//
+// Streams: MAIN carries the trailing updates, PANEL (high priority) the owner's panel factorisation,
+// COMM the panel broadcasts.  One step of look-ahead: the owner of panel k+1 applies panel k to that
+// block column first, factors it on PANEL and the broadcast of panel k+1 runs on COMM while every rank
+// (the owner included) is still applying panel k on MAIN.  Nothing synchronises with the host inside
+// a sweep: a failing pivot is collected in a device word and looked at once at the end.
+//
+// Replaces, for matrices that do not fit one GPU, base-R chol() / forwardsolve() / backsolve() at
+// R/laplace.R:27-30 and R/ep.R:38-42, and the n x n solve behind R/ep.R:42,141.
+#pragma once
+
+#include <stdint.h>
+
+#include <vector>
+
+namespace gpl {
+namespace dist {
+
+enum Stream { S_MAIN = 0, S_PANEL = 1, S_COMM = 2 };
+enum Event { EV_PANEL_READY0 = 0, EV_PANEL_READY1, EV_BCAST_DONE0, EV_BCAST_DONE1, EV_BUF_FREE0,
+             EV_BUF_FREE1, EV_COL_READY, EV_MAIN_DONE, EV_COUNT };
+
+struct Stair { int64_t nb, first, step, bskip; };   // same meaning as gpl::GemmStair
+
+// Ownership / index maps of the 1-D block-cyclic column layout.
+struct Layout {
+  int64_t n = 0, nb = 0, ld = 0;
+  int world = 1, rank = 0;
+  int64_t nblk = 0;
+  int64_t nloc = 0;                 // local columns
+  std::vector<int64_t> lc0;         // local first column of block b (owned blocks only, else -1)
+  void init(int64_t n_, int64_t nb_, int world_, int rank_) {
+    n = n_; nb = nb_; world = world_; rank = rank_;
+    ld = (n + 15) / 16 * 16;
+    nblk = (n + nb - 1) / nb;
+    lc0.assign((size_t)nblk, -1);
+    nloc = 0;
+    for (int64_t b = 0; b < nblk; ++b)
+      if (owner(b) == rank) { lc0[(size_t)b] = nloc; nloc += width(b); }
+  }
+  int owner(int64_t b) const { return (int)(b % world); }
+  int64_t col0(int64_t b) const { return b * nb; }
+  int64_t width(int64_t b) const { return (n - b * nb) < nb ? (n - b * nb) : nb; }
+  // first block >= b owned by this rank (may be >= nblk)
+  int64_t first_owned_from(int64_t b) const {
+    const int64_t r = ((rank - b) % world + world) % world;
+    return b + r;
+  }
+  int64_t ldp(int64_t k) const { return (n - col0(k) + 15) / 16 * 16; }   // packed panel k
+};
+
+// Ops must provide (all asynchronous on the given Stream unless stated):
+//   int fill_block(Stream, int64_t b, double* dst /* slab column lc0[b], row col0(b) */, int64_t ld)
+//        -- rows col0(b) .. n of block column b of B (diagonal block included)
+//   int potrf_diag(Stream, int64_t k, int64_t w, double* A, int64_t lda, int pivot0)   (no host sync)
+//   int trsm_below(Stream, int64_t k, int64_t m, int64_t w, const double* L, int64_t ldl, double* B, int64_t ldb)
+//        -- B <- B L^-T with the factor of diagonal block k
+//   int inv_diag(Stream, int64_t k, int64_t w, const double* L, int64_t ldl, double* out, int64_t ldo)
+//   int gemm(Stream, bool ta, bool tb, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, bool lower, const Stair*)
+//   int copy2d(Stream, double* dst, int64_t ldd, const double* src, int64_t lds, int64_t rows, int64_t cols)
+//   int zero(Stream, double* p, int64_t count)
+//   int trsv(Stream, int64_t k, bool trans, int64_t w, const double* L, int64_t ldl, double* b, double* x)
+//   int gemv(Stream, bool trans, int64_t m, int64_t n, const double* A, int64_t lda, const double* x, double* y)
+//   int axpy(Stream, int64_t n, double a, const double* x, double* y)            y += a x
+//   int sub(Stream, int64_t n, const double* a, const double* b, double* out)    out = a - b
+//   int colsumsq(Stream, int64_t m, int64_t n, const double* A, int64_t lda, double* out)
+//   int diag_logsum(Stream, int64_t w, const double* A, int64_t lda, double* acc)   acc += 2 sum log diag
+//   int record(Event, Stream); int wait(Stream, Event); int sync(Stream)
+//   int bcast(Stream, double* buf, int64_t count, int root)
+//   int allreduce_sum(Stream, double* buf, int64_t count)
+//   int check_info(int* first_bad_pivot)   -- syncs, all-reduces (min) the failing pivot word
+// Every method returns 0 on success; any other value aborts the sweep and is returned unchanged.
+
+#define GPL_DS(call)            \
+  do {                          \
+    int s__ = (call);           \
+    if (s__ != 0) return s__;   \
+  } while (0)
+
+template <class Ops>
+class ShardedChol {
+ public:
+  Layout lay;
+  Ops* ops = nullptr;
+  double* A = nullptr;        // slab: nloc columns, ld rows: B, then its factor L
+  double* X = nullptr;        // second slab (optional): L^-1, then B^-1
+  double* panel[2] = {nullptr, nullptr};   // packed panels, nb * ld doubles each
+  double* tmp = nullptr;      // nb x max(nloc, nb) scratch for the inverse sweeps
+  double* vec[4] = {nullptr, nullptr, nullptr, nullptr};   // n-vectors (solve workspace)
+  double* logdet_acc = nullptr;   // device scalar
+  double bcast_bytes = 0.0;       // panel bytes this rank has put through the collectives
+
+  double* slab(double* S, int64_t b) const { return S + lay.lc0[(size_t)b] * lay.ld; }
+
+  // ---- build + factorise ---------------------------------------------------------------------
+  // B's owned block columns come from ops->fill_block; returns the first failing pivot (0 = ok) in
+  // *info; logdet(B) accumulates into the device scalar logdet_acc (summed over ranks by the caller
+  // through finish_logdet).
+  int factor(int* info) {
+    const Layout& L = lay;
+    const int me = L.rank;
+    GPL_DS(ops->zero(S_MAIN, logdet_acc, 1));
+    for (int64_t b = L.first_owned_from(0); b < L.nblk; b += L.world)
+      GPL_DS(ops->fill_block(S_MAIN, b, slab(A, b) + L.col0(b), L.ld));
+    GPL_DS(ops->record(EV_COL_READY, S_MAIN));
+    GPL_DS(ops->wait(S_PANEL, EV_COL_READY));
+    // both panel buffers start free
+    GPL_DS(ops->record(EV_BUF_FREE0, S_MAIN));
+    GPL_DS(ops->record(EV_BUF_FREE1, S_MAIN));
+    if (L.owner(0) == me) GPL_DS(factor_panel(0));
+    GPL_DS(send_panel(0));
+    for (int64_t k = 0; k < L.nblk; ++k) {
+      const int64_t nxt = k + 1;
+      GPL_DS(ops->wait(S_MAIN, (Event)(EV_BCAST_DONE0 + (k & 1))));
+      if (nxt < L.nblk) {
+        if (L.owner(nxt) == me) {
+          GPL_DS(apply_panel_to(k, nxt, 1));                       // look-ahead column first
+          GPL_DS(ops->record(EV_COL_READY, S_MAIN));
+          GPL_DS(ops->wait(S_PANEL, EV_COL_READY));
+          GPL_DS(factor_panel(nxt));
+        }
+        GPL_DS(send_panel(nxt));
+      }
+      // the rest of this rank's trailing block columns, one staircase product
+      int64_t j = L.first_owned_from(k + 1);
+      if (j == nxt) j += L.world;
+      if (j < L.nblk) {
+        const int64_t cnt = (L.nblk - 1 - j) / L.world + 1;
+        GPL_DS(apply_panel_to(k, j, cnt));
+      }
+      GPL_DS(ops->record((Event)(EV_BUF_FREE0 + (k & 1)), S_MAIN));
+    }
+    GPL_DS(ops->record(EV_PANEL_READY0, S_PANEL));                  // join the side streams
+    GPL_DS(ops->wait(S_MAIN, EV_PANEL_READY0));
+    GPL_DS(ops->record(EV_BCAST_DONE0, S_COMM));
+    GPL_DS(ops->wait(S_MAIN, EV_BCAST_DONE0));
+    return ops->check_info(info);
+  }
+
+  // ---- triangular solves: out = B^-1 rhs (replicated in, replicated out) -------------------------
+  // Block forward / backward substitution; per block one nb-sized all-reduce (forward: the partial
+  // sums sum_j L_kj w_j live with the owners of the columns j) or broadcast (backward).
+  int solve(const double* rhs, double* out) {
+    const Layout& L = lay;
+    const int me = L.rank;
+    const int64_t n = L.n;
+    double *u = vec[0], *wv = vec[1], *t1 = vec[2], *t2 = vec[3];
+    GPL_DS(ops->zero(S_MAIN, u, n));
+    GPL_DS(ops->zero(S_MAIN, wv, n));
+    for (int64_t k = 0; k < L.nblk; ++k) {
+      const int64_t k0 = L.col0(k), w = L.width(k), below = n - k0 - w;
+      GPL_DS(ops->allreduce_sum(S_MAIN, u + k0, w));
+      if (L.owner(k) == me) {
+        const double* Lk = slab(A, k) + k0;
+        GPL_DS(ops->sub(S_MAIN, w, rhs + k0, u + k0, t1));
+        GPL_DS(ops->trsv(S_MAIN, k, false, w, Lk, L.ld, t1, wv + k0));
+        if (below > 0) {
+          GPL_DS(ops->gemv(S_MAIN, false, below, w, Lk + w, L.ld, wv + k0, t2));
+          GPL_DS(ops->axpy(S_MAIN, below, 1.0, t2, u + k0 + w));
+        }
+      } else if (below > 0) {
+        // u[k0 + w ..] of a non-owner holds only its own partial sums: nothing to do
+      }
+      // the entries u[k0 .. k0 + w) were summed in place on every rank; later blocks are untouched
+    }
+    GPL_DS(ops->zero(S_MAIN, out, n));
+    for (int64_t k = L.nblk - 1; k >= 0; --k) {
+      const int64_t k0 = L.col0(k), w = L.width(k), below = n - k0 - w;
+      if (L.owner(k) == me) {
+        const double* Lk = slab(A, k) + k0;
+        if (below > 0) {
+          GPL_DS(ops->gemv(S_MAIN, true, below, w, Lk + w, L.ld, out + k0 + w, t2));
+          GPL_DS(ops->sub(S_MAIN, w, wv + k0, t2, t1));
+        } else {
+          GPL_DS(ops->sub(S_MAIN, w, wv + k0, out + k0, t1));      // out[k0..] is still zero
+        }
+        GPL_DS(ops->trsv(S_MAIN, k, true, w, Lk, L.ld, t1, out + k0));
+      }
+      GPL_DS(ops->bcast(S_MAIN, out + k0, w, L.owner(k)));
+    }
+    return 0;
+  }
+
+  // ---- inverse: B^-1 = X^T X, X = L^-1 (SURVEY 8e "C^-1 + trace term") ----------------------------
+  // Two more sweeps of panel broadcasts, each n^3/3 flops spread like the factorisation.
+  //   X sweep: panel k = [L_kk^-1 ; L[k1:, k]] goes to every rank; for ALL its columns j < k at once a
+  //            rank finishes block row k of X (X_kJ = L_kk^-1 R_kJ) and pushes the update down
+  //            (R[k1:, J] -= L[k1:, k] X_kJ); the running right-hand side R lives in X's slab.
+  //   Y sweep: panel i = X[i0:, i]; Y_iJ = X[i0:, i]^T X[i0:, J] for its columns j <= i, written over
+  //            the block row of X that is no longer needed.
+  // Panels depend only on finished data, so panel k+1 is always in flight during step k.
+  int x_sweep() {
+    const Layout& L = lay;
+    GPL_DS(ops->zero(S_MAIN, X, L.nloc * L.ld));
+    return sweep(true);
+  }
+  int y_sweep() { return sweep(false); }
+
+  // diag(B^-1)_i = sum_k X_ki^2 after x_sweep: column sums of squares of the owned block columns into
+  // out (n, zero elsewhere), then one all-reduce
+  int diag_binv(double* out) {
+    const Layout& L = lay;
+    GPL_DS(ops->zero(S_MAIN, out, L.n));
+    for (int64_t j = L.first_owned_from(0); j < L.nblk; j += L.world) {
+      const int64_t j0 = L.col0(j);
+      GPL_DS(ops->colsumsq(S_MAIN, L.n - j0, L.width(j), slab(X, j) + j0, L.ld, out + j0));
+    }
+    return ops->allreduce_sum(S_MAIN, out, L.n);
+  }
+
+ private:
+  // owner only, on PANEL: potrf of the diagonal block, TRSM of the rows below, pack for broadcast
+  int factor_panel(int64_t k) {
+    const Layout& L = lay;
+    const int64_t k0 = L.col0(k), w = L.width(k), below = L.n - k0 - w;
+    double* Akk = slab(A, k) + k0;
+    GPL_DS(ops->potrf_diag(S_PANEL, k, w, Akk, L.ld, (int)k0));
+    GPL_DS(ops->diag_logsum(S_PANEL, w, Akk, L.ld, logdet_acc));
+    if (below > 0) GPL_DS(ops->trsm_below(S_PANEL, k, below, w, Akk, L.ld, Akk + w, L.ld));
+    GPL_DS(ops->wait(S_PANEL, (Event)(EV_BUF_FREE0 + (k & 1))));
+    GPL_DS(ops->copy2d(S_PANEL, panel[k & 1], L.ldp(k), Akk, L.ld, L.n - k0, w));
+    return ops->record((Event)(EV_PANEL_READY0 + (k & 1)), S_PANEL);
+  }
+
+  // every rank, on COMM: broadcast of packed panel k from its owner
+  int send_panel(int64_t k) {
+    const Layout& L = lay;
+    const int b = (int)(k & 1);
+    if (L.owner(k) == L.rank) GPL_DS(ops->wait(S_COMM, (Event)(EV_PANEL_READY0 + b)));
+    else GPL_DS(ops->wait(S_COMM, (Event)(EV_BUF_FREE0 + b)));
+    const int64_t count = L.ldp(k) * L.width(k);
+    GPL_DS(ops->bcast(S_COMM, panel[b], count, L.owner(k)));
+    bcast_bytes += 8.0 * (double)count;
+    return ops->record((Event)(EV_BCAST_DONE0 + b), S_COMM);
+  }
+
+  // A[j0.., blocks j, j + P, ... (cnt of them)] -= P_k[rows] P_k[block rows]^T on MAIN
+  int apply_panel_to(int64_t k, int64_t j, int64_t cnt) {
+    const Layout& L = lay;
+    const int64_t k0 = L.col0(k), w = L.width(k), j0 = L.col0(j);
+    const int64_t jl = j + (cnt - 1) * L.world;                    // last block of the group
+    const int64_t ncols = (cnt - 1) * L.nb + L.width(jl);
+    const double* P = panel[k & 1];
+    const int64_t ldp = L.ldp(k);
+    Stair st{L.nb, 0, (int64_t)L.world * L.nb, (int64_t)(L.world - 1) * L.nb};
+    return ops->gemm(S_MAIN, false, true, L.n - j0, ncols, w, -1.0, P + (j0 - k0), ldp, P + (j0 - k0), ldp,
+                     1.0, slab(A, j) + j0, L.ld, false, cnt > 1 ? &st : nullptr);
+  }
+
+  // shared skeleton of the two inverse sweeps: prepare (owner, PANEL) -> broadcast (COMM) -> apply (MAIN)
+  int sweep(bool xs) {
+    const Layout& L = lay;
+    const int me = L.rank;
+    GPL_DS(ops->record(EV_COL_READY, S_MAIN));
+    GPL_DS(ops->wait(S_PANEL, EV_COL_READY));
+    GPL_DS(ops->record(EV_BUF_FREE0, S_MAIN));
+    GPL_DS(ops->record(EV_BUF_FREE1, S_MAIN));
+    if (L.owner(0) == me) GPL_DS(xs ? prep_L_panel(0) : prep_X_panel(0));
+    GPL_DS(send_panel(0));
+    for (int64_t k = 0; k < L.nblk; ++k) {
+      GPL_DS(ops->wait(S_MAIN, (Event)(EV_BCAST_DONE0 + (k & 1))));
+      if (k + 1 < L.nblk) {
+        if (L.owner(k + 1) == me) GPL_DS(xs ? prep_L_panel(k + 1) : prep_X_panel(k + 1));
+        GPL_DS(send_panel(k + 1));
+      }
+      GPL_DS(xs ? apply_L_panel(k) : apply_X_panel(k));
+      GPL_DS(ops->record((Event)(EV_BUF_FREE0 + (k & 1)), S_MAIN));
+    }
+    GPL_DS(ops->record(EV_PANEL_READY0, S_PANEL));
+    GPL_DS(ops->wait(S_MAIN, EV_PANEL_READY0));
+    GPL_DS(ops->record(EV_BCAST_DONE0, S_COMM));
+    return ops->wait(S_MAIN, EV_BCAST_DONE0);
+  }
+
+  int prep_L_panel(int64_t k) {
+    const Layout& L = lay;
+    const int64_t k0 = L.col0(k), w = L.width(k), below = L.n - k0 - w, ldp = L.ldp(k);
+    const double* Akk = slab(A, k) + k0;
+    double* pv = panel[k & 1];
+    GPL_DS(ops->wait(S_PANEL, (Event)(EV_BUF_FREE0 + (k & 1))));
+    GPL_DS(ops->copy2d(S_PANEL, pv, ldp, Akk, L.ld, L.n - k0, w));
+    GPL_DS(ops->inv_diag(S_PANEL, k, w, Akk, L.ld, pv, ldp));        // diagonal block <- L_kk^-1
+    // this rank's own column k of X:  X_kk = L_kk^-1,  R[k1:, k] = -L[k1:, k] L_kk^-1
+    double* Xk = slab(X, k) + k0;
+    GPL_DS(ops->copy2d(S_PANEL, Xk, L.ld, pv, ldp, w, w));
+    if (below > 0)
+      GPL_DS(ops->gemm(S_PANEL, false, false, below, w, w, -1.0, pv + w, ldp, pv, ldp, 0.0, Xk + w, L.ld,
+                       false, nullptr));
+    return ops->record((Event)(EV_PANEL_READY0 + (k & 1)), S_PANEL);
+  }
+
+  int apply_L_panel(int64_t k) {
+    const Layout& L = lay;
+    const int64_t k0 = L.col0(k), w = L.width(k), below = L.n - k0 - w, ldp = L.ldp(k);
+    // local columns of the blocks j < k owned by this rank: a contiguous prefix of the slab
+    const int64_t jn = L.first_owned_from(k);                       // first owned block >= k
+    const int64_t nc = jn < L.nblk ? L.lc0[(size_t)jn] : L.nloc;
+    if (nc == 0) return 0;
+    const double* pv = panel[k & 1];
+    double* Xr = X + k0;                                            // block row k of the slab
+    GPL_DS(ops->gemm(S_MAIN, false, false, w, nc, w, 1.0, pv, ldp, Xr, L.ld, 0.0, tmp, w, false, nullptr));
+    if (below > 0)
+      GPL_DS(ops->gemm(S_MAIN, false, false, below, nc, w, -1.0, pv + w, ldp, tmp, w, 1.0, Xr + w, L.ld, false,
+                       nullptr));
+    return ops->copy2d(S_MAIN, Xr, L.ld, tmp, w, w, nc);
+  }
+
+  int prep_X_panel(int64_t i) {
+    const Layout& L = lay;
+    const int64_t i0 = L.col0(i), w = L.width(i);
+    GPL_DS(ops->wait(S_PANEL, (Event)(EV_BUF_FREE0 + (i & 1))));
+    GPL_DS(ops->copy2d(S_PANEL, panel[i & 1], L.ldp(i), slab(X, i) + i0, L.ld, L.n - i0, w));
+    return ops->record((Event)(EV_PANEL_READY0 + (i & 1)), S_PANEL);
+  }
+
+  int apply_X_panel(int64_t i) {
+    const Layout& L = lay;
+    const int64_t i0 = L.col0(i), w = L.width(i), ldp = L.ldp(i);
+    // columns of the blocks j <= i owned by this rank
+    const int64_t jn = L.first_owned_from(i + 1);
+    const int64_t nc = jn < L.nblk ? L.lc0[(size_t)jn] : L.nloc;
+    if (nc == 0) return 0;
+    double* Xr = X + i0;
+    GPL_DS(ops->gemm(S_MAIN, true, false, w, nc, L.n - i0, 1.0, panel[i & 1], ldp, Xr, L.ld, 0.0, tmp, w, false,
+                     nullptr));
+    return ops->copy2d(S_MAIN, Xr, L.ld, tmp, w, w, nc);
+  }
+};
+
+}  // namespace dist
+}  // namespace gpl

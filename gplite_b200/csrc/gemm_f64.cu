@@ -143,6 +143,11 @@ struct GemmArgs {
                   // 2: k starts at the tile's first column (B lower-triangular);
                   // 3: k ends at the tile's last row (A lower-triangular: A[m][k] = 0 for k > m)
   int tiles_m, tiles_n;
+  // Staircase mode (stair_nb > 0), used by the block-cyclic multi-GPU updates: C's columns come in
+  // blocks of stair_nb; block c only exists from row stair_first + c * stair_step on (the rows above
+  // are the never-referenced upper part of a block column of the slab), and its B rows sit at
+  // n + c * stair_bskip in the B operand (the panel rows of every P-th block, read in place).
+  int stair_nb, stair_first, stair_step, stair_bskip;
 };
 
 template <bool TA, bool TB, class CF>
@@ -175,6 +180,13 @@ __global__ void __launch_bounds__(CF::THREADS) gemm_f64_kernel(const GemmArgs p)
     if (p.lower && bn > bm) return;
   }
   const int m0 = bm * BM, n0 = bn * BN;
+  int nb0 = n0, nb_lim = p.N;        // B-operand coordinates of this tile's columns
+  if (p.stair_nb > 0) {
+    const int cblk = n0 / p.stair_nb;
+    if (m0 + BM <= p.stair_first + cblk * p.stair_step) return;
+    nb0 = n0 + cblk * p.stair_bskip;
+    nb_lim = p.N + cblk * p.stair_bskip;
+  }
 
   double acc[MI][NI][2];
 #pragma unroll
@@ -195,7 +207,7 @@ __global__ void __launch_bounds__(CF::THREADS) gemm_f64_kernel(const GemmArgs p)
   TileLoader<TA, BM, CF::THREADS, BK> ldA;
   TileLoader<!TB, BN, CF::THREADS, BK> ldB;
   ldA.init(p.A, p.lda, m0, p.M, tid);
-  ldB.init(p.B, p.ldb, n0, p.N, tid);
+  ldB.init(p.B, p.ldb, nb0, nb_lim, tid);
   ldA.p += (int64_t)kt0 * ldA.kadv;
   ldB.p += (int64_t)kt0 * ldB.kadv;
   // interior tile and K a multiple of BK: no bounds logic in the loads (CTA-uniform)
@@ -406,7 +418,7 @@ int dispatch(Ctx* ctx, const GemmArgs& a, int alias) {
 
 int dgemm(Ctx* ctx, bool ta, bool tb, int64_t m, int64_t n, int64_t k, double alpha,
           const double* A, int64_t lda, const double* B, int64_t ldb, double beta, double* C,
-          int64_t ldc, bool lower, int alias, int kskip) {
+          int64_t ldc, bool lower, int alias, int kskip, const GemmStair* stair) {
   if (m <= 0 || n <= 0) return GPL_OK;
   if ((lda & 1) || (ldb & 1) || ((uintptr_t)A & 15) || ((uintptr_t)B & 15)) {
     set_error("dgemm: operands must be 16-byte aligned with even leading dimensions "
@@ -423,6 +435,15 @@ int dgemm(Ctx* ctx, bool ta, bool tb, int64_t m, int64_t n, int64_t k, double al
   a.alpha = alpha; a.beta = beta; a.lower = lower ? 1 : 0;
   a.kskip = kskip;
   a.tiles_m = a.tiles_n = 0;
+  a.stair_nb = a.stair_first = a.stair_step = a.stair_bskip = 0;
+  if (stair && stair->nb > 0) {
+    if (stair->nb % 128 || alias || lower || kskip) {
+      set_error("dgemm: staircase mode needs column blocks that are multiples of 128 and a plain product");
+      return GPL_ERR_BAD_ARG;
+    }
+    a.stair_nb = (int)stair->nb; a.stair_first = (int)stair->first; a.stair_step = (int)stair->step;
+    a.stair_bskip = (int)stair->bskip;
+  }
   if (ta && tb) {
     set_error("dgemm: TT product not implemented (never needed on the hot path)");
     return GPL_ERR_BAD_ARG;

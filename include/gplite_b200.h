@@ -138,6 +138,9 @@ int gpl_device_count(void);
 int gpl_ctx_create(int device, uint64_t stream, gpl_ctx** out);
 int gpl_ctx_destroy(gpl_ctx* ctx);
 int gpl_ctx_sync(gpl_ctx* ctx);
+/* Give the device memory cached by the context back to the driver (the stream-ordered pool keeps the
+ * multi-GB buffers of finished fits for reuse).  Live gpl_fit handles are not affected. */
+int gpl_ctx_release_cache(gpl_ctx* ctx);
 /* number of kernels this context has launched so far (for bench.py's gpu_launches) */
 int64_t gpl_ctx_launch_count(gpl_ctx* ctx);
 /* Optional per-launch CUDA-event timing of the FP64 tensor-core GEMM/SYRK kernel (the dominant
@@ -387,6 +390,56 @@ int gpl_draw_full(gpl_ctx* ctx, const gpl_fit* fit, const gpl_cf_model* cf, cons
  * pass over Kxz; method_rf: "wmean" (M), "wcov" (M x M).  out must hold rows*cols doubles. */
 int gpl_fit_get(gpl_ctx* ctx, const gpl_fit* fit, const char* what, double* out);
 int gpl_fit_free(gpl_ctx* ctx, gpl_fit* fit);
+
+/* ---- multi-GPU full GP (BASELINE config 5) ---------------------------------------
+ * One process per GPU.  The NCCL communicator lives inside the library: the host only has to carry a
+ * 128-byte id from rank 0 to the other ranks (any channel: a file, a socket, MPI, torch.distributed)
+ * and call gpl_dist_init on every rank.  K is built directly in a 1-D block-cyclic column layout (block
+ * columns of width nb, block b on rank b % world), factorised right-looking with panel broadcasts
+ * (ncclBroadcast over NVLink) and one step of look-ahead; alpha by distributed block substitution;
+ * (K + V)^-1 for the gradient / EP variances by two more panel sweeps.  Every rank passes the SAME
+ * host data and receives the SAME results.  world = 1 is allowed (no NCCL needed).
+ * NCCL is bound at run time (libnccl.so.2; GPL_NCCL_LIB overrides the path); failures return
+ * GPL_ERR_NCCL. */
+typedef struct gpl_dist gpl_dist;
+#define GPL_DIST_ID_BYTES 128
+/* rank 0: fill id128 (ncclGetUniqueId); ship it to every other rank */
+int gpl_dist_unique_id(void* id128);
+/* collective over all ranks of the job; ctx must be a context on this rank's GPU */
+int gpl_dist_init(gpl_ctx* ctx, const void* id128, int32_t rank, int32_t world, gpl_dist** out);
+int gpl_dist_destroy(gpl_dist* dist);
+/* free the cached n x n / world slabs (kept between calls so that Newton / optimiser iterations reuse them) */
+int gpl_dist_release(gpl_dist* dist);
+int gpl_dist_rank(const gpl_dist* dist);
+int gpl_dist_world(const gpl_dist* dist);
+
+typedef struct gpl_dist_timings {   /* seconds on this rank (host clock around stream syncs) */
+  double kbuild_s;    /* upload, features (first call: allocations) */
+  double factor_s;    /* K build in the block-cyclic layout + factorisation */
+  double solve_s;     /* alpha, f, log evidence */
+  double trtri_s;     /* X = L^-1 sweep (+ diag(B^-1) for EP) */
+  double lauum_s;     /* B^-1 = X^T X sweep */
+  double trace_s;     /* gradient trace + all-reduce */
+  double total_s;
+  double nccl_bytes;  /* payload bytes this rank put through NCCL collectives */
+} gpl_dist_timings;
+
+/* fit_laplace / fit_ep .method_full across the ranks (R/gp_fit.R:91-99,150-161; R/laplace.R:13-38,
+ * 274-297; R/ep.R:16-49,286-330), any likelihood with log-concave sites (GPL_ERR_NOT_LOGCONCAVE
+ * otherwise: that branch is single-GPU).  x: n x d host, replicated; outputs as gpl_fit_full (any may
+ * be NULL); nb: block width, a multiple of 128 (0 = 1024). */
+int gpl_dist_fit_full(gpl_dist* dist, const gpl_cf_model* cf, const gpl_lik* lik, const gpl_approx* approx,
+                      const double* x, int64_t n, int32_t d, const double* y, const double* trials,
+                      const double* offset, double jitter, int64_t nb, gpl_fit_out* out, double* fmean,
+                      double* z, double* V, double* alpha, double* fvar, double* cavity_mean,
+                      double* cavity_var, gpl_dist_timings* timings);
+/* gpl_energy_grad across the ranks (lik_gaussian): energy without priors and, when nparam > 0, its
+ * gradient w.r.t. the log-parameters (param_factor / param_slot as in gpl_energy_grad).  nparam = 0:
+ * energy only (one n x n / world slab per GPU instead of two).  alpha (n, may be NULL). */
+int gpl_dist_energy_grad(gpl_dist* dist, const gpl_cf_model* cf, const gpl_lik* lik, const double* x,
+                         int64_t n, int32_t d, const double* y, double jitter, int64_t nb, int32_t nparam,
+                         const int32_t* param_factor, const int32_t* param_slot, double* energy,
+                         double* grad, double* alpha, gpl_dist_timings* timings);
 
 #ifdef __cplusplus
 }

@@ -54,3 +54,21 @@ elif what == "egrad":
     y = np.sin(X[:, 0]) + 0.5 * X[:, 1] ** 2 + X[:, 2] + 0.5 * rng.normal(size=n)
     gp = g.gp_init(cfs=g.cf_matern52(lscale=1.3), lik=g.lik_gaussian(sigma=0.5))
     print(g.gp_energy_grad(gp, X, y, ctx=ctx))
+elif what == "sweeps":
+    # the HBM-bound sweeps of BASELINE config 3 (n = 50000, d = 10, cf_sexp * cf_lin + lik_bernoulli):
+    # two Newton steps (pseudodata_la, build_B, potrf, trsv, gemv_t, loglik) and one EP sweep
+    # (ep_sites + the same linear algebra) -- the ncu targets are the elementwise / GEMV kernels
+    import warnings
+    n = int(sys.argv[2]) if len(sys.argv) > 2 else 50000
+    rng = np.random.default_rng(3)
+    X = rng.normal(size=(n, 10))
+    y = (rng.uniform(size=n) < 1 / (1 + np.exp(-(2 * X[:, 0] - X[:, 1])))).astype(float)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        cfs = g.cf_sexp(lscale=1.0) * g.cf_lin(prior_magn=g.prior_fixed())
+        gp = g.gp_init(cfs=cfs, lik=g.lik_bernoulli(), approx=g.approx_laplace(maxiter=2))
+        g.gp_fit(gp, X, y, ctx=ctx)
+        print("laplace", gp.fit["log_evidence"])
+        gp = g.gp_init(cfs=cfs, lik=g.lik_bernoulli(), approx=g.approx_ep(maxiter=1))
+        g.gp_fit(gp, X, y, ctx=ctx)
+        print("ep", gp.fit["log_evidence"])
