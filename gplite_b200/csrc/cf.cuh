@@ -55,6 +55,11 @@ int prep_features(Ctx* ctx, const HostPlan& hp, const double* d_x, int64_t n, in
 int cf_pairwise(Ctx* ctx, const CfPlan& plan, const double* z1, int64_t n1, int64_t ldz1,
                 const double* z2, int64_t n2, int64_t ldz2, bool same, double jitter, double* K,
                 int64_t ldk);
+// cf_gram.cu: every factor through the FP64 tensor pipe (sums of products, rectangular blocks);
+// *done = 0 when the model does not fit its shared-memory budget
+int cf_pairwise_gram(Ctx* ctx, const CfPlan& plan, const double* z1, int64_t n1, int64_t ldz1,
+                     const double* z2, int64_t n2, int64_t ldz2, bool same, double jitter, double* K,
+                     int64_t ldk, int* done);
 int cf_diag(Ctx* ctx, const CfPlan& plan, const double* z1, int64_t ldz1, const double* z2,
             int64_t ldz2, int64_t n, double add, double* out);
 

@@ -617,6 +617,11 @@ int cf_pairwise(Ctx* ctx, const CfPlan& plan, const double* z1, int64_t n1, int6
                 const double* z2, int64_t n2, int64_t ldz2, bool same, double jitter, double* K,
                 int64_t ldk) {
   if (n1 <= 0 || n2 <= 0) return GPL_OK;
+  {
+    int done = 0;
+    GPL_TRY(cf_pairwise_gram(ctx, plan, z1, n1, ldz1, z2, n2, ldz2, same, jitter, K, ldk, &done));
+    if (done) return GPL_OK;
+  }
   PairArgs a;
   a.z1 = z1; a.z2 = same ? z1 : z2; a.K = K;
   a.ldz1 = ldz1; a.ldz2 = same ? ldz1 : ldz2; a.ldk = ldk;
