@@ -144,6 +144,7 @@ SIGNATURES = {
     "gpl_dist_init": (C.c_int, [_P, _P, _I32, _I32, C.POINTER(_P)]),
     "gpl_dist_destroy": (C.c_int, [_P]),
     "gpl_dist_release": (C.c_int, [_P]),
+    "gpl_dist_bcast_bench": (C.c_int, [_P, _I64, _I32, C.POINTER(_D)]),
     "gpl_dist_rank": (C.c_int, [_P]),
     "gpl_dist_world": (C.c_int, [_P]),
     "gpl_dist_fit_full": (C.c_int, [_P, C.POINTER(CfModel), C.POINTER(Lik), C.POINTER(Approx), _P, _I64, _I32, _P,

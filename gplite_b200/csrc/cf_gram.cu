@@ -23,6 +23,7 @@
 // tile whose scaled norms could cost more than ~5e-13 relative in K through cancellation falls back to
 // direct differences (CTA-uniform branch), so the 1e-12 parity with src/cf.cpp:9-162 holds.
 #include "cf.cuh"
+#include "gram_math.cuh"
 
 #include <math.h>
 #include <stdlib.h>
@@ -36,73 +37,6 @@ constexpr int TILE = 128;
 constexpr int GTHREADS = 256;
 constexpr int GLD = TILE + 4;        // smem row stride, == 4 mod 16: conflict-free fragment loads
 constexpr int MAX_ROWS = 48;         // staged rows per side: 2 CTAs / SM
-
-static __device__ const double kExpTab256[256] = {
-    1.0, 1.0027112750502024854, 1.0054299011128028214, 1.0081558981184175158,
-    1.01088928605170046, 1.0136300849514894388, 1.0163783149109530379, 1.0191339960777379497,
-    1.0218971486541166782, 1.0246677928971356451, 1.0274459491187636965, 1.0302316376860410129,
-    1.0330248790212284225, 1.03582569360195712, 1.0386341019613787906, 1.0414501246883161413,
-    1.0442737824274138403, 1.0471050958792898661, 1.0499440858006872661, 1.0527907730046263271,
-    1.0556451783605571588, 1.0585073227945126901, 1.061377227289262081, 1.0642549128844645498,
-    1.0671404006768236182, 1.0700337118202417735, 1.0729348675259755514, 1.0758438890627910378,
-    1.0787607977571197937, 1.0816856149932152019, 1.0846183622133092378, 1.0875590609177696653,
-    1.0905077326652576592, 1.0934643990728858542, 1.0964290818163768234, 1.0994018026302219855,
-    1.1023825833078409436, 1.1053714457017412556, 1.108368411723678638, 1.1113735033448176039,
-    1.1143867425958925363, 1.1174081515673691991, 1.1204377524096066844, 1.1234755673330198007,
-    1.1265216186082418998, 1.129575928566288146, 1.132638519598719228, 1.1357094141578055142,
-    1.1387886347566916537, 1.1418762039695616227, 1.1449721444318042194, 1.1480764788401790068,
-    1.1511892299529827058, 1.1543104205902160395, 1.1574400736337510296, 1.1605782120274987464,
-    1.1637248587775775138, 1.1668800369524815706, 1.1700437696832501881, 1.1732160801636372475,
-    1.1763969916502812763, 1.1795865274628759455, 1.1827847109843410299, 1.1859915656609938314,
-    1.1892071150027210667, 1.1924313825831512221, 1.1956643920398273746, 1.1989061670743804818,
-    1.2021567314527031421, 1.2054161090051238256, 1.2086843236265815774, 1.2119613992768011945,
-    1.2152473599804688781, 1.2185422298274083618, 1.2218460329727575169, 1.2251587936371454377,
-    1.2284805361068700057, 1.2318112847340759359, 1.2351510639369333057, 1.2384998981998165678,
-    1.2418578120734840486, 1.2452248301752579328, 1.2486009771892047366, 1.2519862778663162701,
-    1.2553807570246910896, 1.2587844395497164431, 1.262197350394250708, 1.2656195145788063242,
-    1.2690509571917332226, 1.2724917033894027512, 1.2759417783963921004, 1.2794012075056692269,
-    1.2828700160787782807, 1.2863482295460255336, 1.2898358734066658122, 1.2933329732290894367,
-    1.2968395546510096659, 1.300355643379650651, 1.3038812651919358986, 1.3074164459346772448,
-    1.3109612115247643419, 1.3145155879493546585, 1.3180796012660639947, 1.3216532776031575143,
-    1.3252366431597412946, 1.3288297242059543955, 1.3324325470831614494, 1.3360451382041457734,
-    1.3396675240533030054, 1.3432997311868352638, 1.3469417862329458358, 1.3505937158920343914,
-    1.3542555469368927283, 1.3579273062129010465, 1.3616090206382247556, 1.3653007172040118154,
-    1.3690024229745906119, 1.3727141650876683693, 1.3764359707545301002, 1.3801678672602380956,
-    1.3839098819638319549, 1.387662042298529159, 1.3914243757719261871, 1.3951969099662001783,
-    1.3989796725383111402, 1.4027726912202047064, 1.4065759938190154425, 1.4103896082172707044,
-    1.4142135623730950488, 1.4180478843204151978, 1.4218926021691655598, 1.4257477441054943068,
-    1.4296133383919700112, 1.4334894133677888425, 1.4373759974489823256, 1.4412731191286256627,
-    1.44518080697704662, 1.4490990896420349805, 1.4530279958490525648, 1.4569675544014438216,
-    1.4609177941806469887, 1.4648787441464058266, 1.4688504333369819269, 1.472832890869367595,
-    1.4768261459394993114, 1.4808302278224717705, 1.4848451658727525005, 1.4888709895243970654,
-    1.4929077282912648492, 1.4969554117672354268, 1.5010140696264255203, 1.5050837316234065441,
-    1.5091644275934227398, 1.5132561874526099022, 1.5173590411982146988, 1.5214730189088145835,
-    1.5255981507445383069, 1.5297344669472870239, 1.5338819978409560018, 1.5380407738316569284,
-    1.5422108254079408236, 1.5463921831410215549, 1.5505848776849999591, 1.5547889397770885721,
-    1.559004400237836967, 1.5632312899713577041, 1.5674696399655528931, 1.5717194812923413692,
-    1.5759808451078864865, 1.5802537626528245268, 1.5845382652524937301, 1.5888343843171639442,
-    1.5931421513422668979, 1.5974615979086270983, 1.6017927556826933538, 1.6061356564167709257,
-    1.6104903319492543082, 1.6148568142048606401, 1.6192351351948637493, 1.6236253270173288318,
-    1.6280274218573477668, 1.6324414519872750703, 1.6368674497669644878, 1.6413054476440062287,
-    1.6457554781539648445, 1.650217573920617751, 1.6546917676561943976, 1.6591780921616160854,
-    1.663676580326736435, 1.6681872651305825067, 1.6727101796415965736, 1.6772453570178785518,
-    1.6817928305074290861, 1.6863526334483932959, 1.690924799269305182, 1.695509361489332695,
-    1.7001063537185234695, 1.7047158096580512237, 1.7093377631004628271, 1.7139722479299260386,
-    1.7186192981224779156, 1.7232789477462738972, 1.7279512309618375622, 1.7326361820223110649,
-    1.737333835273706249, 1.7420442251551564435, 1.7467673861991689401, 1.7515033530318781561,
-    1.7562521603732994831, 1.7610138430375838242, 1.765788435933272821, 1.7705759740635547735,
-    1.7753764925265212526, 1.780190026515424409, 1.7850166113189349801, 1.789856282321400996,
-    1.7947090750031071864, 1.7995750249405350921, 1.8044541678066238803, 1.8093465393710318685,
-    1.8142521755003987562, 1.8191711121586085683, 1.824103385407053311, 1.8290490314048973431,
-    1.8340080864093424635, 1.8389805867758937177, 1.8439665689586259251, 1.8489660695104509284,
-    1.8539791250833855684, 1.8590057724288203846, 1.8640460483977890448, 1.8690999899412385049,
-    1.8741676341102999013, 1.879249018056560178, 1.8843441790323344497, 1.8894531543909391035,
-    1.8945759815869656413, 1.8997126981765552647, 1.9048633418176742037, 1.9100279502703897924,
-    1.9152065613971472939, 1.9203992131630474739, 1.925605943636124929, 1.9308267909876271679,
-    1.9360617934922944506, 1.9413109895286403852, 1.9465744175792332863, 1.9518521162309782959,
-    1.957144124175400269, 1.9624504802089274268, 1.9677712232331757781, 1.9731063922552343129,
-    1.9784560263879509683, 1.9838201648502193699, 1.9891988469672663513, 1.9945921121709402525,
-};
 
 struct GFactor {
   int kind;
@@ -131,49 +65,6 @@ struct GArgs {
   double jitter;
 };
 
-__device__ __forceinline__ void dmma_k4(double& c0, double& c1, double a, double b) {
-  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
-               : "+d"(c0), "+d"(c1)
-               : "d"(a), "d"(b));
-}
-
-// u <- max(u, ~1e-300) on the integer pipe (negative and zero contractions become a tiny positive
-// number; a canonical NaN, 0x7ff8..., compares above and survives), then u <- min(u, 800) for finite u
-__device__ __forceinline__ double clamp_arg(double u) {
-  int hi = __double2hiint(u);
-  const int lo = __double2loint(u);
-  hi = max(hi, 0x01a56e1f);
-  if (hi >= 0x40890000 && hi <= 0x7ff00000) return 800.0;
-  return __hiloint2double(hi, lo);
-}
-
-// exp(-u), 0 <= u <= 800: k = rint(-u * 256/ln2) by the magic-number trick, r = -u - k ln2/256 (two-part),
-// exp(-u) = 2^(k >> 8) * T[k & 255] * p3(r).  8 fp64 instructions; NaN propagates (k = 0 for a NaN).
-__device__ __forceinline__ double exp_m(double u, const double* __restrict__ tab) {
-  const double magic = 6755399441055744.0;                 // 1.5 * 2^52
-  const double t = fma(u, -369.3299304675746322841407, magic);
-  const int k = __double2loint(t);
-  const double kd = t - magic;
-  double r = fma(kd, -0.002707604318857193, -u);
-  r = fma(kd, -1.855205093371747e-09, r);
-  double p = fma(0.1666666806316513, r, 0.500000063263577);
-  p = fma(p, r, 1.0);
-  p = fma(p, r, 1.0);
-  const double v = tab[k & 255] * p;
-  const int e = max(k >> 8, -1022);
-  return __hiloint2double(__double2hiint(v) + (e << 20), __double2loint(v));
-}
-
-// sqrt(u) for u >= 1e-300: MUFU.RSQ64H seed (2^-22), one third-order step (error e^3)
-__device__ __forceinline__ double sqrt_pos(double u) {
-  double y;
-  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(u));
-  const double g0 = u * y;
-  const double e = fma(-g0, y, 1.0);
-  const double p = fma(0.375, e, 0.5);
-  return fma(g0, p * e, g0);
-}
-
 template <int KIND>
 __device__ __forceinline__ double gvalue(const GFactor& f, double s, double rb, double rc,
                                          const double* __restrict__ tab) {
@@ -181,17 +72,18 @@ __device__ __forceinline__ double gvalue(const GFactor& f, double s, double rb, 
   if (KIND == GPL_CF_LIN) return f.magn2 * s;
   if (KIND == GPL_CF_SEXP) return f.magn2 * exp_m(clamp_arg(s), tab);
   if (KIND == GPL_CF_MATERN32) {
-    const double u = clamp_arg(s);
-    const double t = sqrt_pos(u);
+    const double u = clamp_lo(s);                          // u = t^2 may be large; only exp's argument is capped
+    const double t = clamp_hi(sqrt_pos(u));
     return fma(f.magn2, t, f.magn2) * exp_m(t, tab);
   }
   if (KIND == GPL_CF_MATERN52) {
-    const double u = clamp_arg(s);
-    const double t = sqrt_pos(u);
+    const double u = clamp_lo(s);
+    const double t = clamp_hi(sqrt_pos(u));
     return fma(f.m3, u, fma(f.magn2, t, f.magn2)) * exp_m(t, tab);
   }
-  // cf_nn (src/cf.cpp:149-158): magn^2 (2/pi) asin(2a / sqrt((1 + 2b)(1 + 2c))), a = c0 + x1.x2
-  return f.m3 * asin(2.0 * (f.c0 + s) * rb * rc);
+  // cf_nn (src/cf.cpp:149-158): magn^2 (2/pi) asin(2a / sqrt((1 + 2b)(1 + 2c))), a = c0 + x1.x2;
+  // rb * rc first: the symmetric matrix is then symmetric bit for bit
+  return f.m3 * asin(2.0 * (f.c0 + s) * (rb * rc));
 }
 
 __device__ __forceinline__ double gvalue_dyn(const GFactor& f, double s, double rb, double rc,
@@ -212,20 +104,21 @@ __device__ __forceinline__ bool is_stationary(int kind) {
 
 // MODE >= 0: the model is ONE factor of that kind.  MODE == -1: any sum of products.
 // NSUB: 8-column sub-tiles per warp and pass (4: warp tile 32 x 32, two passes; 2: 32 x 16, four passes).
-template <int MODE, int NSUB>
-__global__ void __launch_bounds__(GTHREADS, 2)
+template <int MODE, int NSUB, int MINB>
+__global__ void __launch_bounds__(GTHREADS, MINB)
 gram_kernel(const __grid_constant__ GPlan plan, const GArgs a) {
   extern __shared__ double sm[];
   const int R = plan.rows;
   double* Zs1 = sm;                  // [R][GLD]
   double* Zs2 = sm + R * GLD;
   double* tab = sm + 2 * R * GLD;    // [256]
-  __shared__ int s_bad;
+  __shared__ int s_bad, s_nan;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, t = lane & 3;
   const int wm = warp & 3, wn = warp >> 2;
   tab[tid] = kExpTab256[tid];
-  if (tid == 0) s_bad = 0;
+  if (tid == 0) s_bad = s_nan = 0;
+  __syncthreads();
 
   int bi, bj;
   if (a.same) {
@@ -249,7 +142,11 @@ gram_kernel(const __grid_constant__ GPlan plan, const GArgs a) {
   for (int fi = 0; fi < plan.nfactors; ++fi) {
     const GFactor& f = plan.f[fi];
     const bool stat = is_stationary(f.kind);
-    for (int idx = tid; idx < (f.gk + 1) * TILE; idx += GTHREADS) {
+    // stationary kinds: rows goff, goff + 1 are the two norm columns.  They come FIRST so that they are
+    // summed into a zero accumulator, |a_i|^2 + |b_j|^2 = |a_j|^2 + |b_i|^2 bit for bit, and the
+    // symmetric matrix is exactly symmetric also inside its diagonal tiles.
+    const int aug = stat ? 2 : 0;
+    for (int idx = tid; idx < (f.gk + 1 - aug) * TILE; idx += GTHREADS) {
       const int j = idx >> 7, r = idx & (TILE - 1);
       double v1 = 0.0, v2 = 0.0;
       if (j < f.nf) {
@@ -260,9 +157,10 @@ gram_kernel(const __grid_constant__ GPlan plan, const GArgs a) {
         if (gi < a.n1) v1 = (a.z1[c1 + gi] - ref) * sc;
         if (gj < a.n2) v2 = (a.z2[c2 + gj] - ref) * sc;
         if (stat) v2 *= -2.0;
+        if (v1 != v1 || v2 != v2) s_nan = 1;               // NaN input: the whole tile becomes NaN (below)
       }
-      Zs1[(f.goff + j) * GLD + r] = v1;
-      Zs2[(f.goff + j) * GLD + r] = v2;
+      Zs1[(f.goff + aug + j) * GLD + r] = v1;
+      Zs2[(f.goff + aug + j) * GLD + r] = v2;
     }
   }
   __syncthreads();
@@ -273,18 +171,19 @@ gram_kernel(const __grid_constant__ GPlan plan, const GArgs a) {
     if (!stat && f.kind != GPL_CF_NN) continue;
     double* Zs = (tid < TILE) ? Zs1 : Zs2;
     const int r = tid & (TILE - 1);
+    const int aug = stat ? 2 : 0;
     double sacc = 0.0;
     for (int j = 0; j < f.nf; ++j) {
-      const double v = Zs[(f.goff + j) * GLD + r];
+      const double v = Zs[(f.goff + aug + j) * GLD + r];
       sacc = fma(v, v, sacc);
     }
     if (stat) {
       if (tid >= TILE) sacc *= 0.25;                      // the column side holds -2 b
-      Zs[(f.goff + f.nf) * GLD + r] = (tid < TILE) ? sacc : 1.0;
-      Zs[(f.goff + f.nf + 1) * GLD + r] = (tid < TILE) ? 1.0 : sacc;
+      Zs[f.goff * GLD + r] = (tid < TILE) ? sacc : 1.0;
+      Zs[(f.goff + 1) * GLD + r] = (tid < TILE) ? 1.0 : sacc;
       // cancellation guard: the relative error of K is ~ 4 eps * (scaled |a|^2 + |b|^2) * |dlog k / du|
       // (d log k / du is 1 for sexp and at most 1/2 for the Matern kinds, also as u -> 0)
-      if (!(sacc < 250.0)) s_bad = 1;                     // also catches NaN
+      if (!(sacc < 250.0)) s_bad = 1;
     } else {
       Zs[(f.goff + f.gk) * GLD + r] = rsqrt(1.0 + 2.0 * (f.c0 + sacc));
     }
@@ -336,7 +235,7 @@ gram_kernel(const __grid_constant__ GPlan plan, const GArgs a) {
             for (int c = 0; c < 2; ++c) {
               const int row = wm * 32 + im * 8 + g, col = cbase + in * 8 + 2 * t + c;
               double r2 = 0.0;
-              for (int j = 0; j < f.nf; ++j) {
+              for (int j = 2; j < f.nf + 2; ++j) {
                 const double dlt = fma(0.5, Zs2[(f.goff + j) * GLD + col], Zs1[(f.goff + j) * GLD + row]);
                 r2 = fma(dlt, dlt, r2);
               }
@@ -367,55 +266,86 @@ gram_kernel(const __grid_constant__ GPlan plan, const GArgs a) {
         }
       }
     }
-    // ---- store: thread owns row g, columns 2t, 2t + 1 of each 8 x 8 sub-tile; the mirrored entry pair
-    // is one 16-byte store
-#pragma unroll
-    for (int im = 0; im < 4; ++im) {
-      const int row = wm * 32 + im * 8 + g;
-      const int gi = i0 + row;
+    // ---- store: thread owns row g, columns 2t, 2t + 1 of each 8 x 8 sub-tile.  The common case (interior
+    // tile off the diagonal) is one uniform branch around fully unrolled stores with immediate offsets;
+    // the mirrored entry pair is one 16-byte store.
+    if (interior && !diag_tile && vec_ok) {
+      const int64_t cs = a.ldk;
+      double* p0 = a.K + (int64_t)(j0 + cbase + 2 * t) * cs + (i0 + wm * 32 + g);
 #pragma unroll
       for (int in = 0; in < NSUB; ++in) {
-        const int col = cbase + in * 8 + 2 * t;
-        const int gj = j0 + col;
-        double v0 = out[im][in][0], v1 = out[im][in][1];
-        if (diag_tile) {
-          if (gi == gj) v0 += a.jitter;
-          if (gi == gj + 1) v1 += a.jitter;
+        double* pc = p0 + (int64_t)(in * 8) * cs;
+#pragma unroll
+        for (int im = 0; im < 4; ++im) {
+          pc[im * 8] = out[im][in][0];
+          pc[cs + im * 8] = out[im][in][1];
         }
-        if (interior) {
-          a.K[(int64_t)gj * a.ldk + gi] = v0;
-          a.K[(int64_t)(gj + 1) * a.ldk + gi] = v1;
-          if (mirror) {
-            double* dst = a.K + (int64_t)gi * a.ldk + gj;
-            if (vec_ok) {
-              *reinterpret_cast<double2*>(dst) = make_double2(v0, v1);
-            } else {
-              dst[0] = v0;
-              dst[1] = v1;
+      }
+      if (mirror) {
+        double* q0 = a.K + (int64_t)(i0 + wm * 32 + g) * cs + (j0 + cbase + 2 * t);
+#pragma unroll
+        for (int im = 0; im < 4; ++im) {
+          double* qr = q0 + (int64_t)(im * 8) * cs;
+#pragma unroll
+          for (int in = 0; in < NSUB; ++in)
+            *reinterpret_cast<double2*>(qr + in * 8) = make_double2(out[im][in][0], out[im][in][1]);
+        }
+      }
+    } else {
+#pragma unroll
+      for (int im = 0; im < 4; ++im) {
+        const int gi = i0 + wm * 32 + im * 8 + g;
+#pragma unroll
+        for (int in = 0; in < NSUB; ++in) {
+          const int gj = j0 + cbase + in * 8 + 2 * t;
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            double v = out[im][in][c];
+            if (diag_tile && gi == gj + c) v += a.jitter;
+            if (gi < a.n1 && gj + c < a.n2) {
+              a.K[(int64_t)(gj + c) * a.ldk + gi] = v;
+              if (mirror) a.K[(int64_t)gi * a.ldk + gj + c] = v;
             }
-          }
-        } else {
-          if (gi < a.n1 && gj < a.n2) {
-            a.K[(int64_t)gj * a.ldk + gi] = v0;
-            if (mirror) a.K[(int64_t)gi * a.ldk + gj] = v0;
-          }
-          if (gi < a.n1 && gj + 1 < a.n2) {
-            a.K[(int64_t)(gj + 1) * a.ldk + gi] = v1;
-            if (mirror) a.K[(int64_t)gi * a.ldk + gj + 1] = v1;
           }
         }
       }
     }
   }
+  if (s_nan) {
+    // a NaN among this tile's inputs (the clamps above do not propagate it): R's chol() must see it
+    __syncthreads();
+    const double qnan = __longlong_as_double(0x7ff8000000000000LL);
+    for (int idx = tid; idx < TILE * TILE; idx += GTHREADS) {
+      const int gi = i0 + (idx & (TILE - 1)), gj = j0 + (idx >> 7);
+      if (gi < a.n1 && gj < a.n2) {
+        a.K[(int64_t)gj * a.ldk + gi] = qnan;
+        if (mirror) a.K[(int64_t)gi * a.ldk + gj] = qnan;
+      }
+    }
+  }
 }
 
-template <int MODE, int NSUB>
-int launch_gram(Ctx* ctx, const GPlan& gp, const GArgs& a, int grid) {
+template <int MODE, int NSUB, int MINB>
+int launch_gram1(Ctx* ctx, const GPlan& gp, const GArgs& a, int grid) {
   const int smem = (2 * gp.rows * GLD + 256) * (int)sizeof(double);
-  GPL_CUDA(cudaFuncSetAttribute(gram_kernel<MODE, NSUB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  gram_kernel<MODE, NSUB><<<grid, GTHREADS, smem, ctx->stream>>>(gp, a);
+  GPL_CUDA(cudaFuncSetAttribute(gram_kernel<MODE, NSUB, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  gram_kernel<MODE, NSUB, MINB><<<grid, GTHREADS, smem, ctx->stream>>>(gp, a);
   GPL_LAUNCH_CHECK(ctx);
   return GPL_OK;
+}
+
+// tuning knob GPL_GRAM_VARIANT: 0 = warp tile 32 x 32, 2 CTAs / SM (default); 1 = 32 x 16, 2 CTAs / SM;
+// 2 = 32 x 32, 1 CTA / SM (255 registers); 3 = 32 x 16, 3 CTAs / SM; 4 = 32 x 16, 4 CTAs / SM
+template <int MODE, int NSUB>
+int launch_gram(Ctx* ctx, const GPlan& gp, const GArgs& a, int grid) {
+  static const int variant = getenv("GPL_GRAM_VARIANT") ? atoi(getenv("GPL_GRAM_VARIANT")) : 0;
+  if (NSUB == 4) {
+    if (variant == 1) return launch_gram1<MODE, 2, 2>(ctx, gp, a, grid);
+    if (variant == 2) return launch_gram1<MODE, 4, 1>(ctx, gp, a, grid);
+    if (variant == 3) return launch_gram1<MODE, 2, 3>(ctx, gp, a, grid);
+    if (variant == 4) return launch_gram1<MODE, 2, 4>(ctx, gp, a, grid);
+  }
+  return launch_gram1<MODE, NSUB, 2>(ctx, gp, a, grid);
 }
 
 }  // namespace

@@ -31,6 +31,7 @@ struct NcclApi {
   void* handle = nullptr;
   ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
   ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommInitRankConfig)(ncclComm_t*, int, ncclUniqueId, int, ncclConfig_t*) = nullptr;   // optional
   ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
   ncclResult_t (*Broadcast)(const void*, void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t,
@@ -69,6 +70,7 @@ NcclApi* nccl_api() {
   api.AllGather = (decltype(api.AllGather))sym("ncclAllGather");
   api.GetErrorString = (decltype(api.GetErrorString))sym("ncclGetErrorString");
   api.GetVersion = (decltype(api.GetVersion))sym("ncclGetVersion");
+  api.CommInitRankConfig = (decltype(api.CommInitRankConfig))dlsym(api.handle, "ncclCommInitRankConfig");
   if (!ok) {
     set_error("libnccl.so.2 lacks an expected symbol");
     dlclose(api.handle);
@@ -96,11 +98,12 @@ struct Dist {
   ncclComm_t comm = nullptr;
   int rank = 0, world = 1;
   cudaStream_t comm_stream = nullptr;
+  cudaStream_t aux_stream = nullptr;    // second high-priority stream of the panel chain
   cudaEvent_t ev[dist::EV_COUNT] = {};
   // cached device buffers (cudaMalloc, not the stream-ordered pool: they are tens of GB)
   double* A = nullptr; size_t capA = 0;
   double* X = nullptr; size_t capX = 0;
-  double* panel[2] = {nullptr, nullptr}; size_t capP[2] = {0, 0};
+  double* panel[dist::MAX_WINDOW] = {}; size_t capP[dist::MAX_WINDOW] = {};
   double* tmp = nullptr; size_t capT = 0;
   double* dinv = nullptr; size_t capD = 0;
   int* d_info = nullptr;        // [0] failing pivot (min), [1] scratch
@@ -190,7 +193,8 @@ struct GpuOps {
   double jitter = 0.0;
 
   cudaStream_t st(dist::Stream s_) const {
-    return s_ == dist::S_MAIN ? main_stream : (s_ == dist::S_PANEL ? ctx->panel_stream : d->comm_stream);
+    return s_ == dist::S_MAIN ? main_stream
+           : (s_ == dist::S_PANEL ? ctx->panel_stream : (s_ == dist::S_AUX ? d->aux_stream : d->comm_stream));
   }
   cudaStream_t main_stream = nullptr;
   // every library routine launches on ctx->stream: point it at the requested stream for one call
@@ -273,8 +277,47 @@ struct GpuOps {
     GPL_LAUNCH_CHECK(ctx);
     return GPL_OK;
   }
+  // GPL_DIST_TRACE=<prefix>: every schedule event is also time-stamped (a timing event on the same
+  // stream) and dumped per rank as <prefix>.<rank>.csv after the factorisation -- the device-side timeline
+  struct TraceRec { int ev; int stream; cudaEvent_t t; };
+  std::vector<TraceRec> trace;
+  cudaEvent_t trace_t0 = nullptr;
+  bool tracing = false;
   int record(dist::Event e, dist::Stream S) {
     GPL_CUDA(cudaEventRecord(d->ev[e], st(S)));
+    if (tracing) {
+      cudaEvent_t t;
+      GPL_CUDA(cudaEventCreate(&t));
+      GPL_CUDA(cudaEventRecord(t, st(S)));
+      trace.push_back({(int)e, (int)S, t});
+    }
+    return GPL_OK;
+  }
+  int trace_begin() {
+    const char* p = getenv("GPL_DIST_TRACE");
+    tracing = p && *p;
+    if (!tracing) return GPL_OK;
+    trace.clear();
+    if (!trace_t0) GPL_CUDA(cudaEventCreate(&trace_t0));
+    GPL_CUDA(cudaEventRecord(trace_t0, main_stream));
+    return GPL_OK;
+  }
+  int trace_dump() {
+    if (!tracing) return GPL_OK;
+    GPL_CUDA(cudaDeviceSynchronize());
+    char path[512];
+    snprintf(path, sizeof(path), "%s.%d.csv", getenv("GPL_DIST_TRACE"), d->rank);
+    FILE* f = fopen(path, "w");
+    if (f) fprintf(f, "event,stream,ms\n");
+    for (const TraceRec& r : trace) {
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, trace_t0, r.t);
+      if (f) fprintf(f, "%d,%d,%.4f\n", r.ev, r.stream, ms);
+      cudaEventDestroy(r.t);
+    }
+    if (f) fclose(f);
+    trace.clear();
+    tracing = false;
     return GPL_OK;
   }
   int wait(dist::Stream S, dist::Event e) {
@@ -287,6 +330,10 @@ struct GpuOps {
   }
   int bcast(dist::Stream S, double* buf, int64_t count, int root) {
     if (d->world == 1 || count <= 0) return GPL_OK;
+    // diagnostics only (wrong results): GPL_DIST_NOCOMM=1 skips the panel broadcasts so that a run times
+    // the compute schedule alone
+    static const int nocomm = getenv("GPL_DIST_NOCOMM") ? atoi(getenv("GPL_DIST_NOCOMM")) : 0;
+    if (nocomm && S == dist::S_COMM) return GPL_OK;
     GPL_NCCL(d, d->api->Broadcast(buf, buf, (size_t)count, ncclDouble, root, d->comm, st(S)));
     d->nccl_bytes += 8.0 * (double)count;
     return GPL_OK;
@@ -372,7 +419,11 @@ int dist_setup(Dist* d, DistState& st, const gpl_cf_model* cf, const gpl_lik* li
   const size_t slab = (size_t)(L.nloc > 0 ? L.nloc : 1) * L.ld;
   GPL_TRY(ensure(&d->A, &d->capA, slab));
   if (want_inverse) GPL_TRY(ensure(&d->X, &d->capX, slab));
-  for (int i = 0; i < 2; ++i) GPL_TRY(ensure(&d->panel[i], &d->capP[i], (size_t)nb * L.ld));
+  // panel window: look-ahead depth D = W - 1 (capped by the world size)
+  static const int forced_w = getenv("GPL_DIST_WINDOW") ? atoi(getenv("GPL_DIST_WINDOW")) : 0;
+  int W = d->world >= 4 ? 5 : (d->world >= 2 ? 3 : 2);
+  if (forced_w >= 2 && forced_w <= dist::MAX_WINDOW) W = forced_w;
+  for (int i = 0; i < W; ++i) GPL_TRY(ensure(&d->panel[i], &d->capP[i], (size_t)nb * L.ld));
   if (want_inverse) {
     const int64_t tc = L.nloc > nb ? L.nloc : nb;
     GPL_TRY(ensure(&d->tmp, &d->capT, (size_t)nb * tc));
@@ -391,8 +442,8 @@ int dist_setup(Dist* d, DistState& st, const gpl_cf_model* cf, const gpl_lik* li
   st.ch.ops = &st.ops;
   st.ch.A = d->A;
   st.ch.X = want_inverse ? d->X : nullptr;
-  st.ch.panel[0] = d->panel[0];
-  st.ch.panel[1] = d->panel[1];
+  st.ch.window = W;
+  for (int i = 0; i < W; ++i) st.ch.panel[i] = d->panel[i];
   st.ch.tmp = d->tmp;
   st.ch.vec[0] = st.v[D_W0].d();
   st.ch.vec[1] = st.v[D_W1].d();
@@ -409,7 +460,9 @@ int dist_factor(DistState& st, double* logdet) {
   const int big = INT_MAX;
   GPL_CUDA(cudaMemcpyAsync(d->d_info, &big, sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
   int info = 0;
+  GPL_TRY(st.ops.trace_begin());
   GPL_TRY(st.ch.factor(&info));
+  GPL_TRY(st.ops.trace_dump());
   if (info != 0) {
     set_error("the leading minor of order %d is not positive definite", info);
     return GPL_ERR_NOT_PD;
@@ -764,7 +817,20 @@ int gpl_dist_init(gpl_ctx* h, const void* id128, int32_t rank, int32_t world, gp
     if (!d->api) { delete d; return GPL_ERR_NCCL; }
     ncclUniqueId id;
     memcpy(&id, id128, sizeof(id));
-    ncclResult_t r = d->api->CommInitRank(&d->comm, world, id, rank);
+    // The panel broadcasts overlap the trailing updates, and a rank that reaches a broadcast early SPINS
+    // in NCCL's kernel until the slowest rank joins: every CTA NCCL may use is an SM taken from the
+    // FP64 GEMM for that long.  A few CTAs are plenty (a bare 800 MB broadcast runs at 600+ GB/s with the
+    // default 16; the schedule needs ~60 GB/s), so the communicator is capped (GPL_NCCL_MAX_CTAS, 0 = NCCL default).
+    int max_ctas = getenv("GPL_NCCL_MAX_CTAS") ? atoi(getenv("GPL_NCCL_MAX_CTAS")) : 4;
+    ncclResult_t r;
+    if (max_ctas > 0 && d->api->CommInitRankConfig) {
+      ncclConfig_t cfg = NCCL_CONFIG_INITIALIZER;
+      cfg.maxCTAs = max_ctas;
+      cfg.minCTAs = 1;
+      r = d->api->CommInitRankConfig(&d->comm, world, id, rank, &cfg);
+    } else {
+      r = d->api->CommInitRank(&d->comm, world, id, rank);
+    }
     if (r != ncclSuccess) {
       set_error("ncclCommInitRank: %s", d->api->GetErrorString(r));
       delete d;
@@ -774,6 +840,7 @@ int gpl_dist_init(gpl_ctx* h, const void* id128, int32_t rank, int32_t world, gp
   int lo = 0, hi = 0;
   GPL_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
   GPL_CUDA(cudaStreamCreateWithPriority(&d->comm_stream, cudaStreamNonBlocking, hi));
+  GPL_CUDA(cudaStreamCreateWithPriority(&d->aux_stream, cudaStreamNonBlocking, hi));
   for (int i = 0; i < dist::EV_COUNT; ++i) GPL_CUDA(cudaEventCreateWithFlags(&d->ev[i], cudaEventDisableTiming));
   GPL_CUDA(cudaMalloc(&d->d_info, sizeof(int) * 4));
   GPL_CUDA(cudaMalloc(&d->d_acc, sizeof(double) * 8));
@@ -788,12 +855,15 @@ int gpl_dist_destroy(gpl_dist* h) {
   cudaStreamSynchronize(d->ctx->stream);
   cudaStreamSynchronize(d->comm_stream);
   if (d->comm && d->api) d->api->CommDestroy(d->comm);
-  for (double* p : {d->A, d->X, d->panel[0], d->panel[1], d->tmp, d->dinv, d->d_acc})
+  for (double* p : {d->A, d->X, d->tmp, d->dinv, d->d_acc})
+    if (p) cudaFree(p);
+  for (double* p : d->panel)
     if (p) cudaFree(p);
   if (d->d_info) cudaFree(d->d_info);
   for (int i = 0; i < dist::EV_COUNT; ++i)
     if (d->ev[i]) cudaEventDestroy(d->ev[i]);
   if (d->comm_stream) cudaStreamDestroy(d->comm_stream);
+  if (d->aux_stream) cudaStreamDestroy(d->aux_stream);
   delete d;
   return GPL_OK;
 }
@@ -804,11 +874,43 @@ int gpl_dist_release(gpl_dist* h) {
   GPL_CUDA(cudaSetDevice(d->ctx->device));
   GPL_CUDA(cudaStreamSynchronize(d->ctx->stream));
   GPL_CUDA(cudaStreamSynchronize(d->comm_stream));
-  for (double** p : {&d->A, &d->X, &d->panel[0], &d->panel[1], &d->tmp, &d->dinv}) {
+  for (double** p : {&d->A, &d->X, &d->tmp, &d->dinv}) {
     if (*p) GPL_CUDA(cudaFree(*p));
     *p = nullptr;
   }
-  d->capA = d->capX = d->capP[0] = d->capP[1] = d->capT = d->capD = 0;
+  for (int i = 0; i < dist::MAX_WINDOW; ++i) {
+    if (d->panel[i]) GPL_CUDA(cudaFree(d->panel[i]));
+    d->panel[i] = nullptr;
+    d->capP[i] = 0;
+  }
+  d->capA = d->capX = d->capT = d->capD = 0;
+  return GPL_OK;
+}
+
+int gpl_dist_bcast_bench(gpl_dist* h, int64_t count, int32_t reps, double* seconds) {
+  Dist* d = reinterpret_cast<Dist*>(h);
+  if (!d || count <= 0 || reps <= 0 || !seconds) {
+    set_error("gpl_dist_bcast_bench: bad arguments");
+    return GPL_ERR_BAD_ARG;
+  }
+  GPL_CUDA(cudaSetDevice(d->ctx->device));
+  GPL_TRY(ensure(&d->panel[0], &d->capP[0], (size_t)count));
+  cudaEvent_t e0, e1;
+  GPL_CUDA(cudaEventCreate(&e0));
+  GPL_CUDA(cudaEventCreate(&e1));
+  for (int r = -2; r < reps; ++r) {                      // two warm-up rounds, then `reps` timed ones
+    if (r == 0) GPL_CUDA(cudaEventRecord(e0, d->comm_stream));
+    if (d->world > 1)
+      GPL_NCCL(d, d->api->Broadcast(d->panel[0], d->panel[0], (size_t)count, ncclDouble, (r + 2) % d->world, d->comm,
+                                    d->comm_stream));
+  }
+  GPL_CUDA(cudaEventRecord(e1, d->comm_stream));
+  GPL_CUDA(cudaStreamSynchronize(d->comm_stream));
+  float ms = 0.f;
+  GPL_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  *seconds = ms * 1e-3 / reps;
   return GPL_OK;
 }
 

@@ -18,11 +18,16 @@
 // rank is ONE staircase GEMM per panel (all its remaining block columns at once, the panel rows of
 // every P-th block read in place), instead of one launch per block column.
 //
-// Streams: MAIN carries the trailing updates, PANEL (high priority) the owner's panel factorisation,
-// COMM the panel broadcasts.  One step of look-ahead: the owner of panel k+1 applies panel k to that
-// block column first, factors it on PANEL and the broadcast of panel k+1 runs on COMM while every rank
-// (the owner included) is still applying panel k on MAIN.  Nothing synchronises with the host inside
-// a sweep: a failing pivot is collected in a device word and looked at once at the end.
+// Streams: MAIN carries the bulk of the trailing updates, PANEL (high priority) the critical chain, COMM
+// the panel broadcasts.  Look-ahead of depth D with W = D + 1 panel buffers: when panel k arrives, every
+// rank first applies it ON THE PANEL STREAM to the one block column it owns among the next D
+// ("eager" update; the owner of block k+1 then factors it right away and its broadcast starts), while
+// MAIN applies panel k to everything further away.  The chain panel -> eager update -> potrf -> TRSM ->
+// broadcast therefore never queues behind a bulk update, it may run up to D panels ahead of the slowest
+// rank's bulk work, and the +-1 block-column imbalance between ranks at any single step (5 % at n = 100k
+// on 8 GPUs) averages out over the window instead of being paid at every step.  Nothing synchronises
+// with the host inside a sweep: a failing pivot is collected in a device word and looked at once at the
+// end.
 //
 // Replaces, for matrices that do not fit one GPU, base-R chol() / forwardsolve() / backsolve() at
 // R/laplace.R:27-30 and R/ep.R:38-42, and the n x n solve behind R/ep.R:42,141.
@@ -35,9 +40,15 @@
 namespace gpl {
 namespace dist {
 
-enum Stream { S_MAIN = 0, S_PANEL = 1, S_COMM = 2 };
-enum Event { EV_PANEL_READY0 = 0, EV_PANEL_READY1, EV_BCAST_DONE0, EV_BCAST_DONE1, EV_BUF_FREE0,
-             EV_BUF_FREE1, EV_COL_READY, EV_MAIN_DONE, EV_COUNT };
+enum Stream { S_MAIN = 0, S_PANEL = 1, S_COMM = 2, S_AUX = 3 };
+// events come in families indexed by the panel buffer (k % W) they guard
+constexpr int MAX_WINDOW = 8;
+enum Event { EV_PANEL_READY0 = 0,                       // owner: packed panel is in the buffer
+             EV_BCAST_DONE0 = MAX_WINDOW,               // the broadcast into the buffer has completed
+             EV_BUF_FREE0 = 2 * MAX_WINDOW,             // MAIN no longer reads the buffer (bulk update done)
+             EV_EAGER_DONE0 = 3 * MAX_WINDOW,           // PANEL no longer reads the buffer (eager update done)
+             EV_COL_READY = 4 * MAX_WINDOW, EV_MAIN_DONE, EV_AUX_GO, EV_AUX_DONE, EV_COUNT };
+inline Event ev(Event family, int64_t w) { return (Event)((int)family + (int)w); }
 
 struct Stair { int64_t nb, first, step, bskip; };   // same meaning as gpl::GemmStair
 
@@ -103,7 +114,8 @@ class ShardedChol {
   Ops* ops = nullptr;
   double* A = nullptr;        // slab: nloc columns, ld rows: B, then its factor L
   double* X = nullptr;        // second slab (optional): L^-1, then B^-1
-  double* panel[2] = {nullptr, nullptr};   // packed panels, nb * ld doubles each
+  double* panel[MAX_WINDOW] = {};          // W packed-panel buffers, nb * ld doubles each
+  int window = 2;                          // W; the look-ahead depth is D = min(W - 1, world)
   double* tmp = nullptr;      // nb x max(nloc, nb) scratch for the inverse sweeps
   double* vec[4] = {nullptr, nullptr, nullptr, nullptr};   // n-vectors (solve workspace)
   double* logdet_acc = nullptr;   // device scalar
@@ -118,41 +130,61 @@ class ShardedChol {
   int factor(int* info) {
     const Layout& L = lay;
     const int me = L.rank;
+    const int W = window < 2 ? 2 : (window > MAX_WINDOW ? MAX_WINDOW : window);
+    const int64_t D = (W - 1) < L.world ? (W - 1) : L.world;         // at most one own block per window
     GPL_DS(ops->zero(S_MAIN, logdet_acc, 1));
-    for (int64_t b = L.first_owned_from(0); b < L.nblk; b += L.world)
+    // the first panel's block column is built first so that its factorisation overlaps the rest of the build
+    if (L.owner(0) == me) {
+      GPL_DS(ops->fill_block(S_MAIN, 0, slab(A, 0), L.ld));
+      GPL_DS(ops->record(EV_COL_READY, S_MAIN));
+      GPL_DS(ops->wait(S_PANEL, EV_COL_READY));
+    }
+    for (int w = 0; w < W; ++w) {                                      // every panel buffer starts free
+      GPL_DS(ops->record(ev(EV_BUF_FREE0, w), S_MAIN));
+      GPL_DS(ops->record(ev(EV_EAGER_DONE0, w), S_MAIN));
+    }
+    if (L.owner(0) == me) GPL_DS(factor_panel(0, W));
+    GPL_DS(send_panel(0, W));
+    for (int64_t b = L.first_owned_from(L.owner(0) == me ? 1 : 0); b < L.nblk; b += L.world)
       GPL_DS(ops->fill_block(S_MAIN, b, slab(A, b) + L.col0(b), L.ld));
-    GPL_DS(ops->record(EV_COL_READY, S_MAIN));
-    GPL_DS(ops->wait(S_PANEL, EV_COL_READY));
-    // both panel buffers start free
-    GPL_DS(ops->record(EV_BUF_FREE0, S_MAIN));
-    GPL_DS(ops->record(EV_BUF_FREE1, S_MAIN));
-    if (L.owner(0) == me) GPL_DS(factor_panel(0));
-    GPL_DS(send_panel(0));
+    GPL_DS(ops->record(EV_MAIN_DONE, S_MAIN));                        // all own blocks exist
+    GPL_DS(ops->wait(S_PANEL, EV_MAIN_DONE));
     for (int64_t k = 0; k < L.nblk; ++k) {
-      const int64_t nxt = k + 1;
-      GPL_DS(ops->wait(S_MAIN, (Event)(EV_BCAST_DONE0 + (k & 1))));
-      if (nxt < L.nblk) {
-        if (L.owner(nxt) == me) {
-          GPL_DS(apply_panel_to(k, nxt, 1));                       // look-ahead column first
-          GPL_DS(ops->record(EV_COL_READY, S_MAIN));
-          GPL_DS(ops->wait(S_PANEL, EV_COL_READY));
-          GPL_DS(factor_panel(nxt));
+      const int64_t w = k % W;
+      // ---- eager update (PANEL): this rank's block column among the next D
+      GPL_DS(ops->wait(S_PANEL, ev(EV_BCAST_DONE0, w)));
+      const int64_t b = L.first_owned_from(k + 1);
+      if (b < L.nblk && b <= k + D) {
+        // its first eager update (from panel b - D) must follow the bulk updates by all earlier panels
+        if (b == k + D && k > 0) GPL_DS(ops->wait(S_PANEL, ev(EV_BUF_FREE0, (k - 1) % W)));
+        if (b == k + 1) {
+          // the next panel: only its diagonal block is needed before potrf can start, so the rows below
+          // are updated on a second high-priority stream while the diagonal block is being factored
+          GPL_DS(ops->record(EV_AUX_GO, S_PANEL));
+          GPL_DS(ops->wait(S_AUX, EV_AUX_GO));
+          GPL_DS(apply_panel_rows(S_AUX, k, b, L.width(b), L.n - L.col0(b) - L.width(b), W));
+          GPL_DS(ops->record(EV_AUX_DONE, S_AUX));
+          GPL_DS(apply_panel_rows(S_PANEL, k, b, 0, L.width(b), W));
+          GPL_DS(factor_panel(b, W, true));
+        } else {
+          GPL_DS(apply_panel_to(S_PANEL, k, b, 1, W));
         }
-        GPL_DS(send_panel(nxt));
       }
-      // the rest of this rank's trailing block columns, one staircase product
-      int64_t j = L.first_owned_from(k + 1);
-      if (j == nxt) j += L.world;
+      GPL_DS(ops->record(ev(EV_EAGER_DONE0, w), S_PANEL));
+      if (k + 1 < L.nblk) GPL_DS(send_panel(k + 1, W));
+      // ---- bulk update (MAIN): everything beyond the window, one staircase product
+      GPL_DS(ops->wait(S_MAIN, ev(EV_BCAST_DONE0, w)));
+      const int64_t j = L.first_owned_from(k + D + 1);
       if (j < L.nblk) {
         const int64_t cnt = (L.nblk - 1 - j) / L.world + 1;
-        GPL_DS(apply_panel_to(k, j, cnt));
+        GPL_DS(apply_panel_to(S_MAIN, k, j, cnt, W));
       }
-      GPL_DS(ops->record((Event)(EV_BUF_FREE0 + (k & 1)), S_MAIN));
+      GPL_DS(ops->record(ev(EV_BUF_FREE0, w), S_MAIN));
     }
-    GPL_DS(ops->record(EV_PANEL_READY0, S_PANEL));                  // join the side streams
-    GPL_DS(ops->wait(S_MAIN, EV_PANEL_READY0));
-    GPL_DS(ops->record(EV_BCAST_DONE0, S_COMM));
-    GPL_DS(ops->wait(S_MAIN, EV_BCAST_DONE0));
+    GPL_DS(ops->record(EV_COL_READY, S_PANEL));                       // join the side streams
+    GPL_DS(ops->wait(S_MAIN, EV_COL_READY));
+    GPL_DS(ops->record(EV_MAIN_DONE, S_COMM));
+    GPL_DS(ops->wait(S_MAIN, EV_MAIN_DONE));
     return ops->check_info(info);
   }
 
@@ -229,40 +261,55 @@ class ShardedChol {
 
  private:
   // owner only, on PANEL: potrf of the diagonal block, TRSM of the rows below, pack for broadcast
-  int factor_panel(int64_t k) {
+  int factor_panel(int64_t k, int W, bool rows_on_aux = false) {
     const Layout& L = lay;
-    const int64_t k0 = L.col0(k), w = L.width(k), below = L.n - k0 - w;
+    const int64_t k0 = L.col0(k), w = L.width(k), below = L.n - k0 - w, pb = k % W;
     double* Akk = slab(A, k) + k0;
     GPL_DS(ops->potrf_diag(S_PANEL, k, w, Akk, L.ld, (int)k0));
     GPL_DS(ops->diag_logsum(S_PANEL, w, Akk, L.ld, logdet_acc));
+    if (rows_on_aux) GPL_DS(ops->wait(S_PANEL, EV_AUX_DONE));       // the rows below have their update
     if (below > 0) GPL_DS(ops->trsm_below(S_PANEL, k, below, w, Akk, L.ld, Akk + w, L.ld));
-    GPL_DS(ops->wait(S_PANEL, (Event)(EV_BUF_FREE0 + (k & 1))));
-    GPL_DS(ops->copy2d(S_PANEL, panel[k & 1], L.ldp(k), Akk, L.ld, L.n - k0, w));
-    return ops->record((Event)(EV_PANEL_READY0 + (k & 1)), S_PANEL);
+    GPL_DS(ops->wait(S_PANEL, ev(EV_BUF_FREE0, pb)));               // (its own eager use is earlier in PANEL order)
+    GPL_DS(ops->copy2d(S_PANEL, panel[pb], L.ldp(k), Akk, L.ld, L.n - k0, w));
+    return ops->record(ev(EV_PANEL_READY0, pb), S_PANEL);
   }
 
-  // every rank, on COMM: broadcast of packed panel k from its owner
-  int send_panel(int64_t k) {
+  // every rank, on COMM: broadcast of packed panel k from its owner into buffer k % W
+  int send_panel(int64_t k, int W) {
     const Layout& L = lay;
-    const int b = (int)(k & 1);
-    if (L.owner(k) == L.rank) GPL_DS(ops->wait(S_COMM, (Event)(EV_PANEL_READY0 + b)));
-    else GPL_DS(ops->wait(S_COMM, (Event)(EV_BUF_FREE0 + b)));
+    const int64_t pb = k % W;
+    if (L.owner(k) == L.rank) {
+      GPL_DS(ops->wait(S_COMM, ev(EV_PANEL_READY0, pb)));
+    } else {
+      GPL_DS(ops->wait(S_COMM, ev(EV_BUF_FREE0, pb)));
+      GPL_DS(ops->wait(S_COMM, ev(EV_EAGER_DONE0, pb)));
+    }
     const int64_t count = L.ldp(k) * L.width(k);
-    GPL_DS(ops->bcast(S_COMM, panel[b], count, L.owner(k)));
+    GPL_DS(ops->bcast(S_COMM, panel[pb], count, L.owner(k)));
     bcast_bytes += 8.0 * (double)count;
-    return ops->record((Event)(EV_BCAST_DONE0 + b), S_COMM);
+    return ops->record(ev(EV_BCAST_DONE0, pb), S_COMM);
   }
 
-  // A[j0.., blocks j, j + P, ... (cnt of them)] -= P_k[rows] P_k[block rows]^T on MAIN
-  int apply_panel_to(int64_t k, int64_t j, int64_t cnt) {
+  // rows [r0, r0 + m) (relative to the block's diagonal) of block column j -= P_k[those rows] P_k[block j rows]^T
+  int apply_panel_rows(Stream S, int64_t k, int64_t j, int64_t r0, int64_t m, int W) {
+    const Layout& L = lay;
+    if (m <= 0) return 0;
+    const int64_t k0 = L.col0(k), w = L.width(k), j0 = L.col0(j), ldp = L.ldp(k);
+    const double* P = panel[k % W];
+    return ops->gemm(S, false, true, m, L.width(j), w, -1.0, P + (j0 - k0) + r0, ldp, P + (j0 - k0), ldp, 1.0,
+                     slab(A, j) + j0 + r0, L.ld, false, nullptr);
+  }
+
+  // A[j0.., blocks j, j + P, ... (cnt of them)] -= P_k[rows] P_k[block rows]^T
+  int apply_panel_to(Stream S, int64_t k, int64_t j, int64_t cnt, int W) {
     const Layout& L = lay;
     const int64_t k0 = L.col0(k), w = L.width(k), j0 = L.col0(j);
     const int64_t jl = j + (cnt - 1) * L.world;                    // last block of the group
     const int64_t ncols = (cnt - 1) * L.nb + L.width(jl);
-    const double* P = panel[k & 1];
+    const double* P = panel[k % W];
     const int64_t ldp = L.ldp(k);
     Stair st{L.nb, 0, (int64_t)L.world * L.nb, (int64_t)(L.world - 1) * L.nb};
-    return ops->gemm(S_MAIN, false, true, L.n - j0, ncols, w, -1.0, P + (j0 - k0), ldp, P + (j0 - k0), ldp,
+    return ops->gemm(S, false, true, L.n - j0, ncols, w, -1.0, P + (j0 - k0), ldp, P + (j0 - k0), ldp,
                      1.0, slab(A, j) + j0, L.ld, false, cnt > 1 ? &st : nullptr);
   }
 
@@ -272,23 +319,25 @@ class ShardedChol {
     const int me = L.rank;
     GPL_DS(ops->record(EV_COL_READY, S_MAIN));
     GPL_DS(ops->wait(S_PANEL, EV_COL_READY));
-    GPL_DS(ops->record(EV_BUF_FREE0, S_MAIN));
-    GPL_DS(ops->record(EV_BUF_FREE1, S_MAIN));
+    for (int w = 0; w < 2; ++w) {
+      GPL_DS(ops->record(ev(EV_BUF_FREE0, w), S_MAIN));
+      GPL_DS(ops->record(ev(EV_EAGER_DONE0, w), S_MAIN));
+    }
     if (L.owner(0) == me) GPL_DS(xs ? prep_L_panel(0) : prep_X_panel(0));
-    GPL_DS(send_panel(0));
+    GPL_DS(send_panel(0, 2));
     for (int64_t k = 0; k < L.nblk; ++k) {
-      GPL_DS(ops->wait(S_MAIN, (Event)(EV_BCAST_DONE0 + (k & 1))));
+      GPL_DS(ops->wait(S_MAIN, ev(EV_BCAST_DONE0, k & 1)));
       if (k + 1 < L.nblk) {
         if (L.owner(k + 1) == me) GPL_DS(xs ? prep_L_panel(k + 1) : prep_X_panel(k + 1));
-        GPL_DS(send_panel(k + 1));
+        GPL_DS(send_panel(k + 1, 2));
       }
       GPL_DS(xs ? apply_L_panel(k) : apply_X_panel(k));
-      GPL_DS(ops->record((Event)(EV_BUF_FREE0 + (k & 1)), S_MAIN));
+      GPL_DS(ops->record(ev(EV_BUF_FREE0, k & 1), S_MAIN));
     }
-    GPL_DS(ops->record(EV_PANEL_READY0, S_PANEL));
-    GPL_DS(ops->wait(S_MAIN, EV_PANEL_READY0));
-    GPL_DS(ops->record(EV_BCAST_DONE0, S_COMM));
-    return ops->wait(S_MAIN, EV_BCAST_DONE0);
+    GPL_DS(ops->record(EV_COL_READY, S_PANEL));
+    GPL_DS(ops->wait(S_MAIN, EV_COL_READY));
+    GPL_DS(ops->record(EV_MAIN_DONE, S_COMM));
+    return ops->wait(S_MAIN, EV_MAIN_DONE);
   }
 
   int prep_L_panel(int64_t k) {
@@ -296,7 +345,7 @@ class ShardedChol {
     const int64_t k0 = L.col0(k), w = L.width(k), below = L.n - k0 - w, ldp = L.ldp(k);
     const double* Akk = slab(A, k) + k0;
     double* pv = panel[k & 1];
-    GPL_DS(ops->wait(S_PANEL, (Event)(EV_BUF_FREE0 + (k & 1))));
+    GPL_DS(ops->wait(S_PANEL, ev(EV_BUF_FREE0, k & 1)));
     GPL_DS(ops->copy2d(S_PANEL, pv, ldp, Akk, L.ld, L.n - k0, w));
     GPL_DS(ops->inv_diag(S_PANEL, k, w, Akk, L.ld, pv, ldp));        // diagonal block <- L_kk^-1
     // this rank's own column k of X:  X_kk = L_kk^-1,  R[k1:, k] = -L[k1:, k] L_kk^-1
@@ -305,7 +354,7 @@ class ShardedChol {
     if (below > 0)
       GPL_DS(ops->gemm(S_PANEL, false, false, below, w, w, -1.0, pv + w, ldp, pv, ldp, 0.0, Xk + w, L.ld,
                        false, nullptr));
-    return ops->record((Event)(EV_PANEL_READY0 + (k & 1)), S_PANEL);
+    return ops->record(ev(EV_PANEL_READY0, k & 1), S_PANEL);
   }
 
   int apply_L_panel(int64_t k) {
@@ -327,9 +376,9 @@ class ShardedChol {
   int prep_X_panel(int64_t i) {
     const Layout& L = lay;
     const int64_t i0 = L.col0(i), w = L.width(i);
-    GPL_DS(ops->wait(S_PANEL, (Event)(EV_BUF_FREE0 + (i & 1))));
+    GPL_DS(ops->wait(S_PANEL, ev(EV_BUF_FREE0, i & 1)));
     GPL_DS(ops->copy2d(S_PANEL, panel[i & 1], L.ldp(i), slab(X, i) + i0, L.ld, L.n - i0, w));
-    return ops->record((Event)(EV_PANEL_READY0 + (i & 1)), S_PANEL);
+    return ops->record(ev(EV_PANEL_READY0, i & 1), S_PANEL);
   }
 
   int apply_X_panel(int64_t i) {

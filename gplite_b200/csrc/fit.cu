@@ -1225,6 +1225,10 @@ int fit_get_impl(Ctx* ctx, const Fit* fit, const char* what, double* out) {
   }
   if (fit->method == 1 && (!strcmp(what, "Kxz") || !strcmp(what, "Kz_chol"))) {
     const bool kxz = !strcmp(what, "Kxz");
+    if (kxz && !fit->Kxz.p) {
+      set_error("gpl_fit_get: this fit streamed Kxz (never materialised); refit with GPL_FITC_STREAM_GB raised");
+      return GPL_ERR_BAD_ARG;
+    }
     const int64_t rows = kxz ? fit->n : fit->m, cols = fit->m;
     const double* src = kxz ? fit->Kxz.d() : fit->Kz_chol.d();
     const int64_t lds = kxz ? fit->ldkxz : fit->ldm;

@@ -1,9 +1,13 @@
 // method_fitc (R/gp_fit.R:101-123,163-188; R/laplace.R:122-152,299-325; R/ep.R:148-185,333-374;
 // R/linear_algebra.R:3-126; R/gp_pred.R:234-296).
 //
-// n x m work (Kxz, 65.5 GB at n = 2M, m = 4096) is built once and kept resident; everything
-// that the reference does with further n x m temporaries (forwardsolve(Kz_chol, t(Kxz)),
-// inv_D_U, Kt_aux1 ...) is streamed through one row-chunk workspace:
+// Kxz (n x m; 65.5 GB at n = 2M, m = 4096) is either kept resident (small problems: every pass reads
+// it back) or, beyond GPL_FITC_STREAM_GB (default 8), NEVER MATERIALISED: each pass regenerates the
+// row chunk it works on from the prepared inputs with the tensor-path K build (cf_gram.cu) -- a chunk
+// costs about as much to rebuild as to read, and the fit then needs two m x m matrices, one row-chunk
+// workspace and a handful of n-vectors instead of 65.5 GB.  Everything that the
+// reference does with further n x m temporaries (forwardsolve(Kz_chol, t(Kxz)), inv_D_U, Kt_aux1 ...)
+// goes through that one row-chunk workspace:
 //   D_i     = k_ii + jitter - |Lz^-1 k_zi|^2          right-TRSM on a chunk + row sums of squares
 //   A       = Kz + Kzx S^-1 Kxz                        chunk scaled by S^-1/2, SYRK-accumulated (DMMA)
 //   alpha   = z/S - S^-1 Kxz A^-1 Kzx (z/S)            two GEMVs over Kxz + m-sized solves
@@ -14,8 +18,10 @@
 #include "fit.cuh"
 
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
+#include <chrono>
 #include <vector>
 
 namespace gpl {
@@ -104,6 +110,28 @@ __global__ void copy_lower_add_kernel(int64_t n, const double* __restrict__ A, i
   if (i < n && j < n && i >= j) B[j * ldb + i] = A[j * lda + i];
 }
 
+// GPL_TIMING=1: per-phase wall times on stderr (each phase fenced by a stream synchronise)
+struct FitcTimer {
+  Ctx* ctx;
+  bool on;
+  std::chrono::steady_clock::time_point t0;
+  explicit FitcTimer(Ctx* c) : ctx(c) {
+    on = getenv("GPL_TIMING") && atoi(getenv("GPL_TIMING")) != 0;
+    if (on) {
+      cudaStreamSynchronize(ctx->stream);
+      t0 = std::chrono::steady_clock::now();
+    }
+  }
+  void mark(const char* what) {
+    if (!on) return;
+    cudaStreamSynchronize(ctx->stream);
+    auto t1 = std::chrono::steady_clock::now();
+    fprintf(stderr, "[gpl timing fitc] %-40s %9.3f ms\n", what,
+            std::chrono::duration<double, std::milli>(t1 - t0).count());
+    t0 = t1;
+  }
+};
+
 struct FitcState {
   int64_t n = 0, m = 0, ldx = 0, ldm = 0, chunk = 0, ldw = 0;
   int d = 0;
@@ -111,7 +139,8 @@ struct FitcState {
   DevBuf Kz;        // m x m with jitter (symmetric, kept)
   DevBuf Lz, Lz_dinv;
   DevBuf A, A_dinv; // m x m work / factor of Kz + Kzx S^-1 Kxz
-  DevBuf Kxz;       // n x m
+  DevBuf Kxz;       // n x m (resident mode only)
+  bool streamed = false;   // Kxz is regenerated chunk by chunk, never materialised
   DevBuf W;         // chunk x m workspace
   DevBuf Kdiag, Dg, S, rs;     // n
   DevBuf v[14];                // n-vectors
@@ -124,11 +153,46 @@ struct FitcState {
 
 enum { F_F = 0, F_Z, F_V, F_ALPHA, F_FNEW, F_T1, F_T2, F_FVAR, F_P, F_CM, F_CV, F_LOGZ, F_W, F_T3 };
 
+// W <- rows [r0, r0 + c) of Kxz, row i scaled by s[r0 + i] when s != NULL: a scaled copy of the resident
+// matrix, or regenerated from the prepared inputs (K(x_chunk, z): R/gp_fit.R:106)
+int chunk_into_W(Ctx* ctx, FitcState& st, int64_t r0, int64_t c, const double* s) {
+  if (!st.streamed)
+    return scaled_copy_rows(ctx, c, st.m, st.Kxz.d() + r0, st.ldx, s ? s + r0 : nullptr, st.W.d(), st.ldw);
+  GPL_TRY(cf_pairwise(ctx, st.hp.plan, st.Zx.d() + r0, c, st.n, st.Zz.d(), st.m, st.m, false, 0.0, st.W.d(),
+                      st.ldw));
+  if (s) GPL_TRY(scale_rows(ctx, c, st.m, st.W.d(), st.ldw, s + r0));
+  return GPL_OK;
+}
+
+// y (m) = Kzx x (n)
+int kxz_gemv_t(Ctx* ctx, FitcState& st, const double* x, double* y) {
+  if (!st.streamed) return gemv_t(ctx, st.n, st.m, st.Kxz.d(), st.ldx, x, y);
+  GPL_TRY(vec_op(ctx, VOP_FILL, st.m, nullptr, nullptr, y, 0.0));
+  for (int64_t r0 = 0; r0 < st.n; r0 += st.chunk) {
+    const int64_t c = (st.n - r0) < st.chunk ? (st.n - r0) : st.chunk;
+    GPL_TRY(chunk_into_W(ctx, st, r0, c, nullptr));
+    GPL_TRY(gemv_t(ctx, c, st.m, st.W.d(), st.ldw, x + r0, st.mv[5].d()));
+    GPL_TRY(vec_op(ctx, VOP_ADD, st.m, y, st.mv[5].d(), y));
+  }
+  return GPL_OK;
+}
+
+// y (n) = Kxz x (m)
+int kxz_gemv_n(Ctx* ctx, FitcState& st, const double* x, double* y) {
+  if (!st.streamed) return gemv_n(ctx, st.n, st.m, st.Kxz.d(), st.ldx, x, y);
+  for (int64_t r0 = 0; r0 < st.n; r0 += st.chunk) {
+    const int64_t c = (st.n - r0) < st.chunk ? (st.n - r0) : st.chunk;
+    GPL_TRY(chunk_into_W(ctx, st, r0, c, nullptr));
+    GPL_TRY(gemv_n(ctx, c, st.m, st.W.d(), st.ldw, x, y + r0));
+  }
+  return GPL_OK;
+}
+
 // rows-of-(Kxz L^-T) squared norms, streamed through the chunk workspace
 int row_norms_via(Ctx* ctx, FitcState& st, const double* L, const double* dinv, double* out) {
   for (int64_t r0 = 0; r0 < st.n; r0 += st.chunk) {
     const int64_t c = (st.n - r0) < st.chunk ? (st.n - r0) : st.chunk;
-    GPL_TRY(scaled_copy_rows(ctx, c, st.m, st.Kxz.d() + r0, st.ldx, nullptr, st.W.d(), st.ldw));
+    GPL_TRY(chunk_into_W(ctx, st, r0, c, nullptr));
     GPL_TRY(dtrsm_right_with(ctx, const_cast<double*>(dinv), true, c, st.m, L, st.ldm, st.W.d(), st.ldw));
     GPL_TRY(rowsumsq(ctx, c, st.m, st.W.d(), st.ldw, out + r0));
   }
@@ -138,6 +202,7 @@ int row_norms_via(Ctx* ctx, FitcState& st, const double* L, const double* dinv, 
 int fitc_setup(Ctx* ctx, FitcState& st, const gpl_cf_model* cf, const gpl_lik* lik, const double* x,
                int64_t n, int d, const double* zind, int64_t m, const double* y,
                const double* trials, const double* offset, double jitter) {
+  FitcTimer tm(ctx);
   st.n = n; st.m = m; st.d = d;
   st.jitter = jitter;
   st.ldx = round_up(n, 16);
@@ -177,11 +242,16 @@ int fitc_setup(Ctx* ctx, FitcState& st, const gpl_cf_model* cf, const gpl_lik* l
   const size_t dv = sizeof(double) * ((m + NB - 1) / NB) * NB * NB;
   GPL_TRY(st.Lz_dinv.alloc(ctx, dv));
   GPL_TRY(st.A_dinv.alloc(ctx, dv));
-  GPL_TRY(st.Kxz.alloc(ctx, sizeof(double) * st.ldx * m));
+  {
+    const double stream_gb = getenv("GPL_FITC_STREAM_GB") ? atof(getenv("GPL_FITC_STREAM_GB")) : 8.0;
+    st.streamed = 8.0 * (double)n * (double)m > stream_gb * 1e9;
+  }
+  if (!st.streamed) GPL_TRY(st.Kxz.alloc(ctx, sizeof(double) * st.ldx * m));
   // chunk: ~2 GB workspace, multiple of 128 rows
   int64_t chunk = (int64_t)(2.0e9 / (8.0 * (double)m));
   chunk = chunk / 128 * 128;
   if (chunk < 1024) chunk = 1024;
+  if (getenv("GPL_FITC_CHUNK")) chunk = round_up(atoll(getenv("GPL_FITC_CHUNK")) > 0 ? atoll(getenv("GPL_FITC_CHUNK")) : 1, 128);
   if (chunk > n) chunk = n;
   st.chunk = chunk;
   st.ldw = round_up(chunk, 16);
@@ -193,6 +263,7 @@ int fitc_setup(Ctx* ctx, FitcState& st, const gpl_cf_model* cf, const gpl_lik* l
   for (auto& b : st.v) GPL_TRY(b.alloc(ctx, sizeof(double) * n));
   for (auto& b : st.mv) GPL_TRY(b.alloc(ctx, sizeof(double) * m));
 
+  tm.mark("upload + features + allocations");
   // Kz (+ jitter), its factor, Kxz, diag K(x, x) + jitter          R/gp_fit.R:105-110
   GPL_TRY(cf_pairwise(ctx, st.hp.plan, st.Zz.d(), m, m, nullptr, m, m, true, jitter, st.Kz.d(), st.ldm));
   dim3 g2((unsigned)((m + 255) / 256), (unsigned)m);
@@ -200,11 +271,14 @@ int fitc_setup(Ctx* ctx, FitcState& st, const gpl_cf_model* cf, const gpl_lik* l
   GPL_LAUNCH_CHECK(ctx);
   int32_t info = 0;
   GPL_TRY(dpotrf_with(ctx, st.Lz_dinv.d(), m, st.Lz.d(), st.ldm, &info, &st.logdet_z));
-  GPL_TRY(cf_pairwise(ctx, st.hp.plan, st.Zx.d(), n, n, st.Zz.d(), m, m, false, 0.0, st.Kxz.d(), st.ldx));
+  if (!st.streamed)
+    GPL_TRY(cf_pairwise(ctx, st.hp.plan, st.Zx.d(), n, n, st.Zz.d(), m, m, false, 0.0, st.Kxz.d(), st.ldx));
   GPL_TRY(cf_diag(ctx, st.hp.plan, st.Zx.d(), n, st.Zx.d(), n, n, jitter, st.Kdiag.d()));
+  tm.mark(st.streamed ? "Kz, chol(Kz), diag K (Kxz streamed)" : "Kz, chol(Kz), Kxz (resident), diag K");
   // D = K_diag - colSums(forwardsolve(Kz_chol, t(Kxz))^2)
   GPL_TRY(row_norms_via(ctx, st, st.Lz.d(), st.Lz_dinv.d(), st.v[F_T1].d()));
   GPL_TRY(vec_op(ctx, VOP_SUB, n, st.Kdiag.d(), st.v[F_T1].d(), st.Dg.d()));
+  tm.mark("D: chunk -> TRSM -> row norms (m^2 n flops)");
   return GPL_OK;
 }
 
@@ -215,6 +289,7 @@ int fitc_alpha_f(Ctx* ctx, FitcState& st, const double* mask);
 //   slot 0: sum log S, slot 1: 2 sum log diag L (via logdetA), slot 2: f . alpha
 int fitc_core(Ctx* ctx, FitcState& st, double* logdetA) {
   const int64_t n = st.n, m = st.m;
+  FitcTimer tm(ctx);
   GPL_TRY(vec_op(ctx, VOP_ADD, n, st.Dg.d(), st.v[F_V].d(), st.S.d()));
   GPL_TRY(fvec(ctx, 3, n, st.S.d(), nullptr, nullptr, nullptr, st.rs.d()));
   // A = Kz + Kzx S^-1 Kxz  (lower)
@@ -223,13 +298,16 @@ int fitc_core(Ctx* ctx, FitcState& st, double* logdetA) {
   GPL_LAUNCH_CHECK(ctx);
   for (int64_t r0 = 0; r0 < n; r0 += st.chunk) {
     const int64_t c = (n - r0) < st.chunk ? (n - r0) : st.chunk;
-    GPL_TRY(scaled_copy_rows(ctx, c, m, st.Kxz.d() + r0, st.ldx, st.rs.d() + r0, st.W.d(), st.ldw));
+    GPL_TRY(chunk_into_W(ctx, st, r0, c, st.rs.d()));
     GPL_TRY(dgemm(ctx, true, false, m, m, c, 1.0, st.W.d(), st.ldw, st.W.d(), st.ldw, 1.0, st.A.d(),
                   st.ldm, true));
   }
+  tm.mark("A = Kz + Kzx S^-1 Kxz: chunk -> SYRK (n m^2 flops)");
   int32_t info = 0;
   GPL_TRY(dpotrf_with(ctx, st.A_dinv.d(), m, st.A.d(), st.ldm, &info, logdetA));
-  return fitc_alpha_f(ctx, st, nullptr);
+  const int rc = fitc_alpha_f(ctx, st, nullptr);
+  tm.mark("chol(A), alpha, f (4 passes over Kxz)");
+  return rc;
 }
 
 // alpha = C^-1 z by the inversion lemma from the factor in A (any non-zero S), f = Kxz Kz^-1 Kzx alpha
@@ -240,17 +318,17 @@ int fitc_alpha_f(Ctx* ctx, FitcState& st, const double* mask) {
   // alpha = z/S - S^-1 Kxz A^-1 Kzx (z/S)
   GPL_TRY(vec_op(ctx, VOP_DIV, n, st.v[F_Z].d(), st.S.d(), st.v[F_T1].d()));
   if (mask) GPL_TRY(vec_op(ctx, VOP_MUL, n, st.v[F_T1].d(), mask, st.v[F_T1].d()));
-  GPL_TRY(gemv_t(ctx, n, m, st.Kxz.d(), st.ldx, st.v[F_T1].d(), st.mv[0].d()));
+  GPL_TRY(kxz_gemv_t(ctx, st, st.v[F_T1].d(), st.mv[0].d()));
   GPL_TRY(trsv_lower(ctx, st.A_dinv.d(), false, m, st.A.d(), st.ldm, st.mv[0].d(), st.mv[1].d()));
   GPL_TRY(trsv_lower(ctx, st.A_dinv.d(), true, m, st.A.d(), st.ldm, st.mv[1].d(), st.mv[0].d()));
-  GPL_TRY(gemv_n(ctx, n, m, st.Kxz.d(), st.ldx, st.mv[0].d(), st.v[F_T2].d()));
+  GPL_TRY(kxz_gemv_n(ctx, st, st.mv[0].d(), st.v[F_T2].d()));
   GPL_TRY(fvec(ctx, 0, n, st.v[F_T1].d(), st.v[F_T2].d(), st.S.d(), nullptr, st.v[F_ALPHA].d()));
   if (mask) GPL_TRY(vec_op(ctx, VOP_MUL, n, st.v[F_ALPHA].d(), mask, st.v[F_ALPHA].d()));
   // f = Kxz Kz^-1 Kzx alpha + D alpha ;  beta = Kz^-1 Kzx alpha is kept in mv[2]
-  GPL_TRY(gemv_t(ctx, n, m, st.Kxz.d(), st.ldx, st.v[F_ALPHA].d(), st.mv[3].d()));
+  GPL_TRY(kxz_gemv_t(ctx, st, st.v[F_ALPHA].d(), st.mv[3].d()));
   GPL_TRY(trsv_lower(ctx, st.Lz_dinv.d(), false, m, st.Lz.d(), st.ldm, st.mv[3].d(), st.mv[4].d()));
   GPL_TRY(trsv_lower(ctx, st.Lz_dinv.d(), true, m, st.Lz.d(), st.ldm, st.mv[4].d(), st.mv[2].d()));
-  GPL_TRY(gemv_n(ctx, n, m, st.Kxz.d(), st.ldx, st.mv[2].d(), st.v[F_T2].d()));
+  GPL_TRY(kxz_gemv_n(ctx, st, st.mv[2].d(), st.v[F_T2].d()));
   GPL_TRY(fvec(ctx, 1, n, st.v[F_T2].d(), st.Dg.d(), st.v[F_ALPHA].d(), nullptr, st.v[F_FNEW].d()));
   return GPL_OK;
 }
@@ -271,6 +349,11 @@ struct FitcBad {
 
 int fitc_bad_iter(Ctx* ctx, FitcState& st, bool ep, FitcBad& fb, double* log_evidence,
                   double* log_post_unnorm) {
+  if (st.streamed) {
+    set_error("FITC: pseudo-variance <= 0 and Kxz is streamed; the non-log-concave branch (R/laplace.R:153-232, "
+              "R/ep.R:186-272) needs the resident matrix: raise GPL_FITC_STREAM_GB");
+    return GPL_ERR_NOT_LOGCONCAVE;
+  }
   const int64_t n = st.n, m = st.m, ldm = st.ldm;
   double sc[8];
   // ---- permutation good-first (only n-vectors are permuted)
@@ -713,6 +796,10 @@ int pred_fitc_impl(Ctx* ctx, const Fit* fit, const gpl_cf_model* cf, const doubl
 // not part of the fit.  out: n doubles on the host.
 int fitc_var_train(Ctx* ctx, const Fit* fit, double* out) {
   const int64_t n = fit->n, m = fit->m;
+  if (!fit->Kxz.p) {
+    set_error("var_train: this fit streamed Kxz (never materialised); refit with GPL_FITC_STREAM_GB raised");
+    return GPL_ERR_BAD_ARG;
+  }
   int64_t chunk = (int64_t)(2.0e9 / (8.0 * (double)m));
   chunk = chunk / 128 * 128;
   if (chunk < 1024) chunk = 1024;

@@ -7,8 +7,10 @@
 // feature rows, exactly like the K build, and never materialised; Binv is read once (lower
 // triangle, coalesced along columns).  One partial per CTA and a deterministic second-stage sum.
 #include "fit.cuh"
+#include "gram_math.cuh"
 
 #include <math.h>
+#include <stdlib.h>
 
 namespace gpl {
 
@@ -233,6 +235,210 @@ grad_trace_kernel(const __grid_constant__ CfPlan plan, const GradArgs a) {
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Fast path: ONE stationary factor (cf_sexp / cf_matern32 / cf_matern52 -- BASELINE configs 2 and 5),
+// parameters among {lscale, magn}.  Same machinery as the K build (cf_gram.cu): the scaled squared
+// distance of a 128 x 128 tile comes out of one DMMA.8x8x4 chain over the staged, shifted, augmented
+// feature rows; exp / sqrt are the branch-free replacements; both derivative sums stay in registers.
+// Per lower-triangle entry: ~25 fp64 instructions and one 8-byte read of Binv, against ~200
+// instructions (libm exp / sqrt, per-entry arrays) in the generic kernel below -- 15.1 ms -> the HBM
+// roofline of the Binv read is 0.66 ms at n = 32768.
+constexpr int FLD = GT + 4;
+
+struct FastArgs {
+  const double* z;
+  const double* Binv;
+  const double* s;
+  const double* alpha;
+  const double* u;
+  double* partial;     // [grid][GP]: slot 0 = sum W dK/dlog(lscale), slot 1 = sum W 2 K
+  int64_t ldz, ldb;
+  int n, nf, gk;       // gk = pad4(nf + 2)
+  int block_mode, col_tile0, col_end;
+  double sc, magn2, m3;
+};
+
+template <int KIND>
+__global__ void __launch_bounds__(GTHREADS, 2)
+grad_trace_fast_kernel(const FastArgs a) {
+  extern __shared__ double sm[];
+  double* Zs1 = sm;                    // [gk][FLD]
+  double* Zs2 = sm + a.gk * FLD;
+  double* tab = sm + 2 * a.gk * FLD;   // [256]
+  double* vec = tab + 256;             // s, alpha, u for rows then columns: [6][GT]
+  __shared__ double red[GTHREADS / 32][2];
+  __shared__ int s_bad;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  const int wm = warp & 3, wn = warp >> 2;
+  tab[tid] = kExpTab256[tid];
+  if (tid == 0) s_bad = 0;
+  int bi, bj;
+  int64_t pslot;
+  if (a.block_mode) {
+    bi = blockIdx.x;
+    bj = a.col_tile0 + blockIdx.y;
+    pslot = (int64_t)blockIdx.y * gridDim.x + blockIdx.x;
+    if (bi < bj) {                               // above the diagonal: nothing to add
+      if (tid < GP) a.partial[pslot * GP + tid] = 0.0;
+      return;
+    }
+  } else {
+    const int L = blockIdx.x;
+    bi = (int)((sqrt(8.0 * (double)L + 1.0) - 1.0) * 0.5);
+    while ((int64_t)bi * (bi + 1) / 2 > L) --bi;
+    while ((int64_t)(bi + 1) * (bi + 2) / 2 <= L) ++bi;
+    bj = L - bi * (bi + 1) / 2;
+    pslot = L;
+  }
+  const int i0 = bi * GT, j0 = bj * GT;
+  const int64_t bcol0 = a.block_mode ? (int64_t)a.col_tile0 * GT : 0;
+
+  for (int idx = tid; idx < (a.gk - 2) * GT; idx += GTHREADS) {
+    const int j = idx >> 7, r = idx & (GT - 1);
+    double v1 = 0.0, v2 = 0.0;
+    if (j < a.nf) {
+      const double ref = a.z[(int64_t)j * a.ldz];
+      if (i0 + r < a.n) v1 = (a.z[(int64_t)j * a.ldz + i0 + r] - ref) * a.sc;
+      if (j0 + r < a.n) v2 = (a.z[(int64_t)j * a.ldz + j0 + r] - ref) * a.sc * -2.0;
+    }
+    Zs1[(j + 2) * FLD + r] = v1;          // rows 0, 1: the two norm columns (as in cf_gram.cu)
+    Zs2[(j + 2) * FLD + r] = v2;
+  }
+  if (tid < GT) {
+    const bool ok = i0 + tid < a.n;
+    vec[0 * GT + tid] = ok ? a.s[i0 + tid] : 0.0;
+    vec[1 * GT + tid] = ok ? a.alpha[i0 + tid] : 0.0;
+    vec[2 * GT + tid] = (ok && a.u) ? a.u[i0 + tid] : 0.0;
+  } else {
+    const int r = tid - GT;
+    const bool ok = j0 + r < a.n;
+    vec[3 * GT + r] = ok ? a.s[j0 + r] : 0.0;
+    vec[4 * GT + r] = ok ? a.alpha[j0 + r] : 0.0;
+    vec[5 * GT + r] = (ok && a.u) ? a.u[j0 + r] : 0.0;
+  }
+  __syncthreads();
+  {
+    double* Zs = (tid < GT) ? Zs1 : Zs2;
+    const int r = tid & (GT - 1);
+    double sacc = 0.0;
+    for (int j = 2; j < a.nf + 2; ++j) {
+      const double v = Zs[j * FLD + r];
+      sacc = fma(v, v, sacc);
+    }
+    if (tid >= GT) sacc *= 0.25;
+    Zs[r] = (tid < GT) ? sacc : 1.0;
+    Zs[FLD + r] = (tid < GT) ? 1.0 : sacc;
+    if (!(sacc < 250.0)) s_bad = 1;
+  }
+  __syncthreads();
+  const bool bad = s_bad != 0;
+  const bool diag_tile = bi == bj;
+
+  double G0 = 0.0, G1 = 0.0;
+#pragma unroll 1
+  for (int pass = 0; pass < 4; ++pass) {          // warp tile 32 x 16 per pass: keeps the kernel at 128 registers
+    const int cbase = pass * 32 + wn * 16;
+    double acc[4][2][2];
+#pragma unroll
+    for (int im = 0; im < 4; ++im)
+#pragma unroll
+      for (int in = 0; in < 2; ++in) acc[im][in][0] = acc[im][in][1] = 0.0;
+    if (!bad) {
+      for (int ks = 0; ks < a.gk; ks += 4) {
+        const int kk = ks + t;
+        double av[4], bv[2];
+#pragma unroll
+        for (int im = 0; im < 4; ++im) av[im] = Zs1[kk * FLD + wm * 32 + im * 8 + g];
+#pragma unroll
+        for (int in = 0; in < 2; ++in) bv[in] = Zs2[kk * FLD + cbase + in * 8 + g];
+#pragma unroll
+        for (int im = 0; im < 4; ++im)
+#pragma unroll
+          for (int in = 0; in < 2; ++in) dmma_k4(acc[im][in][0], acc[im][in][1], av[im], bv[in]);
+      }
+    }
+#pragma unroll
+    for (int im = 0; im < 4; ++im) {
+      const int row = wm * 32 + im * 8 + g;
+      const int gi = i0 + row;
+      const double si = vec[0 * GT + row], ai = vec[1 * GT + row], ui = vec[2 * GT + row];
+#pragma unroll
+      for (int in = 0; in < 2; ++in) {
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          const int col = cbase + in * 8 + 2 * t + c;
+          const int gj = j0 + col;
+          // lower triangle of the matrix, inside the covered columns
+          const bool live = gi < a.n && gj < a.col_end && gi >= gj;
+          double uarg;
+          if (!bad) {
+            uarg = acc[im][in][c];
+          } else {
+            uarg = 0.0;
+            for (int j = 2; j < a.nf + 2; ++j) {
+              const double dlt = fma(0.5, Zs2[j * FLD + col], Zs1[j * FLD + row]);
+              uarg = fma(dlt, dlt, uarg);
+            }
+          }
+          if (diag_tile && row == col) uarg = 0.0;
+          double kv, dl;                            // K and d K / d log(lscale)
+          if (KIND == GPL_CF_SEXP) {
+            uarg = clamp_arg(uarg);
+            kv = a.magn2 * exp_m(uarg, tab);
+            dl = kv * (2.0 * uarg);
+          } else {
+            const double tt = clamp_hi(sqrt_pos(clamp_lo(uarg)));   // only exp's argument is capped
+            const double t2 = tt * tt;
+            const double e = a.magn2 * exp_m(tt, tab);
+            if (KIND == GPL_CF_MATERN32) {
+              kv = fma(e, tt, e);
+              dl = e * t2;
+            } else {
+              const double e1 = fma(e, tt, e);       // magn^2 (1 + t) e^-t
+              kv = fma(e * (1.0 / 3.0), t2, e1);
+              dl = e1 * (t2 * (1.0 / 3.0));
+            }
+          }
+          const double bij = live ? a.Binv[((int64_t)gj - bcol0) * a.ldb + gi] : 0.0;
+          const double sk = vec[3 * GT + col], ak = vec[4 * GT + col], uk = vec[5 * GT + col];
+          double W = fma(ai, ak, -(si * bij) * sk);
+          W = fma(-ui, uk, W);
+          W = live ? ((gi == gj) ? W : 2.0 * W) : 0.0;
+          G0 = fma(W, dl, G0);
+          G1 = fma(W, kv, G1);
+        }
+      }
+    }
+  }
+  G1 *= 2.0;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    G0 += __shfl_xor_sync(0xffffffffu, G0, o);
+    G1 += __shfl_xor_sync(0xffffffffu, G1, o);
+  }
+  if (lane == 0) {
+    red[warp][0] = G0;
+    red[warp][1] = G1;
+  }
+  __syncthreads();
+  if (tid < GP) {
+    double v = 0.0;
+    if (tid < 2)
+      for (int w = 0; w < GTHREADS / 32; ++w) v += red[w][tid];
+    a.partial[pslot * GP + tid] = v;
+  }
+}
+
+template <int KIND>
+int launch_fast(Ctx* ctx, const FastArgs& a, dim3 grid) {
+  const int smem = (2 * a.gk * FLD + 256 + 6 * GT) * (int)sizeof(double);
+  GPL_CUDA(cudaFuncSetAttribute(grad_trace_fast_kernel<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  grad_trace_fast_kernel<KIND><<<grid, GTHREADS, smem, ctx->stream>>>(a);
+  GPL_LAUNCH_CHECK(ctx);
+  return GPL_OK;
+}
+
 __global__ void sum_grad_partials_kernel(const double* __restrict__ partial, int grid, int nparam,
                                          double* __restrict__ out) {
   __shared__ double red[32];
@@ -275,6 +481,38 @@ int grad_trace(Ctx* ctx, const CfPlan& plan, const double* z, int64_t ldz, const
                                 smem));
   DevBuf part;
   GPL_TRY(part.alloc(ctx, sizeof(double) * (size_t)grid * GP));
+  // single stationary factor, parameters among {lscale, magn}: the tensor-path kernel
+  static const int no_fast = getenv("GPL_GRAD_GENERIC") ? atoi(getenv("GPL_GRAD_GENERIC")) : 0;
+  bool fast_ok = !no_fast && plan.nfactors == 1 && plan.f[0].auxoff < 0 && nparam <= 2 && plan.f[0].nf >= 1 &&
+                 plan.f[0].nf <= 38 &&
+                 (plan.f[0].kind == GPL_CF_SEXP || plan.f[0].kind == GPL_CF_MATERN32 ||
+                  plan.f[0].kind == GPL_CF_MATERN52);
+  for (int p = 0; p < nparam && fast_ok; ++p)
+    if (params[p].factor != 0 || params[p].slot < 0 || params[p].slot > 1) fast_ok = false;
+  if (fast_ok && nparam == 2 && params[0].slot == params[1].slot) fast_ok = false;
+  if (fast_ok) {
+    const FactorDev& f = plan.f[0];
+    FastArgs a;
+    a.z = z + (int64_t)f.off * ldz; a.Binv = Binv; a.s = s; a.alpha = alpha; a.u = u; a.partial = part.d();
+    a.ldz = ldz; a.ldb = ldb;
+    a.n = (int)n; a.nf = f.nf; a.gk = (f.nf + 2 + 3) & ~3;
+    a.block_mode = block_mode ? 1 : 0;
+    a.col_tile0 = block_mode ? (int)(col0 / GT) : 0;
+    a.col_end = block_mode ? (int)(col0 + ncols) : (int)n;
+    a.sc = f.kind == GPL_CF_SEXP ? sqrt(-f.c0) : f.c0;
+    a.magn2 = f.magn2;
+    a.m3 = f.magn2 / 3.0;
+    const dim3 g = block_mode ? dim3((unsigned)tiles, (unsigned)ctiles) : dim3((unsigned)grid);
+    if (f.kind == GPL_CF_SEXP) GPL_TRY(launch_fast<GPL_CF_SEXP>(ctx, a, g));
+    else if (f.kind == GPL_CF_MATERN32) GPL_TRY(launch_fast<GPL_CF_MATERN32>(ctx, a, g));
+    else GPL_TRY(launch_fast<GPL_CF_MATERN52>(ctx, a, g));
+    // partial slot 0 holds the lscale sum, slot 1 the magn sum: route them to the callers' order
+    for (int p = 0; p < nparam; ++p) {
+      sum_grad_partials_kernel<<<1, 256, 0, ctx->stream>>>(part.d() + params[p].slot, grid, 1, d_out + p);
+      GPL_LAUNCH_CHECK(ctx);
+    }
+    return GPL_OK;
+  }
   for (int p0 = 0; p0 < nparam; p0 += GP) {
     GradArgs a;
     a.z = z; a.zaux = zaux; a.Binv = Binv; a.s = s; a.alpha = alpha; a.u = u; a.partial = part.d();

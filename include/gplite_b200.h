@@ -410,6 +410,9 @@ int gpl_dist_init(gpl_ctx* ctx, const void* id128, int32_t rank, int32_t world, 
 int gpl_dist_destroy(gpl_dist* dist);
 /* free the cached n x n / world slabs (kept between calls so that Newton / optimiser iterations reuse them) */
 int gpl_dist_release(gpl_dist* dist);
+/* diagnostics: average seconds of one ncclBroadcast of `count` doubles on the library's communicator and
+ * stream (roots rotate over the ranks), nothing else running */
+int gpl_dist_bcast_bench(gpl_dist* dist, int64_t count, int32_t reps, double* seconds);
 int gpl_dist_rank(const gpl_dist* dist);
 int gpl_dist_world(const gpl_dist* dist);
 

@@ -165,20 +165,15 @@ struct SimOps {
     return 0;
   }
   int check_info(int* bad) {
-    double v = first_bad == 0 ? 1e18 : (double)first_bad, neg = -v;    // min through a sum-free trick:
-    // gather the minimum as -max via repeated allreduce is not available; use sum of indicator instead
-    (void)neg;
-    // the callbacks only offer sum: encode min over ranks as a two-step reduction
-    double cnt = first_bad != 0 ? 1.0 : 0.0;
-    if (lay->world > 1) cb_allreduce(&cnt, 1);
-    if (cnt == 0.0) { *bad = 0; return 0; }
-    // rare path (tests with a non-PD matrix): every rank contributes its pivot or 0, rank by rank
+    // min over ranks of the failing pivot through the sum-only callback: every rank contributes its
+    // pivot (or 0) in its own slot
     std::vector<double> all((size_t)lay->world, 0.0);
     all[(size_t)lay->rank] = (double)first_bad;
+    ++collectives;
     if (lay->world > 1) cb_allreduce(all.data(), lay->world);
     double best = 0.0;
-    for (double a : all)
-      if (a > 0.0 && (best == 0.0 || a < best)) best = a;
+    for (double v : all)
+      if (v > 0.0 && (best == 0.0 || v < best)) best = v;
     *bad = (int)best;
     return 0;
   }
@@ -187,7 +182,7 @@ struct SimOps {
 // Runs factor / solve / x sweep / diag / y sweep on this rank.  Outputs: logdet (local part, caller
 // sums), solution (n), diag(B^-1) (n), and the owned block columns of L and of B^-1 (nloc * ld each,
 // slab layout) for inspection.
-extern "C" int sim_run(int rank, int world, int64_t n, int64_t nb, const double* Bfull, const double* rhs,
+extern "C" int sim_run(int rank, int world, int64_t n, int64_t nb, int window, const double* Bfull, const double* rhs,
                        bcast_cb cbb, allreduce_cb cba, int do_inverse, double* logdet_local, double* sol,
                        double* diag_binv, double* Lslab, double* Yslab, int64_t* nloc_out, int64_t* ld_out,
                        int* info, int64_t* ncollectives) {
@@ -203,14 +198,15 @@ extern "C" int sim_run(int rank, int world, int64_t n, int64_t nb, const double*
   ch.ops = &ops;
   const size_t slab = (size_t)(lay.nloc > 0 ? lay.nloc : 1) * lay.ld;
   // fill with NaN so that any read of a never-written entry shows up in the results
-  std::vector<double> A(slab, NAN), X(slab, NAN), p0((size_t)(nb * lay.ld), NAN), p1((size_t)(nb * lay.ld), NAN);
+  std::vector<double> A(slab, NAN), X(slab, NAN);
+  std::vector<std::vector<double>> pbuf((size_t)window, std::vector<double>((size_t)(nb * lay.ld), NAN));
   std::vector<double> tmp((size_t)(nb * (lay.nloc > nb ? lay.nloc : nb)), NAN);
   std::vector<double> v0((size_t)n), v1((size_t)n), v2((size_t)n), v3((size_t)n);
   double acc = 0.0;
   ch.A = A.data();
   ch.X = X.data();
-  ch.panel[0] = p0.data();
-  ch.panel[1] = p1.data();
+  ch.window = window;
+  for (int w = 0; w < window; ++w) ch.panel[w] = pbuf[(size_t)w].data();
   ch.tmp = tmp.data();
   ch.vec[0] = v0.data(); ch.vec[1] = v1.data(); ch.vec[2] = v2.data(); ch.vec[3] = v3.data();
   ch.logdet_acc = &acc;

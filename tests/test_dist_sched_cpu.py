@@ -52,7 +52,7 @@ BCAST = C.CFUNCTYPE(None, C.POINTER(C.c_double), C.c_int64, C.c_int)
 ALLRED = C.CFUNCTYPE(None, C.POINTER(C.c_double), C.c_int64)
 
 
-def _run_rank(rank, world, n, nb, B, rhs, dist, do_inverse=True):
+def _run_rank(rank, world, n, nb, B, rhs, dist, do_inverse=True, window=2):
     import torch
     lib = C.CDLL(SIM_SO)
 
@@ -74,7 +74,7 @@ def _run_rank(rank, world, n, nb, B, rhs, dist, do_inverse=True):
     Ls, Ys = np.zeros(slab), np.zeros(slab)
     nloc_o, ld_o, info, ncoll = C.c_int64(), C.c_int64(), C.c_int(), C.c_int64()
     P = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
-    rc = lib.sim_run(rank, world, C.c_int64(n), C.c_int64(nb), P(B), P(rhs), cb1, cb2, int(do_inverse),
+    rc = lib.sim_run(rank, world, C.c_int64(n), C.c_int64(nb), int(window), P(B), P(rhs), cb1, cb2, int(do_inverse),
                      C.byref(logdet), P(sol), P(dg), P(Ls), P(Ys), C.byref(nloc_o), C.byref(ld_o), C.byref(info),
                      C.byref(ncoll))
     assert rc == 0
@@ -114,11 +114,11 @@ class _NoDist:
     all_reduce = broadcast
 
 
-@pytest.mark.parametrize("n,nb", [(640, 128), (700, 128), (100, 128), (1030, 256)])
-def test_schedule_single_rank(n, nb):
+@pytest.mark.parametrize("n,nb,window", [(640, 128, 2), (700, 128, 3), (100, 128, 2), (1030, 256, 5)])
+def test_schedule_single_rank(n, nb, window):
     _build_sim()
     B, rhs = _problem(n, n)
-    out = _run_rank(0, 1, n, nb, B, rhs, _NoDist)
+    out = _run_rank(0, 1, n, nb, B, rhs, _NoDist, window=window)
     _check([out], 1, n, nb, B, rhs)
 
 
@@ -130,7 +130,7 @@ def test_schedule_reports_first_bad_pivot():
     assert out["info"] == n // 2 + 1
 
 
-def _worker(rank, world, port, n, nb, q, pd):
+def _worker(rank, world, port, n, nb, q, pd, window):
     sys.path.insert(0, ROOT)
     import torch.distributed as dist
     os.environ["MASTER_ADDR"] = "127.0.0.1"
@@ -138,19 +138,19 @@ def _worker(rank, world, port, n, nb, q, pd):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         B, rhs = _problem(n, n + world, pd=pd)
-        out = _run_rank(rank, world, n, nb, B, rhs, dist)
+        out = _run_rank(rank, world, n, nb, B, rhs, dist, window=window)
         q.put(out)
     finally:
         dist.destroy_process_group()
 
 
-def _spawn(world, n, nb, pd=True):
+def _spawn(world, n, nb, pd=True, window=2):
     import torch.multiprocessing as mp
     _build_sim()
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, n, nb, q, pd)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, n, nb, q, pd, window)) for r in range(world)]
     for p in procs:
         p.start()
     outs = [q.get(timeout=240) for _ in procs]
@@ -160,11 +160,13 @@ def _spawn(world, n, nb, pd=True):
     return sorted(outs, key=lambda o: o["rank"])
 
 
-@pytest.mark.parametrize("world,n,nb", [(2, 1000, 128), (3, 1111, 128), (4, 300, 128), (2, 1300, 256)])
-def test_schedule_over_gloo(world, n, nb):
-    """world 2 and 3 with ragged last blocks; world 4 with 3 blocks (one rank owns nothing but still
-    joins every collective); nb = 256."""
-    outs = _spawn(world, n, nb)
+@pytest.mark.parametrize("world,n,nb,window", [(2, 1000, 128, 2), (2, 1000, 128, 3), (3, 1111, 128, 3),
+                                               (4, 300, 128, 5), (2, 1300, 256, 4), (4, 1500, 128, 5),
+                                               (4, 1500, 128, 3)])
+def test_schedule_over_gloo(world, n, nb, window):
+    """world 2 - 4 with ragged last blocks, panel windows W = 2 .. 5 (look-ahead depth min(W - 1, world));
+    world 4 with 3 blocks (one rank owns nothing but still joins every collective); nb = 256."""
+    outs = _spawn(world, n, nb, window=window)
     B, rhs = _problem(n, n + world)
     _check(outs, world, n, nb, B, rhs)
 

@@ -85,9 +85,12 @@ def test_model_grid_composition(ctx):
             K = g.eval_cf(gp.cfs, a, b, ctx=ctx)
             want = o.eval_cf(gp.cfs, a, a if b is None else b)
             assert np.max(np.abs(K - want)) <= TOL * np.max(np.abs(want)), cfs
-            # entries that are not tiny must also agree relatively
-            big = np.abs(want) > 1e-6 * np.max(np.abs(want))
-            assert rel_err(K[big], want[big]) < 1e-11, cfs
+            # every entry must also agree relative to the size of ITS OWN terms (a sum with a cf_lin
+            # term can cancel, so |K_ij| itself is not the scale of the rounding errors)
+            bb = a if b is None else b
+            scale = sum(np.abs(o.eval_cf(gp.cfs, a, bb, cfind=[k])) for k in range(len(gp.cfs)))
+            ok = np.abs(K - want) <= 1e-11 * np.maximum(scale, 1e-300 + 1e-6 * np.max(scale))
+            assert np.all(ok), cfs
         kd = g.eval_cf(gp.cfs, xt, x, diag_only=True, ctx=ctx)
         assert np.max(np.abs(kd - o.eval_cf(gp.cfs, xt, x, diag_only=True))) < TOL * max(1, np.max(np.abs(kd)))
     with warnings.catch_warnings():

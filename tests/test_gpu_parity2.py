@@ -133,9 +133,13 @@ def test_config3_model_at_4096(ctx, approx):
     assert scaled_err(p["var"], po["var"]) < TOL
 
 
-def test_config4_shape_fitc_20000(ctx):
+@pytest.mark.parametrize("streamed", [False, True])
+def test_config4_shape_fitc_20000(ctx, streamed, monkeypatch):
     """BASELINE config 4's shape -- method_fitc, d = 6, X ~ U(-3, 3), inducing points = rows of a seeded
-    permutation, cf_sexp(lscale=1) + lik_gaussian(sigma=0.5) -- at n = 20000, m = 512."""
+    permutation, cf_sexp(lscale=1) + lik_gaussian(sigma=0.5) -- at n = 20000, m = 512; with Kxz resident
+    and with Kxz streamed (never materialised: what the n = 2M fit does)."""
+    monkeypatch.setenv("GPL_FITC_STREAM_GB", "0" if streamed else "1000")
+    monkeypatch.setenv("GPL_FITC_CHUNK", "4096")              # several row chunks
     rng = np.random.default_rng(4)
     n, m, d = 20000, 512, 6
     X = rng.uniform(-3, 3, size=(n, d))
@@ -152,3 +156,32 @@ def test_config4_shape_fitc_20000(ctx):
     p, po = g.gp_pred(gp, Xt, var=True), o.gp_pred(gpo, Xt, var=True)
     assert scaled_err(p["mean"], po["mean"]) < TOL
     assert scaled_err(p["var"], po["var"]) < 1e-7          # the reference's own formula cancels at ~1e-9
+
+
+@pytest.mark.parametrize("approx", ["laplace", "ep"])
+def test_fitc_streamed_non_gaussian(ctx, approx, monkeypatch):
+    """Newton / EP loops of method_fitc with Kxz regenerated chunk by chunk in every pass (several chunks:
+    GPL_FITC_STREAM_GB=0 and a small workspace are forced), vs the oracle."""
+    monkeypatch.setenv("GPL_FITC_STREAM_GB", "0")
+    monkeypatch.setenv("GPL_FITC_CHUNK", "1024")
+    rng = np.random.default_rng(12)
+    n, m = 5000, 96
+    X = rng.normal(size=(n, 2))
+    f = 2 * X[:, 0] - X[:, 1]
+    y = (rng.uniform(size=n) < 1 / (1 + np.exp(-f))).astype(float)
+    Zi = X[rng.permutation(n)[:m]].copy()
+    ap = g.approx_laplace() if approx == "laplace" else g.approx_ep()
+    gp = g.gp_init(cfs=g.cf_matern52(lscale=1.2), lik=g.lik_bernoulli(), method=g.method_fitc(inducing=Zi), approx=ap)
+    gpo = copy.deepcopy(gp)
+    g.gp_fit(gp, X, y, ctx=ctx)
+    o.gp_fit(gpo, X, y)
+    assert gp.fit["iters"] == gpo.fit["iters"]
+    assert abs(gp.fit["log_evidence"] - gpo.fit["log_evidence"]) < TOL * abs(gpo.fit["log_evidence"])
+    assert scaled_err(gp.fit["fmean"], gpo.fit["fmean"]) < TOL
+    if approx == "ep":
+        assert scaled_err(gp.fit["fvar"], gpo.fit["fvar"]) < 1e-7
+    Xt = rng.normal(size=(30, 2))
+    p, po = g.gp_pred(gp, Xt, var=True), o.gp_pred(gpo, Xt, var=True)
+    assert scaled_err(p["mean"], po["mean"]) < TOL and scaled_err(p["var"], po["var"]) < 1e-7
+    with pytest.raises(g.GplError):
+        g.fit_member(gp, "Kxz")               # never materialised

@@ -41,6 +41,7 @@ def main():
     ap.add_argument("--reps", type=int, default=1)
     ap.add_argument("--bernoulli", action="store_true", help="config 3 style: lik_bernoulli + cf_sexp*cf_lin, Laplace")
     ap.add_argument("--ep", action="store_true", help="with --bernoulli: parallel EP instead of Laplace")
+    ap.add_argument("--bcast-test", action="store_true", help="time bare panel broadcasts on the library's communicator")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -57,6 +58,19 @@ def main():
         return dict(zip(keys, [float(v) for v in t]))
 
     n = args.n
+    if args.bcast_test:
+        import ctypes as C
+        from gplite_b200 import _lib
+        for rows in (n, n // 2, n // 4, n // 8):
+            sec = C.c_double()
+            _lib.check(comm.lib.gpl_dist_bcast_bench(comm.h, rows * 1024, 10, C.byref(sec)))
+            if rank == 0:
+                print(json.dumps({"bcast_test": True, "n_gpus": world, "panel_rows": rows, "mbytes": rows * 1024 * 8 / 1e6,
+                                  "seconds": sec.value, "gbs": rows * 1024 * 8 / sec.value / 1e9}), flush=True)
+        comm.close()
+        dist.barrier()
+        dist.destroy_process_group()
+        return
     if args.bernoulli:
         import warnings
         rng = np.random.default_rng(3)

@@ -72,3 +72,14 @@ elif what == "sweeps":
         gp = g.gp_init(cfs=cfs, lik=g.lik_bernoulli(), approx=g.approx_ep(maxiter=1))
         g.gp_fit(gp, X, y, ctx=ctx)
         print("ep", gp.fit["log_evidence"])
+elif what == "gemv":
+    # f = K alpha at config 3's size: one pass over a 50000 x 50000 matrix (20 GB)
+    n = int(sys.argv[2]) if len(sys.argv) > 2 else 50000
+    A = torch.randn(n, n, dtype=torch.float64, device="cuda")
+    x = torch.randn(n, dtype=torch.float64, device="cuda")
+    y = torch.empty(n, dtype=torch.float64, device="cuda")
+    torch.cuda.synchronize()
+    for _ in range(2):
+        _lib.check(ctx.lib.gpl_dgemv_dev(ctx.h, 1, n, n, P(A), n, P(x), P(y)))
+        _lib.check(ctx.lib.gpl_dgemv_dev(ctx.h, 0, n, n, P(A), n, P(x), P(y)))
+    ctx.sync()
