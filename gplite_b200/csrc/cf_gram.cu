@@ -338,14 +338,23 @@ int launch_gram1(Ctx* ctx, const GPlan& gp, const GArgs& a, int grid) {
 // 2 = 32 x 32, 1 CTA / SM (255 registers); 3 = 32 x 16, 3 CTAs / SM; 4 = 32 x 16, 4 CTAs / SM
 template <int MODE, int NSUB>
 int launch_gram(Ctx* ctx, const GPlan& gp, const GArgs& a, int grid) {
-  static const int variant = getenv("GPL_GRAM_VARIANT") ? atoi(getenv("GPL_GRAM_VARIANT")) : 0;
-  if (NSUB == 4) {
+  // Measured at n = 32768, d = 8 (profiles/r02_kbuild_variants.jsonl): the kernel is latency bound, so
+  // occupancy beats per-thread tile size -- cf_matern52 symmetric 2.29 / 1.98 / 2.88 / 1.71 / 1.58 ms for
+  // variants 0..4; 4 (warp tile 32 x 16, 64 registers, 4 CTAs = 32 warps per SM) is the default.
+  static const int variant = getenv("GPL_GRAM_VARIANT") ? atoi(getenv("GPL_GRAM_VARIANT")) : 4;
+  const int smem = (2 * gp.rows * GLD + 256) * (int)sizeof(double);
+  if constexpr (MODE >= 0) {
+    if (variant == 0) return launch_gram1<MODE, 4, 2>(ctx, gp, a, grid);
     if (variant == 1) return launch_gram1<MODE, 2, 2>(ctx, gp, a, grid);
     if (variant == 2) return launch_gram1<MODE, 4, 1>(ctx, gp, a, grid);
-    if (variant == 3) return launch_gram1<MODE, 2, 3>(ctx, gp, a, grid);
-    if (variant == 4) return launch_gram1<MODE, 2, 4>(ctx, gp, a, grid);
+    if (variant == 3 || 4 * smem > 220 * 1024) return launch_gram1<MODE, 2, 3>(ctx, gp, a, grid);
+    return launch_gram1<MODE, 2, 4>(ctx, gp, a, grid);
+  } else {
+    // sums of products keep acc + prod + out per entry: warp tile 32 x 8 to stay at 3-4 CTAs per SM
+    if (variant == 0) return launch_gram1<MODE, 2, 2>(ctx, gp, a, grid);
+    if (variant == 3 || 4 * smem > 220 * 1024) return launch_gram1<MODE, 1, 3>(ctx, gp, a, grid);
+    return launch_gram1<MODE, 1, 4>(ctx, gp, a, grid);
   }
-  return launch_gram1<MODE, NSUB, 2>(ctx, gp, a, grid);
 }
 
 }  // namespace

@@ -95,7 +95,8 @@ NcclApi* nccl_api() {
 struct Dist {
   Ctx* ctx = nullptr;
   NcclApi* api = nullptr;
-  ncclComm_t comm = nullptr;
+  ncclComm_t comm = nullptr;       // capped at a few CTAs: broadcasts that overlap the trailing updates
+  ncclComm_t comm_wide = nullptr;  // NCCL's default CTA count: the latency-bound tail, where the SMs idle anyway
   int rank = 0, world = 1;
   cudaStream_t comm_stream = nullptr;
   cudaStream_t aux_stream = nullptr;    // second high-priority stream of the panel chain
@@ -222,10 +223,11 @@ struct GpuOps {
     Scope sc(ctx, st(S));
     return dpotrf_nosync(ctx, dinv_of(k), w, A, lda, d->d_info, pivot0);
   }
-  int trsm_below(dist::Stream S, int64_t k, int64_t m, int64_t w, const double* L, int64_t ldl, double* B,
-                 int64_t ldb) {
+  int trsm_below(dist::Stream S, int64_t k, int64_t c0, int64_t wc, int64_t m, int64_t w, const double* L,
+                 int64_t ldl, double* B, int64_t ldb) {
+    (void)wc;
     Scope sc(ctx, st(S));
-    return dtrsm_right_with(ctx, dinv_of(k), true, m, w, L, ldl, B, ldb);
+    return dtrsm_right_with(ctx, dinv_of(k) + (c0 / NB) * NB * NB, true, m, w, L, ldl, B, ldb);
   }
   int inv_diag(dist::Stream S, int64_t k, int64_t w, const double* L, int64_t ldl, double* out, int64_t ldo) {
     Scope sc(ctx, st(S));
@@ -334,7 +336,10 @@ struct GpuOps {
     // the compute schedule alone
     static const int nocomm = getenv("GPL_DIST_NOCOMM") ? atoi(getenv("GPL_DIST_NOCOMM")) : 0;
     if (nocomm && S == dist::S_COMM) return GPL_OK;
-    GPL_NCCL(d, d->api->Broadcast(buf, buf, (size_t)count, ncclDouble, root, d->comm, st(S)));
+    // panels shorter than ~4 nb P rows belong to the latency-bound tail of a sweep (the trailing updates no
+    // longer cover the panel chain): there the uncapped communicator is used
+    const bool tail = d->comm_wide && S == dist::S_COMM && count < 4 * lay->nb * lay->nb * (int64_t)lay->world;
+    GPL_NCCL(d, d->api->Broadcast(buf, buf, (size_t)count, ncclDouble, root, tail ? d->comm_wide : d->comm, st(S)));
     d->nccl_bytes += 8.0 * (double)count;
     return GPL_OK;
   }
@@ -421,7 +426,7 @@ int dist_setup(Dist* d, DistState& st, const gpl_cf_model* cf, const gpl_lik* li
   if (want_inverse) GPL_TRY(ensure(&d->X, &d->capX, slab));
   // panel window: look-ahead depth D = W - 1 (capped by the world size)
   static const int forced_w = getenv("GPL_DIST_WINDOW") ? atoi(getenv("GPL_DIST_WINDOW")) : 0;
-  int W = d->world >= 4 ? 5 : (d->world >= 2 ? 3 : 2);
+  int W = d->world >= 8 ? 8 : (d->world >= 4 ? 5 : (d->world >= 2 ? 3 : 2));
   if (forced_w >= 2 && forced_w <= dist::MAX_WINDOW) W = forced_w;
   for (int i = 0; i < W; ++i) GPL_TRY(ensure(&d->panel[i], &d->capP[i], (size_t)nb * L.ld));
   if (want_inverse) {
@@ -443,6 +448,7 @@ int dist_setup(Dist* d, DistState& st, const gpl_cf_model* cf, const gpl_lik* li
   st.ch.A = d->A;
   st.ch.X = want_inverse ? d->X : nullptr;
   st.ch.window = W;
+  st.ch.chunked_tail = !(getenv("GPL_DIST_TAIL") && atoi(getenv("GPL_DIST_TAIL")) == 0);
   for (int i = 0; i < W; ++i) st.ch.panel[i] = d->panel[i];
   st.ch.tmp = d->tmp;
   st.ch.vec[0] = st.v[D_W0].d();
@@ -836,6 +842,24 @@ int gpl_dist_init(gpl_ctx* h, const void* id128, int32_t rank, int32_t world, gp
       delete d;
       return GPL_ERR_NCCL;
     }
+    // second communicator without the cap; its id travels over the first one
+    if (max_ctas > 0 && d->api->CommInitRankConfig) {
+      ncclUniqueId id2;
+      if (rank == 0) {
+        r = d->api->GetUniqueId(&id2);
+        if (r != ncclSuccess) { set_error("ncclGetUniqueId: %s", d->api->GetErrorString(r)); delete d; return GPL_ERR_NCCL; }
+      }
+      void* dbuf = nullptr;
+      GPL_CUDA(cudaMalloc(&dbuf, sizeof(id2)));
+      if (rank == 0) GPL_CUDA(cudaMemcpy(dbuf, &id2, sizeof(id2), cudaMemcpyHostToDevice));
+      r = d->api->Broadcast(dbuf, dbuf, sizeof(id2), ncclChar, 0, d->comm, 0);
+      if (r != ncclSuccess) { set_error("ncclBroadcast (id): %s", d->api->GetErrorString(r)); delete d; return GPL_ERR_NCCL; }
+      GPL_CUDA(cudaStreamSynchronize(0));
+      GPL_CUDA(cudaMemcpy(&id2, dbuf, sizeof(id2), cudaMemcpyDeviceToHost));
+      GPL_CUDA(cudaFree(dbuf));
+      r = d->api->CommInitRank(&d->comm_wide, world, id2, rank);
+      if (r != ncclSuccess) { set_error("ncclCommInitRank (wide): %s", d->api->GetErrorString(r)); delete d; return GPL_ERR_NCCL; }
+    }
   }
   int lo = 0, hi = 0;
   GPL_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
@@ -854,6 +878,7 @@ int gpl_dist_destroy(gpl_dist* h) {
   cudaSetDevice(d->ctx->device);
   cudaStreamSynchronize(d->ctx->stream);
   cudaStreamSynchronize(d->comm_stream);
+  if (d->comm_wide && d->api) d->api->CommDestroy(d->comm_wide);
   if (d->comm && d->api) d->api->CommDestroy(d->comm);
   for (double* p : {d->A, d->X, d->tmp, d->dinv, d->d_acc})
     if (p) cudaFree(p);

@@ -29,6 +29,14 @@
 // with the host inside a sweep: a failing pivot is collected in a device word and looked at once at the
 // end.
 //
+// The tail.  Once the trailing matrix is small ((n - k) < 4 nb P rows) a step's bulk update no longer
+// covers the panel chain, and what remains is a latency chain through ONE GPU per step: update of the
+// next block column, potrf, TRSM, broadcast (measured at n = 100k on 8 GPUs: the last 38 of 98 steps took
+// 196 ms for 77 ms of arithmetic).  There the panel is produced, broadcast and consumed in MAX_CHUNKS
+// column chunks: while chunk c is on the wire, the owner already solves chunk c + 1 and the next owner
+// already applies chunk c - 1 to its block column (a K = nb / 4 product), so the chain per step shrinks
+// from (update + TRSM + broadcast + potrf) to about (TRSM + potrf + one chunk's update and broadcast).
+//
 // Replaces, for matrices that do not fit one GPU, base-R chol() / forwardsolve() / backsolve() at
 // R/laplace.R:27-30 and R/ep.R:38-42, and the n x n solve behind R/ep.R:42,141.
 #pragma once
@@ -47,8 +55,13 @@ enum Event { EV_PANEL_READY0 = 0,                       // owner: packed panel i
              EV_BCAST_DONE0 = MAX_WINDOW,               // the broadcast into the buffer has completed
              EV_BUF_FREE0 = 2 * MAX_WINDOW,             // MAIN no longer reads the buffer (bulk update done)
              EV_EAGER_DONE0 = 3 * MAX_WINDOW,           // PANEL no longer reads the buffer (eager update done)
-             EV_COL_READY = 4 * MAX_WINDOW, EV_MAIN_DONE, EV_AUX_GO, EV_AUX_DONE, EV_COUNT };
+             EV_COL_READY = 4 * MAX_WINDOW, EV_MAIN_DONE, EV_AUX_GO, EV_AUX_DONE,
+             EV_CHUNK_READY0,                                       // + slot * MAX_CHUNKS + chunk
+             EV_CHUNK_DONE0 = EV_CHUNK_READY0 + MAX_WINDOW * 4,
+             EV_COUNT = EV_CHUNK_DONE0 + MAX_WINDOW * 4 };
+constexpr int MAX_CHUNKS = 4;
 inline Event ev(Event family, int64_t w) { return (Event)((int)family + (int)w); }
+inline Event evc(Event family, int64_t w, int c) { return (Event)((int)family + (int)w * MAX_CHUNKS + c); }
 
 struct Stair { int64_t nb, first, step, bskip; };   // same meaning as gpl::GemmStair
 
@@ -83,8 +96,9 @@ struct Layout {
 //   int fill_block(Stream, int64_t b, double* dst /* slab column lc0[b], row col0(b) */, int64_t ld)
 //        -- rows col0(b) .. n of block column b of B (diagonal block included)
 //   int potrf_diag(Stream, int64_t k, int64_t w, double* A, int64_t lda, int pivot0)   (no host sync)
-//   int trsm_below(Stream, int64_t k, int64_t m, int64_t w, const double* L, int64_t ldl, double* B, int64_t ldb)
-//        -- B <- B L^-T with the factor of diagonal block k
+//   int trsm_below(Stream, int64_t k, int64_t c0, int64_t wc, int64_t m, int64_t w, const double* L, int64_t ldl,
+//                  double* B, int64_t ldb)
+//        -- B (m x w) <- B L^-T, L = the w x w diagonal sub-block starting at column c0 of diagonal block k
 //   int inv_diag(Stream, int64_t k, int64_t w, const double* L, int64_t ldl, double* out, int64_t ldo)
 //   int gemm(Stream, bool ta, bool tb, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, bool lower, const Stair*)
 //   int copy2d(Stream, double* dst, int64_t ldd, const double* src, int64_t lds, int64_t rows, int64_t cols)
@@ -122,6 +136,15 @@ class ShardedChol {
   double bcast_bytes = 0.0;       // panel bytes this rank has put through the collectives
 
   double* slab(double* S, int64_t b) const { return S + lay.lc0[(size_t)b] * lay.ld; }
+  bool chunked_tail = true;       // GPL_DIST_TAIL=0 switches the chunked tail off (tuning / diagnostics)
+  int chunk_align = 128;          // a chunk must be a whole number of the back end's diagonal sub-blocks
+  // panel k travels in MAX_CHUNKS column chunks (tail of the factorisation)?
+  int chunks_of(int64_t k) const {
+    const Layout& L = lay;
+    if (!chunked_tail || L.world < 2) return 1;
+    if (L.width(k) != L.nb || L.nb % (chunk_align * MAX_CHUNKS) != 0) return 1;
+    return (L.n - L.col0(k)) < 4 * L.nb * (int64_t)L.world ? MAX_CHUNKS : 1;
+  }
 
   // ---- build + factorise ---------------------------------------------------------------------
   // B's owned block columns come from ops->fill_block; returns the first failing pivot (0 = ok) in
@@ -152,8 +175,9 @@ class ShardedChol {
     for (int64_t k = 0; k < L.nblk; ++k) {
       const int64_t w = k % W;
       // ---- eager update (PANEL): this rank's block column among the next D
-      GPL_DS(ops->wait(S_PANEL, ev(EV_BCAST_DONE0, w)));
       const int64_t b = L.first_owned_from(k + 1);
+      // (the next owner consumes a chunked panel chunk by chunk; everyone else waits for all of it)
+      if (!(b == k + 1 && b < L.nblk && chunks_of(k) > 1)) GPL_DS(ops->wait(S_PANEL, ev(EV_BCAST_DONE0, w)));
       if (b < L.nblk && b <= k + D) {
         // its first eager update (from panel b - D) must follow the bulk updates by all earlier panels
         if (b == k + D && k > 0) GPL_DS(ops->wait(S_PANEL, ev(EV_BUF_FREE0, (k - 1) % W)));
@@ -162,9 +186,17 @@ class ShardedChol {
           // are updated on a second high-priority stream while the diagonal block is being factored
           GPL_DS(ops->record(EV_AUX_GO, S_PANEL));
           GPL_DS(ops->wait(S_AUX, EV_AUX_GO));
-          GPL_DS(apply_panel_rows(S_AUX, k, b, L.width(b), L.n - L.col0(b) - L.width(b), W));
+          const int C = chunks_of(k);
+          const int64_t wc = L.width(k) / C;
+          for (int c = 0; c < C; ++c) {                              // (C > 1: as the chunks of panel k arrive)
+            if (C > 1) {
+              GPL_DS(ops->wait(S_AUX, evc(EV_CHUNK_DONE0, w, c)));
+              GPL_DS(ops->wait(S_PANEL, evc(EV_CHUNK_DONE0, w, c)));
+            }
+            GPL_DS(apply_panel_rows(S_AUX, k, b, L.width(b), L.n - L.col0(b) - L.width(b), W, c * wc, wc));
+            GPL_DS(apply_panel_rows(S_PANEL, k, b, 0, L.width(b), W, c * wc, wc));
+          }
           GPL_DS(ops->record(EV_AUX_DONE, S_AUX));
-          GPL_DS(apply_panel_rows(S_PANEL, k, b, 0, L.width(b), W));
           GPL_DS(factor_panel(b, W, true));
         } else {
           GPL_DS(apply_panel_to(S_PANEL, k, b, 1, W));
@@ -268,9 +300,28 @@ class ShardedChol {
     GPL_DS(ops->potrf_diag(S_PANEL, k, w, Akk, L.ld, (int)k0));
     GPL_DS(ops->diag_logsum(S_PANEL, w, Akk, L.ld, logdet_acc));
     if (rows_on_aux) GPL_DS(ops->wait(S_PANEL, EV_AUX_DONE));       // the rows below have their update
-    if (below > 0) GPL_DS(ops->trsm_below(S_PANEL, k, below, w, Akk, L.ld, Akk + w, L.ld));
     GPL_DS(ops->wait(S_PANEL, ev(EV_BUF_FREE0, pb)));               // (its own eager use is earlier in PANEL order)
-    GPL_DS(ops->copy2d(S_PANEL, panel[pb], L.ldp(k), Akk, L.ld, L.n - k0, w));
+    const int C = chunks_of(k);
+    if (C == 1) {
+      if (below > 0) GPL_DS(ops->trsm_below(S_PANEL, k, 0, w, below, w, Akk, L.ld, Akk + w, L.ld));
+      GPL_DS(ops->copy2d(S_PANEL, panel[pb], L.ldp(k), Akk, L.ld, L.n - k0, w));
+      return ops->record(ev(EV_PANEL_READY0, pb), S_PANEL);
+    }
+    // tail: column chunk c of the rows below is solved (after the update by the chunks to its left),
+    // packed and released to the broadcast while chunk c + 1 is being solved
+    const int64_t wc = w / C, ldp = L.ldp(k);
+    double* B = Akk + w;                                            // rows below the diagonal block
+    for (int c = 0; c < C; ++c) {
+      const int64_t c0 = c * wc;
+      if (below > 0) {
+        if (c > 0)
+          GPL_DS(ops->gemm(S_PANEL, false, true, below, wc, c0, -1.0, B, L.ld, Akk + c0, L.ld, 1.0, B + c0 * L.ld, L.ld,
+                           false, nullptr));
+        GPL_DS(ops->trsm_below(S_PANEL, k, c0, wc, below, wc, Akk + c0 * L.ld + c0, L.ld, B + c0 * L.ld, L.ld));
+      }
+      GPL_DS(ops->copy2d(S_PANEL, panel[pb] + c0 * ldp, ldp, Akk + c0 * L.ld, L.ld, L.n - k0, wc));
+      GPL_DS(ops->record(evc(EV_CHUNK_READY0, pb, c), S_PANEL));
+    }
     return ops->record(ev(EV_PANEL_READY0, pb), S_PANEL);
   }
 
@@ -278,25 +329,34 @@ class ShardedChol {
   int send_panel(int64_t k, int W) {
     const Layout& L = lay;
     const int64_t pb = k % W;
-    if (L.owner(k) == L.rank) {
-      GPL_DS(ops->wait(S_COMM, ev(EV_PANEL_READY0, pb)));
-    } else {
+    const int C = chunks_of(k);
+    const bool own = L.owner(k) == L.rank;
+    if (!own) {
       GPL_DS(ops->wait(S_COMM, ev(EV_BUF_FREE0, pb)));
       GPL_DS(ops->wait(S_COMM, ev(EV_EAGER_DONE0, pb)));
+    } else if (C == 1) {
+      GPL_DS(ops->wait(S_COMM, ev(EV_PANEL_READY0, pb)));
     }
-    const int64_t count = L.ldp(k) * L.width(k);
-    GPL_DS(ops->bcast(S_COMM, panel[pb], count, L.owner(k)));
-    bcast_bytes += 8.0 * (double)count;
+    const int64_t count = L.ldp(k) * L.width(k) / C;
+    for (int c = 0; c < C; ++c) {
+      if (own && C > 1) GPL_DS(ops->wait(S_COMM, evc(EV_CHUNK_READY0, pb, c)));
+      GPL_DS(ops->bcast(S_COMM, panel[pb] + c * count, count, L.owner(k)));
+      bcast_bytes += 8.0 * (double)count;
+      if (C > 1) GPL_DS(ops->record(evc(EV_CHUNK_DONE0, pb, c), S_COMM));
+    }
     return ops->record(ev(EV_BCAST_DONE0, pb), S_COMM);
   }
 
   // rows [r0, r0 + m) (relative to the block's diagonal) of block column j -= P_k[those rows] P_k[block j rows]^T
-  int apply_panel_rows(Stream S, int64_t k, int64_t j, int64_t r0, int64_t m, int W) {
+  // (only the panel columns [kc0, kc0 + kw) when kw > 0: one chunk of a chunked panel)
+  int apply_panel_rows(Stream S, int64_t k, int64_t j, int64_t r0, int64_t m, int W, int64_t kc0 = 0,
+                       int64_t kw = 0) {
     const Layout& L = lay;
     if (m <= 0) return 0;
-    const int64_t k0 = L.col0(k), w = L.width(k), j0 = L.col0(j), ldp = L.ldp(k);
-    const double* P = panel[k % W];
-    return ops->gemm(S, false, true, m, L.width(j), w, -1.0, P + (j0 - k0) + r0, ldp, P + (j0 - k0), ldp, 1.0,
+    const int64_t k0 = L.col0(k), j0 = L.col0(j), ldp = L.ldp(k);
+    if (kw <= 0) kw = L.width(k);
+    const double* P = panel[k % W] + kc0 * ldp;
+    return ops->gemm(S, false, true, m, L.width(j), kw, -1.0, P + (j0 - k0) + r0, ldp, P + (j0 - k0), ldp, 1.0,
                      slab(A, j) + j0 + r0, L.ld, false, nullptr);
   }
 

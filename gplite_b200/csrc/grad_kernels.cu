@@ -258,8 +258,8 @@ struct FastArgs {
   double sc, magn2, m3;
 };
 
-template <int KIND>
-__global__ void __launch_bounds__(GTHREADS, 2)
+template <int KIND, int MINB, int NS>
+__global__ void __launch_bounds__(GTHREADS, MINB)
 grad_trace_fast_kernel(const FastArgs a) {
   extern __shared__ double sm[];
   double* Zs1 = sm;                    // [gk][FLD]
@@ -337,25 +337,25 @@ grad_trace_fast_kernel(const FastArgs a) {
 
   double G0 = 0.0, G1 = 0.0;
 #pragma unroll 1
-  for (int pass = 0; pass < 4; ++pass) {          // warp tile 32 x 16 per pass: keeps the kernel at 128 registers
-    const int cbase = pass * 32 + wn * 16;
-    double acc[4][2][2];
+  for (int pass = 0; pass < GT / (16 * NS); ++pass) {   // warp tile 32 x (8 NS) per pass
+    const int cbase = pass * (16 * NS) + wn * (8 * NS);
+    double acc[4][NS][2];
 #pragma unroll
     for (int im = 0; im < 4; ++im)
 #pragma unroll
-      for (int in = 0; in < 2; ++in) acc[im][in][0] = acc[im][in][1] = 0.0;
+      for (int in = 0; in < NS; ++in) acc[im][in][0] = acc[im][in][1] = 0.0;
     if (!bad) {
       for (int ks = 0; ks < a.gk; ks += 4) {
         const int kk = ks + t;
-        double av[4], bv[2];
+        double av[4], bv[NS];
 #pragma unroll
         for (int im = 0; im < 4; ++im) av[im] = Zs1[kk * FLD + wm * 32 + im * 8 + g];
 #pragma unroll
-        for (int in = 0; in < 2; ++in) bv[in] = Zs2[kk * FLD + cbase + in * 8 + g];
+        for (int in = 0; in < NS; ++in) bv[in] = Zs2[kk * FLD + cbase + in * 8 + g];
 #pragma unroll
         for (int im = 0; im < 4; ++im)
 #pragma unroll
-          for (int in = 0; in < 2; ++in) dmma_k4(acc[im][in][0], acc[im][in][1], av[im], bv[in]);
+          for (int in = 0; in < NS; ++in) dmma_k4(acc[im][in][0], acc[im][in][1], av[im], bv[in]);
       }
     }
 #pragma unroll
@@ -364,7 +364,7 @@ grad_trace_fast_kernel(const FastArgs a) {
       const int gi = i0 + row;
       const double si = vec[0 * GT + row], ai = vec[1 * GT + row], ui = vec[2 * GT + row];
 #pragma unroll
-      for (int in = 0; in < 2; ++in) {
+      for (int in = 0; in < NS; ++in) {
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
           const int col = cbase + in * 8 + 2 * t + c;
@@ -430,13 +430,24 @@ grad_trace_fast_kernel(const FastArgs a) {
   }
 }
 
-template <int KIND>
-int launch_fast(Ctx* ctx, const FastArgs& a, dim3 grid) {
-  const int smem = (2 * a.gk * FLD + 256 + 6 * GT) * (int)sizeof(double);
-  GPL_CUDA(cudaFuncSetAttribute(grad_trace_fast_kernel<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  grad_trace_fast_kernel<KIND><<<grid, GTHREADS, smem, ctx->stream>>>(a);
+template <int KIND, int MINB>
+int launch_fast1(Ctx* ctx, const FastArgs& a, dim3 grid, int smem) {
+  constexpr int NS = MINB >= 3 ? 1 : 2;
+  GPL_CUDA(cudaFuncSetAttribute(grad_trace_fast_kernel<KIND, MINB, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                smem));
+  grad_trace_fast_kernel<KIND, MINB, NS><<<grid, GTHREADS, smem, ctx->stream>>>(a);
   GPL_LAUNCH_CHECK(ctx);
   return GPL_OK;
+}
+
+// like the K build this kernel is latency bound: occupancy first (GPL_GRAD_MINB = 2 / 3 / 4 CTAs per SM)
+template <int KIND>
+int launch_fast(Ctx* ctx, const FastArgs& a, dim3 grid) {
+  static const int minb = getenv("GPL_GRAD_MINB") ? atoi(getenv("GPL_GRAD_MINB")) : 3;
+  const int smem = (2 * a.gk * FLD + 256 + 6 * GT) * (int)sizeof(double);
+  if (minb >= 4 && 4 * smem <= 220 * 1024) return launch_fast1<KIND, 4>(ctx, a, grid, smem);
+  if (minb >= 3 && 3 * smem <= 220 * 1024) return launch_fast1<KIND, 3>(ctx, a, grid, smem);
+  return launch_fast1<KIND, 2>(ctx, a, grid, smem);
 }
 
 __global__ void sum_grad_partials_kernel(const double* __restrict__ partial, int grid, int nparam,

@@ -62,7 +62,8 @@ struct SimOps {
       }
     return 0;
   }
-  int trsm_below(Stream, int64_t, int64_t m, int64_t w, const double* L, int64_t ldl, double* B, int64_t ldb) {
+  int trsm_below(Stream, int64_t, int64_t, int64_t, int64_t m, int64_t w, const double* L, int64_t ldl, double* B,
+                 int64_t ldb) {
     for (int64_t j = 0; j < w; ++j)          // B <- B L^-T, column by column
       for (int64_t i = 0; i < m; ++i) {
         double v = B[j * ldb + i];
@@ -206,6 +207,7 @@ extern "C" int sim_run(int rank, int world, int64_t n, int64_t nb, int window, c
   ch.A = A.data();
   ch.X = X.data();
   ch.window = window;
+  ch.chunk_align = 32;            // the host back end solves against any sub-block
   for (int w = 0; w < window; ++w) ch.panel[w] = pbuf[(size_t)w].data();
   ch.tmp = tmp.data();
   ch.vec[0] = v0.data(); ch.vec[1] = v1.data(); ch.vec[2] = v2.data(); ch.vec[3] = v3.data();
