@@ -269,6 +269,11 @@ def sharded_record(ctx, rank, world, dist, nb=1024):
 
     # ---- strong scaling point: the same n = 100000 factorisation at every N the driver runs
     rec["n100k_factor"] = run(100000, False)
+    # the N = 1 time of this same code on this pool (profiles/r02_dist_schedule_v2_window_sweep.jsonl), so that a
+    # single line already shows the strong-scaling efficiency; the driver's own N = 1 line is the authority
+    ref1 = 10.544
+    rec["n100k_factor"]["strong_scaling_efficiency_vs_n1_reference"] = ref1 / (world * rec["n100k_factor"]["factor_s"])
+    rec["n100k_factor"]["n1_reference_factor_s"] = ref1
     # ---- n = 200000 where it fits (one slab of 320 / N GB per GPU; two for the gradient)
     if world >= 4:
         rec["n200k_factor"] = run(200000, False)

@@ -150,6 +150,9 @@ SIGNATURES = {
     "gpl_dist_fit_full": (C.c_int, [_P, C.POINTER(CfModel), C.POINTER(Lik), C.POINTER(Approx), _P, _I64, _I32, _P,
                                     _P, _P, _D, _I64, C.POINTER(FitOut), _P, _P, _P, _P, _P, _P, _P,
                                     C.POINTER(DistTimings)]),
+    "gpl_dist_fit_fitc": (C.c_int, [_P, C.POINTER(CfModel), C.POINTER(Lik), C.POINTER(Approx), _P, _I64, _I32, _P,
+                                    _I64, _P, _P, _P, _D, C.POINTER(FitOut), _P, _P, _P, _P, _P, _P, _P,
+                                    C.POINTER(_P)]),
     "gpl_dist_energy_grad": (C.c_int, [_P, C.POINTER(CfModel), C.POINTER(Lik), _P, _I64, _I32, _P, _D, _I64, _I32,
                                        _P, _P, C.POINTER(_D), _P, _P, C.POINTER(DistTimings)]),
 }

@@ -29,6 +29,8 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <type_traits>
+
 namespace gpl {
 
 namespace {
@@ -84,18 +86,6 @@ __device__ __forceinline__ double gvalue(const GFactor& f, double s, double rb, 
   // cf_nn (src/cf.cpp:149-158): magn^2 (2/pi) asin(2a / sqrt((1 + 2b)(1 + 2c))), a = c0 + x1.x2;
   // rb * rc first: the symmetric matrix is then symmetric bit for bit
   return f.m3 * asin(2.0 * (f.c0 + s) * (rb * rc));
-}
-
-__device__ __forceinline__ double gvalue_dyn(const GFactor& f, double s, double rb, double rc,
-                                             const double* __restrict__ tab) {
-  switch (f.kind) {
-    case GPL_CF_CONST: return gvalue<GPL_CF_CONST>(f, s, rb, rc, tab);
-    case GPL_CF_LIN: return gvalue<GPL_CF_LIN>(f, s, rb, rc, tab);
-    case GPL_CF_SEXP: return gvalue<GPL_CF_SEXP>(f, s, rb, rc, tab);
-    case GPL_CF_MATERN32: return gvalue<GPL_CF_MATERN32>(f, s, rb, rc, tab);
-    case GPL_CF_MATERN52: return gvalue<GPL_CF_MATERN52>(f, s, rb, rc, tab);
-    default: return gvalue<GPL_CF_NN>(f, s, rb, rc, tab);
-  }
 }
 
 __device__ __forceinline__ bool is_stationary(int kind) {
@@ -242,27 +232,46 @@ gram_kernel(const __grid_constant__ GPlan plan, const GArgs a) {
               acc[im][in][c] = r2;
             }
       }
-      const bool is_nn = kind == GPL_CF_NN;
+      // values of this factor for the thread's entries, folded into the running product / sum.  The kind is
+      // dispatched ONCE per factor and pass (a CTA-uniform switch around fully unrolled, branch-free entry
+      // loops), never per entry.
+      auto fold = [&](auto kind_tag) {
+        constexpr int K = decltype(kind_tag)::value;
+        constexpr bool kstat = K == GPL_CF_SEXP || K == GPL_CF_MATERN32 || K == GPL_CF_MATERN52;
 #pragma unroll
-      for (int im = 0; im < 4; ++im) {
-        const int row = wm * 32 + im * 8 + g;
-        const double rb = is_nn ? Zs1[(f.goff + f.gk) * GLD + row] : 0.0;
+        for (int im = 0; im < 4; ++im) {
+          const int row = wm * 32 + im * 8 + g;
+          const double rb = K == GPL_CF_NN ? Zs1[(f.goff + f.gk) * GLD + row] : 0.0;
 #pragma unroll
-        for (int in = 0; in < NSUB; ++in) {
+          for (int in = 0; in < NSUB; ++in) {
 #pragma unroll
-          for (int c = 0; c < 2; ++c) {
-            const int col = cbase + in * 8 + 2 * t + c;
-            const double rc = is_nn ? Zs2[(f.goff + f.gk) * GLD + col] : 0.0;
-            double s = acc[im][in][c];
-            if (diag_tile && stat && row == col) s = 0.0;          // k(x, x) exactly
-            const double v = MODE < 0 ? gvalue_dyn(f, s, rb, rc, tab) : gvalue<MODE < 0 ? 0 : MODE>(f, s, rb, rc, tab);
-            if (MODE < 0) {
-              prod[im][in][c] = f.first ? v : prod[im][in][c] * v;
-              if (f.last) out[im][in][c] += prod[im][in][c];
-            } else {
-              out[im][in][c] = v;
+            for (int c = 0; c < 2; ++c) {
+              const int col = cbase + in * 8 + 2 * t + c;
+              const double rc = K == GPL_CF_NN ? Zs2[(f.goff + f.gk) * GLD + col] : 0.0;
+              double s = acc[im][in][c];
+              if (kstat && diag_tile && row == col) s = 0.0;        // k(x, x) exactly
+              const double v = gvalue<K>(f, s, rb, rc, tab);
+              if (MODE < 0) {
+                const double pr = f.first ? v : prod[im][in][c] * v;
+                prod[im][in][c] = pr;
+                if (f.last) out[im][in][c] += pr;
+              } else {
+                out[im][in][c] = v;
+              }
             }
           }
+        }
+      };
+      if (MODE >= 0) {
+        fold(std::integral_constant<int, (MODE < 0 ? 0 : MODE)>{});
+      } else {
+        switch (kind) {
+          case GPL_CF_CONST: fold(std::integral_constant<int, GPL_CF_CONST>{}); break;
+          case GPL_CF_LIN: fold(std::integral_constant<int, GPL_CF_LIN>{}); break;
+          case GPL_CF_SEXP: fold(std::integral_constant<int, GPL_CF_SEXP>{}); break;
+          case GPL_CF_MATERN32: fold(std::integral_constant<int, GPL_CF_MATERN32>{}); break;
+          case GPL_CF_MATERN52: fold(std::integral_constant<int, GPL_CF_MATERN52>{}); break;
+          default: fold(std::integral_constant<int, GPL_CF_NN>{}); break;
         }
       }
     }

@@ -493,6 +493,27 @@ int dist_alpha(DistState& st) {
 
 }  // namespace
 
+// ---- interface for the row-sharded FITC fit (fitc.cu) ---------------------------------------------
+Ctx* dist_ctx(Dist* d) { return d->ctx; }
+int dist_rank(const Dist* d) { return d->rank; }
+int dist_world(const Dist* d) { return d->world; }
+
+int dist_allreduce_f64(Dist* d, Ctx* ctx, double* buf, int64_t count, int op) {
+  if (d->world == 1 || count <= 0) return GPL_OK;
+  const ncclRedOp_t o = op == 0 ? ncclSum : (op == 1 ? ncclMax : ncclMin);
+  // m x m sums are bandwidth-sized (134 MB at m = 4096): the uncapped communicator when there is one
+  ncclComm_t c = (count >= (1 << 20) && d->comm_wide) ? d->comm_wide : d->comm;
+  GPL_NCCL(d, d->api->AllReduce(buf, buf, (size_t)count, ncclDouble, o, c, ctx->stream));
+  d->nccl_bytes += 8.0 * (double)count;
+  return GPL_OK;
+}
+
+int dist_allreduce_i32_max(Dist* d, Ctx* ctx, int* buf, int64_t count) {
+  if (d->world == 1 || count <= 0) return GPL_OK;
+  GPL_NCCL(d, d->api->AllReduce(buf, buf, (size_t)count, ncclInt32, ncclMax, d->comm, ctx->stream));
+  return GPL_OK;
+}
+
 // ---- Laplace / EP over the sharded factor --------------------------------------------------------
 int dist_fit_full_impl(Dist* d, const gpl_cf_model* cf, const gpl_lik* lik, const gpl_approx* approx,
                        const double* x, int64_t n, int dcols, const double* y, const double* trials,

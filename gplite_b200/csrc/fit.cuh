@@ -209,6 +209,15 @@ struct Fit {
 };
 
 int fitc_var_train(Ctx* ctx, const Fit* fit, double* out);
+
+// ---- dist.cu: the communicator object behind gpl_dist, as seen by the row-sharded FITC fit ----------
+struct Dist;
+Ctx* dist_ctx(Dist* d);
+int dist_rank(const Dist* d);
+int dist_world(const Dist* d);
+// in-place all-reduce of device doubles on ctx->stream: op 0 sum, 1 max, 2 min
+int dist_allreduce_f64(Dist* d, Ctx* ctx, double* buf, int64_t count, int op);
+int dist_allreduce_i32_max(Dist* d, Ctx* ctx, int* buf, int64_t count);
 // joint predictions on the device (mean nt, cov nt x nt with jitter on the diagonal)
 int pred_full_cov_dev(Ctx* ctx, const Fit* fit, const gpl_cf_model* cf, const double* xt, int64_t nt,
                       uint64_t term_mask, double jitter, double* d_mean, double* d_cov, int64_t ldc);

@@ -133,6 +133,10 @@ struct FitcTimer {
 };
 
 struct FitcState {
+  // multi-GPU (gpl_dist_fit_fitc): this rank holds rows [row0, row0 + n) of the n_total training points;
+  // Kz and the two m x m factors are replicated, the m x m sum and the m-vectors / scalars are all-reduced
+  Dist* dist = nullptr;
+  int64_t n_total = 0, row0 = 0;
   int64_t n = 0, m = 0, ldx = 0, ldm = 0, chunk = 0, ldw = 0;
   int d = 0;
   DevBuf x, zind, y, trials, offset, Zx, Zz;
@@ -153,6 +157,34 @@ struct FitcState {
 
 enum { F_F = 0, F_Z, F_V, F_ALPHA, F_FNEW, F_T1, F_T2, F_FVAR, F_P, F_CM, F_CV, F_LOGZ, F_W, F_T3 };
 
+// the first nsum scalar slots are sums over the sites, the next nmax maxima, the next nmin minima: combined
+// over the ranks (when sharded) and fetched
+int fetch_site_scalars(Ctx* ctx, FitcState& st, int nsum, int nmax, int nmin, double* host) {
+  if (st.dist) {
+    if (nsum) GPL_TRY(dist_allreduce_f64(st.dist, ctx, ctx->d_scal, nsum, 0));
+    if (nmax) GPL_TRY(dist_allreduce_f64(st.dist, ctx, ctx->d_scal + nsum, nmax, 1));
+    if (nmin) GPL_TRY(dist_allreduce_f64(st.dist, ctx, ctx->d_scal + nsum + nmax, nmin, 2));
+  }
+  return fetch_scalars(ctx, nsum + nmax + nmin, host);
+}
+
+__global__ void spread_flags_kernel(int* f) {       // f[0] bitmask -> f[1..3] one int per bit
+  if (threadIdx.x < 3) f[1 + threadIdx.x] = (f[0] >> threadIdx.x) & 1;
+}
+__global__ void gather_flags_kernel(int* f) {
+  if (threadIdx.x == 0) f[0] = (f[1] ? 1 : 0) | (f[2] ? 2 : 0) | (f[3] ? 4 : 0);
+}
+// EP site flags (bit 0 quadrature, bit 1 NaN, bit 2 V <= 0): OR over the ranks
+int combine_flags(Ctx* ctx, FitcState& st, int* d_flags) {
+  if (!st.dist) return GPL_OK;
+  spread_flags_kernel<<<1, 32, 0, ctx->stream>>>(d_flags);
+  GPL_LAUNCH_CHECK(ctx);
+  GPL_TRY(dist_allreduce_i32_max(st.dist, ctx, d_flags + 1, 3));
+  gather_flags_kernel<<<1, 32, 0, ctx->stream>>>(d_flags);
+  GPL_LAUNCH_CHECK(ctx);
+  return GPL_OK;
+}
+
 // W <- rows [r0, r0 + c) of Kxz, row i scaled by s[r0 + i] when s != NULL: a scaled copy of the resident
 // matrix, or regenerated from the prepared inputs (K(x_chunk, z): R/gp_fit.R:106)
 int chunk_into_W(Ctx* ctx, FitcState& st, int64_t r0, int64_t c, const double* s) {
@@ -166,19 +198,25 @@ int chunk_into_W(Ctx* ctx, FitcState& st, int64_t r0, int64_t c, const double* s
 
 // y (m) = Kzx x (n)
 int kxz_gemv_t(Ctx* ctx, FitcState& st, const double* x, double* y) {
-  if (!st.streamed) return gemv_t(ctx, st.n, st.m, st.Kxz.d(), st.ldx, x, y);
-  GPL_TRY(vec_op(ctx, VOP_FILL, st.m, nullptr, nullptr, y, 0.0));
-  for (int64_t r0 = 0; r0 < st.n; r0 += st.chunk) {
-    const int64_t c = (st.n - r0) < st.chunk ? (st.n - r0) : st.chunk;
-    GPL_TRY(chunk_into_W(ctx, st, r0, c, nullptr));
-    GPL_TRY(gemv_t(ctx, c, st.m, st.W.d(), st.ldw, x + r0, st.mv[5].d()));
-    GPL_TRY(vec_op(ctx, VOP_ADD, st.m, y, st.mv[5].d(), y));
+  if (!st.streamed) {
+    if (st.n > 0) GPL_TRY(gemv_t(ctx, st.n, st.m, st.Kxz.d(), st.ldx, x, y));
+    else GPL_TRY(vec_op(ctx, VOP_FILL, st.m, nullptr, nullptr, y, 0.0));
+  } else {
+    GPL_TRY(vec_op(ctx, VOP_FILL, st.m, nullptr, nullptr, y, 0.0));
+    for (int64_t r0 = 0; r0 < st.n; r0 += st.chunk) {
+      const int64_t c = (st.n - r0) < st.chunk ? (st.n - r0) : st.chunk;
+      GPL_TRY(chunk_into_W(ctx, st, r0, c, nullptr));
+      GPL_TRY(gemv_t(ctx, c, st.m, st.W.d(), st.ldw, x + r0, st.mv[5].d()));
+      GPL_TRY(vec_op(ctx, VOP_ADD, st.m, y, st.mv[5].d(), y));
+    }
   }
+  if (st.dist) GPL_TRY(dist_allreduce_f64(st.dist, ctx, y, st.m, 0));      // sum over the row shards
   return GPL_OK;
 }
 
 // y (n) = Kxz x (m)
 int kxz_gemv_n(Ctx* ctx, FitcState& st, const double* x, double* y) {
+  if (st.n <= 0) return GPL_OK;
   if (!st.streamed) return gemv_n(ctx, st.n, st.m, st.Kxz.d(), st.ldx, x, y);
   for (int64_t r0 = 0; r0 < st.n; r0 += st.chunk) {
     const int64_t c = (st.n - r0) < st.chunk ? (st.n - r0) : st.chunk;
@@ -200,29 +238,45 @@ int row_norms_via(Ctx* ctx, FitcState& st, const double* L, const double* dinv, 
 }
 
 int fitc_setup(Ctx* ctx, FitcState& st, const gpl_cf_model* cf, const gpl_lik* lik, const double* x,
-               int64_t n, int d, const double* zind, int64_t m, const double* y,
-               const double* trials, const double* offset, double jitter) {
+               int64_t n_total, int d, const double* zind, int64_t m, const double* y,
+               const double* trials, const double* offset, double jitter, Dist* dist) {
   FitcTimer tm(ctx);
+  st.dist = dist;
+  st.n_total = n_total;
+  st.row0 = 0;
+  int64_t n = n_total;
+  if (dist) {                                      // this rank's rows of x, y, trials, offset
+    const int64_t P = dist_world(dist), r = dist_rank(dist);
+    st.row0 = n_total * r / P;
+    n = n_total * (r + 1) / P - st.row0;
+    x += st.row0; y += st.row0;
+    if (trials) trials += st.row0;
+    if (offset) offset += st.row0;
+  }
   st.n = n; st.m = m; st.d = d;
   st.jitter = jitter;
-  st.ldx = round_up(n, 16);
+  st.ldx = round_up(n > 0 ? n : 1, 16);
   st.ldm = round_up(m, 16);
-  GPL_TRY(st.x.alloc(ctx, sizeof(double) * n * d));
+  const int64_t na = n > 0 ? n : 1;               // (a rank may own no rows)
+  GPL_TRY(st.x.alloc(ctx, sizeof(double) * na * d));
   GPL_TRY(st.zind.alloc(ctx, sizeof(double) * m * d));
-  GPL_TRY(st.y.alloc(ctx, sizeof(double) * n));
-  GPL_CUDA(cudaMemcpyAsync(st.x.p, x, sizeof(double) * n * d, cudaMemcpyHostToDevice, ctx->stream));
+  GPL_TRY(st.y.alloc(ctx, sizeof(double) * na));
+  if (n > 0) {
+    GPL_CUDA(cudaMemcpy2DAsync(st.x.p, sizeof(double) * n, x, sizeof(double) * n_total, sizeof(double) * n, d,
+                               cudaMemcpyHostToDevice, ctx->stream));
+    GPL_CUDA(cudaMemcpyAsync(st.y.p, y, sizeof(double) * n, cudaMemcpyHostToDevice, ctx->stream));
+  }
   GPL_CUDA(cudaMemcpyAsync(st.zind.p, zind, sizeof(double) * m * d, cudaMemcpyHostToDevice, ctx->stream));
-  GPL_CUDA(cudaMemcpyAsync(st.y.p, y, sizeof(double) * n, cudaMemcpyHostToDevice, ctx->stream));
   st.lik.kind = lik->kind; st.lik.link = lik->link; st.lik.param = lik->param;
   st.lik.trials = nullptr; st.lik.offset = nullptr;
   if (trials) {
-    GPL_TRY(st.trials.alloc(ctx, sizeof(double) * n));
-    GPL_CUDA(cudaMemcpyAsync(st.trials.p, trials, sizeof(double) * n, cudaMemcpyHostToDevice, ctx->stream));
+    GPL_TRY(st.trials.alloc(ctx, sizeof(double) * na));
+    if (n > 0) GPL_CUDA(cudaMemcpyAsync(st.trials.p, trials, sizeof(double) * n, cudaMemcpyHostToDevice, ctx->stream));
     st.lik.trials = st.trials.d();
   }
   if (offset) {
-    GPL_TRY(st.offset.alloc(ctx, sizeof(double) * n));
-    GPL_CUDA(cudaMemcpyAsync(st.offset.p, offset, sizeof(double) * n, cudaMemcpyHostToDevice, ctx->stream));
+    GPL_TRY(st.offset.alloc(ctx, sizeof(double) * na));
+    if (n > 0) GPL_CUDA(cudaMemcpyAsync(st.offset.p, offset, sizeof(double) * n, cudaMemcpyHostToDevice, ctx->stream));
     st.lik.offset = st.offset.d();
   }
   if ((lik->kind == GPL_LIK_BINOMIAL || lik->kind == GPL_LIK_BETABINOM) && !trials) {
@@ -292,16 +346,21 @@ int fitc_core(Ctx* ctx, FitcState& st, double* logdetA) {
   FitcTimer tm(ctx);
   GPL_TRY(vec_op(ctx, VOP_ADD, n, st.Dg.d(), st.v[F_V].d(), st.S.d()));
   GPL_TRY(fvec(ctx, 3, n, st.S.d(), nullptr, nullptr, nullptr, st.rs.d()));
-  // A = Kz + Kzx S^-1 Kxz  (lower)
+  // A = Kz + Kzx S^-1 Kxz  (lower).  Sharded: every rank sums its rows, rank 0 contributes Kz, ONE all-reduce
+  // of the m x m matrix (134 MB at m = 4096) assembles it everywhere.
   dim3 g2((unsigned)((m + 255) / 256), (unsigned)m);
-  copy_lower_add_kernel<<<g2, 256, 0, ctx->stream>>>(m, st.Kz.d(), st.ldm, st.A.d(), st.ldm);
-  GPL_LAUNCH_CHECK(ctx);
+  if (st.dist) GPL_CUDA(cudaMemsetAsync(st.A.p, 0, sizeof(double) * st.ldm * m, ctx->stream));
+  if (!st.dist || dist_rank(st.dist) == 0) {
+    copy_lower_add_kernel<<<g2, 256, 0, ctx->stream>>>(m, st.Kz.d(), st.ldm, st.A.d(), st.ldm);
+    GPL_LAUNCH_CHECK(ctx);
+  }
   for (int64_t r0 = 0; r0 < n; r0 += st.chunk) {
     const int64_t c = (n - r0) < st.chunk ? (n - r0) : st.chunk;
     GPL_TRY(chunk_into_W(ctx, st, r0, c, st.rs.d()));
     GPL_TRY(dgemm(ctx, true, false, m, m, c, 1.0, st.W.d(), st.ldw, st.W.d(), st.ldw, 1.0, st.A.d(),
                   st.ldm, true));
   }
+  if (st.dist) GPL_TRY(dist_allreduce_f64(st.dist, ctx, st.A.d(), st.ldm * m, 0));
   tm.mark("A = Kz + Kzx S^-1 Kxz: chunk -> SYRK (n m^2 flops)");
   int32_t info = 0;
   GPL_TRY(dpotrf_with(ctx, st.A_dinv.d(), m, st.A.d(), st.ldm, &info, logdetA));
@@ -546,9 +605,13 @@ int fit_fitc_impl(Ctx* ctx, const gpl_cf_model* cf, const gpl_lik* lik, const gp
                   const double* x, int64_t n, int d, const double* zind, int64_t m, const double* y,
                   const double* trials, const double* offset, double jitter, gpl_fit_out* out,
                   double* h_fmean, double* h_z, double* h_V, double* h_alpha, double* h_fvar,
-                  double* h_cm, double* h_cv, Fit** fit) {
+                  double* h_cm, double* h_cv, Fit** fit, Dist* dist) {
   if (n <= 0 || d <= 0 || m <= 0 || !x || !y || !zind || !out) {
     set_error("gpl_fit_fitc: bad arguments");
+    return GPL_ERR_BAD_ARG;
+  }
+  if (dist && n < dist_world(dist)) {
+    set_error("gpl_dist_fit_fitc: fewer training points than ranks");
     return GPL_ERR_BAD_ARG;
   }
   if (m > 65535) {          // the m-indexed helper kernels map inducing points to gridDim.y
@@ -556,12 +619,25 @@ int fit_fitc_impl(Ctx* ctx, const gpl_cf_model* cf, const gpl_lik* lik, const gp
     return GPL_ERR_BAD_ARG;
   }
   FitcState st;
-  GPL_TRY(fitc_setup(ctx, st, cf, lik, x, n, d, zind, m, y, trials, offset, jitter));
+  GPL_TRY(fitc_setup(ctx, st, cf, lik, x, n, d, zind, m, y, trials, offset, jitter, dist));
+  const int64_t n_total = n;
+  n = st.n;                                    // from here on: this rank's rows
   memset(out, 0, sizeof(*out));
   out->quad_ok = 1;
   double sc[8];
+  DevBuf gather;
+  if (dist) GPL_TRY(gather.alloc(ctx, sizeof(double) * n_total));
+  // n-vectors go back whole on every rank: each rank drops its rows into a zeroed n_total-vector, one sum
   auto dl = [&](double* h, const double* dptr) -> int {
-    if (h) GPL_CUDA(cudaMemcpyAsync(h, dptr, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->stream));
+    if (!h) return GPL_OK;
+    if (!dist) {
+      GPL_CUDA(cudaMemcpyAsync(h, dptr, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->stream));
+      return GPL_OK;
+    }
+    GPL_CUDA(cudaMemsetAsync(gather.p, 0, sizeof(double) * n_total, ctx->stream));
+    GPL_CUDA(cudaMemcpyAsync(gather.d() + st.row0, dptr, sizeof(double) * n, cudaMemcpyDeviceToDevice, ctx->stream));
+    GPL_TRY(dist_allreduce_f64(dist, ctx, gather.d(), n_total, 0));
+    GPL_CUDA(cudaMemcpyAsync(h, gather.p, sizeof(double) * n_total, cudaMemcpyDeviceToHost, ctx->stream));
     return GPL_OK;
   };
 
@@ -575,7 +651,11 @@ int fit_fitc_impl(Ctx* ctx, const gpl_cf_model* cf, const gpl_lik* lik, const gp
     for (it = 1; it <= maxiter; ++it) {
       GPL_TRY(lik_pseudodata_la(ctx, st.lik, n, st.v[F_F].d(), st.y.d(), st.v[F_Z].d(), st.v[F_V].d()));
       GPL_TRY(reduce(ctx, RED_MIN, n, st.v[F_V].d(), nullptr, 0));
-      GPL_TRY(fetch_scalars(ctx, 1, sc));
+      GPL_TRY(fetch_site_scalars(ctx, st, 0, 0, 1, sc));
+      if (!(sc[0] > 0.0) && dist) {
+        set_error("pseudo-variance <= 0: the non-log-concave branch (R/laplace.R:153-232) is single-GPU only");
+        return GPL_ERR_NOT_LOGCONCAVE;
+      }
       if (!(sc[0] > 0.0)) {                                   // R/laplace.R:153-232
         FitcBad fb;
         double log_post = 0.0;
@@ -600,7 +680,7 @@ int fit_fitc_impl(Ctx* ctx, const gpl_cf_model* cf, const gpl_lik* lik, const gp
       GPL_TRY(reduce(ctx, RED_SUMLOG, n, st.v[F_V].d(), nullptr, 1));
       GPL_TRY(reduce(ctx, RED_DOT, n, st.v[F_FNEW].d(), st.v[F_ALPHA].d(), 2));
       GPL_TRY(lik_loglik_sum(ctx, st.lik, n, st.v[F_FNEW].d(), st.y.d(), 3));
-      GPL_TRY(fetch_scalars(ctx, 4, sc));
+      GPL_TRY(fetch_site_scalars(ctx, st, 4, 0, 0, sc));
       const double C_logdet = sc[0] - st.logdet_z + logdetA;               // R/linear_algebra.R:32
       log_evidence = sc[3] - 0.5 * sc[2] + 0.5 * (sc[1] - C_logdet);       // R/laplace.R:143-150
       const double log_post = sc[3] - 0.5 * sc[2];
@@ -657,6 +737,7 @@ int fit_fitc_impl(Ctx* ctx, const gpl_cf_model* cf, const gpl_lik* lik, const gp
     ea.quad_order = approx->quad_order;
     ea.quad_x = qx.d(); ea.quad_w = qw.d();
     GPL_TRY(lik_ep_sites(ctx, st.lik, n, ea, static_cast<int*>(flags.p)));
+    GPL_TRY(combine_flags(ctx, st, static_cast<int*>(flags.p)));
     int hflags = 0;
     GPL_CUDA(cudaMemcpyAsync(&hflags, flags.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     GPL_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -667,6 +748,10 @@ int fit_fitc_impl(Ctx* ctx, const gpl_cf_model* cf, const gpl_lik* lik, const gp
       out->quad_ok = quad_ok;
       set_error("EP (FITC): NaN pseudo-data");
       return GPL_ERR_NONFINITE;
+    }
+    if ((hflags & 4) && dist) {
+      set_error("pseudo-variance <= 0: the non-log-concave branch (R/ep.R:186-272) is single-GPU only");
+      return GPL_ERR_NOT_LOGCONCAVE;
     }
     if (hflags & 4) {                                                        // R/ep.R:186-272
       FitcBad fb;
@@ -697,7 +782,7 @@ int fit_fitc_impl(Ctx* ctx, const gpl_cf_model* cf, const gpl_lik* lik, const gp
       GPL_TRY(ep_evidence_terms(ctx, n, st.v[F_LOGZ].d(), st.v[F_CV].d(), st.v[F_CM].d(), st.v[F_Z].d(),
                                 st.v[F_V].d(), 2));
       GPL_TRY(reduce(ctx, RED_MAXABSDIFF, n, fmean_old.d(), st.v[F_FNEW].d(), 3));
-      GPL_TRY(fetch_scalars(ctx, 4, sc));
+      GPL_TRY(fetch_site_scalars(ctx, st, 3, 1, 0, sc));
       const double C_logdet = sc[0] - st.logdet_z + logdetA;
       log_evidence = -0.5 * C_logdet - 0.5 * sc[1] + sc[2];                  // R/ep.R:182-184
       diff_new = sc[3];
@@ -885,9 +970,29 @@ int gpl_fit_fitc(gpl_ctx* h, const gpl_cf_model* cf, const gpl_lik* lik, const g
   if (fit) *fit = nullptr;
   int rc = fit_fitc_impl(reinterpret_cast<Ctx*>(h), cf, lik, approx, x, n, d, zind, m, y, trials,
                          offset, jitter, out, fmean, z, V, alpha, fvar, cavity_mean, cavity_var,
-                         fit ? &f : nullptr);
+                         fit ? &f : nullptr, nullptr);
   if (fit) *fit = reinterpret_cast<gpl_fit*>(f);
   if (rc != GPL_OK) cudaStreamSynchronize(reinterpret_cast<Ctx*>(h)->stream);
+  return rc;
+}
+
+int gpl_dist_fit_fitc(gpl_dist* dh, const gpl_cf_model* cf, const gpl_lik* lik, const gpl_approx* approx,
+                      const double* x, int64_t n, int32_t d, const double* zind, int64_t m,
+                      const double* y, const double* trials, const double* offset, double jitter,
+                      gpl_fit_out* out, double* fmean, double* z, double* V, double* alpha, double* fvar,
+                      double* cavity_mean, double* cavity_var, gpl_fit** fit) {
+  Dist* dist = reinterpret_cast<Dist*>(dh);
+  if (!dist) {
+    set_error("gpl_dist_fit_fitc: no communicator");
+    return GPL_ERR_BAD_ARG;
+  }
+  Ctx* ctx = dist_ctx(dist);
+  Fit* f = nullptr;
+  if (fit) *fit = nullptr;
+  int rc = fit_fitc_impl(ctx, cf, lik, approx, x, n, d, zind, m, y, trials, offset, jitter, out, fmean, z, V,
+                         alpha, fvar, cavity_mean, cavity_var, fit ? &f : nullptr, dist_world(dist) > 1 ? dist : nullptr);
+  if (fit) *fit = reinterpret_cast<gpl_fit*>(f);
+  if (rc != GPL_OK) cudaStreamSynchronize(ctx->stream);
   return rc;
 }
 

@@ -73,21 +73,31 @@ def gp_init(cfs=None, lik=None, method=None, approx=None):
 
 
 # ------------------------------------------------------------------------------- parameters
+def _param_names(items):
+    """R's named vector may repeat a name (two cf_sexp summands); a dict cannot: later repeats get '#2', '#3' ..."""
+    seen, out = {}, []
+    for name, _, _ in items:
+        seen[name] = seen.get(name, 0) + 1
+        out.append(name if seen[name] == 1 else f"{name}#{seen[name]}")
+    return out
+
+
 def get_param(gp):
     """Named vector of log-parameters, R/gp.R:150-155."""
     items = M.get_param_objs(gp.cfs, gp.lik)
-    return {name: math.log(getattr(owner, attr)) for name, owner, attr in items}
+    return {nm: math.log(getattr(owner, attr)) for nm, (_, owner, attr) in zip(_param_names(items), items)}
 
 
 def get_param_vector(gp):
-    return np.array(list(get_param(gp).values()), dtype=np.float64)
+    items = M.get_param_objs(gp.cfs, gp.lik)
+    return np.array([math.log(getattr(owner, attr)) for _, owner, attr in items], dtype=np.float64)
 
 
 def set_param(gp, param):
     """R/gp.R:158-165: unpack log-parameters in get_param order; marks the model stale."""
     items = M.get_param_objs(gp.cfs, gp.lik)
     if isinstance(param, dict):
-        if list(param.keys()) != [n for n, _, _ in items]:
+        if list(param.keys()) != _param_names(items):
             raise ValueError("parameter names do not match get_param(gp)")
         values = list(param.values())
     else:

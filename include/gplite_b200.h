@@ -444,6 +444,19 @@ int gpl_dist_energy_grad(gpl_dist* dist, const gpl_cf_model* cf, const gpl_lik* 
                          const int32_t* param_factor, const int32_t* param_slot, double* energy,
                          double* grad, double* alpha, gpl_dist_timings* timings);
 
+/* fit_laplace / fit_ep .method_fitc across the ranks (SURVEY 8e "FITC: one reduction"; R/gp_fit.R:101-123,
+ * 163-188, R/laplace.R:122-152,299-325, R/ep.R:148-185,333-374, R/linear_algebra.R:3-126): rank r works on
+ * rows [n r / P, n (r + 1) / P) of x (every rank passes the SAME full host arrays), Kz and the two m x m
+ * factorisations are replicated, and per Newton step / EP sweep the data plane is ONE all-reduce of the
+ * m x m matrix Kzx S^-1 Kxz plus a few m-vectors and scalars.  Outputs as gpl_fit_fitc, whole n-vectors,
+ * identical on every rank; *fit (may be NULL) is a rank-local handle good for gpl_pred_fitc.
+ * GPL_ERR_NOT_LOGCONCAVE when a pseudo-variance is <= 0 (that branch is single-GPU). */
+int gpl_dist_fit_fitc(gpl_dist* dist, const gpl_cf_model* cf, const gpl_lik* lik, const gpl_approx* approx,
+                      const double* x, int64_t n, int32_t d, const double* zind, int64_t m,
+                      const double* y, const double* trials, const double* offset, double jitter,
+                      gpl_fit_out* out, double* fmean, double* z, double* V, double* alpha, double* fvar,
+                      double* cavity_mean, double* cavity_var, gpl_fit** fit);
+
 #ifdef __cplusplus
 }
 #endif

@@ -24,29 +24,6 @@ from oracle import gplite_oracle as o        # noqa: E402
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-class OneRank:      # stand-in for torch.distributed used by the (still host-driven) FITC row sharding
-    class ReduceOp:
-        MAX = "max"
-        SUM = "sum"
-        MIN = "min"
-
-    @staticmethod
-    def get_rank():
-        return 0
-
-    @staticmethod
-    def get_world_size():
-        return 1
-
-    @staticmethod
-    def broadcast(t, src=0, async_op=False):
-        return None
-
-    @staticmethod
-    def all_reduce(t, op=None):
-        return None
-
-
 @pytest.fixture(scope="module")
 def comm(ctx):
     c = DistComm.single(ctx)
@@ -144,8 +121,11 @@ def test_ep_driver_single_rank_matches_oracle(comm, lik):
         assert np.max(np.abs(a - gpo.fit[k])) < 1e-6 * np.max(np.abs(gpo.fit[k])), k
 
 
-def test_fitc_driver_single_rank_matches_oracle():
+@pytest.mark.parametrize("streamed", [False, True])
+def test_fitc_driver_single_rank_matches_oracle(comm, streamed, monkeypatch):
     from gplite_b200.dist import dist_fit_fitc_gaussian
+    monkeypatch.setenv("GPL_FITC_STREAM_GB", "0" if streamed else "1000")
+    monkeypatch.setenv("GPL_FITC_CHUNK", "512")
     rng = np.random.default_rng(8)
     n, m = 1203, 150
     X = rng.uniform(-3, 3, size=(n, 2))
@@ -154,17 +134,20 @@ def test_fitc_driver_single_rank_matches_oracle():
     gp = g.gp_init(cfs=[g.cf_sexp(lscale=1.1), g.cf_const(magn=0.2)], lik=g.lik_gaussian(sigma=0.4),
                    method=g.method_fitc(inducing=Zi))
     gpo = copy.deepcopy(gp)
-    res = dist_fit_fitc_gaussian(gp, X, y, dist=OneRank, chunk_rows=512)
+    res = dist_fit_fitc_gaussian(gp, X, y, comm=comm)
     o.gp_fit(gpo, X, y)
     assert abs(res["log_evidence"] - gpo.fit["log_evidence"]) < 1e-8 * abs(gpo.fit["log_evidence"])
-    a = res["alpha_local"].cpu().numpy()
-    assert np.max(np.abs(a - gpo.fit["alpha"])) < 1e-6 * np.max(np.abs(gpo.fit["alpha"]))
-    f = res["fmean_local"].cpu().numpy()
-    assert np.max(np.abs(f - gpo.fit["fmean"])) < 1e-8 * np.max(np.abs(gpo.fit["fmean"]))
+    assert np.max(np.abs(res["alpha"] - gpo.fit["alpha"])) < 1e-6 * np.max(np.abs(gpo.fit["alpha"]))
+    assert np.max(np.abs(res["fmean"] - gpo.fit["fmean"])) < 1e-8 * np.max(np.abs(gpo.fit["fmean"]))
+    Xt = rng.uniform(-3, 3, size=(40, 2))
+    p, po = g.gp_pred(gp, Xt, var=True), o.gp_pred(gpo, Xt, var=True)      # the rank-local handle predicts
+    assert np.max(np.abs(p["mean"] - po["mean"])) < 1e-8 * np.max(np.abs(po["mean"]))
+    assert np.max(np.abs(p["var"] - po["var"])) < 1e-7 * np.max(np.abs(po["var"]))
 
 
-def test_fitc_laplace_driver_single_rank_matches_oracle():
-    """Row-sharded FITC with the Laplace Newton loop on the local rows (gpl_lik_*_dev)."""
+@pytest.mark.parametrize("approx", ["laplace", "ep"])
+def test_fitc_laplace_ep_driver_single_rank_matches_oracle(comm, approx):
+    """Row-sharded FITC entry with the Newton / EP loops (world 1 here; 2 ranks in the NCCL test below)."""
     from gplite_b200.dist import dist_fit_fitc
     rng = np.random.default_rng(9)
     n, m = 1100, 120
@@ -172,14 +155,16 @@ def test_fitc_laplace_driver_single_rank_matches_oracle():
     f = np.sin(X[:, 0]) + 0.3 * X[:, 1]
     y = (rng.uniform(size=n) < 1 / (1 + np.exp(-2 * f))).astype(float)
     Zi = X[rng.permutation(n)[:m]].copy()
-    gp = g.gp_init(cfs=g.cf_matern32(lscale=1.2), lik=g.lik_bernoulli(), method=g.method_fitc(inducing=Zi))
+    ap = g.approx_laplace() if approx == "laplace" else g.approx_ep()
+    gp = g.gp_init(cfs=g.cf_matern32(lscale=1.2), lik=g.lik_bernoulli(), method=g.method_fitc(inducing=Zi), approx=ap)
     gpo = copy.deepcopy(gp)
-    res = dist_fit_fitc(gp, X, y, dist=OneRank, chunk_rows=512)
+    res = dist_fit_fitc(gp, X, y, comm=comm)
     o.gp_fit(gpo, X, y)
     assert res["iters"] == gpo.fit["iters"] and res["iters"] > 2
     assert abs(res["log_evidence"] - gpo.fit["log_evidence"]) < 1e-8 * abs(gpo.fit["log_evidence"])
-    fm = res["fmean_local"].cpu().numpy()
-    assert np.max(np.abs(fm - gpo.fit["fmean"])) < 1e-7 * np.max(np.abs(gpo.fit["fmean"]))
+    assert np.max(np.abs(res["fmean"] - gpo.fit["fmean"])) < 1e-7 * np.max(np.abs(gpo.fit["fmean"]))
+    if approx == "ep":
+        assert np.max(np.abs(res["fvar"] - gpo.fit["fvar"])) < 1e-7 * np.max(np.abs(gpo.fit["fvar"]))
 
 
 def test_config5_kernel_at_8192(comm):
@@ -231,7 +216,14 @@ def _nccl_worker(rank, world, port, q):
         yb = (y > 0.5).astype(float)
         gpe = g.gp_init(cfs=g.cf_matern32(lscale=1.3), lik=g.lik_bernoulli(), approx=g.approx_ep())
         rese = dist_fit_ep(gpe, X[:1500], yb[:1500], nb=128, comm=comm)
-        q.put((rank, e, gr, alpha, rese["log_evidence"], rese["iters"], rese["fvar"]))
+        from gplite_b200.dist import dist_fit_fitc
+        Zi = X[:: n // 64][:64].copy()
+        resf = {}
+        for nm, ap in (("laplace", g.approx_laplace()), ("ep", g.approx_ep())):
+            gpf = g.gp_init(cfs=g.cf_sexp(lscale=1.1), lik=g.lik_bernoulli(), method=g.method_fitc(inducing=Zi), approx=ap)
+            r = dist_fit_fitc(gpf, X[:2001], yb[:2001], comm=comm)           # odd n: uneven row shards
+            resf[nm] = (r["log_evidence"], r["iters"], r["fmean"], g.gp_pred(gpf, X[:7], var=True)["var"])
+        q.put((rank, e, gr, alpha, rese["log_evidence"], rese["iters"], rese["fvar"], resf))
         comm.close()
     finally:
         dist.destroy_process_group()
@@ -262,7 +254,20 @@ def test_nccl_two_ranks_equal_single_gpu(ctx):
     e1, g1 = g.gp_energy_grad(gp, X, y, ctx=ctx)
     gpe = g.gp_init(cfs=g.cf_matern32(lscale=1.3), lik=g.lik_bernoulli(), approx=g.approx_ep())
     g.gp_fit(gpe, X[:1500], (y > 0.5).astype(float)[:1500], ctx=ctx)
-    for rank, e, gr, alpha, lee, ite, fvar in outs:
+    yb = (y > 0.5).astype(float)
+    Zi = X[:: n // 64][:64].copy()
+    single = {}
+    for nm, ap in (("laplace", g.approx_laplace()), ("ep", g.approx_ep())):
+        gpf = g.gp_init(cfs=g.cf_sexp(lscale=1.1), lik=g.lik_bernoulli(), method=g.method_fitc(inducing=Zi), approx=ap)
+        g.gp_fit(gpf, X[:2001], yb[:2001], ctx=ctx)
+        single[nm] = (gpf.fit["log_evidence"], gpf.fit["iters"], gpf.fit["fmean"], g.gp_pred(gpf, X[:7], var=True)["var"])
+    for rank, e, gr, alpha, lee, ite, fvar, resf in outs:
+        for nm in ("laplace", "ep"):
+            le2, it2, fm2, pv2 = resf[nm]
+            le1, it1, fm1, pv1 = single[nm]
+            assert it2 == it1 and abs(le2 - le1) < 1e-10 * abs(le1)
+            assert np.max(np.abs(fm2 - fm1)) < 1e-9 * np.max(np.abs(fm1))
+            assert np.max(np.abs(pv2 - pv1)) < 1e-8 * np.max(np.abs(pv1))
         assert abs(e - e1) < 1e-10 * abs(e1)
         assert np.max(np.abs(gr - g1)) < 1e-9 * np.max(np.abs(g1))
         assert ite == gpe.fit["iters"]

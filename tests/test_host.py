@@ -105,3 +105,45 @@ def test_unfitted_and_unsupported_paths_need_no_gpu():
     gp = g.gp_init()
     with pytest.raises(RuntimeError):
         g.gp_energy(gp)
+
+
+def test_models_own_copies_of_their_components():
+    """R value semantics: a cf / lik object reused in two models, or twice in one model, is never
+    aliased by set_param; products own copies of their members."""
+    import gplite_b200 as g
+    from gplite_b200 import model as M
+    cf = g.cf_sexp(lscale=0.5)
+    lik = g.lik_gaussian(sigma=0.3)
+    gp1 = g.gp_init(cfs=cf, lik=lik)
+    gp2 = g.gp_init(cfs=cf, lik=lik)
+    g.set_param(gp1, g.get_param_vector(gp1) + 1.0)
+    assert gp2.cfs[0].lscale == 0.5 and gp2.lik.sigma == 0.3 and cf.lscale == 0.5
+    gp3 = g.gp_init(cfs=[cf, cf])                      # the same object twice: two independent summands
+    assert len(g.get_param(gp3)) == 5
+    p = g.get_param_vector(gp3)
+    p[0] += 1.0
+    g.set_param(gp3, p)
+    assert gp3.cfs[0].lscale != gp3.cfs[1].lscale
+    factors, where = M.flatten_cfs(gp3.cfs)
+    assert len(set(where.values())) == 4               # every free cf parameter maps to its own (factor, slot)
+    prod = cf * g.cf_lin(prior_magn=g.prior_fixed())
+    prod.cfs[0].lscale = 9.0
+    assert cf.lscale == 0.5
+
+
+def test_cfind_validation_and_lost_handle():
+    import copy
+    import pytest
+    import gplite_b200 as g
+    from gplite_b200.gp import _mask_of
+    assert _mask_of(None, 3) == 0 and _mask_of([0, 2], 3) == 5
+    with pytest.raises(ValueError):
+        _mask_of([], 3)                                # "no terms" must not silently mean "all terms"
+    with pytest.raises(ValueError):
+        _mask_of([3], 3)
+    gp = g.gp_init()
+    gp.fitted, gp.fit = True, dict(type="analytic", alpha=np.zeros(2), log_evidence=0.0)
+    gp.x = np.zeros((2, 1))
+    gp2 = copy.deepcopy(gp)                            # device handles do not travel
+    with pytest.raises(RuntimeError, match="gp_fit again"):
+        g.gp_pred(gp2, np.zeros((1, 1)))
