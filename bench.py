@@ -92,6 +92,19 @@ class ClockSampler(threading.Thread):
 
 
 # ------------------------------------------------------------------------------------- CPU arm
+def use_all_host_threads():
+    """torchrun exports OMP_NUM_THREADS=1 to its workers; the CPU arm is meant to use every host core the
+    reference's LAPACK could (round-1 SCALE ran it on one thread at N > 1).  Returns the thread count in force."""
+    n = os.cpu_count() or 1
+    try:
+        import threadpoolctl
+        threadpoolctl.threadpool_limits(limits=n)
+        got = [p.get("num_threads") for p in threadpoolctl.threadpool_info() if p.get("user_api") == "blas"]
+        return max(got) if got else n
+    except Exception:
+        return int(os.environ.get("OMP_NUM_THREADS", n))
+
+
 def cpu_kbuild_slab(n, d, rows):
     """seconds for `rows` rows of the n x n K build by the reference's loops (src/cf.cpp:86-119), 1 thread"""
     from oracle import gplite_oracle as o
@@ -143,18 +156,19 @@ def cpu_eval_seconds(n_full, d, rows, n_la, p):
 
 def cpu_baseline(d):
     from oracle import gplite_oracle as o
+    threads = use_all_host_threads()
     rows, n1, n2 = 1024, 8192, 16384
     tk = cpu_kbuild_slab(N_FULL, d, rows)
     t1, _, _ = cpu_linalg_eval(n1, d)
     t2, _, _ = cpu_linalg_eval(n2, d)
     p = float(np.log(t2 / t1) / np.log(n2 / n1))
     t_full = tk * (N_FULL / rows) + t2 * (N_FULL / n2) ** p
-    return {"value": 1.0 / t_full, "unit": "evals/s", "cores": os.cpu_count(),
+    return {"value": 1.0 / t_full, "unit": "evals/s", "cores": threads,
             "kind": "reference" if o.ref_available() else "port", "extrapolated": True,
             "exponent_measured": p, "kbuild_slab_s": tk, "linalg_s": {str(n1): t1, str(n2): t2},
             "sample": (f"K build: {rows} of the {N_FULL} rows of the n={N_FULL} matrix by the reference's src/cf.cpp on "
                        f"1 thread ({tk:.2f} s, x{N_FULL // rows}); dpotrf + solves + dpotri + trace by LAPACK on "
-                       f"{os.cpu_count()} threads at n={n1} ({t1:.2f} s) and n={n2} ({t2:.2f} s): measured exponent "
+                       f"{threads} threads at n={n1} ({t1:.2f} s) and n={n2} ({t2:.2f} s): measured exponent "
                        f"{p:.2f}, extrapolated from n={n2} to n={N_FULL} with it")}
 
 
@@ -162,6 +176,7 @@ def run_reference(args, rank, world):
     if rank != 0:
         return
     from oracle import gplite_oracle as o
+    threads = use_all_host_threads()
     rows, n_la, p = 384, 8192, 3.0
     vals = []
     parts = []
@@ -174,7 +189,7 @@ def run_reference(args, rank, world):
     val = 1.0 / t
     tk, tl = np.mean(parts, axis=0)
     sample = (f"each step: {rows} of the {args.n} rows of the K build by the reference's src/cf.cpp on 1 thread "
-              f"({tk:.2f} s, x{args.n / rows:.0f}) + dpotrf / solves / dpotri / trace by LAPACK on {os.cpu_count()} threads "
+              f"({tk:.2f} s, x{args.n / rows:.0f}) + dpotrf / solves / dpotri / trace by LAPACK on {threads} threads "
               f"at n={n_la} ({tl:.2f} s, x(n/{n_la})^{p:.0f}; cpu_baseline of the GPU arm measures the exponent)")
     line = {"impl": "reference", "metric": "gp_energy+grad evals/sec at n=32k fp64", "value": val,
             "unit": "evals/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
@@ -183,7 +198,7 @@ def run_reference(args, rank, world):
             "config": {"workload": f"cfg2: n={args.n}, d={D_FULL}, cf_matern52 + lik_gaussian, method_full, "
                                    "energy + analytic gradient (reference path on host cores, sampled and "
                                    "extrapolated: see cpu_baseline.sample)"},
-            "cpu_baseline": {"value": val, "unit": "evals/s", "cores": os.cpu_count(),
+            "cpu_baseline": {"value": val, "unit": "evals/s", "cores": threads,
                              "kind": "reference" if o.ref_available() else "port", "extrapolated": True,
                              "sample": sample},
             "e2e": {"value": val, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}

@@ -92,7 +92,9 @@ __device__ __forceinline__ bool is_stationary(int kind) {
   return kind == GPL_CF_SEXP || kind == GPL_CF_MATERN32 || kind == GPL_CF_MATERN52;
 }
 
-// MODE >= 0: the model is ONE factor of that kind.  MODE == -1: any sum of products.
+// MODE >= 0: the model is ONE factor of that kind.  MODE == -1: any sum of products.  MODE == -2: ONE product
+// term (BASELINE config 3's cf_sexp * cf_lin): the running product is the result, so the per-entry `out`
+// accumulators of the general case are not needed (a third fewer live registers per entry).
 // NSUB: 8-column sub-tiles per warp and pass (4: warp tile 32 x 32, two passes; 2: 32 x 16, four passes).
 template <int MODE, int NSUB, int MINB>
 __global__ void __launch_bounds__(GTHREADS, MINB)
@@ -186,7 +188,7 @@ gram_kernel(const __grid_constant__ GPlan plan, const GArgs a) {
   for (int pass = 0; pass < TILE / PASS_COLS; ++pass) {
     const int cbase = pass * PASS_COLS + wn * (8 * NSUB);
     double out[4][NSUB][2], prod[4][NSUB][2];
-    if (MODE < 0) {
+    if (MODE == -1) {
 #pragma unroll
       for (int im = 0; im < 4; ++im)
 #pragma unroll
@@ -251,10 +253,12 @@ gram_kernel(const __grid_constant__ GPlan plan, const GArgs a) {
               double s = acc[im][in][c];
               if (kstat && diag_tile && row == col) s = 0.0;        // k(x, x) exactly
               const double v = gvalue<K>(f, s, rb, rc, tab);
-              if (MODE < 0) {
+              if (MODE == -1) {
                 const double pr = f.first ? v : prod[im][in][c] * v;
                 prod[im][in][c] = pr;
                 if (f.last) out[im][in][c] += pr;
+              } else if (MODE == -2) {
+                out[im][in][c] = (fi == 0) ? v : out[im][in][c] * v;
               } else {
                 out[im][in][c] = v;
               }
@@ -359,8 +363,10 @@ int launch_gram(Ctx* ctx, const GPlan& gp, const GArgs& a, int grid) {
     if (variant == 3 || 4 * smem > 220 * 1024) return launch_gram1<MODE, 2, 3>(ctx, gp, a, grid);
     return launch_gram1<MODE, 2, 4>(ctx, gp, a, grid);
   } else {
-    // sums of products keep acc + prod + out per entry: warp tile 32 x 8 to stay at 3-4 CTAs per SM
+    // sums of products keep acc + prod + out per entry (one product term: acc + out): warp tile 32 x 8 to stay
+    // at 3-4 CTAs per SM; GPL_GRAM_VARIANT 0 / 1: warp tile 32 x 16 at 2 / 3 CTAs per SM
     if (variant == 0) return launch_gram1<MODE, 2, 2>(ctx, gp, a, grid);
+    if (variant == 1 && 3 * smem <= 220 * 1024) return launch_gram1<MODE, 2, 3>(ctx, gp, a, grid);
     if (variant == 3 || 4 * smem > 220 * 1024) return launch_gram1<MODE, 1, 3>(ctx, gp, a, grid);
     return launch_gram1<MODE, 1, 4>(ctx, gp, a, grid);
   }
@@ -428,6 +434,14 @@ int cf_pairwise_gram(Ctx* ctx, const CfPlan& plan, const double* z1, int64_t n1,
       default: break;
     }
   }
+  // one product term (every factor in the same term): bit-identical values from fewer registers (measured at
+  // n = 32768: cf_sexp * cf_lin 2.67 -> 2.39 ms symmetric, 4.25 -> 3.77 ms rectangular).  GPL_GRAM_ONE_TERM=0
+  // keeps it on the general kernel.
+  static const int one_term_ok = getenv("GPL_GRAM_ONE_TERM") ? atoi(getenv("GPL_GRAM_ONE_TERM")) : 1;
+  bool one_term = one_term_ok != 0;
+  for (int i = 0; i < plan.nfactors; ++i)
+    if (plan.f[i].term != plan.f[0].term) one_term = false;
+  if (one_term) return launch_gram<-2, 2>(ctx, gp, a, grid);
   return launch_gram<-1, 2>(ctx, gp, a, grid);
 }
 

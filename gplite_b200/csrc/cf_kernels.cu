@@ -617,7 +617,7 @@ int cf_pairwise(Ctx* ctx, const CfPlan& plan, const double* z1, int64_t n1, int6
                 const double* z2, int64_t n2, int64_t ldz2, bool same, double jitter, double* K,
                 int64_t ldk) {
   if (n1 <= 0 || n2 <= 0) return GPL_OK;
-  {
+  if (!ctx->cf_direct) {
     int done = 0;
     GPL_TRY(cf_pairwise_gram(ctx, plan, z1, n1, ldz1, z2, n2, ldz2, same, jitter, K, ldk, &done));
     if (done) return GPL_OK;
@@ -632,7 +632,7 @@ int cf_pairwise(Ctx* ctx, const CfPlan& plan, const double* z1, int64_t n1, int6
   a.jitter = same ? jitter : 0.0;
   const int grid = same ? a.tiles_i * (a.tiles_i + 1) / 2 : a.tiles_i * a.tiles_j;
   static const int direct_only = getenv("GPL_KBUILD_DIRECT") ? atoi(getenv("GPL_KBUILD_DIRECT")) : 0;
-  if (plan.nfactors == 1 && plan.nfeat >= 1 && plan.nfeat <= 32 && !direct_only) {
+  if (plan.nfactors == 1 && plan.nfeat >= 1 && plan.nfeat <= 32 && !direct_only && !ctx->cf_direct) {
     switch (plan.f[0].kind) {
       case GPL_CF_SEXP: return launch_pair_gram<GPL_CF_SEXP>(ctx, plan, a, grid);
       case GPL_CF_MATERN32: return launch_pair_gram<GPL_CF_MATERN32>(ctx, plan, a, grid);

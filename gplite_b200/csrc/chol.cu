@@ -12,6 +12,7 @@
 // R/laplace.R:28-29, R/ep.R:39-42, R/gp_fit.R:108-110, R/linear_algebra.R:28-32,
 // R/gp_pred.R:218.
 #include "common.cuh"
+#include <atomic>
 
 #include <math.h>
 #include <stdlib.h>
@@ -282,11 +283,12 @@ struct Fac {
 };
 
 int potf2(const Fac& f, double* A, int64_t lda, int64_t n, int64_t blk0) {
-  static bool configured[64] = {false};
-  if (!configured[f.ctx->device & 63]) {
+  static std::atomic<bool> configured[64];       // see gemm_f64.cu launch(): idempotent, release / acquire
+  std::atomic<bool>& cfgd = configured[f.ctx->device & 63];
+  if (!cfgd.load(std::memory_order_acquire)) {
     GPL_CUDA(cudaFuncSetAttribute(potf2_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   POTF2_SMEM));
-    configured[f.ctx->device & 63] = true;
+    cfgd.store(true, std::memory_order_release);
   }
   potf2_inv_kernel<<<1, POTF2_THREADS, POTF2_SMEM, f.ctx->stream>>>(
       A, lda, (int)n, f.dinv + blk0 * NB * NB, f.info ? f.info : f.ctx->d_info,

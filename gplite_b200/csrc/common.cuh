@@ -42,6 +42,10 @@ struct Ctx {
   // pair per launch on the launching stream, harvested by gpl_ctx_profile_read
   bool profile = false;
   int gemm_force = 0;   // tuning knob: 0 = automatic tile choice, 1/2/3 = force the 128/64/32 tile
+  // cf_pairwise: direct differences on the fp64 pipe (the reference's own arithmetic, src/cf.cpp:27-36) instead of
+  // the Gram contraction on the tensor pipe.  Set by the FITC code around its K builds: Kz + jitter I is nearly
+  // singular by construction, and the rounding of |a|^2 + |b|^2 - 2 a.b (1e-14 relative in K) is amplified there.
+  bool cf_direct = false;
   std::vector<cudaEvent_t> ev_pool;
   size_t ev_used = 0;
   double prof_flops = 0.0;

@@ -20,6 +20,7 @@
 #include <string.h>
 
 #include <chrono>
+#include <mutex>
 #include <vector>
 
 namespace gpl {
@@ -39,13 +40,21 @@ struct NcclApi {
   ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
   const char* (*GetErrorString)(ncclResult_t) = nullptr;
   ncclResult_t (*GetVersion)(int*) = nullptr;
+  char load_error[512] = {0};
 };
 
+NcclApi* nccl_api_load(NcclApi& api);
+
+// loaded once per process (std::call_once: several host threads may create communicators)
 NcclApi* nccl_api() {
   static NcclApi api;
-  static bool tried = false;
-  if (tried) return api.handle ? &api : nullptr;
-  tried = true;
+  static std::once_flag once;
+  std::call_once(once, [] { nccl_api_load(api); });
+  if (!api.handle) set_error("%s", api.load_error);       // the message is thread-local: repeat it per caller
+  return api.handle ? &api : nullptr;
+}
+
+NcclApi* nccl_api_load(NcclApi& api) {
   const char* names[] = {getenv("GPL_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
   for (const char* nm : names) {
     if (!nm) continue;
@@ -53,7 +62,7 @@ NcclApi* nccl_api() {
     if (api.handle) break;
   }
   if (!api.handle) {
-    set_error("cannot load NCCL (libnccl.so.2): %s", dlerror());
+    snprintf(api.load_error, sizeof(api.load_error), "cannot load NCCL (libnccl.so.2): %s", dlerror());
     return nullptr;
   }
   bool ok = true;
@@ -72,7 +81,7 @@ NcclApi* nccl_api() {
   api.GetVersion = (decltype(api.GetVersion))sym("ncclGetVersion");
   api.CommInitRankConfig = (decltype(api.CommInitRankConfig))dlsym(api.handle, "ncclCommInitRankConfig");
   if (!ok) {
-    set_error("libnccl.so.2 lacks an expected symbol");
+    snprintf(api.load_error, sizeof(api.load_error), "libnccl.so.2 lacks an expected symbol");
     dlclose(api.handle);
     api.handle = nullptr;
     return nullptr;

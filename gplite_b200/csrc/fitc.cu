@@ -28,6 +28,18 @@ namespace gpl {
 
 namespace {
 
+// K builds of the FITC path (Kz, Kxz chunks, Ktz): see Ctx::cf_direct.  GPL_FITC_DIRECT_K=0 / 1 overrides.
+int fitc_cf_pairwise(Ctx* ctx, const CfPlan& plan, const double* z1, int64_t n1, int64_t ldz1, const double* z2,
+                     int64_t n2, int64_t ldz2, bool same, double jitter, double* K, int64_t ldk) {
+  static const int direct = getenv("GPL_FITC_DIRECT_K") ? atoi(getenv("GPL_FITC_DIRECT_K")) : 0;
+  const bool prev = ctx->cf_direct;
+  ctx->cf_direct = direct != 0;
+  const int rc = cf_pairwise(ctx, plan, z1, n1, ldz1, z2, n2, ldz2, same, jitter, K, ldk);
+  ctx->cf_direct = prev;
+  return rc;
+}
+
+
 __global__ void scaled_copy_rows_kernel(int64_t rows, int64_t m, const double* __restrict__ src,
                                         int64_t lds, const double* __restrict__ s,
                                         double* __restrict__ dst, int64_t ldd) {
@@ -190,7 +202,7 @@ int combine_flags(Ctx* ctx, FitcState& st, int* d_flags) {
 int chunk_into_W(Ctx* ctx, FitcState& st, int64_t r0, int64_t c, const double* s) {
   if (!st.streamed)
     return scaled_copy_rows(ctx, c, st.m, st.Kxz.d() + r0, st.ldx, s ? s + r0 : nullptr, st.W.d(), st.ldw);
-  GPL_TRY(cf_pairwise(ctx, st.hp.plan, st.Zx.d() + r0, c, st.n, st.Zz.d(), st.m, st.m, false, 0.0, st.W.d(),
+  GPL_TRY(fitc_cf_pairwise(ctx, st.hp.plan, st.Zx.d() + r0, c, st.n, st.Zz.d(), st.m, st.m, false, 0.0, st.W.d(),
                       st.ldw));
   if (s) GPL_TRY(scale_rows(ctx, c, st.m, st.W.d(), st.ldw, s + r0));
   return GPL_OK;
@@ -319,14 +331,14 @@ int fitc_setup(Ctx* ctx, FitcState& st, const gpl_cf_model* cf, const gpl_lik* l
 
   tm.mark("upload + features + allocations");
   // Kz (+ jitter), its factor, Kxz, diag K(x, x) + jitter          R/gp_fit.R:105-110
-  GPL_TRY(cf_pairwise(ctx, st.hp.plan, st.Zz.d(), m, m, nullptr, m, m, true, jitter, st.Kz.d(), st.ldm));
+  GPL_TRY(fitc_cf_pairwise(ctx, st.hp.plan, st.Zz.d(), m, m, nullptr, m, m, true, jitter, st.Kz.d(), st.ldm));
   dim3 g2((unsigned)((m + 255) / 256), (unsigned)m);
   copy_lower_add_kernel<<<g2, 256, 0, ctx->stream>>>(m, st.Kz.d(), st.ldm, st.Lz.d(), st.ldm);
   GPL_LAUNCH_CHECK(ctx);
   int32_t info = 0;
   GPL_TRY(dpotrf_with(ctx, st.Lz_dinv.d(), m, st.Lz.d(), st.ldm, &info, &st.logdet_z));
   if (!st.streamed)
-    GPL_TRY(cf_pairwise(ctx, st.hp.plan, st.Zx.d(), n, n, st.Zz.d(), m, m, false, 0.0, st.Kxz.d(), st.ldx));
+    GPL_TRY(fitc_cf_pairwise(ctx, st.hp.plan, st.Zx.d(), n, n, st.Zz.d(), m, m, false, 0.0, st.Kxz.d(), st.ldx));
   GPL_TRY(cf_diag(ctx, st.hp.plan, st.Zx.d(), n, st.Zx.d(), n, n, jitter, st.Kdiag.d()));
   tm.mark(st.streamed ? "Kz, chol(Kz), diag K (Kxz streamed)" : "Kz, chol(Kz), Kxz (resident), diag K");
   // D = K_diag - colSums(forwardsolve(Kz_chol, t(Kxz))^2)
@@ -854,7 +866,7 @@ int pred_fitc_impl(Ctx* ctx, const Fit* fit, const gpl_cf_model* cf, const doubl
   const double* beta = fit->sqrtV.d();
   for (int64_t r0 = 0; r0 < nt; r0 += chunk) {
     const int64_t c = (nt - r0) < chunk ? (nt - r0) : chunk;
-    GPL_TRY(cf_pairwise(ctx, hp.plan, Zt.d() + r0, c, nt, Zz.d(), m, m, false, 0.0, Ktz.d(), ldk));
+    GPL_TRY(fitc_cf_pairwise(ctx, hp.plan, Zt.d() + r0, c, nt, Zz.d(), m, m, false, 0.0, Ktz.d(), ldk));
     GPL_TRY(gemv_n(ctx, c, m, Ktz.d(), ldk, beta, dmean.d() + r0));
     if (var) {
       GPL_TRY(cf_diag(ctx, hp.plan, Zt.d() + r0, nt, Zt.d() + r0, nt, c, 0.0, dvar.d() + r0));
@@ -938,7 +950,7 @@ int pred_fitc_cov_dev(Ctx* ctx, const Fit* fit, const gpl_cf_model* cf, const do
   GPL_TRY(W.alloc(ctx, sizeof(double) * ldk * m));
   GPL_TRY(dt.alloc(ctx, sizeof(double) * nt));
   GPL_TRY(t1.alloc(ctx, sizeof(double) * nt));
-  GPL_TRY(cf_pairwise(ctx, hp.plan, Zt.d(), nt, nt, Zz.d(), m, m, false, 0.0, Ktz.d(), ldk));
+  GPL_TRY(fitc_cf_pairwise(ctx, hp.plan, Zt.d(), nt, nt, Zz.d(), m, m, false, 0.0, Ktz.d(), ldk));
   GPL_TRY(gemv_n(ctx, nt, m, Ktz.d(), ldk, fit->sqrtV.d(), d_mean));          // beta rides in sqrtV
   GPL_TRY(cf_diag(ctx, hp.plan, Zt.d(), nt, Zt.d(), nt, nt, 0.0, dt.d()));
   GPL_TRY(scaled_copy_rows(ctx, nt, m, Ktz.d(), ldk, nullptr, W.d(), ldk));

@@ -14,6 +14,7 @@
 
 #include <stdlib.h>
 
+#include <atomic>
 #include <type_traits>
 
 namespace gpl {
@@ -39,6 +40,10 @@ struct Cfg {
 };
 using CfgL = Cfg<128, 128, 32, 64, 32, 3>;
 using CfgL16 = Cfg<128, 128, 32, 32, 32, 3>;   // same CTA tile, 16 warps (4 per scheduler) of 32x32
+// 128 x 64 CTA tile, 4 warps of 32 x 64 (the same warp tile and LDS : DMMA ratio as L), 90 KB of shared memory:
+// TWO CTAs per SM, so that one CTA's prologue / epilogue (un-overlapped at 1 CTA / SM, ~3 % of a K = 2048
+// update) runs under the other's main loop.  Opt-in (GPL_GEMM_L2X=1) until measured.
+using CfgL2 = Cfg<128, 64, 32, 64, 16, 3>;
 using CfgM = Cfg<64, 64, 32, 32, 16, 4>;
 using CfgS = Cfg<32, 32, 16, 16, 16, 4>;
 // In-place products (C aliases an operand) are only race-free when one CTA owns the whole
@@ -177,9 +182,9 @@ __global__ void __launch_bounds__(CF::THREADS) gemm_f64_kernel(const GemmArgs p)
     const int r = L - group * per_group;
     bm = first_m + r % gsz;
     bn = r / gsz;
-    if (p.lower && bn > bm) return;
   }
   const int m0 = bm * BM, n0 = bn * BN;
+  if (p.lower && n0 >= m0 + BM) return;      // the whole tile lies above the diagonal (BM != BN allowed)
   int nb0 = n0, nb_lim = p.N;        // B-operand coordinates of this tile's columns
   if (p.stair_nb > 0) {
     const int cblk = n0 / p.stair_nb;
@@ -295,7 +300,7 @@ __global__ void __launch_bounds__(CF::THREADS) gemm_f64_kernel(const GemmArgs p)
   // a batch of sub-tiles are all loaded before the first store: interleaved load/store pairs cannot
   // be reordered by the compiler (possible aliasing), which serialised 64 L2 round trips per thread
   // (~16 us per 128x128 tile, as much as 7 k-tiles of the main loop).
-  const bool diag_tile = p.lower && (bm == bn);
+  const bool diag_tile = p.lower && (n0 + BN > m0);      // the tile reaches above the diagonal
   const bool rmw = p.beta != 0.0;
   constexpr int IMB = (MI % 2 == 0) ? 2 : 1;
 #pragma unroll
@@ -334,11 +339,14 @@ __global__ void __launch_bounds__(CF::THREADS) gemm_f64_kernel(const GemmArgs p)
 
 template <bool TA, bool TB, class CF>
 int launch(Ctx* ctx, GemmArgs a) {
-  static bool configured[64] = {false};      // per device: the attribute is per-context
-  if (!configured[ctx->device & 63]) {
+  // per device (the attribute is per-context).  Atomic flags: two host threads driving two contexts may
+  // both set the attribute (idempotent), but neither can observe the flag before its own call returned.
+  static std::atomic<bool> configured[64];
+  std::atomic<bool>& cfgd = configured[ctx->device & 63];
+  if (!cfgd.load(std::memory_order_acquire)) {
     GPL_CUDA(cudaFuncSetAttribute(gemm_f64_kernel<TA, TB, CF>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, CF::SMEM_BYTES));
-    configured[ctx->device & 63] = true;
+    cfgd.store(true, std::memory_order_release);
   }
   a.tiles_m = (a.M + CF::BM - 1) / CF::BM;
   a.tiles_n = (a.N + CF::BN - 1) / CF::BN;
@@ -408,8 +416,11 @@ int dispatch(Ctx* ctx, const GemmArgs& a, int alias) {
   const double cost_m = cost(64, 2, 0.044, 231e3, 4.5, false);
   const double cost_s = cost(32, 5, 0.016, 220e3, 3.0, true);
   static const int use_l16 = getenv("GPL_GEMM_L16") ? atoi(getenv("GPL_GEMM_L16")) : 0;
-  if (cost_l <= cost_m && cost_l <= cost_s)
+  static const int use_l2x = getenv("GPL_GEMM_L2X") ? atoi(getenv("GPL_GEMM_L2X")) : 0;
+  if (cost_l <= cost_m && cost_l <= cost_s) {
+    if (use_l2x) return launch<TA, TB, CfgL2>(ctx, a);
     return use_l16 ? launch<TA, TB, CfgL16>(ctx, a) : launch<TA, TB, CfgL>(ctx, a);
+  }
   if (cost_m <= cost_s) return launch<TA, TB, CfgM>(ctx, a);
   return launch<TA, TB, CfgS>(ctx, a);
 }

@@ -11,6 +11,11 @@
  *   gplb_energy_grad                  gp_energy through gp_fit (R/gp.R:138-147) + gradient
  *   gplb_pred_full / gplb_pred_fitc   gp_pred_post.method_full / .method_fitc (R/gp_pred.R:202-296)
  *   gplb_fit_get                      gp$fit$C_chol, $Kxz ... materialised on demand
+ *   gplb_set_device, gplb_dist_unique_id, gplb_dist_init, gplb_dist_fit_full,
+ *   gplb_dist_energy_grad, gplb_dist_free
+ *                                     the same fits for problems larger than one GPU: one R worker
+ *                                     process per GPU (parallel::makeCluster), NCCL inside the library
+ *                                     
  *
  * Build inside the package:  PKG_CPPFLAGS = -I$(GPLITE_B200_HOME)/include
  *                            PKG_LIBS     = -L$(GPLITE_B200_HOME) -lgplite_b200
@@ -29,9 +34,10 @@
 #include "gplite_b200.h"
 
 static gpl_ctx* ctx_ = NULL;
+static int device_ = 0;      /* gplb_set_device(): the GPU of this R process (multi-GPU workers) */
 
 static gpl_ctx* ctx(void) {
-  if (!ctx_ && gpl_ctx_create(0, 0, &ctx_) != GPL_OK) Rf_error("gplite_b200: %s", gpl_last_error());
+  if (!ctx_ && gpl_ctx_create(device_, 0, &ctx_) != GPL_OK) Rf_error("gplite_b200: %s", gpl_last_error());
   return ctx_;
 }
 
@@ -322,6 +328,123 @@ SEXP gplb_fit_get(SEXP handle, SEXP what, SEXP rows, SEXP cols) {
   return out;
 }
 
+/* ---- multi-GPU (one R process per GPU; include/gplite_b200.h "multi-GPU full GP") ------------- */
+
+/* choose this process's GPU; must precede the first library call of the process */
+SEXP gplb_set_device(SEXP dev) {
+  if (ctx_) Rf_error("gplite_b200: gplb_set_device must be called before the first fit of this process");
+  device_ = Rf_asInteger(dev);
+  return R_NilValue;
+}
+
+/* rank 0: 128 raw bytes to ship to the other workers (clusterApply argument) */
+SEXP gplb_dist_unique_id(void) {
+  SEXP id = PROTECT(Rf_allocVector(RAWSXP, GPL_DIST_ID_BYTES));
+  const int st = gpl_dist_unique_id(RAW(id));
+  UNPROTECT(1);
+  if (st != GPL_OK) Rf_error("gplite_b200: %s", gpl_last_error());
+  return id;
+}
+
+static void dist_finalizer(SEXP p) {
+  gpl_dist* d = (gpl_dist*)R_ExternalPtrAddr(p);
+  if (d) {
+    gpl_dist_destroy(d);
+    R_ClearExternalPtr(p);
+  }
+}
+
+/* collective over the workers: id (raw, may be NULL when world == 1), rank (0-based), world */
+SEXP gplb_dist_init(SEXP id, SEXP rank, SEXP world) {
+  gpl_dist* d = NULL;
+  if (!Rf_isNull(id) && XLENGTH(id) != GPL_DIST_ID_BYTES) Rf_error("gplite_b200: the id must be 128 raw bytes");
+  const int st = gpl_dist_init(ctx(), Rf_isNull(id) ? NULL : (const void*)RAW(id), Rf_asInteger(rank),
+                               Rf_asInteger(world), &d);
+  if (st != GPL_OK) Rf_error("gplite_b200: %s", gpl_last_error());
+  SEXP p = PROTECT(R_MakeExternalPtr(d, R_NilValue, R_NilValue));
+  R_RegisterCFinalizerEx(p, dist_finalizer, TRUE);
+  UNPROTECT(1);
+  return p;
+}
+
+/* explicit release (the destroy is a collective: call it on every worker) */
+SEXP gplb_dist_free(SEXP dist) {
+  dist_finalizer(dist);
+  return R_NilValue;
+}
+
+/* fit_laplace / fit_ep .method_full across the workers' GPUs; every worker passes the same data and gets
+ * the same gp$fit back (no device handle: predictions go through alpha, as gp_pred_post's mean does) */
+SEXP gplb_dist_fit_full(SEXP dist, SEXP model, SEXP lik, SEXP approx, SEXP x, SEXP y, SEXP trials, SEXP offset,
+                        SEXP jitter, SEXP nb) {
+  model_buf mb;
+  gpl_lik lk;
+  gpl_approx ap;
+  gpl_dist* d = (gpl_dist*)R_ExternalPtrAddr(dist);
+  if (!d) Rf_error("gplite_b200: the multi-GPU communicator has been released");
+  if (!unpack_model(model, &mb)) Rf_error("gplite_b200: out of memory");
+  unpack_lik(lik, &lk);
+  unpack_approx(approx, &ap);
+  const int64_t n = Rf_nrows(x);
+  const int dd = Rf_ncols(x);
+  SEXP vec[7];
+  for (int i = 0; i < 7; ++i) vec[i] = PROTECT(Rf_allocVector(REALSXP, (R_xlen_t)n));
+  gpl_fit_out o;
+  const int st = gpl_dist_fit_full(d, &mb.m, &lk, &ap, REAL(x), n, dd, REAL(y), opt_real(trials), opt_real(offset),
+                                   Rf_asReal(jitter), (int64_t)Rf_asInteger(nb), &o, REAL(vec[0]), REAL(vec[1]),
+                                   REAL(vec[2]), REAL(vec[3]), REAL(vec[4]), REAL(vec[5]), REAL(vec[6]), NULL);
+  free(mb.f);
+  static const char* names[] = {"fmean", "z", "V", "alpha", "fvar", "cavity_mean", "cavity_var",
+                                "log_evidence", "iters", "converged", "quad_ok"};
+  if (st == GPL_ERR_NONFINITE) {          /* R/ep.R:30-32 */
+    static const char* nm1[] = {"log_evidence"};
+    SEXP out = PROTECT(named_list(1, nm1));
+    SET_VECTOR_ELT(out, 0, Rf_ScalarReal(R_NegInf));
+    UNPROTECT(8);
+    return out;
+  }
+  if (st != GPL_OK) {
+    UNPROTECT(7);
+    Rf_error("gplite_b200: %s", gpl_last_error());
+  }
+  SEXP out = PROTECT(named_list(11, names));
+  for (int i = 0; i < 7; ++i) SET_VECTOR_ELT(out, i, vec[i]);
+  SET_VECTOR_ELT(out, 7, Rf_ScalarReal(o.log_evidence));
+  SET_VECTOR_ELT(out, 8, Rf_ScalarInteger(o.iters));
+  SET_VECTOR_ELT(out, 9, Rf_ScalarLogical(o.converged));
+  SET_VECTOR_ELT(out, 10, Rf_ScalarLogical(o.quad_ok));
+  UNPROTECT(8);
+  return out;
+}
+
+/* gplb_energy_grad across the workers' GPUs (lik_gaussian): list(energy =, grad =) */
+SEXP gplb_dist_energy_grad(SEXP dist, SEXP model, SEXP lik, SEXP x, SEXP y, SEXP jitter, SEXP nb, SEXP pfactor,
+                           SEXP pslot) {
+  model_buf mb;
+  gpl_lik lk;
+  gpl_dist* d = (gpl_dist*)R_ExternalPtrAddr(dist);
+  if (!d) Rf_error("gplite_b200: the multi-GPU communicator has been released");
+  if (!unpack_model(model, &mb)) Rf_error("gplite_b200: out of memory");
+  unpack_lik(lik, &lk);
+  const int np = (int)XLENGTH(pfactor);
+  SEXP grad = PROTECT(Rf_allocVector(REALSXP, np));
+  double energy = 0.0;
+  const int st = gpl_dist_energy_grad(d, &mb.m, &lk, REAL(x), Rf_nrows(x), Rf_ncols(x), REAL(y), Rf_asReal(jitter),
+                                      (int64_t)Rf_asInteger(nb), np, (const int32_t*)INTEGER(pfactor),
+                                      (const int32_t*)INTEGER(pslot), &energy, REAL(grad), NULL, NULL);
+  free(mb.f);
+  if (st != GPL_OK) {
+    UNPROTECT(1);
+    Rf_error("gplite_b200: %s", gpl_last_error());
+  }
+  static const char* names[] = {"energy", "grad"};
+  SEXP out = PROTECT(named_list(2, names));
+  SET_VECTOR_ELT(out, 0, Rf_ScalarReal(energy));
+  SET_VECTOR_ELT(out, 1, grad);
+  UNPROTECT(2);
+  return out;
+}
+
 static const R_CallMethodDef CallEntries[] = {
     {"_gplite_cf_sexp_c", (DL_FUNC)&_gplite_cf_sexp_c, 5},
     {"_gplite_cf_matern32_c", (DL_FUNC)&_gplite_cf_matern32_c, 5},
@@ -333,6 +456,12 @@ static const R_CallMethodDef CallEntries[] = {
     {"gplb_pred_full", (DL_FUNC)&gplb_pred_full, 5},
     {"gplb_pred_fitc", (DL_FUNC)&gplb_pred_fitc, 5},
     {"gplb_fit_get", (DL_FUNC)&gplb_fit_get, 4},
+    {"gplb_set_device", (DL_FUNC)&gplb_set_device, 1},
+    {"gplb_dist_unique_id", (DL_FUNC)&gplb_dist_unique_id, 0},
+    {"gplb_dist_init", (DL_FUNC)&gplb_dist_init, 3},
+    {"gplb_dist_free", (DL_FUNC)&gplb_dist_free, 1},
+    {"gplb_dist_fit_full", (DL_FUNC)&gplb_dist_fit_full, 10},
+    {"gplb_dist_energy_grad", (DL_FUNC)&gplb_dist_energy_grad, 9},
     {NULL, NULL, 0}};
 
 void R_init_gplite(DllInfo* dll) { /* replaces src/RcppExports.cpp:84-87 */

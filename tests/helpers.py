@@ -54,3 +54,19 @@ def outlier_counts(seed, n=150, n_out=15):
     idx = rng.choice(n, n_out, replace=False)
     y[idx] = np.where(f[idx] > 0, 0.0, trials[idx])
     return X, y, trials
+
+
+def oracle_evidence_noise(fit_evidence, n, m, reps=5, seed=0):
+    """Relative spread of the ORACLE's own log evidence under mathematically neutral permutations of the
+    training rows and of the inducing points (only the floating-point summation order changes).
+    `fit_evidence(row_perm, inducing_perm)` refits the oracle and returns its log evidence.  Nearly singular
+    Kz + jitter I (inducing points drawn from crowded training points) makes the FITC evidence -- the
+    difference of two log-determinants with eigenvalues down at the jitter -- uncertain at cond(Kz) * eps;
+    a parity tolerance below this floor cannot be met by ANY second fp64 implementation, the reference's
+    own R code included."""
+    rs = np.random.default_rng(seed)
+    vals = [fit_evidence(np.arange(n), np.arange(m))]
+    for _ in range(reps - 1):
+        vals.append(fit_evidence(rs.permutation(n), rs.permutation(m)))
+    vals = np.asarray(vals)
+    return float((vals.max() - vals.min()) / abs(vals[0]))

@@ -12,7 +12,7 @@ extern "C" {
 #endif
 typedef ptrdiff_t R_xlen_t;
 typedef struct shim_sexprec* SEXP;
-typedef enum { NILSXP = 0, LGLSXP = 10, INTSXP = 13, REALSXP = 14, STRSXP = 16, VECSXP = 19, EXTPTRSXP = 22,
+typedef enum { NILSXP = 0, LGLSXP = 10, INTSXP = 13, REALSXP = 14, STRSXP = 16, VECSXP = 19, EXTPTRSXP = 22, RAWSXP = 24,
                CHARSXP = 9, SYMSXP = 1 } SEXPTYPE;
 typedef enum { FALSE = 0, TRUE } Rboolean;
 extern SEXP R_NilValue, R_NamesSymbol;
@@ -22,6 +22,8 @@ SEXP Rf_allocMatrix(SEXPTYPE, int, int);
 double* REAL(SEXP);
 int* INTEGER(SEXP);
 int* LOGICAL(SEXP);
+typedef unsigned char Rbyte;
+Rbyte* RAW(SEXP);
 int Rf_nrows(SEXP);
 int Rf_ncols(SEXP);
 R_xlen_t XLENGTH(SEXP);

@@ -51,6 +51,7 @@ SEXP Rf_allocVector(SEXPTYPE t, R_xlen_t n) {
     case REALSXP: return new_obj(t, n, sizeof(double));
     case INTSXP: case LGLSXP: return new_obj(t, n, sizeof(int));
     case VECSXP: case STRSXP: return new_obj(t, n, sizeof(SEXP));
+    case RAWSXP: return new_obj(t, n, 1);
     default: Rf_error("shim: allocVector type %d", (int)t);
   }
 }
@@ -62,6 +63,7 @@ SEXP Rf_allocMatrix(SEXPTYPE t, int nr, int nc) {
 }
 double* REAL(SEXP s) { if (s->type != REALSXP) Rf_error("shim: REAL() on type %d", (int)s->type); return (double*)s->data; }
 int* INTEGER(SEXP s) { if (s->type != INTSXP) Rf_error("shim: INTEGER() on type %d", (int)s->type); return (int*)s->data; }
+Rbyte* RAW(SEXP s) { if (s->type != RAWSXP) Rf_error("shim: RAW() on type %d", (int)s->type); return (Rbyte*)s->data; }
 int* LOGICAL(SEXP s) { if (s->type != LGLSXP) Rf_error("shim: LOGICAL() on type %d", (int)s->type); return (int*)s->data; }
 int Rf_nrows(SEXP s) { return s->nrow; }
 int Rf_ncols(SEXP s) { return s->ncol; }
@@ -155,7 +157,7 @@ SEXP shim_list_get(SEXP list, const char* name) {
 }
 int shim_type(SEXP s) { return (int)s->type; }
 void shim_run_finalizer(SEXP s) { if (s->fin) s->fin(s); }
-/* call a registered .Call routine by name with up to 9 SEXP arguments; returns NULL (C) when the
+/* call a registered .Call routine by name with 0 .. 10 SEXP arguments; returns NULL (C) when the
  * routine raised through Rf_error (message in shim_last_error) */
 SEXP shim_call(const char* name, int nargs, SEXP* a) {
   for (int i = 0; routines && routines[i].name; ++i) {
@@ -165,6 +167,10 @@ SEXP shim_call(const char* name, int nargs, SEXP* a) {
     error_jmp = &jb;
     SEXP out = NULL;
     if (setjmp(jb) == 0) {
+      typedef SEXP (*f0)(void);
+      typedef SEXP (*f1)(SEXP);
+      typedef SEXP (*f3)(SEXP, SEXP, SEXP);
+      typedef SEXP (*f10)(SEXP, SEXP, SEXP, SEXP, SEXP, SEXP, SEXP, SEXP, SEXP, SEXP);
       typedef SEXP (*f5)(SEXP, SEXP, SEXP, SEXP, SEXP);
       typedef SEXP (*f4)(SEXP, SEXP, SEXP, SEXP);
       typedef SEXP (*f6)(SEXP, SEXP, SEXP, SEXP, SEXP, SEXP);
@@ -173,6 +179,10 @@ SEXP shim_call(const char* name, int nargs, SEXP* a) {
       typedef SEXP (*f9)(SEXP, SEXP, SEXP, SEXP, SEXP, SEXP, SEXP, SEXP, SEXP);
       DL_FUNC f = routines[i].fun;
       switch (nargs) {
+        case 0: out = ((f0)f)(); break;
+        case 1: out = ((f1)f)(a[0]); break;
+        case 3: out = ((f3)f)(a[0], a[1], a[2]); break;
+        case 10: out = ((f10)f)(a[0], a[1], a[2], a[3], a[4], a[5], a[6], a[7], a[8], a[9]); break;
         case 4: out = ((f4)f)(a[0], a[1], a[2], a[3]); break;
         case 5: out = ((f5)f)(a[0], a[1], a[2], a[3], a[4]); break;
         case 6: out = ((f6)f)(a[0], a[1], a[2], a[3], a[4], a[5]); break;

@@ -73,6 +73,11 @@ def test_registration_matches_reference(glue):
     for extra in ("gplb_fit_full", "gplb_fit_fitc", "gplb_energy_grad", "gplb_pred_full", "gplb_pred_fitc",
                   "gplb_fit_get"):
         assert extra in table
+    # the multi-GPU routines
+    assert {k: table.get(k) for k in ("gplb_set_device", "gplb_dist_unique_id", "gplb_dist_init", "gplb_dist_free",
+                                      "gplb_dist_fit_full", "gplb_dist_energy_grad")} == {
+        "gplb_set_device": 1, "gplb_dist_unique_id": 0, "gplb_dist_init": 3, "gplb_dist_free": 1,
+        "gplb_dist_fit_full": 10, "gplb_dist_energy_grad": 9}
     ref = "/root/reference/src/RcppExports.cpp"              # only in the build container
     if os.path.exists(ref):
         found = dict((m.group(1), int(m.group(2))) for m in
@@ -80,11 +85,25 @@ def test_registration_matches_reference(glue):
         assert found == REF_ARITY
 
 
+def test_unique_id_is_128_raw_bytes(glue):
+    """gplb_dist_unique_id() -> the RAWSXP an R host ships to its workers (ncclGetUniqueId needs no GPU)."""
+    out = _call(glue, "gplb_dist_unique_id")
+    assert out, glue.shim_last_error()
+    assert glue.XLENGTH(out) == 128
+    glue.RAW.restype = C.c_void_p
+    glue.RAW.argtypes = [C.c_void_p]
+    raw = bytes((C.c_ubyte * 128).from_address(glue.RAW(out)))
+    assert any(raw)
+    again = bytes((C.c_ubyte * 128).from_address(glue.RAW(_call(glue, "gplb_dist_unique_id"))))
+    assert again != raw                                        # ids are unique per call
+
+
 def test_r_side_helpers_are_documented():
     """INTEGRATION.md names the glue file and every routine it registers."""
     text = open(os.path.join(ROOT, "INTEGRATION.md")).read()
     assert "r_glue/gplite_b200_glue.c" in text
-    for name in list(REF_ARITY) + ["gplb_fit_full", "gplb_pred_full", "gplb_energy_grad"]:
+    for name in list(REF_ARITY) + ["gplb_fit_full", "gplb_pred_full", "gplb_energy_grad", "gplb_dist_init",
+                                   "gplb_dist_fit_full", "gplb_dist_unique_id"]:
         assert name in text
 
 
@@ -186,3 +205,57 @@ def test_dot_call_fit_and_predict_equal_host_layer(glue, ctx):
                 glue.Rf_ScalarReal(1e-6))
     assert not bad
     assert b"gplite_b200" in glue.shim_last_error()
+
+
+@pytest.mark.gpu
+def test_dot_call_multi_gpu_routines_world_one(glue, ctx):
+    """The multi-GPU .Call routines driven as an R worker would drive them, with a one-rank communicator (no
+    NCCL needed): gplb_dist_fit_full / gplb_dist_energy_grad return what gplb_fit_full / gplb_energy_grad
+    return for the same data (the block-cyclic schedule with world = 1 is a different summation order, hence
+    1e-10 instead of bit equality), and a released communicator raises an R error."""
+    rng = np.random.default_rng(32005)
+    n, d = 700, 3
+    x = rng.normal(size=(n, d))
+    y = np.sin(x[:, 0]) + 0.3 * x[:, 1] + 0.2 * rng.normal(size=n)
+    factor = _named(glue, kind=glue.Rf_ScalarInteger(3), term=glue.Rf_ScalarInteger(0),
+                    p=_mat(glue, np.array([1.3, 0.9])))                       # cf_matern32 (config 5's kernel)
+    model = glue.shim_list(1)
+    glue.shim_list_set(model, 0, b"", factor)
+    lik = _named(glue, kind=glue.Rf_ScalarInteger(0), link=glue.Rf_ScalarInteger(0), param=glue.Rf_ScalarReal(0.4))
+    approx = _named(glue, kind=glue.Rf_ScalarInteger(0), maxiter=glue.Rf_ScalarInteger(30), tol=glue.Rf_ScalarReal(1e-4))
+    nil = glue.shim_nil()
+    jit = glue.Rf_ScalarReal(1e-6)
+    one = _call(glue, "gplb_fit_full", model, lik, approx, _mat(glue, x), _mat(glue, y), nil, nil, jit)
+    assert one, glue.shim_last_error()
+    dist = _call(glue, "gplb_dist_init", nil, glue.Rf_ScalarInteger(0), glue.Rf_ScalarInteger(1))
+    assert dist, glue.shim_last_error()
+    many = _call(glue, "gplb_dist_fit_full", dist, model, lik, approx, _mat(glue, x), _mat(glue, y), nil, nil, jit,
+                 glue.Rf_ScalarInteger(256))
+    assert many, glue.shim_last_error()
+    le1 = glue.Rf_asReal(glue.shim_list_get(one, b"log_evidence"))
+    leN = glue.Rf_asReal(glue.shim_list_get(many, b"log_evidence"))
+    assert abs(le1 - leN) <= 1e-10 * abs(le1)
+    a1 = _real(glue, glue.shim_list_get(one, b"alpha"))[:, 0]
+    aN = _real(glue, glue.shim_list_get(many, b"alpha"))[:, 0]
+    assert np.max(np.abs(a1 - aN)) <= 1e-8 * np.max(np.abs(a1))
+    f1 = _real(glue, glue.shim_list_get(one, b"fmean"))[:, 0]
+    fN = _real(glue, glue.shim_list_get(many, b"fmean"))[:, 0]
+    assert np.max(np.abs(f1 - fN)) <= 1e-9 * np.max(np.abs(f1))
+    pf = np.array([0, 0, -1], dtype=np.int32)
+    ps = np.array([0, 1, 0], dtype=np.int32)
+    ivec = lambda a: glue.shim_int_vector(a.ctypes.data_as(C.c_void_p), len(a))
+    eg1 = _call(glue, "gplb_energy_grad", model, lik, _mat(glue, x), _mat(glue, y), jit, ivec(pf), ivec(ps))
+    egN = _call(glue, "gplb_dist_energy_grad", dist, model, lik, _mat(glue, x), _mat(glue, y), jit,
+                glue.Rf_ScalarInteger(256), ivec(pf), ivec(ps))
+    assert eg1 and egN, glue.shim_last_error()
+    e1 = glue.Rf_asReal(glue.shim_list_get(eg1, b"energy"))
+    eN = glue.Rf_asReal(glue.shim_list_get(egN, b"energy"))
+    assert abs(e1 - eN) <= 1e-10 * abs(e1)
+    g1 = _real(glue, glue.shim_list_get(eg1, b"grad"))[:, 0]
+    gN = _real(glue, glue.shim_list_get(egN, b"grad"))[:, 0]
+    assert np.max(np.abs(g1 - gN)) <= 1e-8 * np.max(np.abs(g1))
+    _call(glue, "gplb_dist_free", dist)
+    gone = _call(glue, "gplb_dist_fit_full", dist, model, lik, approx, _mat(glue, x), _mat(glue, y), nil, nil, jit,
+                 glue.Rf_ScalarInteger(256))
+    assert not gone and b"released" in glue.shim_last_error()
+    glue.shim_run_finalizer(glue.shim_list_get(one, b"handle"))

@@ -19,6 +19,7 @@ from gplite_b200 import _lib               # noqa: E402
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 32768
 only = sys.argv[2].split(",") if len(sys.argv) > 2 else None
+REPS = int(os.environ.get("GPL_PROBE_REPS", "5"))       # 1 under ncu: one warm-up + one timed launch per case
 ctx = _lib.Context(0, 1)      # the legacy default stream, so that torch.cuda.Event sees the kernels
 P = lambda t: C.c_void_p(t.data_ptr())
 try:
@@ -52,11 +53,11 @@ for name, (cfs, d) in cases.items():
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        for _ in range(5):
+        for _ in range(REPS):
             run()
         e1.record()
         torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1) / 5
+        ms = e0.elapsed_time(e1) / REPS
         gbs = (8.0 * n * n + 16.0 * d * n) / (ms * 1e-3) / 1e9
         print(json.dumps({"case": name, "shape": "symmetric" if same else "rectangular", "n": n, "ms": round(ms, 4),
                           "gbs": round(gbs, 1), "frac_of_hbm_peak": round(gbs / hbm, 4),
