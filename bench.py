@@ -232,7 +232,8 @@ def sharded_record(ctx, rank, world, dist, nb=1024):
         return dict(zip(keys, [float(v) for v in t]))
 
     rec = {"layout": f"1-D block-cyclic by block columns, nb={nb}, block b on rank b % {world}; panels by "
-                     "ncclBroadcast on the library's own stream, one step of look-ahead",
+                     "ncclBroadcast inside the library (own comm stream, communicator capped at 4 CTAs), look-ahead "
+                     "window of 8 panel buffers, column-chunked panel pipeline in the tail (csrc/dist_sched.hpp)",
            "model": "cfg5: cf_matern32(lscale=1.3) + lik_gaussian(sigma=0.5), d=8, method_full, fp64",
            "n_gpus": world}
     # ---- in-run parity at a check size: N ranks vs the single-GPU path vs the oracle
@@ -282,8 +283,13 @@ def sharded_record(ctx, rank, world, dist, nb=1024):
                                                                      + t["lauum_s"] + t["trace_s"]) / 1e12)
         return out
 
-    # ---- strong scaling point: the same n = 100000 factorisation at every N the driver runs
-    rec["n100k_factor"] = run(100000, False)
+    # ---- strong scaling point: the same n = 100000 factorisation at every N the driver runs.  Two repetitions,
+    # the faster one is the record (the first also pays the 80 / N GB slab allocation and NCCL's lazy
+    # connection set-up: 2.5 s vs 1.4 s on 8 GPUs, profiles/r02_dist8_n100k_nccl_cta_cap_and_windows.jsonl);
+    # both times are kept in the record
+    reps = [run(100000, False) for _ in range(2)]
+    rec["n100k_factor"] = dict(min(reps, key=lambda r: r["factor_s"]))
+    rec["n100k_factor"]["factor_s_each_repetition"] = [r["factor_s"] for r in reps]
     # the N = 1 time of this same code on this pool (profiles/r02_dist_schedule_v2_window_sweep.jsonl), so that a
     # single line already shows the strong-scaling efficiency; the driver's own N = 1 line is the authority
     ref1 = 10.544

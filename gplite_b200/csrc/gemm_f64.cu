@@ -40,10 +40,9 @@ struct Cfg {
 };
 using CfgL = Cfg<128, 128, 32, 64, 32, 3>;
 using CfgL16 = Cfg<128, 128, 32, 32, 32, 3>;   // same CTA tile, 16 warps (4 per scheduler) of 32x32
-// 128 x 64 CTA tile, 4 warps of 32 x 64 (the same warp tile and LDS : DMMA ratio as L), 90 KB of shared memory:
-// TWO CTAs per SM, so that one CTA's prologue / epilogue (un-overlapped at 1 CTA / SM, ~3 % of a K = 2048
-// update) runs under the other's main loop.  Opt-in (GPL_GEMM_L2X=1) until measured.
-using CfgL2 = Cfg<128, 64, 32, 64, 16, 3>;
+// (A 128 x 64 tile with two CTAs per SM -- one CTA's prologue / epilogue under the other's main loop -- was
+// measured in round 2 and did not pay: potrf 395-412 vs 392-403 ms, lauum 330-331 vs 332 ms, trtri slower;
+// profiles/r02_phase_timing_l2x_experiment.log.  The lower-triangular mode below accepts BM != BN since then.)
 using CfgM = Cfg<64, 64, 32, 32, 16, 4>;
 using CfgS = Cfg<32, 32, 16, 16, 16, 4>;
 // In-place products (C aliases an operand) are only race-free when one CTA owns the whole
@@ -416,11 +415,8 @@ int dispatch(Ctx* ctx, const GemmArgs& a, int alias) {
   const double cost_m = cost(64, 2, 0.044, 231e3, 4.5, false);
   const double cost_s = cost(32, 5, 0.016, 220e3, 3.0, true);
   static const int use_l16 = getenv("GPL_GEMM_L16") ? atoi(getenv("GPL_GEMM_L16")) : 0;
-  static const int use_l2x = getenv("GPL_GEMM_L2X") ? atoi(getenv("GPL_GEMM_L2X")) : 0;
-  if (cost_l <= cost_m && cost_l <= cost_s) {
-    if (use_l2x) return launch<TA, TB, CfgL2>(ctx, a);
+  if (cost_l <= cost_m && cost_l <= cost_s)
     return use_l16 ? launch<TA, TB, CfgL16>(ctx, a) : launch<TA, TB, CfgL>(ctx, a);
-  }
   if (cost_m <= cost_s) return launch<TA, TB, CfgM>(ctx, a);
   return launch<TA, TB, CfgS>(ctx, a);
 }

@@ -31,7 +31,7 @@ def comm(ctx):
     c.close()
 
 
-@pytest.mark.parametrize("n,nb", [(768, 128), (700, 128), (1500, 256), (2048, 1024)])
+@pytest.mark.parametrize("n,nb", [(768, 128), (700, 128), (1111, 256), (1500, 256), (2048, 1024)])   # 1111: odd n
 def test_driver_single_rank_matches_oracle(comm, n, nb):
     rng = np.random.default_rng(n)
     X = rng.normal(size=(n, 3))
@@ -79,7 +79,7 @@ def test_laplace_driver_single_rank_matches_oracle(comm, lik):
     assert np.max(np.abs(fm - gpo.fit["fmean"])) < 1e-8 * np.max(np.abs(gpo.fit["fmean"]))
 
 
-@pytest.mark.parametrize("n,nb", [(768, 128), (1100, 256), (2048, 1024)])
+@pytest.mark.parametrize("n,nb", [(768, 128), (1100, 256), (1101, 128), (2048, 1024)])   # 1101: odd n
 def test_energy_grad_driver_single_rank_matches_oracle(comm, n, nb):
     """SURVEY 8e "C^-1 + trace term": block-cyclic trtri / lauum sweeps + gpl_grad_trace_block_dev."""
     from gplite_b200.dist import dist_energy_grad
