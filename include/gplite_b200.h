@@ -396,7 +396,7 @@ int gpl_fit_free(gpl_ctx* ctx, gpl_fit* fit);
  * 128-byte id from rank 0 to the other ranks (any channel: a file, a socket, MPI, torch.distributed)
  * and call gpl_dist_init on every rank.  K is built directly in a 1-D block-cyclic column layout (block
  * columns of width nb, block b on rank b % world), factorised right-looking with panel broadcasts
- * (ncclBroadcast over NVLink) and one step of look-ahead; alpha by distributed block substitution;
+ * (ncclBroadcast over NVLink) inside a look-ahead window of panel buffers; alpha by distributed block substitution;
  * (K + V)^-1 for the gradient / EP variances by two more panel sweeps.  Every rank passes the SAME
  * host data and receives the SAME results.  world = 1 is allowed (no NCCL needed).
  * NCCL is bound at run time (libnccl.so.2; GPL_NCCL_LIB overrides the path); failures return
