@@ -82,3 +82,31 @@ def test_clamp_constants():
     hi = struct.unpack("<d", struct.pack("<II", 0, int(re.search(r"min\(__double2hiint\(x\), (0x[0-9a-f]+)\)", SRC).group(1), 16)))[0]
     assert 1e-301 < lo < 1e-299                       # sqrt_pos never sees 0 * inf
     assert 708.0 <= hi < 708.5 and math.exp(-hi) > 2.3e-308       # exp_m's exponent arithmetic cannot wrap
+
+
+def test_gram_contraction_cancellation_stays_inside_the_tile_guard():
+    """cf_gram.cu forms u = |a|^2 + |b|^2 - 2 a.b on shifted, scaled rows and falls back to direct differences when
+    a tile's scaled norms reach 250.  Below the guard the absolute error of u -- which IS the relative error of
+    cf_sexp's K and bounds the Matern kinds' -- must stay under 5e-13."""
+    rng = np.random.default_rng(2)
+    worst = 0.0
+    for d in (1, 2, 6, 8, 10, 38):
+        for scale in (1.0, 5.0, 11.0, 15.5):
+            a = rng.normal(size=(400, d))
+            b = a[rng.integers(0, 400, 400)] + rng.normal(size=(400, d)) * rng.choice([1e-6, 1e-2, 1.0], size=(400, 1))
+            a = a / np.linalg.norm(a, axis=1, keepdims=True) * rng.uniform(0, scale, (400, 1))
+            b = b / np.maximum(np.linalg.norm(b, axis=1, keepdims=True), 1e-300) * rng.uniform(0, scale, (400, 1))
+            na = np.zeros(400)
+            nb = np.zeros(400)
+            for k in range(d):                      # per-row norms, fma order of the staging loop
+                na = na + a[:, k] * a[:, k]
+                nb = nb + b[:, k] * b[:, k]
+            keep = (na < 250.0) & (nb < 250.0)      # the kernel's guard
+            u = na + nb                              # the two augmented columns come first in the DMMA chain
+            for k in range(d):
+                u = u + a[:, k] * (-2.0 * b[:, k])
+            al, bl = a.astype(np.longdouble), b.astype(np.longdouble)
+            exact = np.sum((al - bl) ** 2, axis=1)
+            err = np.abs(u.astype(np.longdouble) - exact)[keep]
+            worst = max(worst, float(err.max()))
+    assert worst < 5e-13
