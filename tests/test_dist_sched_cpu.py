@@ -162,10 +162,13 @@ def _spawn(world, n, nb, pd=True, window=2):
 
 @pytest.mark.parametrize("world,n,nb,window", [(2, 1000, 128, 2), (2, 1000, 128, 3), (3, 1111, 128, 3),
                                                (4, 300, 128, 5), (2, 1300, 256, 4), (4, 1500, 128, 5),
-                                               (4, 1500, 128, 3)])
+                                               (4, 1500, 128, 3), (2, 1400, 128, 8), (3, 1700, 128, 8)])
 def test_schedule_over_gloo(world, n, nb, window):
     """world 2 - 4 with ragged last blocks, panel windows W = 2 .. 5 (look-ahead depth min(W - 1, world));
-    world 4 with 3 blocks (one rank owns nothing but still joins every collective); nb = 256."""
+    world 4 with 3 blocks (one rank owns nothing but still joins every collective); nb = 256.  The last two
+    cases use the production window (8) and are long enough (11 / 14 panels) that the factorisation starts with
+    whole-panel broadcasts and SWITCHES to the column-chunked tail once (n - k) < 4 nb P, as the n = 100k runs do
+    (in the shorter cases every panel is already in the tail)."""
     outs = _spawn(world, n, nb, window=window)
     B, rhs = _problem(n, n + world)
     _check(outs, world, n, nb, B, rhs)
